@@ -1,0 +1,235 @@
+/*
+ * libtextreid_b200 -- C ABI of the B200-native TextReID hot path.
+ *
+ * The reference (BrandonHanx/TextReID) is pure PyTorch and exposes no FFI; its "operator
+ * surface" is a set of Python call shapes.  Each entry point below names the reference code
+ * it replaces (paths relative to the reference root).  The Python host in `textreid_b200/`
+ * binds these with ctypes and mirrors the reference signatures; INTEGRATION.md shows the stub
+ * a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named `host_*`; the caller owns all memory,
+ *     including outputs and workspaces (sizes from the trb_*_bytes helpers);
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), never synchronise,
+ *     never allocate, keep no state between calls, and are CUDA-graph capturable;
+ *   - matrices are dense row-major; fp32 unless stated; ids / indices are int64 like the
+ *     reference's LongTensors;
+ *   - return value: 0 on success, TRB_ERR_* (negative) for rejected arguments, or a positive
+ *     cudaError_t.  trb_last_error_string() describes the last failure on the calling thread;
+ *   - there is no CPU fallback anywhere in this library.
+ *
+ * Ranking order (north star): similarity descending, ties by ascending gallery index, i.e.
+ * torch.argsort(descending=True, stable=True).  TRB_TOPK = 10 = max(topk) of the reference
+ * (lib/engine/inference.py:95 hard-codes topk=[1,5,10]).
+ */
+#ifndef TEXTREID_B200_H
+#define TEXTREID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRB_VERSION 100          /* 0.1.0 */
+#define TRB_TOPK_DEPTH 10
+
+#define TRB_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
+#define TRB_ERR_UNSUPPORTED (-2) /* valid request this build cannot serve (e.g. D not a multiple of 64 on the tensor-core path) */
+#define TRB_ERR_WORKSPACE (-3)   /* workspace too small */
+
+typedef void* trb_stream_t;
+
+int trb_version(void);
+const char* trb_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Row utilities
+ * ---------------------------------------------------------------------------------------- */
+
+/* y[r,:] = x[r,:] / max(||x[r,:]||_2, eps); optionally inv_norm[r] = 1/max(||x||, eps).
+ * Replaces F.normalize(p=2, dim=1): head.py:128-129,139,145; losses.py:112-113;
+ * evaluation.py:117-118.  x and y may alias.  inv_norm may be NULL. */
+int trb_l2_normalize_rows_f32(const float* x, float* y, float* inv_norm, int64_t rows, int64_t dim,
+                              float eps, trb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Retrieval evaluation  (lib/data/metrics/evaluation.py:11-37 rank(), :117-120 similarity)
+ *
+ * The [Q,G] similarity matrix is never written.  Work is split into
+ *   thresholds : similarity of every (query, relevant gallery item) pair       (small)
+ *   stream     : one pass over the gallery -> per-query top-10 candidates and, for every
+ *                relevant item, the number of gallery items ranking before it   (the GEMM)
+ *   finish     : merge candidate lists (gallery splits / ranks), hit ranks, AP  (small)
+ *   metrics    : CMC@k and mAP scalars                                          (tiny)
+ * "Relevant" = gallery pid equals the query pid (evaluation.py:20-21).  The relevant sets are
+ * a CSR over queries: rel_ptr[Q+1] int64, one slot per (query, relevant item).
+ * A gallery may be one shard of a larger one: g_base is the global index of local row 0 and
+ * every index leaving the library is global.
+ * ---------------------------------------------------------------------------------------- */
+
+/* thr[slot] = <qn[q,:], gn[rel_row[slot],:]> accumulated in k-ascending FFMA order, bit-identical
+ * to the value the fp32 stream kernel computes for the same pair.  rel_row holds LOCAL gallery rows;
+ * slots whose rel_row is < 0 (item lives on another shard) are left untouched. */
+int trb_retrieval_thresholds_f32(const float* qn, const float* gn, const int64_t* rel_ptr,
+                                 const int64_t* rel_row, float* thr, int64_t Q, int64_t D,
+                                 trb_stream_t stream);
+
+/* One pass over a (shard of the) gallery in fp32 FFMA arithmetic.
+ *   qn [Q,D], gn [G,D]   L2-normalised rows
+ *   rel_ptr [Q+1], thr [total], thr_gidx [total]  thresholds and the GLOBAL gallery index of each
+ *                         relevant item (tie-break); may all be NULL when ranks are not wanted
+ *   nsplit               the gallery is cut into nsplit contiguous pieces processed by different CTAs
+ *   cand_sim/cand_idx    [Q, nsplit, 10] best-first candidates of each piece (idx global, int64;
+ *                         unused entries: -inf / INT64_MAX)
+ *   cnt [total] int32    += #{local g : (s_g, g) ranks before (thr, thr_gidx)}; caller zeroes it
+ */
+int trb_retrieval_stream_f32(const float* qn, const float* gn, int64_t Q, int64_t G, int64_t D,
+                             int64_t g_base, const int64_t* rel_ptr, const float* thr,
+                             const int64_t* thr_gidx, int nsplit, float* cand_sim, int64_t* cand_idx,
+                             int32_t* cnt, trb_stream_t stream);
+
+/* Same contract as the thresholds/stream pair, from a MATERIALISED similarity matrix
+ * (drop-in for rank(similarity, ...), evaluation.py:11).  sim is [Q,G] with element strides
+ * (row_stride, col_stride) so that similarity.t() needs no copy.  rel_col holds gallery columns.
+ * Produces one candidate list per query (nsplit = 1) and cnt (may be NULL with rel_ptr NULL). */
+int trb_rank_similarity_f32(const float* sim, int64_t row_stride, int64_t col_stride, int64_t Q,
+                            int64_t G, const int64_t* rel_ptr, const int64_t* rel_col,
+                            float* cand_sim, int64_t* cand_idx, int32_t* cnt, trb_stream_t stream);
+
+/* sim[Q,G] = qn @ gn^T, materialised (evaluation.py:120).  Compatibility only: the npz cache
+ * (evaluation.py:126-142), re-ranking, and callers of rank().  Same k-ascending FFMA order as above. */
+int trb_similarity_f32(const float* qn, const float* gn, float* sim, int64_t Q, int64_t G, int64_t D,
+                       trb_stream_t stream);
+
+/* Merge `nlists` candidate lists per query into the final top-10 and derive the per-query
+ * ranking artefacts.
+ *   cand_sim/cand_idx [Q, nlists, 10]
+ *   q_pids [Q], g_pids [G_total] (global gallery pids)
+ *   rel_ptr/cnt       NULL in top-k-only mode (rank(get_mAP=False), evaluation.py:16-19)
+ * outputs
+ *   top_sim/top_idx [Q,10]  best-first; idx int64 global
+ *   first_hit [Q] int32     0-based rank of the best relevant item; in top-k-only mode the
+ *                           position of the first pid match inside the top-10, else INT32_MAX
+ *   hit_ranks [total] int32 per query, ascending 0-based ranks of its relevant items (NULL ok)
+ *   ap [Q]                  sum_j fl((j+1)/(rank_j+1)) / num_rel, rank-ascending fp32 sum;
+ *                           NaN when num_rel == 0 like the reference's 0/0 (NULL ok)
+ */
+int trb_retrieval_finish(const float* cand_sim, const int64_t* cand_idx, int nlists, int64_t Q,
+                         const int64_t* q_pids, const int64_t* g_pids, int64_t G_total,
+                         const int64_t* rel_ptr, const int32_t* cnt, float* top_sim, int64_t* top_idx,
+                         int32_t* first_hit, int32_t* hit_ranks, float* ap, trb_stream_t stream);
+
+/* cmc[i] = fl(#{q : first_hit[q] < topk[i]} / Q) * 100 and mAP = mean(ap) * 100
+ * (evaluation.py:23-26,35-36).  The AP mean is a fixed-order fp64 reduction rounded once to fp32;
+ * the bit-exact-to-torch-CPU mean is taken on the host by the Python layer in parity mode.
+ * topk is a HOST array of n <= 8 cut-offs.  map_out may be NULL. */
+int trb_retrieval_metrics(const int32_t* first_hit, const float* ap, int64_t Q, const int32_t* host_topk,
+                          int n_topk, float* cmc_out, float* map_out, trb_stream_t stream);
+
+/* ---- bf16 tensor-core path (tcgen05 + TMEM, operands staged by cp.async.bulk) ------------
+ * Operands live in HBM in a packed, tile-major, pre-swizzled bf16 layout that is byte-identical
+ * to the shared-memory image tcgen05.mma reads (128-row x 64-column K-major SWIZZLE_128B blocks),
+ * so a tile load is one contiguous bulk copy.  trb_pack_rows_bf16 produces it, fusing the L2
+ * normalisation (evaluation.py:117-118) and an optional row gather. */
+int64_t trb_packed_rows(int64_t rows);                 /* rows rounded up to the 128-row block */
+int64_t trb_packed_bytes(int64_t rows, int64_t dim);   /* bytes of the packed image, 0 if dim % 64 */
+
+/* src: [*, dim] fp32 (src_is_bf16 = 0) or bf16 (1).  Row r of the packed image is source row
+ * perm[r] (perm may be NULL = identity); rows >= `rows` are zero.  normalize != 0 applies
+ * x / max(||x||, eps) in fp32 before the single rounding to bf16. */
+int trb_pack_rows_bf16(const void* src, int src_is_bf16, const int64_t* perm, int normalize, float eps,
+                       void* packed, int64_t rows, int64_t dim, trb_stream_t stream);
+
+/* Tensor-core stream over a packed gallery shard.  Rows of both packed operands may be permuted:
+ * q_row_id [Qp] / g_row_id [Gp] give, per packed row, the query number (slot owner) and the GLOBAL
+ * gallery index (-1 for padding rows).  Everything else as trb_retrieval_stream_f32.
+ * mode 0: top-10 candidates + counts against thr (thr may be NULL -> top-k only)
+ * mode 1: threshold capture -- for packed query row i the gallery rows [band_lo[i], band_hi[i]) of
+ *         this shard are its relevant items; writes thr[rel_ptr[q] + rel_off[i] + (g - band_lo[i])]
+ *         and thr_gidx likewise, using the same MMA instruction sequence as mode 0 so that the
+ *         captured values are bit-identical to the streamed ones. */
+int trb_retrieval_stream_tc(const void* q_packed, const void* g_packed, int64_t Q, int64_t G, int64_t D,
+                            const int64_t* q_row_id, const int64_t* g_row_id, const int64_t* rel_ptr,
+                            float* thr, int64_t* thr_gidx, const int32_t* band_lo, const int32_t* band_hi,
+                            const int32_t* rel_off, int mode, int nsplit, float* cand_sim,
+                            int64_t* cand_idx, int32_t* cnt, trb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MoCo loss step  (lib/models/embeddings/moco_head/head.py:126-175, moco_head/loss.py:21-39,
+ *                  lib/models/losses.py:6-62,102-128,206-217)
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct trb_moco_shape {
+    int32_t N;      /* batch */
+    int32_t D;      /* embedding size, cfg.MODEL.EMBEDDING.FEATURE_SIZE */
+    int32_t K;      /* queue length, cfg.MODEL.MOCO.K */
+    int32_t C;      /* cfg.MODEL.NUM_CLASSES */
+} trb_moco_shape;
+
+typedef struct trb_moco_hparams {
+    float T;            /* 0.07, moco_head/loss.py:18 */
+    float epsilon;      /* label smoothing, cfg.MODEL.EMBEDDING.EPSILON */
+    float alpha, beta;  /* 0.6, 0.4  losses.py:106-107 */
+    float scale_pos, scale_neg; /* 10, 40 losses.py:108-109 */
+} trb_moco_hparams;
+
+int64_t trb_moco_loss_workspace_bytes(const trb_moco_shape* shape, int precision);
+
+/* Loss dict and its gradients in one stream-ordered call (fwd and bwd fused: the softmax
+ * statistics are consumed where they are produced, nothing is saved for a later backward).
+ *   v_embed, t_embed [N,D]   post-Linear, un-normalised (instance + global-align inputs)
+ *   v_qraw, t_qraw   [N,D]   InfoNCE query inputs before normalisation; pass the embeds
+ *                            themselves when cfg.MODEL.MOCO.FC is False (head.py:126-129)
+ *   v_key, t_key     [N,D]   key embeddings; normalised here when normalize_keys != 0
+ *                            (head.py:139,145) and written to v_key_n / t_key_n [N,D]
+ *   labels [N] int64; v_queue, t_queue [D,K]; id_queue [K] int64 (-1 = empty slot)
+ *   projection [D,C]
+ *   precision: 0 = fp32 FFMA path (parity, 1e-5); 1 = bf16 tcgen05 path (1e-3)
+ * outputs
+ *   losses [3]               instance, infonce, global_align (each with upstream grad 1)
+ *   d_inst, d_nce, d_ga      [2,N,D] per-loss gradients w.r.t. (v,t) embeds / qraw; NULL skips bwd
+ *   d_projection [D,C]       gradient of instance_loss w.r.t. projection
+ * The queue column mask (head.py:148-157) is evaluated on the device; no host sync. */
+int trb_moco_loss(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
+                  const float* v_key, const float* t_key, int normalize_keys, float* v_key_n,
+                  float* t_key_n, const int64_t* labels, const float* v_queue, const float* t_queue,
+                  const int64_t* id_queue, const float* projection, const trb_moco_shape* shape,
+                  const trb_moco_hparams* hp, int precision, float* losses, float* d_inst, float* d_nce,
+                  float* d_ga, float* d_projection, void* workspace, int64_t workspace_bytes,
+                  trb_stream_t stream);
+
+/* out = g[0]*a + g[1]*b + g[2]*c with g a DEVICE array of 3 upstream gradients (any of a,b,c may
+ * be NULL).  Backward of the loss dict without a host sync (trainer.py:82,90 uses g = 1,1,1). */
+int trb_combine3_f32(float* out, const float* a, const float* b, const float* c, const float* g,
+                     int64_t n, trb_stream_t stream);
+
+/* x *= g[0] unless g[0] == 1 (then no memory traffic). */
+int trb_scale_inplace_f32(float* x, const float* g, int64_t n, trb_stream_t stream);
+
+/* Momentum update p_k <- fl(fl(p_k*m) + fl(p_q*(1-m))), exactly the reference's two products and
+ * one add (head.py:78-94); one_minus_m is passed separately because the reference forms 1-m in
+ * double.  Flat form: one contiguous parameter arena. */
+int trb_ema_update_f32(float* p_k, const float* p_q, int64_t n, float m, float one_minus_m,
+                       trb_stream_t stream);
+
+/* Multi-tensor form: a device table of `nchunks` (k_ptr, q_ptr, count) chunks built once by the host. */
+typedef struct trb_ema_chunk {
+    float* k;
+    const float* q;
+    int64_t n;
+} trb_ema_chunk;
+int trb_ema_update_chunks_f32(const trb_ema_chunk* chunks, int64_t nchunks, int64_t max_chunk, float m,
+                              float one_minus_m, trb_stream_t stream);
+
+/* _dequeue_and_enqueue (head.py:96-109): queue[:, ptr:ptr+N] = keys^T for both queues and the ids,
+ * then ptr = (ptr+N) % K, with ptr read and written on the device.  Requires K % N == 0 like the
+ * reference's assert.  v_keys, t_keys [N,D] normalised; queues [D,K]; id_queue [K]; queue_ptr [1]. */
+int trb_enqueue(float* v_queue, float* t_queue, int64_t* id_queue, int64_t* queue_ptr,
+                const float* v_keys, const float* t_keys, const int64_t* ids, int32_t N, int32_t D,
+                int32_t K, trb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXTREID_B200_H */

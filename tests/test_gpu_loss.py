@@ -1,0 +1,201 @@
+"""GPU parity tests of the MoCo loss step (loss dict + gradients, EMA, enqueue) against the golden
+fixtures of the unmodified reference and against the CPU oracle.  `pytest -m gpu` on a B200."""
+import copy
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+import textreid_b200 as trb
+from oracle import textreid_oracle as O
+
+DEV = "cuda"
+KEYS = ("instance_loss", "infonce_loss", "global_align_loss")
+
+
+def load(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name + ".npz")).items()}
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a)).to(DEV)
+
+
+def run_fused(g_or_inputs, eps, weights=(1.0, 1.0, 1.0), precision="fp32", enqueue=False):
+    a = {k: (T(v) if isinstance(v, np.ndarray) else v.to(DEV)) for k, v in g_or_inputs.items()}
+    ve = a["v_embed"].clone().requires_grad_(True)
+    te = a["t_embed"].clone().requires_grad_(True)
+    pr = a["projection"].clone().requires_grad_(True)
+    K = a["v_queue"].shape[1]
+    ptr = torch.zeros(1, dtype=torch.int64, device=DEV)
+    d = trb.moco_loss_dict(ve, te, a["v_key"], a["t_key"], a["labels"], a["v_queue"].clone(), a["t_queue"].clone(),
+                           a["id_queue"].reshape(1, K).clone(), ptr, pr, epsilon=eps, enqueue=enqueue, precision=precision)
+    total = sum(w * d[k] for w, k in zip(weights, KEYS))
+    total.backward()
+    return d, ve.grad, te.grad, pr.grad
+
+
+@pytest.mark.parametrize("name", ["loss_fn_small", "loss_fn_nomask", "loss_fn_allmask", "loss_fn_eps0"])
+def test_loss_dict_matches_reference_golden(golden_dir, name):
+    g = load(golden_dir, name)
+    eps = float(g["eps"])
+    inputs = {k: g[k] for k in ("v_embed", "t_embed", "v_key", "t_key", "labels", "v_queue", "t_queue", "id_queue", "projection")}
+    for i, (key, short) in enumerate(zip(KEYS, ("instance", "infonce", "global_align"))):
+        w = [0.0, 0.0, 0.0]
+        w[i] = 1.0
+        d, gv, gt, gp = run_fused(inputs, eps, w)
+        torch.testing.assert_close(d[key].cpu(), torch.from_numpy(g[key]), rtol=1e-5, atol=1e-6)      # north star: 1e-5 fp32
+        torch.testing.assert_close(gv.cpu(), torch.from_numpy(g[f"grad.{short}.v"]), rtol=1e-4, atol=2e-6)
+        torch.testing.assert_close(gt.cpu(), torch.from_numpy(g[f"grad.{short}.t"]), rtol=1e-4, atol=2e-6)
+        if f"grad.{short}.p" in g:
+            torch.testing.assert_close(gp.cpu(), torch.from_numpy(g[f"grad.{short}.p"]), rtol=1e-4, atol=2e-6)
+        else:
+            assert float(gp.abs().max()) == 0.0
+
+
+from textreid_b200.synthetic import loss_inputs as synth_loss_inputs
+
+
+@pytest.mark.parametrize("N,D,K,C,masked", [(128, 256, 2048, 11003, "some"), (256, 256, 4096, 11003, "some"),
+                                              (32, 64, 128, 1000, "empty"), (20, 48, 60, 77, "some")])
+def test_loss_dict_vs_oracle_full_size(N, D, K, C, masked):
+    inp = synth_loss_inputs(N, D, K, C, seed=N + K, masked=masked)
+    eps = 0.1
+    d, gv, gt, gp = run_fused(inp, eps)
+    args = [inp[k].double() if inp[k].dtype.is_floating_point else inp[k]
+            for k in ("v_embed", "t_embed", "v_key", "t_key", "labels", "v_queue", "t_queue", "id_queue", "projection")]
+    losses, rv, rt, rp = O.moco_loss_dict_with_grads(*args, epsilon=eps)          # fp64 oracle
+    for k in KEYS:
+        torch.testing.assert_close(d[k].cpu().double(), losses[k], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gv.cpu().double(), rv, rtol=2e-4, atol=1e-6)
+    torch.testing.assert_close(gt.cpu().double(), rt, rtol=2e-4, atol=1e-6)
+    torch.testing.assert_close(gp.cpu().double(), rp, rtol=2e-4, atol=1e-7)
+
+
+def test_upstream_gradient_weights_are_applied_on_device():
+    inp = synth_loss_inputs(16, 32, 64, 101, seed=4)
+    w = (0.5, 2.0, -1.5)
+    d, gv, gt, gp = run_fused(inp, 0.1, w)
+    args = [inp[k] for k in ("v_embed", "t_embed", "v_key", "t_key", "labels", "v_queue", "t_queue", "id_queue", "projection")]
+    _, rv, rt, rp = O.moco_loss_dict_with_grads(*args, weights=w, epsilon=0.1)
+    torch.testing.assert_close(gv.cpu(), rv, rtol=2e-4, atol=2e-6)
+    torch.testing.assert_close(gt.cpu(), rt, rtol=2e-4, atol=2e-6)
+    torch.testing.assert_close(gp.cpu(), rp, rtol=2e-4, atol=2e-6)
+
+
+class StubEncoder(nn.Module):
+    def __init__(self, in_dim, out_channels, take_captions=False):
+        super().__init__()
+        self.out_channels = out_channels
+        self.take_captions = take_captions
+        self.lin = nn.Linear(in_dim, out_channels)
+
+    def forward(self, x):
+        if self.take_captions:
+            x = torch.stack([c.feat for c in x])
+        return self.lin(x)
+
+
+class StubCaption:
+    def __init__(self, feat, pid):
+        self.feat, self._id = feat, pid
+
+    def get_field(self, name):
+        return self._id
+
+
+@pytest.mark.parametrize("name", ["moco_head_small", "moco_head_fc"])
+def test_fused_moco_head_replays_reference_steps(golden_dir, name):
+    """FusedMoCoHead loaded with the reference's state dict reproduces, step by step, the reference
+    MoCoHead's losses, parameter gradients, EMA'd key encoders (bit-exact) and queue contents."""
+    g = load(golden_dir, name)
+    N, F, D, K, C, steps, fc = [int(x) for x in g["meta"]]
+    cfg = SimpleNamespace(MODEL=SimpleNamespace(EMBEDDING=SimpleNamespace(FEATURE_SIZE=D, EPSILON=float(g["eps"])),
+                                                MOCO=SimpleNamespace(K=K, M=0.999, FC=bool(fc)), NUM_CLASSES=C))
+    head = trb.FusedMoCoHead(cfg, StubEncoder(F, F), StubEncoder(F, F, take_captions=True))
+    state = {k[len("state0."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state0.")}
+    missing, unexpected = head.load_state_dict(state, strict=True)      # same names/shapes as the reference
+    head.to(DEV).train()
+    for s in range(steps):
+        images, cfeat, labels = T(g[f"s{s}.images"]), T(g[f"s{s}.cfeat"]), T(g[f"s{s}.labels"])
+        caps = [StubCaption(cfeat[i], labels[i]) for i in range(N)]
+        head.zero_grad()
+        losses = head(images, caps)
+        assert set(losses) == set(KEYS)
+        sum(losses.values()).backward()
+        for k in KEYS:
+            torch.testing.assert_close(losses[k].detach().cpu(), torch.from_numpy(g[f"s{s}.loss.{k}"]), rtol=1e-5, atol=2e-6)
+        for k, p in head.named_parameters():
+            gk = f"s{s}.grad.{k}"
+            if gk in g:
+                torch.testing.assert_close(p.grad.cpu(), torch.from_numpy(g[gk]), rtol=3e-4, atol=3e-6)
+        sd = head.state_dict()
+        for k in sd:
+            gk = f"s{s}.state.{k}"
+            if gk not in g:
+                continue
+            ref = torch.from_numpy(g[gk])
+            if "encoder_k" in k or "fc_k" in k or not ref.dtype.is_floating_point:
+                assert torch.equal(sd[k].cpu(), ref), k            # EMA / ids / pointer: bit-exact
+            else:
+                torch.testing.assert_close(sd[k].cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_fused_head_eval_branch_and_checkpoint_layout():
+    cfg = SimpleNamespace(MODEL=SimpleNamespace(EMBEDDING=SimpleNamespace(FEATURE_SIZE=32, EPSILON=0.1),
+                                                MOCO=SimpleNamespace(K=64, M=0.999, FC=False), NUM_CLASSES=50))
+    head = trb.FusedMoCoHead(cfg, StubEncoder(8, 16), StubEncoder(8, 16, take_captions=True)).to(DEV).eval()
+    sd = head.state_dict()
+    assert sd["t_queue"].shape == (32, 64) and sd["v_queue"].dtype == torch.float32
+    assert sd["id_queue"].shape == (1, 64) and sd["id_queue"].dtype == torch.int64 and int(sd["id_queue"].max()) == -1
+    assert sd["queue_ptr"].shape == (1,) and sd["queue_ptr"].dtype == torch.int64
+    assert sd["loss_evaluator.projection"].shape == (32, 50)
+    x = torch.randn(4, 8, device=DEV)
+    caps = [StubCaption(x[i], torch.tensor(i)) for i in range(4)]
+    out = head(x, caps)
+    assert isinstance(out, list) and len(out) == 2 and out[0].shape == (4, 32)      # un-normalised [v_embed, t_embed]
+
+
+def test_enqueue_wraps_and_rejects_indivisible_batch():
+    D, K, N = 16, 24, 8
+    vq, tq = torch.zeros(D, K, device=DEV), torch.zeros(D, K, device=DEV)
+    idq = -torch.ones(1, K, dtype=torch.int64, device=DEV)
+    ptr = torch.tensor([16], dtype=torch.int64, device=DEV)
+    rv, rt, rid, rptr = vq.cpu().clone(), tq.cpu().clone(), idq.cpu().clone(), ptr.cpu().clone()
+    for step in range(4):           # 16 -> 0 -> 8 -> 16 -> 0 : wraps twice
+        vk, tk = torch.randn(N, D), torch.randn(N, D)
+        ids = torch.arange(N) + 100 * step
+        trb.dequeue_and_enqueue(vq, tq, idq, ptr, vk.to(DEV), tk.to(DEV), ids.to(DEV))
+        O.enqueue(rv, rt, rid, rptr, vk, tk, ids)
+        assert torch.equal(vq.cpu(), rv) and torch.equal(tq.cpu(), rt)
+        assert torch.equal(idq.cpu(), rid) and torch.equal(ptr.cpu(), rptr)
+    with pytest.raises(AssertionError):
+        trb.dequeue_and_enqueue(vq, tq, idq, ptr, torch.randn(5, D, device=DEV), torch.randn(5, D, device=DEV),
+                                torch.arange(5, device=DEV))
+
+
+@pytest.mark.parametrize("n", [1, 3, 4099, 1 << 20])
+def test_ema_bit_exact(golden_dir, n):
+    g = torch.Generator().manual_seed(n)
+    k, q = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    want = k * 0.999 + q * (1.0 - 0.999)          # the reference expression, head.py:81
+    kd = k.to(DEV)
+    trb.ema_update_flat(kd, q.to(DEV), 0.999)
+    assert torch.equal(kd.cpu(), want)
+    # multi-tensor table, including a mis-aligned view
+    big_k, big_q = torch.randn(n + 3, generator=g).to(DEV), torch.randn(n + 3, generator=g).to(DEV)
+    pk, pq = [kd.clone(), big_k[1:n + 1]], [q.to(DEV), big_q[1:n + 1]]
+    want2 = [p.cpu() * 0.999 + r.cpu() * (1.0 - 0.999) for p, r in zip(pk, pq)]
+    upd = trb.MomentumUpdater(0.999)
+    upd(pk, pq)
+    for a, b in zip(pk, want2):
+        assert torch.equal(a.cpu(), b)
+    g2 = load(golden_dir, "ema")
+    kd = T(g2["k"]).clone()
+    trb.ema_update_flat(kd, T(g2["q"]), float(g2["m"]))
+    assert torch.equal(kd.cpu(), torch.from_numpy(g2["k1"]))

@@ -1,0 +1,276 @@
+"""GPU parity tests of the retrieval evaluation path: CUDA (through the C ABI) vs the CPU oracle and
+vs the golden fixtures produced by the unmodified reference.  Run with `pytest -m gpu` on a B200."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import textreid_b200 as trb
+from textreid_b200.evaluation import reference_tail_from_hit_ranks
+from textreid_b200.rerank import similarity_matrix
+from oracle import textreid_oracle as O
+
+DEV = "cuda"
+
+
+def load(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name + ".npz")).items()}
+
+
+def T(a, dev=DEV):
+    return torch.from_numpy(np.asarray(a)).to(dev)
+
+
+def nan_equal(a, b):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    return torch.equal(a, b) or bool(torch.isnan(a).all() and torch.isnan(b).all())
+
+
+# ----------------------------------------------------------------------------------------------
+# rank() on a materialised similarity: golden vectors of the reference
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rank_gauss", "rank_exact", "rank_exact_le2"])
+def test_rank_matches_reference_golden(golden_dir, name):
+    g = load(golden_dir, name)
+    sim, tp, ip = T(g["similarity"]), T(g["text_pid"]), T(g["image_pid"])
+    for direction, s, qp, gp in (("t2i", sim, tp, ip), ("i2t", sim.t(), ip, tp)):   # .t(): strided, no copy
+        cmc, mAP, idx = trb.rank(s, qp, gp, [1, 5, 10], get_mAP=True)
+        assert torch.equal(cmc.cpu(), torch.from_numpy(g[direction + "_cmc"])), direction      # R@k bit-exact
+        assert torch.equal(idx.cpu(), torch.from_numpy(g[direction + "_top10"])), direction    # indices bit-exact
+        ref_map = torch.from_numpy(g[direction + "_mAP"])
+        if torch.isnan(ref_map):
+            assert torch.isnan(mAP.cpu())                                                      # num_rel = 0 -> NaN
+        else:
+            torch.testing.assert_close(mAP.cpu(), ref_map, rtol=2e-6, atol=0)
+        # parity mode: reference summation order on the kernel's integer artefacts -> bit-exact mAP
+        cmc_p, mAP_p, _ = trb.rank(s, qp, gp, [1, 5, 10], get_mAP=True, parity=True)
+        assert torch.equal(cmc_p.cpu(), torch.from_numpy(g[direction + "_cmc"]))
+        assert nan_equal(mAP_p, ref_map)
+    if "t2i_cmc_topk" in g:
+        cmc, idx = trb.rank(sim, tp, ip, [1, 5, 10], get_mAP=False)
+        assert torch.equal(cmc.cpu(), torch.from_numpy(g["t2i_cmc_topk"]))
+        assert torch.equal(idx.cpu(), torch.from_numpy(g["t2i_idx_topk"]))
+
+
+def test_rank_le2_fixture_ap_vector_bit_exact(golden_dir):
+    """With <= 2 relevant items per query the per-query AP is summation-order free: the fused AP vector
+    and its mean must equal the reference bit for bit (hard parts)."""
+    g = load(golden_dir, "rank_exact_le2")
+    sim, tp, ip = T(g["similarity"]), T(g["text_pid"]), T(g["image_pid"])
+    res = trb.rank_artifacts(sim, tp, ip, [1, 5, 10], True)
+    order = torch.argsort(sim.cpu(), dim=1, descending=True, stable=True)
+    hit = ip.cpu()[order] == tp.cpu().view(-1, 1)
+    run = hit.cumsum(1)
+    ap_ref = ((run.float() / torch.arange(1, sim.shape[1] + 1, dtype=torch.float32)) * hit).sum(1) / hit.sum(1)
+    assert torch.equal(res.ap.cpu(), ap_ref)
+    assert torch.equal((res.ap.cpu().mean() * 100), torch.from_numpy(g["t2i_mAP"]))
+
+
+# ----------------------------------------------------------------------------------------------
+# retrieve(): fused path, no similarity matrix
+# ----------------------------------------------------------------------------------------------
+def make_case(Q, G, D, n_ids, seed, exact=False, noise=1.0):
+    gen = torch.Generator().manual_seed(seed)
+    ipid = torch.randint(0, n_ids, (G,), generator=gen)
+    src = torch.randint(0, G, (Q,), generator=gen)
+    tpid = ipid[src].clone()
+    tpid[::17] = n_ids + 5                      # some queries without any relevant item (AP = NaN)
+    if exact:
+        scale = {256: 16.0, 64: 8.0, 1024: 32.0}[D]
+        image = (torch.randint(0, 2, (G, D), generator=gen).float() * 2 - 1) / scale
+        text = (torch.randint(0, 2, (Q, D), generator=gen).float() * 2 - 1) / scale
+    else:
+        image = torch.randn(G, D, generator=gen)
+        text = 0.5 * image[src] + noise * torch.randn(Q, D, generator=gen)
+    return text, image, tpid, ipid
+
+
+def check_against_matrix(res, sim_cpu, tpid, ipid, topk=(1, 5, 10), exact_ap=False):
+    """Ranking-stage exactness given a similarity matrix that is bit-identical to what the kernel saw."""
+    Q, G = sim_cpu.shape
+    cmc, mAP, order = O.rank(sim_cpu, tpid, ipid, topk, get_mAP=True, per_column_loop=False)
+    k = min(10, G)
+    assert torch.equal(res.top_idx.cpu()[:, :k], order[:, :k])
+    assert torch.equal(res.top_sim.cpu()[:, :k], torch.gather(sim_cpu, 1, order[:, :k]))
+    assert torch.equal(res.cmc.cpu(), cmc)
+    ranks = O.hit_ranks(sim_cpu, tpid, ipid)
+    rel_ptr = res.rel_ptr.cpu()
+    hr = res.hit_ranks.cpu()
+    for q in range(Q):
+        assert torch.equal(hr[rel_ptr[q]:rel_ptr[q + 1]].long(), ranks[q]), q
+    # per-query AP: same terms, canonical rank-ascending fp32 sum; <= 2 ulp from torch's order
+    hit = ipid[order] == tpid.view(-1, 1)
+    ap_ref = ((hit.cumsum(1).float() / torch.arange(1, G + 1, dtype=torch.float32)) * hit).sum(1) / hit.sum(1)
+    ap = res.ap.cpu()
+    nan = torch.isnan(ap_ref)
+    assert torch.equal(torch.isnan(ap), nan)
+    if exact_ap:
+        assert torch.equal(ap[~nan], ap_ref[~nan])
+    else:
+        torch.testing.assert_close(ap[~nan], ap_ref[~nan], rtol=3e-7, atol=0)
+    if nan.any():
+        assert torch.isnan(res.mAP.cpu())
+    else:
+        torch.testing.assert_close(res.mAP.cpu(), mAP, rtol=2e-6, atol=0)
+    # parity tail reproduces the reference scalars bit for bit
+    cmc_p, mAP_p = reference_tail_from_hit_ranks(res, G, topk)
+    assert torch.equal(cmc_p, cmc) and nan_equal(mAP_p, mAP)
+
+
+@pytest.mark.parametrize("Q,G,D,nsplit", [(300, 517, 64, None), (129, 1031, 256, 3), (77, 9, 32, None),
+                                           (1, 1, 16, None), (513, 300, 256, 2)])
+def test_retrieve_fp32_ranking_exact_vs_oracle(Q, G, D, nsplit):
+    text, image, tpid, ipid = make_case(Q, G, D, n_ids=max(G // 3, 1), seed=Q + G)
+    res = trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), get_mAP=True, precision="fp32", nsplit=nsplit)
+    # the kernel's own similarities (same FFMA order) -> CPU oracle ranking must agree exactly
+    qn, gn = trb.l2_normalize_rows(T(text)), trb.l2_normalize_rows(T(image))
+    sim = similarity_matrix(qn, gn).cpu()
+    check_against_matrix(res, sim, tpid, ipid)
+    # and the similarities are the reference's within 1e-5 (relative, with an absolute floor)
+    ref = O.similarity_matrix(text.double(), image.double())
+    torch.testing.assert_close(sim.double(), ref, rtol=1e-5, atol=1e-6)
+    # thresholds are bit-identical to the streamed values: relevant items inside the top-10 sit at their rank
+    top_idx, first_hit = res.top_idx.cpu(), res.first_hit.cpu()
+    for q in range(Q):
+        hits = (ipid[top_idx[q].clamp(min=0)] == tpid[q]) & (top_idx[q] >= 0)
+        want = int(hits.nonzero()[0]) if hits.any() else None
+        if want is not None:
+            assert int(first_hit[q]) == want
+
+
+def test_retrieve_fp32_golden_exact_fixture(golden_dir):
+    """End-to-end bit-exactness on the +-1/16 fixture (every dot product exact, tie-heavy)."""
+    for name in ("rank_exact", "rank_exact_le2"):
+        g = load(golden_dir, name)
+        res = trb.retrieve(T(g["text"]), T(g["image"]), T(g["text_pid"]), T(g["image_pid"]), (1, 5, 10), True, "fp32")
+        assert torch.equal(res.cmc.cpu(), torch.from_numpy(g["t2i_cmc"]))
+        assert torch.equal(res.top_idx.cpu(), torch.from_numpy(g["t2i_top10"]))
+        cmc_p, mAP_p = reference_tail_from_hit_ranks(res, g["image"].shape[0], (1, 5, 10))
+        assert torch.equal(mAP_p, torch.from_numpy(g["t2i_mAP"]))
+        res = trb.retrieve(T(g["image"]), T(g["text"]), T(g["image_pid"]), T(g["text_pid"]), (1, 5, 10), True, "fp32")
+        assert torch.equal(res.cmc.cpu(), torch.from_numpy(g["i2t_cmc"]))
+        assert torch.equal(res.top_idx.cpu(), torch.from_numpy(g["i2t_top10"]))
+    g = load(golden_dir, "rank_exact_le2")
+    res = trb.retrieve(T(g["text"]), T(g["image"]), T(g["text_pid"]), T(g["image_pid"]), (1, 5, 10), True, "fp32")
+    assert torch.equal(res.mAP.cpu(), torch.from_numpy(g["t2i_mAP"]))      # fused scalar, no parity tail needed
+
+
+def test_retrieve_topk_only_mode(golden_dir):
+    g = load(golden_dir, "rank_gauss")
+    for prec in ("fp32",):
+        res = trb.retrieve(T(g["text"]), T(g["image"]), T(g["text_pid"]), T(g["image_pid"]), [1, 5, 10], False, prec)
+        assert res.mAP is None and res.ap is None
+        assert torch.equal(res.cmc.cpu(), torch.from_numpy(g["t2i_cmc_topk"]))
+        assert torch.equal(res.top_idx.cpu(), torch.from_numpy(g["t2i_idx_topk"]))
+
+
+def test_many_relevant_items_overflow_path():
+    """More relevant items per query than the kernel keeps in registers (RREG / RT = 8)."""
+    text, image, tpid, ipid = make_case(200, 700, 64, n_ids=20, seed=3)     # ~35 images per id
+    res = trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "fp32")
+    sim = similarity_matrix(trb.l2_normalize_rows(T(text)), trb.l2_normalize_rows(T(image))).cpu()
+    check_against_matrix(res, sim, tpid, ipid)
+    res2 = trb.rank_artifacts(sim.to(DEV), T(tpid), T(ipid), (1, 5, 10), True)     # > 64 slots per row path too
+    assert torch.equal(res2.hit_ranks.cpu(), res.hit_ranks.cpu())
+    assert torch.equal(res2.top_idx.cpu(), res.top_idx.cpu())
+
+
+# ----------------------------------------------------------------------------------------------
+# bf16 tensor-core path (tcgen05 / TMEM / bulk-copy staged packed operands)
+# ----------------------------------------------------------------------------------------------
+def bf16_reference_sim(text, image):
+    tn = O.normalize_rows(text).to(torch.bfloat16).double()
+    im = O.normalize_rows(image).to(torch.bfloat16).double()
+    return tn @ im.t()
+
+
+@pytest.mark.parametrize("Q,G,D,nsplit", [(80, 70, 256, None), (300, 1000, 256, 2), (129, 257, 64, None),
+                                           (1000, 3074, 256, None), (64, 600, 512, None)])
+def test_retrieve_bf16_exact_arithmetic_fixture(Q, G, D, nsplit):
+    """+-2^-k Rademacher embeddings: unit norm, every dot product exact in bf16 x bf16 -> fp32 under ANY
+    summation order, heavy ties.  The tensor-core path must then be bit-exact with the stable-sort oracle:
+    indices, R@k, hit ranks, AP terms."""
+    gen = torch.Generator().manual_seed(Q * 7 + G)
+    scale = float(D) ** 0.5
+    image = (torch.randint(0, 2, (G, D), generator=gen).float() * 2 - 1) / scale
+    text = (torch.randint(0, 2, (Q, D), generator=gen).float() * 2 - 1) / scale
+    if D == 512:   # sqrt(512) is not a power of two: use a 256-sparse support instead
+        image[:, 256:] = 0; text[:, 256:] = 0
+        image[:, :256] = image[:, :256].sign() / 16.0; text[:, :256] = text[:, :256].sign() / 16.0
+    ipid = torch.randint(0, max(G // 4, 1), (G,), generator=gen)
+    tpid = ipid[torch.randint(0, G, (Q,), generator=gen)].clone()
+    tpid[::13] = 10 ** 6
+    res = trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "bf16", nsplit=nsplit)
+    sim = O.similarity_matrix(text, image)     # exact on this fixture
+    check_against_matrix(res, sim, tpid, ipid)
+    # threshold capture (banded run) is bit-identical to the streamed values
+    rel_ptr = res.rel_ptr.cpu()
+    thr = res.thresholds.cpu()
+    rel = trb.build_relevance(tpid, ipid)
+    for q in range(0, Q, 7):
+        cols = rel.rel_col[rel.rel_ptr[q]:rel.rel_ptr[q + 1]]
+        assert torch.equal(thr[rel_ptr[q]:rel_ptr[q + 1]], sim[q, cols])
+
+
+@pytest.mark.parametrize("Q,G", [(500, 2000), (130, 300)])
+def test_retrieve_bf16_gaussian_similarity_tolerance_and_self_consistency(Q, G):
+    D = 256
+    text, image, tpid, ipid = make_case(Q, G, D, n_ids=G // 4, seed=11)
+    res = trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "bf16")
+    ref = bf16_reference_sim(text, image)                       # same rounded operands, fp64 accumulate
+    top_idx = res.top_idx.cpu()
+    got = res.top_sim.cpu().double()
+    want = torch.gather(ref, 1, top_idx)
+    torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-5)     # north star: 1e-3 on the bf16 path
+    # vs the fp32 reference similarity: bf16 operand rounding only
+    ref32 = O.similarity_matrix(text.double(), image.double())
+    assert (torch.gather(ref32, 1, top_idx) - got).abs().max() < 2e-2
+    # self-consistency: thresholds bit-identical to streamed values (relevant item found in the top-10
+    # carries exactly its captured similarity and its rank equals its top-10 position)
+    rel_ptr, thr, hr = res.rel_ptr.cpu(), res.thresholds.cpu(), res.hit_ranks.cpu()
+    rel = trb.build_relevance(tpid, ipid)
+    checked = 0
+    for q in range(Q):
+        cols = rel.rel_col[rel.rel_ptr[q]:rel.rel_ptr[q + 1]]
+        for j in range(10):
+            gi = int(top_idx[q, j])
+            pos = (cols == gi).nonzero()
+            if pos.numel():
+                slot = int(rel_ptr[q]) + int(pos[0])
+                assert float(thr[slot]) == float(res.top_sim[q, j])
+                assert j in hr[rel_ptr[q]:rel_ptr[q + 1]].tolist()
+                checked += 1
+    assert checked > Q // 4
+    # ranks are exactly what a stable sort of the fp64-accumulated bf16 similarities gives wherever the
+    # ordering is not within accumulation noise: compare R@k
+    cmc, _, _ = O.rank(ref.float(), tpid, ipid, (1, 5, 10), True, per_column_loop=False)
+    assert (res.cmc.cpu() - cmc).abs().max() <= 100.0 * 3 / Q
+
+
+def test_retrieve_bf16_accepts_bf16_storage_and_topk_only():
+    text, image, tpid, ipid = make_case(256, 512, 256, n_ids=100, seed=5)
+    a = trb.retrieve(T(text).bfloat16(), T(image).bfloat16(), T(tpid), T(ipid), (1, 5, 10), False, "bf16")
+    assert a.mAP is None and a.top_idx.shape == (256, 10)
+    assert int((a.top_idx >= 0).all())
+
+
+def test_sharded_gallery_merge_single_device():
+    """Two gallery shards processed separately (g_base offsets) then merged by trb_retrieval_finish give the
+    single-pass result: the host logic of the multi-GPU path without NCCL."""
+    from textreid_b200.sharded import retrieve_sharded_local
+    text, image, tpid, ipid = make_case(200, 900, 64, n_ids=150, seed=9)
+    full = trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "fp32")
+    for prec, D in (("fp32", 64), ("bf16", 64)):
+        parts = retrieve_sharded_local(T(text), [T(image[:400]), T(image[400:])], T(tpid), [T(ipid[:400]), T(ipid[400:])],
+                                       (1, 5, 10), True, prec)
+        if prec == "fp32":
+            assert torch.equal(parts.top_idx, full.top_idx)
+            assert torch.equal(parts.hit_ranks, full.hit_ranks)
+            assert torch.equal(parts.cmc, full.cmc) and torch.equal(parts.mAP, full.mAP)
+        else:
+            one = trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "bf16")
+            assert torch.equal(parts.top_idx, one.top_idx)
+            assert torch.equal(parts.hit_ranks, one.hit_ranks)

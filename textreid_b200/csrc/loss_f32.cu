@@ -1,0 +1,349 @@
+// fp32 (FFMA) MoCo loss dict + gradients: the parity path (1e-5) of the north star.
+//
+// Math (SURVEY.md section 8a', verified against the reference's autograd):
+//   mask[k]  = any_n(id_queue[k] == y[n])                                   head.py:148-157
+//   InfoNCE  z = [<q,key> | q@queue (masked -> -inf)] / T, CE target 0       head.py:160-170, losses.py:206-217
+//   instance z = e @ (W/||W||_col), label-smoothed CE                        losses.py:42-62, 6-39
+//   align    S = q_v q_t^T, log(1+exp(.)) on same-id / other pairs           losses.py:102-128
+// Forward and backward are one stream-ordered launch sequence: logits are materialised in the
+// caller's workspace (a few MB), turned into their gradients in place, and contracted back.
+// The bf16 tcgen05 path (precision = 1) lives in loss_tc.cu and keeps them on chip instead.
+#include "common.cuh"
+#include "sgemm.cuh"
+
+namespace {
+
+__global__ void reduce_partials_kernel(float* __restrict__ out, const float* __restrict__ part, int nsplit, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int z = 0; z < nsplit; ++z) s += part[(int64_t)z * n + i];
+    out[i] = s;
+}
+
+// ---------------------------------------------------------------------------
+// prologue: normalised rows, positive logits, stacked embeds, queue column mask, column norms
+// ---------------------------------------------------------------------------
+// rows [0,N): v ; [N,2N): t.  One warp per row.
+__global__ void __launch_bounds__(256)
+prologue_rows_kernel(const float* __restrict__ v_embed, const float* __restrict__ t_embed, const float* __restrict__ v_qraw,
+                     const float* __restrict__ t_qraw, const float* __restrict__ v_key, const float* __restrict__ t_key,
+                     int normalize_keys, float* __restrict__ v_key_n, float* __restrict__ t_key_n, float* __restrict__ E2,
+                     float* __restrict__ en, float* __restrict__ inv_e, float* __restrict__ qn, float* __restrict__ inv_q,
+                     float* __restrict__ pos, int N, int D) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= 2 * N) return;
+    const int mod = row / N, n = row % N;
+    const float* e = (mod ? t_embed : v_embed) + (int64_t)n * D;
+    const float* r = (mod ? t_qraw : v_qraw) + (int64_t)n * D;
+    // v queries pair with TEXT keys, t queries with IMAGE keys (head.py:160,166)
+    const float* kin = (mod ? v_key : t_key) + (int64_t)n * D;
+    float* kout = (mod ? v_key_n : t_key_n) + (int64_t)n * D;
+    float se = 0.f, sr = 0.f, sk = 0.f;
+    for (int k = lane; k < D; k += 32) {
+        const float a = e[k], b = r[k], c = kin[k];
+        se = fmaf(a, a, se); sr = fmaf(b, b, sr); sk = fmaf(c, c, sk);
+    }
+    se = warp_sum(se); sr = warp_sum(sr); sk = warp_sum(sk);
+    const float ne = fmaxf(sqrtf(se), 1e-12f), nr = fmaxf(sqrtf(sr), 1e-12f);
+    const float nk = normalize_keys ? fmaxf(sqrtf(sk), 1e-12f) : 1.0f;
+    float dot = 0.f;
+    for (int k = lane; k < D; k += 32) {
+        const float a = e[k];
+        const float qv = __fdiv_rn(r[k], nr);
+        const float kv = normalize_keys ? __fdiv_rn(kin[k], nk) : kin[k];
+        E2[(int64_t)row * D + k] = a;
+        en[(int64_t)row * D + k] = __fdiv_rn(a, ne);
+        qn[(int64_t)row * D + k] = qv;
+        kout[k] = kv;
+        dot = fmaf(qv, kv, dot);
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) { inv_e[row] = __fdiv_rn(1.0f, ne); inv_q[row] = __fdiv_rn(1.0f, nr); pos[row] = dot; }
+}
+
+__global__ void __launch_bounds__(256)
+queue_mask_kernel(const int64_t* __restrict__ id_queue, const int64_t* __restrict__ labels, uint8_t* __restrict__ mask, int N, int K) {
+    extern __shared__ int64_t lab[];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) lab[i] = labels[i];
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int64_t id = id_queue[k];
+    bool hit = false;
+    for (int n = 0; n < N; ++n) hit |= (lab[n] == id);
+    mask[k] = hit ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+column_inv_norm_kernel(const float* __restrict__ W, float* __restrict__ inv_c, int D, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float ss = 0.f;
+    for (int d = 0; d < D; ++d) { const float w = W[(int64_t)d * C + c]; ss = fmaf(w, w, ss); }
+    inv_c[c] = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));
+}
+
+// ---------------------------------------------------------------------------
+// row kernels: logits -> loss contribution and logits gradient in place
+// ---------------------------------------------------------------------------
+// InfoNCE (losses.py:206-217).  S row [K] holds q@queue; column 0 of the reference's logits is pos.
+__global__ void __launch_bounds__(256)
+nce_rows_kernel(float* __restrict__ S, const float* __restrict__ pos, const uint8_t* __restrict__ mask, float T, int N, int K,
+                float* __restrict__ loss_row, float* __restrict__ dpos, int want_grad) {
+    __shared__ float red[32];
+    const int row = blockIdx.x;
+    float* s = S + (int64_t)row * K;
+    const float z0 = __fdiv_rn(pos[row], T);
+    float mx = z0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        if (!mask[k]) mx = fmaxf(mx, __fdiv_rn(s[k], T));
+    mx = block_max(mx, red);
+    float se = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        if (!mask[k]) se += expf(__fdiv_rn(s[k], T) - mx);
+    se = block_sum(se, red);
+    se += expf(z0 - mx);
+    const float lse = mx + logf(se);
+    if (threadIdx.x == 0) loss_row[row] = lse - z0;
+    if (!want_grad) return;
+    const float gscale = 1.0f / ((float)N * T);
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        s[k] = mask[k] ? 0.f : expf(__fdiv_rn(s[k], T) - lse) * gscale;
+    if (threadIdx.x == 0) dpos[row] = (expf(z0 - lse) - 1.0f) * gscale;
+}
+
+// instance loss with label smoothing (losses.py:26-39, 53-60).  Z row [C].
+__global__ void __launch_bounds__(256)
+instance_rows_kernel(float* __restrict__ Z, const int64_t* __restrict__ labels, float eps, int N, int C,
+                     float* __restrict__ loss_row, int want_grad) {
+    __shared__ float red[32];
+    const int row = blockIdx.x;
+    float* z = Z + (int64_t)row * C;
+    const int y = (int)labels[row % N];
+    float mx = -CUDART_INF_F, sz = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { const float v = z[c]; mx = fmaxf(mx, v); sz += v; }
+    mx = block_max(mx, red);
+    sz = block_sum(sz, red);
+    float se = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) se += expf(z[c] - mx);
+    se = block_sum(se, red);
+    const float lse = mx + logf(se);
+    const float zy = z[y];
+    __syncthreads();
+    if (threadIdx.x == 0) loss_row[row] = lse - (1.0f - eps) * zy - (eps / (float)C) * sz;
+    if (!want_grad) return;
+    const float invN = 1.0f / (float)N, uni = eps / (float)C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float t = uni + ((c == y) ? (1.0f - eps) : 0.f);
+        z[c] = (expf(z[c] - lse) - t) * invN;
+    }
+}
+
+// global align (losses.py:114-127): S [N,N] -> per-row loss sums, dS in place
+__global__ void __launch_bounds__(128)
+align_rows_kernel(float* __restrict__ S, const int64_t* __restrict__ labels, float alpha, float beta, float sp, float sn,
+                  int N, float* __restrict__ loss_row, int want_grad) {
+    __shared__ float red[32];
+    const int i = blockIdx.x;
+    const int64_t yi = labels[i];
+    const float two_over_n = 2.0f / (float)N;
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const float s = S[(int64_t)i * N + j];
+        const bool same = labels[j] == yi;
+        const float x = same ? -sp * (s - alpha) : sn * (s - beta);
+        const float e = expf(x);
+        acc += logf(1.0f + e);
+        if (want_grad) S[(int64_t)i * N + j] = (same ? -sp : sn) * (e / (1.0f + e)) * two_over_n;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) loss_row[i] = acc;
+}
+
+// de = (dq + dpos*key - <.,q> q) * inv_norm : backward of x -> x/||x||   (one warp per row)
+__global__ void __launch_bounds__(256)
+normalize_backward_kernel(const float* __restrict__ dq, const float* __restrict__ dpos, const float* __restrict__ key_v,
+                          const float* __restrict__ key_t, const float* __restrict__ qn, const float* __restrict__ inv_norm,
+                          float* __restrict__ out, int N, int D) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= 2 * N) return;
+    const float* g = dq + (int64_t)row * D;
+    const float* q = qn + (int64_t)row * D;
+    const float* key = nullptr;
+    float dp = 0.f;
+    if (dpos) { dp = dpos[row]; key = (row < N ? key_t : key_v) + (int64_t)(row % N) * D; }
+    float dot = 0.f;
+    for (int k = lane; k < D; k += 32) {
+        const float gv = g[k] + (key ? dp * key[k] : 0.f);
+        dot = fmaf(gv, q[k], dot);
+    }
+    dot = warp_sum(dot);
+    const float inv = inv_norm[row];
+    for (int k = lane; k < D; k += 32) {
+        const float gv = g[k] + (key ? dp * key[k] : 0.f);
+        out[(int64_t)row * D + k] = (gv - dot * q[k]) * inv;
+    }
+}
+
+// dW = (dWhat - <dWhat, What>_col What) / ||W||_col, What = W * inv_c   (thread per column, in place)
+__global__ void __launch_bounds__(256)
+projection_backward_kernel(float* __restrict__ dW, const float* __restrict__ W, const float* __restrict__ inv_c, int D, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float ic = inv_c[c];
+    float dot = 0.f;
+    for (int d = 0; d < D; ++d) dot = fmaf(dW[(int64_t)d * C + c], W[(int64_t)d * C + c] * ic, dot);
+    for (int d = 0; d < D; ++d) {
+        const int64_t o = (int64_t)d * C + c;
+        dW[o] = (dW[o] - dot * (W[o] * ic)) * ic;
+    }
+}
+
+// losses[0] = sum(inst rows)/N ; losses[1] = sum(nce rows)/N ; losses[2] = sum(align rows)*2/N
+__global__ void __launch_bounds__(256)
+loss_reduce_kernel(const float* __restrict__ inst_rows, const float* __restrict__ nce_rows, const float* __restrict__ ga_rows,
+                   int N, float* __restrict__ losses) {
+    __shared__ float red[32];
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) { a += inst_rows[i]; b += nce_rows[i]; }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) c += ga_rows[i];
+    a = block_sum(a, red); b = block_sum(b, red); c = block_sum(c, red);
+    if (threadIdx.x == 0) {
+        losses[0] = a / (float)N;
+        losses[1] = b / (float)N;
+        losses[2] = c * 2.0f / (float)N;
+    }
+}
+
+struct Workspace {
+    float *E2, *en, *qn, *inv_e, *inv_q, *pos, *dpos, *S_nce, *Z, *inv_c, *S_ga, *dq_nce, *dq_ga, *part, *rows_inst,
+        *rows_nce, *rows_ga;
+    uint8_t* mask;
+    int64_t bytes;
+};
+
+constexpr int SPLIT_NCE = 8, SPLIT_INST = 32;
+
+Workspace carve(void* base, int N, int D, int K, int C) {
+    Workspace w;
+    char* p = static_cast<char*>(base);
+    auto take = [&](int64_t nfloats) {
+        float* r = reinterpret_cast<float*>(p);
+        p += ((nfloats * 4 + 255) / 256) * 256;
+        return r;
+    };
+    const int64_t ND2 = 2LL * N * D;
+    w.E2 = take(ND2); w.en = take(ND2); w.qn = take(ND2);
+    w.inv_e = take(2 * N); w.inv_q = take(2 * N); w.pos = take(2 * N); w.dpos = take(2 * N);
+    w.S_nce = take(2LL * N * K);
+    w.Z = take(2LL * N * C);
+    w.inv_c = take(C);
+    w.S_ga = take((int64_t)N * N);
+    w.dq_nce = take(ND2); w.dq_ga = take(ND2);
+    const int64_t part = (int64_t)(SPLIT_INST > SPLIT_NCE ? SPLIT_INST : SPLIT_NCE) * ND2;
+    w.part = take(part);
+    w.rows_inst = take(2 * N); w.rows_nce = take(2 * N); w.rows_ga = take(N);
+    w.mask = reinterpret_cast<uint8_t*>(take((K + 3) / 4));
+    w.bytes = p - static_cast<char*>(base);
+    return w;
+}
+
+}  // namespace
+
+int64_t trb_moco_loss_workspace_bytes_f32(const trb_moco_shape* s) {
+    return carve(nullptr, s->N, s->D, s->K, s->C).bytes;
+}
+
+int trb_moco_loss_f32(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
+                      const float* v_key, const float* t_key, int normalize_keys, float* v_key_n, float* t_key_n,
+                      const int64_t* labels, const float* v_queue, const float* t_queue, const int64_t* id_queue,
+                      const float* projection, const trb_moco_shape* shape, const trb_moco_hparams* hp, float* losses,
+                      float* d_inst, float* d_nce, float* d_ga, float* d_projection, void* workspace,
+                      int64_t workspace_bytes, cudaStream_t st) {
+    const int N = shape->N, D = shape->D, K = shape->K, C = shape->C;
+    Workspace w = carve(workspace, N, D, K, C);
+    if (workspace_bytes < w.bytes) {
+        trb_set_error("moco_loss: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)w.bytes);
+        return TRB_ERR_WORKSPACE;
+    }
+    const bool grads = d_inst != nullptr;
+    const int rows = 2 * N;
+
+    prologue_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, normalize_keys,
+                                                          v_key_n, t_key_n, w.E2, w.en, w.inv_e, w.qn, w.inv_q, w.pos, N, D);
+    TRB_LAUNCH_OK();
+    queue_mask_kernel<<<(K + 255) / 256, 256, N * sizeof(int64_t), st>>>(id_queue, labels, w.mask, N, K);
+    TRB_LAUNCH_OK();
+    column_inv_norm_kernel<<<(C + 255) / 256, 256, 0, st>>>(projection, w.inv_c, D, C);
+    TRB_LAUNCH_OK();
+
+    int rc;
+    // ---- InfoNCE logits: v queries x text queue, t queries x image queue (head.py:164,170)
+    for (int mod = 0; mod < 2; ++mod) {
+        GemmArgs g{w.qn + (int64_t)mod * N * D, D, 1, mod ? v_queue : t_queue, K, 1,
+                   w.S_nce + (int64_t)mod * N * K, K, 0, N, K, D, nullptr, nullptr, 1};
+        if ((rc = launch_gemm(g, st))) return rc;
+    }
+    nce_rows_kernel<<<rows, 256, 0, st>>>(w.S_nce, w.pos, w.mask, hp->T, N, K, w.rows_nce, w.dpos, grads);
+    TRB_LAUNCH_OK();
+
+    // ---- instance logits for both modalities at once (losses.py:53-54)
+    {
+        GemmArgs g{w.E2, D, 1, projection, C, 1, w.Z, C, 0, rows, C, D, nullptr, w.inv_c, 1};
+        if ((rc = launch_gemm(g, st))) return rc;
+    }
+    instance_rows_kernel<<<rows, 256, 0, st>>>(w.Z, labels, hp->epsilon, N, C, w.rows_inst, grads);
+    TRB_LAUNCH_OK();
+
+    // ---- global align similarity (losses.py:114)
+    {
+        GemmArgs g{w.en, D, 1, w.en + (int64_t)N * D, 1, D, w.S_ga, N, 0, N, N, D, nullptr, nullptr, 1};
+        if ((rc = launch_gemm(g, st))) return rc;
+    }
+    align_rows_kernel<<<N, 128, 0, st>>>(w.S_ga, labels, hp->alpha, hp->beta, hp->scale_pos, hp->scale_neg, N, w.rows_ga, grads);
+    TRB_LAUNCH_OK();
+
+    loss_reduce_kernel<<<1, 256, 0, st>>>(w.rows_inst, w.rows_nce, w.rows_ga, N, losses);
+    TRB_LAUNCH_OK();
+    if (!grads) return 0;
+
+    const int64_t ND = (int64_t)N * D;
+    // ---- InfoNCE backward: dq = dS @ queue^T (+ dpos * key), through the normalisation
+    for (int mod = 0; mod < 2; ++mod) {
+        GemmArgs g{w.S_nce + (int64_t)mod * N * K, K, 1, mod ? v_queue : t_queue, 1, K,
+                   w.part, D, ND, N, D, K, nullptr, nullptr, SPLIT_NCE};
+        if ((rc = launch_gemm(g, st))) return rc;
+        reduce_partials_kernel<<<(unsigned)((ND + 255) / 256), 256, 0, st>>>(w.dq_nce + mod * ND, w.part, SPLIT_NCE, ND);
+        TRB_LAUNCH_OK();
+    }
+    normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w.dq_nce, w.dpos, v_key_n, t_key_n, w.qn, w.inv_q, d_nce, N, D);
+    TRB_LAUNCH_OK();
+
+    // ---- instance backward: dE = dZ @ What^T (split over classes), dWhat = E^T @ dZ
+    {
+        GemmArgs g{w.Z, C, 1, projection, 1, C, w.part, D, 2 * ND, rows, D, C, w.inv_c, nullptr, SPLIT_INST};
+        if ((rc = launch_gemm(g, st))) return rc;
+        reduce_partials_kernel<<<(unsigned)((2 * ND + 255) / 256), 256, 0, st>>>(d_inst, w.part, SPLIT_INST, 2 * ND);
+        TRB_LAUNCH_OK();
+    }
+    if (d_projection) {
+        GemmArgs g{w.E2, 1, D, w.Z, C, 1, d_projection, C, 0, D, C, rows, nullptr, nullptr, 1};
+        if ((rc = launch_gemm(g, st))) return rc;
+        projection_backward_kernel<<<(C + 255) / 256, 256, 0, st>>>(d_projection, projection, w.inv_c, D, C);
+        TRB_LAUNCH_OK();
+    }
+
+    // ---- global align backward: dq_v = dS @ q_t, dq_t = dS^T @ q_v, through the normalisation
+    {
+        GemmArgs gv{w.S_ga, N, 1, w.en + ND, D, 1, w.dq_ga, D, 0, N, D, N, nullptr, nullptr, 1};
+        if ((rc = launch_gemm(gv, st))) return rc;
+        GemmArgs gt{w.S_ga, 1, N, w.en, D, 1, w.dq_ga + ND, D, 0, N, D, N, nullptr, nullptr, 1};
+        if ((rc = launch_gemm(gt, st))) return rc;
+    }
+    normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w.dq_ga, nullptr, nullptr, nullptr, w.en, w.inv_e, d_ga, N, D);
+    TRB_LAUNCH_OK();
+    return 0;
+}

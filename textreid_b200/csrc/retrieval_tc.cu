@@ -1,0 +1,453 @@
+// bf16 tensor-core retrieval stream for sm_100a: tcgen05.mma (M=128, N=256, K=16, fp32 accumulate in
+// TMEM), operands staged into shared memory by cp.async.bulk (TMA engine) from the packed
+// pre-swizzled HBM layout of tc_common.cuh, a 4-stage mbarrier ring, double-buffered TMEM
+// accumulators, and an epilogue that consumes the similarity tile straight out of TMEM:
+// per-query top-10 and exact rank counts.  The [Q,G] similarity matrix never exists in HBM.
+//
+// Replaces (with evaluation.py:117-120 fused in by trb_pack_rows_bf16) the reference's
+//   similarity = text @ image.T ; argsort ; matches ; cumsum        lib/data/metrics/evaluation.py:11-37,120
+//
+// Warp roles (384 threads, one persistent CTA per SM):
+//   warp 0 lane 0 : producer  - bulk copies: query tile (resident per work unit) + gallery k-chunk ring
+//   warp 1 lane 0 : MMA issuer - tcgen05.mma into TMEM buffer t&1, tcgen05.commit -> barriers
+//   warp 2        : TMEM allocator / deallocator
+//   warps 4..11   : epilogue  - warp w reads TMEM lanes 32*(w%4).. (its 32 query rows) and the
+//                   column half (w-4)/4 of the 256-column accumulator
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int TILE_M = 128;          // queries per CTA tile (TMEM lanes)
+constexpr int TILE_N = 256;          // gallery rows per MMA tile (TMEM columns per buffer)
+constexpr int UMMA_K = 16;
+constexpr int STAGE_BYTES = 2 * BLOCK_BYTES;   // 256 gallery rows x 64 k  = 32 KiB
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int RT = 8;                // thresholds kept in registers per query row
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_MAX = 232448;      // 227 KiB opt-in limit per CTA on sm_100
+
+struct Params {
+    const uint8_t* q_packed;
+    const uint8_t* g_packed;
+    int64_t Q, G;            // valid (unpadded) row counts
+    int kchunks;             // D / 64
+    int nstages;
+    const int64_t* q_row_id; // [Qp] original query number per packed row, -1 = padding
+    const int64_t* g_row_id; // [Gp] global gallery index per packed row, -1 = padding
+    const int64_t* rel_ptr;  // [Qorig+1]
+    float* thr;              // [total]  (mode 0: read, mode 1: written)
+    int64_t* thr_gidx;       // [total]
+    const int32_t* band_lo;  // mode 1, per packed query row
+    const int32_t* band_hi;
+    const int32_t* rel_off;
+    int nsplit;
+    float* cand_sim;         // [Qorig, 2*nsplit, 10]
+    int64_t* cand_idx;
+    int32_t* cnt;            // [total]
+    int64_t num_qtiles, num_gtiles, num_units;
+};
+
+struct UnitInfo {
+    int64_t qt, split, t_lo, t_hi;
+};
+
+template <int MODE>
+__device__ __forceinline__ UnitInfo unit_info(const Params& p, int64_t u) {
+    UnitInfo ui;
+    if (MODE == 0) {
+        ui.split = u / p.num_qtiles;
+        ui.qt = u % p.num_qtiles;
+        ui.t_lo = p.num_gtiles * ui.split / p.nsplit;
+        ui.t_hi = p.num_gtiles * (ui.split + 1) / p.nsplit;
+    } else {
+        ui.split = 0;
+        ui.qt = u;
+        const int64_t r0 = ui.qt * TILE_M;
+        const int64_t r1 = min(r0 + TILE_M, p.Q) - 1;
+        const int64_t lo = p.band_lo[r0], hi = p.band_hi[r1];   // both monotone in the pid-sorted row order
+        ui.t_lo = lo / TILE_N;
+        ui.t_hi = hi > lo ? (hi + TILE_N - 1) / TILE_N : ui.t_lo;
+    }
+    return ui;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int KC = p.kchunks, NS = p.nstages;
+    uint8_t* sA = smem;                                   // KC x 16 KiB: the query tile, all of K
+    uint8_t* sB = sA + (size_t)KC * BLOCK_BYTES;          // NS x 32 KiB ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)NS * STAGE_BYTES);
+    uint64_t* a_full = bars + 0;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* t_full = bars + 2;      // [2]
+    uint64_t* t_empty = bars + 4;     // [2]
+    uint64_t* b_full = bars + 6;      // [NS]
+    uint64_t* b_empty = bars + 6 + MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * MAX_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, NUM_EPI_WARPS); }
+        for (int i = 0; i < NS; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------- producer -------------------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t bphase = 0, aphase = 0;
+            for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+                const UnitInfo ui = unit_info<MODE>(p, u);
+                if (ui.t_lo >= ui.t_hi) continue;
+                mbar_wait(a_empty, aphase ^ 1);
+                mbar_expect_tx(a_full, (uint32_t)KC * BLOCK_BYTES);
+                for (int kc = 0; kc < KC; ++kc)
+                    bulk_g2s(sA + (size_t)kc * BLOCK_BYTES, p.q_packed + ((size_t)ui.qt * KC + kc) * BLOCK_BYTES, BLOCK_BYTES, a_full);
+                aphase ^= 1;
+                for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
+                    for (int kc = 0; kc < KC; ++kc) {
+                        mbar_wait(b_empty + stage, bphase ^ 1);
+                        mbar_expect_tx(b_full + stage, STAGE_BYTES);
+                        uint8_t* dst = sB + (size_t)stage * STAGE_BYTES;
+                        bulk_g2s(dst, p.g_packed + ((size_t)(2 * t) * KC + kc) * BLOCK_BYTES, BLOCK_BYTES, b_full + stage);
+                        bulk_g2s(dst + BLOCK_BYTES, p.g_packed + ((size_t)(2 * t + 1) * KC + kc) * BLOCK_BYTES, BLOCK_BYTES, b_full + stage);
+                        if (++stage == NS) { stage = 0; bphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------- MMA issuer -----------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
+            int stage = 0, tbuf = 0;
+            uint32_t bphase = 0, aphase = 0, tphase = 0;
+            const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+            for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+                const UnitInfo ui = unit_info<MODE>(p, u);
+                if (ui.t_lo >= ui.t_hi) continue;
+                mbar_wait(a_full, aphase);
+                aphase ^= 1;
+                tc_fence_after();
+                for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
+                    mbar_wait(t_empty + tbuf, tphase ^ 1);     // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)tbuf * TILE_N;
+                    for (int kc = 0; kc < KC; ++kc) {
+                        mbar_wait(b_full + stage, bphase);
+                        tc_fence_after();
+                        const uint32_t a0 = a_addr + (uint32_t)kc * BLOCK_BYTES;
+                        const uint32_t b0 = b_addr + (uint32_t)stage * STAGE_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                            umma_bf16(d_tmem, umma_desc_sw128(a0 + kk * UMMA_K * 2), umma_desc_sw128(b0 + kk * UMMA_K * 2), idesc,
+                                      (uint32_t)((kc | kk) != 0));
+                        umma_commit(b_empty + stage);          // smem slot reusable once these MMAs retire
+                        if (++stage == NS) { stage = 0; bphase ^= 1; }
+                    }
+                    umma_commit(t_full + tbuf);                // accumulator complete -> epilogue
+                    tbuf ^= 1;
+                    if (tbuf == 0) tphase ^= 1;
+                }
+                umma_commit(a_empty);                          // query tile may be overwritten
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ------------------------------- epilogue -------------------------------------------
+        const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+        const int half = (warp - EPI_WARP0) >> 2;        // which 128 of the 256 accumulator columns
+        const int row = quarter * 32 + lane;
+        int tbuf = 0;
+        uint32_t tphase = 0;
+        for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            const UnitInfo ui = unit_info<MODE>(p, u);
+            if (ui.t_lo >= ui.t_hi) continue;
+            const int64_t prow = ui.qt * TILE_M + row;                 // packed query row
+            const int64_t q = prow < p.Q ? p.q_row_id[prow] : -1;      // original query number
+            // per-unit row state
+            TopK top;
+            float kth = -CUDART_INF_F, thr_min = CUDART_INF_F;
+            float thr[RT];
+            int64_t tgidx[RT];
+            int rcnt[RT];
+            int64_t s_lo = 0, s_hi = 0;
+            int32_t blo = 0, bhi = 0;
+            int64_t slot_base = 0;
+            if (MODE == 0) {
+                top.init();
+#pragma unroll
+                for (int r = 0; r < RT; ++r) { thr[r] = CUDART_INF_F; tgidx[r] = -1; rcnt[r] = 0; }
+                if (q >= 0 && p.rel_ptr != nullptr) {
+                    s_lo = p.rel_ptr[q];
+                    s_hi = p.rel_ptr[q + 1];
+#pragma unroll
+                    for (int r = 0; r < RT; ++r)
+                        if (s_lo + r < s_hi) { thr[r] = p.thr[s_lo + r]; tgidx[r] = p.thr_gidx[s_lo + r]; thr_min = fminf(thr_min, thr[r]); }
+                    if (s_hi - s_lo > RT) thr_min = -CUDART_INF_F;     // overflow thresholds: always take the exact path
+                }
+            } else if (q >= 0) {
+                blo = p.band_lo[prow];
+                bhi = p.band_hi[prow];
+                slot_base = p.rel_ptr[q] + p.rel_off[prow];
+            }
+
+            for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
+                mbar_wait(t_full + tbuf, tphase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int chunk = 0; chunk < 4; ++chunk) {
+                    float v[32];
+                    __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tbuf * TILE_N + half * 128 + chunk * 32);
+                    tmem_ld32(taddr, v);
+                    if (chunk == 3) {                      // accumulator fully read by this warp: hand it back
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(t_empty + tbuf);
+                    }
+                    const int64_t g0 = t * TILE_N + half * 128 + chunk * 32;   // packed gallery row of v[0]
+                    if (q < 0) continue;
+                    if (MODE == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int64_t g = g0 + j;
+                            if (g >= blo && g < bhi) {
+                                p.thr[slot_base + (g - blo)] = v[j];
+                                p.thr_gidx[slot_base + (g - blo)] = p.g_row_id[g];
+                            }
+                        }
+                        continue;
+                    }
+                    if (g0 + 32 > p.G) {                   // padded gallery rows (zero vectors) never rank
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (g0 + j >= p.G) v[j] = -CUDART_INF_F;
+                    }
+                    float cmax = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
+                    if (cmax >= kth) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (v[j] >= top.s[TRB_TOPK - 1]) {
+                                const int64_t gi = p.g_row_id[g0 + j];
+                                if (gi >= 0) top.push(v[j], gi);
+                            }
+                        }
+                        kth = top.s[TRB_TOPK - 1];
+                    }
+                    if (s_hi > s_lo && cmax >= thr_min) {
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) {
+                            const float th = thr[r];
+                            int c = 0;
+                            bool tie = false;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { c += (v[j] > th) ? 1 : 0; tie |= (v[j] == th); }
+                            if (tie) {                     // exact ties are ordered by gallery index
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (v[j] == th) {
+                                        const int64_t gi = p.g_row_id[g0 + j];
+                                        c += (gi >= 0 && gi < tgidx[r]) ? 1 : 0;
+                                    }
+                            }
+                            rcnt[r] += c;
+                        }
+                        for (int64_t slot = s_lo + RT; slot < s_hi; ++slot) {    // rare: > RT relevant items
+                            const float th = p.thr[slot];
+                            const int64_t ti = p.thr_gidx[slot];
+                            int c = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (v[j] > th) ++c;
+                                else if (v[j] == th) { const int64_t gi = p.g_row_id[g0 + j]; c += (gi >= 0 && gi < ti) ? 1 : 0; }
+                            }
+                            if (c) atomicAdd(p.cnt + slot, c);
+                        }
+                    }
+                }
+                tbuf ^= 1;
+                if (tbuf == 0) tphase ^= 1;
+            }
+
+            if (MODE == 0 && q >= 0) {
+                const int64_t nlists = 2 * (int64_t)p.nsplit;
+                const int64_t list = ui.split * 2 + half;
+                float* cs = p.cand_sim + (q * nlists + list) * TRB_TOPK;
+                int64_t* ci = p.cand_idx + (q * nlists + list) * TRB_TOPK;
+#pragma unroll
+                for (int k = 0; k < TRB_TOPK; ++k) { cs[k] = top.s[k]; ci[k] = top.i[k]; }
+#pragma unroll
+                for (int r = 0; r < RT; ++r)
+                    if (s_lo + r < s_hi && rcnt[r]) atomicAdd(p.cnt + s_lo + r, rcnt[r]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: optional gather + L2 normalise + round to bf16 + write the pre-swizzled tile-major image
+// one warp per packed row; each lane moves 16-byte (8 x bf16) chunks
+// ---------------------------------------------------------------------------------------------
+template <bool SRC_BF16>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const void* __restrict__ src, const int64_t* __restrict__ perm, int normalize, float eps,
+                 uint8_t* __restrict__ packed, int64_t rows, int64_t rows_padded, int64_t dim) {
+    const int lane = threadIdx.x & 31;
+    const int64_t prow = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (prow >= rows_padded) return;
+    const int64_t nchunk = dim >> 3, kchunks = dim >> 6;
+    if (prow >= rows) {
+        for (int64_t c = lane; c < nchunk; c += 32)
+            *reinterpret_cast<uint4*>(packed + packed_offset_bytes(prow, c, kchunks)) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const int64_t srow = perm ? perm[prow] : prow;
+    float ss = 0.f;
+    // first pass: norm (skipped when not normalising)
+    if (normalize) {
+        for (int64_t c = lane; c < nchunk; c += 32) {
+            float x[8];
+            if (SRC_BF16) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(src) + srow * dim + c * 8);
+                const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = __bfloat162float(h[i]);
+            } else {
+                const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(src) + srow * dim + c * 8);
+                const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(src) + srow * dim + c * 8 + 4);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss = fmaf(x[i], x[i], ss);
+        }
+        ss = warp_sum(ss);
+    }
+    const float nrm = normalize ? fmaxf(sqrtf(ss), eps) : 1.0f;
+    for (int64_t c = lane; c < nchunk; c += 32) {
+        float x[8];
+        if (SRC_BF16) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(src) + srow * dim + c * 8);
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __bfloat162float(h[i]);
+        } else {
+            const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(src) + srow * dim + c * 8);
+            const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(src) + srow * dim + c * 8 + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        }
+        uint4 out;
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(&out);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(normalize ? __fdiv_rn(x[i], nrm) : x[i]);
+        *reinterpret_cast<uint4*>(packed + packed_offset_bytes(prow, c, kchunks)) = out;
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t trb_packed_rows(int64_t rows) { return rows <= 0 ? 0 : ((rows + TILE_N - 1) / TILE_N) * TILE_N; }
+
+extern "C" int64_t trb_packed_bytes(int64_t rows, int64_t dim) {
+    if (dim <= 0 || dim % 64 != 0) return 0;
+    return trb_packed_rows(rows) * dim * 2;
+}
+
+extern "C" int trb_pack_rows_bf16(const void* src, int src_is_bf16, const int64_t* perm, int normalize, float eps, void* packed,
+                                  int64_t rows, int64_t dim, trb_stream_t stream) {
+    TRB_REQUIRE(src && packed, "pack_rows: null pointer");
+    TRB_REQUIRE(rows >= 0 && dim > 0, "pack_rows: bad shape");
+    if (dim % 64 != 0) { trb_set_error("pack_rows: dim=%lld must be a multiple of 64 on the tensor-core path", (long long)dim); return TRB_ERR_UNSUPPORTED; }
+    TRB_REQUIRE(trb_aligned16(src) && trb_aligned16(packed), "pack_rows: buffers must be 16-byte aligned");
+    const int64_t rp = trb_packed_rows(rows);
+    if (rp == 0) return 0;
+    const unsigned grid = (unsigned)trb_ceil_div(rp, 8);
+    if (src_is_bf16)
+        pack_rows_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(src, perm, normalize, eps, (uint8_t*)packed, rows, rp, dim);
+    else
+        pack_rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src, perm, normalize, eps, (uint8_t*)packed, rows, rp, dim);
+    TRB_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packed, int64_t Q, int64_t G, int64_t D,
+                                       const int64_t* q_row_id, const int64_t* g_row_id, const int64_t* rel_ptr, float* thr,
+                                       int64_t* thr_gidx, const int32_t* band_lo, const int32_t* band_hi, const int32_t* rel_off,
+                                       int mode, int nsplit, float* cand_sim, int64_t* cand_idx, int32_t* cnt,
+                                       trb_stream_t stream) {
+    TRB_REQUIRE(q_packed && g_packed && q_row_id && g_row_id, "stream_tc: null pointer");
+    TRB_REQUIRE(Q >= 0 && G >= 0, "stream_tc: bad shape");
+    TRB_REQUIRE(mode == 0 || mode == 1, "stream_tc: mode must be 0 (stream) or 1 (threshold capture)");
+    if (D <= 0 || D % 64 != 0 || D > 512) {
+        trb_set_error("stream_tc: D=%lld unsupported on the tensor-core path (needs a multiple of 64, <= 512)", (long long)D);
+        return TRB_ERR_UNSUPPORTED;
+    }
+    TRB_REQUIRE((reinterpret_cast<uintptr_t>(q_packed) & 127) == 0 && (reinterpret_cast<uintptr_t>(g_packed) & 127) == 0,
+                "stream_tc: packed operands must be 128-byte aligned");
+    if (mode == 0) {
+        TRB_REQUIRE(cand_sim && cand_idx, "stream_tc: candidate buffers are required in mode 0");
+        TRB_REQUIRE(nsplit >= 1, "stream_tc: nsplit must be >= 1");
+        TRB_REQUIRE((rel_ptr == nullptr) == (thr == nullptr) && (thr == nullptr) == (thr_gidx == nullptr) &&
+                        (thr == nullptr) == (cnt == nullptr),
+                    "stream_tc: rel_ptr, thr, thr_gidx and cnt must be given together");
+    } else {
+        TRB_REQUIRE(rel_ptr && thr && thr_gidx && band_lo && band_hi && rel_off, "stream_tc: mode 1 needs rel_ptr, thr, thr_gidx and the band arrays");
+        nsplit = 1;
+    }
+    if (Q == 0 || G == 0) return 0;
+
+    Params p;
+    p.q_packed = static_cast<const uint8_t*>(q_packed);
+    p.g_packed = static_cast<const uint8_t*>(g_packed);
+    p.Q = Q; p.G = G;
+    p.kchunks = (int)(D / 64);
+    const int a_bytes = p.kchunks * BLOCK_BYTES;
+    const int fixed_bytes = (6 + 2 * MAX_STAGES) * 8 + 16 + 1024;   // barriers + TMEM slot + alignment slack
+    int ns = (SMEM_MAX - fixed_bytes - a_bytes) / STAGE_BYTES;
+    p.nstages = ns > MAX_STAGES ? MAX_STAGES : ns;
+    TRB_REQUIRE(p.nstages >= 2, "stream_tc: not enough shared memory for a 2-stage ring at D=%lld", (long long)D);
+    p.q_row_id = q_row_id; p.g_row_id = g_row_id; p.rel_ptr = rel_ptr; p.thr = thr; p.thr_gidx = thr_gidx;
+    p.band_lo = band_lo; p.band_hi = band_hi; p.rel_off = rel_off;
+    p.nsplit = nsplit; p.cand_sim = cand_sim; p.cand_idx = cand_idx; p.cnt = cnt;
+    p.num_qtiles = trb_ceil_div(Q, TILE_M);
+    p.num_gtiles = trb_ceil_div(G, TILE_N);
+    TRB_REQUIRE(nsplit <= p.num_gtiles, "stream_tc: nsplit=%d exceeds the number of gallery tiles %lld", nsplit, (long long)p.num_gtiles);
+    p.num_units = mode == 0 ? p.num_qtiles * nsplit : p.num_qtiles;
+
+    const int smem_bytes = a_bytes + p.nstages * STAGE_BYTES + fixed_bytes;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(p.num_units < sms ? p.num_units : sms);
+    if (mode == 0) {
+        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        retrieval_tc_kernel<0><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    } else {
+        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        retrieval_tc_kernel<1><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    }
+    TRB_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,416 @@
+"""Text-to-image retrieval evaluation on B200: host side.
+
+Mirrors the reference's call shapes
+
+    rank(similarity, q_pids, g_pids, topk, get_mAP)           lib/data/metrics/evaluation.py:11-37
+    evaluation(dataset, predictions, output_folder, topk,     lib/data/metrics/evaluation.py:76-173
+               save_data, rerank)
+    inference(model, data_loader, dataset_name, device,       lib/engine/inference.py:48-96
+              output_folder, save_data, rerank)
+
+and adds the embedding-level entry ``retrieve`` that never materialises the [Q, G] similarity
+matrix.  All arithmetic on the hot path runs in libtextreid_b200.so (hand-written sm_100a CUDA);
+torch is used for memory, streams, index bookkeeping (sorting pids, prefix sums) and collectives.
+There is no CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+TOPK_DEPTH = _lib.TOPK_DEPTH
+_SM_COUNT_FALLBACK = 148
+
+
+# --------------------------------------------------------------------------------------------
+# relevance index: which gallery rows share the query's pid (evaluation.py:20-21)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class RelevanceIndex:
+    rel_ptr: torch.Tensor      # [Q+1] int64, CSR offsets (one slot per (query, relevant gallery item))
+    rel_col: torch.Tensor      # [total] int64, global gallery index of every slot, ascending per query
+    total: int
+
+
+def build_relevance(q_pids: torch.Tensor, g_pids: torch.Tensor) -> RelevanceIndex:
+    """CSR of relevant gallery items per query from the pid vectors (index bookkeeping in torch;
+    one host sync for the total slot count)."""
+    q_pids = q_pids.reshape(-1).to(torch.int64)
+    g_pids = g_pids.reshape(-1).to(torch.int64)
+    dev = q_pids.device
+    if g_pids.numel() == 0:
+        z = torch.zeros(q_pids.numel() + 1, dtype=torch.int64, device=dev)
+        return RelevanceIndex(z, torch.zeros(1, dtype=torch.int64, device=dev)[:0], 0)
+    sorted_pid, order = torch.sort(g_pids, stable=True)
+    lo = torch.searchsorted(sorted_pid, q_pids, right=False)
+    hi = torch.searchsorted(sorted_pid, q_pids, right=True)
+    counts = hi - lo
+    rel_ptr = torch.zeros(q_pids.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=rel_ptr[1:])
+    total = int(rel_ptr[-1].item())
+    slot_q = torch.repeat_interleave(torch.arange(q_pids.numel(), device=dev), counts, output_size=total)
+    within = torch.arange(total, device=dev) - rel_ptr[:-1][slot_q]
+    store = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)   # never a NULL device pointer
+    store[:total] = order[lo[slot_q] + within]   # stable sort => ascending gallery index inside a pid group
+    return RelevanceIndex(rel_ptr, store[:total], total)
+
+
+# --------------------------------------------------------------------------------------------
+# result container
+# --------------------------------------------------------------------------------------------
+@dataclass
+class RetrievalResult:
+    cmc: torch.Tensor                     # [len(topk)] fp32 percent (R@k)
+    mAP: Optional[torch.Tensor]           # 0-d fp32 percent, None in top-k-only mode
+    top_idx: torch.Tensor                 # [Q, 10] int64 global gallery indices, best first (-1 padding)
+    top_sim: torch.Tensor                 # [Q, 10] fp32
+    first_hit: torch.Tensor               # [Q] int32
+    ap: Optional[torch.Tensor]            # [Q] fp32
+    hit_ranks: Optional[torch.Tensor]     # [total] int32, ascending per query
+    rel_ptr: Optional[torch.Tensor]       # [Q+1] int64
+    thresholds: Optional[torch.Tensor] = None   # [total] fp32 similarity of every relevant pair (debug / tests)
+
+
+def _topk_host_array(topk) -> Tuple[C.Array, int, List[int]]:
+    vals = [int(k) for k in (topk.tolist() if torch.is_tensor(topk) else list(topk))]
+    if not 1 <= len(vals) <= 8:
+        raise ValueError("topk must hold between 1 and 8 cut-offs")
+    if max(vals) > TOPK_DEPTH or min(vals) < 1:
+        raise ValueError("topk cut-offs must lie in [1, %d] (the reference uses [1, 5, 10])" % TOPK_DEPTH)
+    return (C.c_int32 * len(vals))(*vals), len(vals), vals
+
+
+def _sm_count(device) -> int:
+    try:
+        return torch.cuda.get_device_properties(device).multi_processor_count
+    except Exception:  # pragma: no cover
+        return _SM_COUNT_FALLBACK
+
+
+def _finish_and_metrics(cand_sim, cand_idx, nlists, q_pids, g_pids, rel: Optional[RelevanceIndex], cnt, topk,
+                        want_hit_ranks=True) -> RetrievalResult:
+    lib = _lib.load()
+    dev = cand_sim.device
+    Q = q_pids.numel()
+    st = _lib.stream_ptr(dev)
+    top_sim = torch.empty(Q, TOPK_DEPTH, dtype=torch.float32, device=dev)
+    top_idx = torch.empty(Q, TOPK_DEPTH, dtype=torch.int64, device=dev)
+    first_hit = torch.empty(Q, dtype=torch.int32, device=dev)
+    get_map = rel is not None
+    ap = torch.empty(Q, dtype=torch.float32, device=dev) if get_map else None
+    hit_ranks = torch.empty(max(rel.total, 1), dtype=torch.int32, device=dev) if (get_map and want_hit_ranks) else None
+    _lib.check(lib.trb_retrieval_finish(
+        _lib.ptr(cand_sim), _lib.ptr(cand_idx), nlists, Q, _lib.ptr(q_pids), _lib.ptr(g_pids), g_pids.numel(),
+        _lib.ptr(rel.rel_ptr) if get_map else None, _lib.ptr(cnt) if get_map else None,
+        _lib.ptr(top_sim), _lib.ptr(top_idx), _lib.ptr(first_hit), _lib.ptr(hit_ranks), _lib.ptr(ap), st),
+        "trb_retrieval_finish")
+    arr, n, _ = _topk_host_array(topk)
+    cmc = torch.empty(n, dtype=torch.float32, device=dev)
+    mAP = torch.empty((), dtype=torch.float32, device=dev) if get_map else None
+    _lib.check(lib.trb_retrieval_metrics(_lib.ptr(first_hit), _lib.ptr(ap), Q, arr, n, _lib.ptr(cmc),
+                                         _lib.ptr(mAP), st), "trb_retrieval_metrics")
+    if hit_ranks is not None:
+        hit_ranks = hit_ranks[:rel.total]
+    return RetrievalResult(cmc, mAP, top_idx, top_sim, first_hit, ap, hit_ranks,
+                           rel.rel_ptr if get_map else None)
+
+
+def reference_tail_from_hit_ranks(res: RetrievalResult, G: int, topk) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Parity mode: evaluate the reference's float reductions (evaluation.py:23-26,31-36), in the
+    reference's own summation order on the CPU, on the integer artefacts the kernels produced
+    (hit ranks).  Bit-exact to the reference run on CPU; O(Q*G) memory, for CUHK-PEDES-sized cases."""
+    Q = res.first_hit.numel()
+    rel_ptr = res.rel_ptr.cpu()
+    ranks = res.hit_ranks.cpu().to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(Q), rel_ptr[1:] - rel_ptr[:-1])
+    matches = torch.zeros(Q, G, dtype=torch.bool)
+    matches[rows, ranks] = True
+    topk_t = torch.as_tensor([int(k) for k in (topk.tolist() if torch.is_tensor(topk) else topk)])
+    depth = int(topk_t.max())
+    all_cmc = matches[:, :depth].cumsum(1)
+    all_cmc[all_cmc > 1] = 1
+    all_cmc = all_cmc.float().mean(0) * 100
+    all_cmc = all_cmc[topk_t - 1]
+    num_rel = matches.sum(1)
+    tmp_cmc = matches.cumsum(1)
+    denom = torch.arange(1, G + 1, dtype=torch.float32)
+    tmp_cmc = (tmp_cmc.to(torch.float32) / denom) * matches
+    AP = tmp_cmc.sum(1) / num_rel
+    return all_cmc, AP.mean() * 100
+
+
+# --------------------------------------------------------------------------------------------
+# rank(): drop-in for evaluation.py:11-37 on a materialised similarity matrix
+# --------------------------------------------------------------------------------------------
+def rank_artifacts(similarity: torch.Tensor, q_pids: torch.Tensor, g_pids: torch.Tensor, topk=(1, 5, 10),
+                   get_mAP: bool = True) -> RetrievalResult:
+    _lib.require_cuda(similarity, q_pids, g_pids)
+    if similarity.dim() != 2 or similarity.dtype != torch.float32:
+        raise ValueError("similarity must be a 2-D float32 tensor")
+    lib = _lib.load()
+    dev = similarity.device
+    Q, G = similarity.shape
+    q_pids = q_pids.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+    g_pids = g_pids.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+    if q_pids.numel() != Q or g_pids.numel() != G:
+        raise ValueError("pid vectors do not match the similarity shape")
+    rel = build_relevance(q_pids, g_pids) if get_mAP else None
+    cand_sim = torch.empty(Q, TOPK_DEPTH, dtype=torch.float32, device=dev)
+    cand_idx = torch.empty(Q, TOPK_DEPTH, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=dev) if get_mAP else None
+    _lib.check(lib.trb_rank_similarity_f32(
+        _lib.ptr(similarity), similarity.stride(0), similarity.stride(1), Q, G,
+        _lib.ptr(rel.rel_ptr) if get_mAP else None, _lib.ptr(rel.rel_col) if get_mAP else None,
+        _lib.ptr(cand_sim), _lib.ptr(cand_idx), _lib.ptr(cnt), _lib.stream_ptr(dev)), "trb_rank_similarity_f32")
+    return _finish_and_metrics(cand_sim, cand_idx, 1, q_pids, g_pids, rel, cnt, topk)
+
+
+def rank(similarity, q_pids, g_pids, topk=[1, 5, 10], get_mAP=True, full_indices=False, parity=False):
+    """Same signature and return tuple as the reference's ``rank``: ``(all_cmc, mAP, indices)`` when
+    ``get_mAP`` else ``(all_cmc, indices)``; ties are ordered by gallery index (stable sort).
+
+    ``indices`` holds the best max(topk)... 10 gallery indices per query ([Q, 10]); every caller in the
+    reference discards it (evaluation.py:147-170).  ``full_indices=True`` returns the full [Q, G]
+    permutation for compatibility (computed with torch.sort, outside the hot path).
+    ``parity=True`` re-evaluates the final float reductions in the reference's CPU summation order.
+    """
+    res = rank_artifacts(similarity, q_pids, g_pids, topk, get_mAP)
+    cmc, mAP = res.cmc, res.mAP
+    if parity and get_mAP:
+        cmc, mAP = reference_tail_from_hit_ranks(res, similarity.shape[1], topk)
+        cmc, mAP = cmc.to(similarity.device), mAP.to(similarity.device)
+    if full_indices and get_mAP:
+        indices = torch.argsort(similarity, dim=1, descending=True, stable=True)
+    else:
+        depth = max(int(k) for k in (topk.tolist() if torch.is_tensor(topk) else topk))
+        indices = res.top_idx[:, :depth] if not get_mAP else res.top_idx
+    if not get_mAP:
+        return cmc, indices
+    return cmc, mAP, indices
+
+
+# --------------------------------------------------------------------------------------------
+# retrieve(): fused normalise + similarity + top-k + ranks, no [Q, G] matrix
+# --------------------------------------------------------------------------------------------
+def l2_normalize_rows(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    _lib.require_cuda(x)
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().trb_l2_normalize_rows_f32(_lib.ptr(x), _lib.ptr(y), None, x.shape[0], x.shape[1],
+                                                      eps, _lib.stream_ptr(x.device)), "trb_l2_normalize_rows_f32")
+    return y
+
+
+def _choose_nsplit(Q: int, G: int, tile_m: int, tile_n: int, sms: int) -> int:
+    q_tiles = max(1, -(-Q // tile_m))
+    g_tiles = max(1, -(-G // tile_n))
+    want = -(-2 * sms // q_tiles)
+    return int(max(1, min(want, g_tiles, 1024)))
+
+
+def _stream_fp32(qn, gn, g_base, rel_ptr, thr, thr_gidx, cnt, nsplit):
+    lib = _lib.load()
+    dev = qn.device
+    Q, D = qn.shape
+    G = gn.shape[0]
+    cand_sim = torch.empty(Q, nsplit, TOPK_DEPTH, dtype=torch.float32, device=dev)
+    cand_idx = torch.empty(Q, nsplit, TOPK_DEPTH, dtype=torch.int64, device=dev)
+    _lib.check(lib.trb_retrieval_stream_f32(
+        _lib.ptr(qn), _lib.ptr(gn), Q, G, D, g_base, _lib.ptr(rel_ptr), _lib.ptr(thr), _lib.ptr(thr_gidx), nsplit,
+        _lib.ptr(cand_sim), _lib.ptr(cand_idx), _lib.ptr(cnt), _lib.stream_ptr(dev)), "trb_retrieval_stream_f32")
+    return cand_sim, cand_idx
+
+
+def retrieve(text_embed: torch.Tensor, image_embed: torch.Tensor, text_pid: torch.Tensor, image_pid: torch.Tensor,
+             topk=(1, 5, 10), get_mAP: bool = True, precision: str = "fp32", normalized: bool = False,
+             nsplit: Optional[int] = None) -> RetrievalResult:
+    """Embedding-level retrieval evaluation: queries = text, gallery = image (evaluation.py:117-120 + rank).
+
+    precision "fp32": FFMA path, indices / R@k / mAP bit-exact with the stable-sort reference on
+    exactly representable inputs, similarities within 1e-5.  "bf16": tcgen05 path (1e-3).
+    """
+    _lib.require_cuda(text_embed, image_embed, text_pid, image_pid)
+    if text_embed.dim() != 2 or image_embed.dim() != 2 or text_embed.shape[1] != image_embed.shape[1]:
+        raise ValueError("embeddings must be [Q, D] and [G, D]")
+    dev = text_embed.device
+    q_pids = text_pid.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+    g_pids = image_pid.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+    if precision == "bf16":
+        from .retrieval_tc import retrieve_tc
+        return retrieve_tc(text_embed, image_embed, q_pids, g_pids, topk, get_mAP, normalized, nsplit)
+    if precision != "fp32":
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    lib = _lib.load()
+    Q, D = text_embed.shape
+    G = image_embed.shape[0]
+    qn = text_embed.contiguous().float() if normalized else l2_normalize_rows(text_embed)
+    gn = image_embed.contiguous().float() if normalized else l2_normalize_rows(image_embed)
+    rel = build_relevance(q_pids, g_pids) if get_mAP else None
+    thr = cnt = None
+    if get_mAP:
+        thr = torch.zeros(max(rel.total, 1), dtype=torch.float32, device=dev)
+        cnt = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=dev)
+        _lib.check(lib.trb_retrieval_thresholds_f32(_lib.ptr(qn), _lib.ptr(gn), _lib.ptr(rel.rel_ptr),
+                                                    _lib.ptr(rel.rel_col), _lib.ptr(thr), Q, D,
+                                                    _lib.stream_ptr(dev)), "trb_retrieval_thresholds_f32")
+    if nsplit is None:
+        nsplit = _choose_nsplit(Q, G, 128, 128, _sm_count(dev))
+    cand_sim, cand_idx = _stream_fp32(qn, gn, 0, rel.rel_ptr if get_mAP else None, thr,
+                                      rel.rel_col if get_mAP else None, cnt, nsplit)
+    return _finish_and_metrics(cand_sim, cand_idx, nsplit, q_pids, g_pids, rel, cnt, topk)
+
+
+# --------------------------------------------------------------------------------------------
+# evaluation() / inference(): the reference's entry points
+# --------------------------------------------------------------------------------------------
+def first_occurrence_index(image_ids: Sequence[int], device) -> torch.Tensor:
+    """evaluation.py:68-73 (get_unique), vectorised: index of the first appearance of each image id,
+    in order of first appearance."""
+    ids = torch.as_tensor(np.asarray(image_ids), device=device)
+    uniq, inverse = torch.unique(ids, return_inverse=True)
+    first = torch.full((uniq.numel(),), ids.numel(), dtype=torch.int64, device=device)
+    first.scatter_reduce_(0, inverse, torch.arange(ids.numel(), device=device), reduce="amin")
+    return torch.sort(first)[0]
+
+
+def _table(rows, headers):
+    try:
+        from tabulate import tabulate
+        return tabulate(rows, tablefmt="psql", headers=headers, numalign="left")
+    except Exception:  # pragma: no cover
+        return "\n".join(str(r) for r in [headers] + list(rows))
+
+
+def evaluation(dataset, predictions, output_folder, topk, save_data=True, rerank=True, precision="fp32"):
+    """Drop-in for lib/data/metrics/evaluation.py:76-173.  Returns t2i R@1 (0-d fp32 tensor, percent).
+
+    ``predictions``: {dataset_index: [image_embed(D), text_embed(D)]} or None to read
+    ``inference_data.npz`` from ``output_folder`` like the reference.  Re-ranking (k-reciprocal,
+    evaluation.py:40-65) is applied when ``rerank`` is True.
+    """
+    from .rerank import jaccard_rerank_rank
+    logger = logging.getLogger("PersonSearch.inference")
+    data_dir = os.path.join(output_folder, "inference_data.npz")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    topk_list = [int(k) for k in (topk.tolist() if torch.is_tensor(topk) else topk)]
+
+    if predictions is None:
+        data = np.load(data_dir)
+        logger.info("Load inference data from {}".format(data_dir))
+        image_pid = torch.as_tensor(data["image_pid"], device=dev)
+        text_pid = torch.as_tensor(data["text_pid"], device=dev)
+        similarity = torch.as_tensor(data["similarity"], device=dev)
+        image_n = text_n = None
+        rvn_mat = torch.as_tensor(data["rvn_mat"], device=dev) if rerank else None
+        rtn_mat = torch.as_tensor(data["rtn_mat"], device=dev) if rerank else None
+    else:
+        keys = list(predictions.keys())
+        image_ids, pids = [], []
+        for idx in keys:
+            image_id, pid = dataset.get_id_info(idx)
+            image_ids.append(image_id)
+            pids.append(pid)
+        pid_t = torch.as_tensor(np.asarray(pids), device=dev)
+        image_all = torch.stack([predictions[i][0] for i in keys], dim=0).to(dev)
+        text_all = torch.stack([predictions[i][1] for i in keys], dim=0).to(dev)
+        keep = first_occurrence_index(image_ids, dev)
+        image_pid, text_pid = pid_t[keep], pid_t
+        image_n = l2_normalize_rows(image_all[keep])
+        text_n = l2_normalize_rows(text_all)
+        similarity = rvn_mat = rtn_mat = None
+
+    results = {}
+    if similarity is None and not save_data and not rerank:
+        # fast path (trainer.py:124): nothing needs the matrix
+        t2i = retrieve(text_n, image_n, text_pid, image_pid, topk_list, get_mAP=False, precision=precision, normalized=True)
+        i2t = retrieve(image_n, text_n, image_pid, text_pid, topk_list, get_mAP=False, precision=precision, normalized=True)
+        results["t2i"], results["i2t"] = t2i.cmc, i2t.cmc
+    else:
+        if similarity is None:
+            from .rerank import similarity_matrix
+            similarity = similarity_matrix(text_n, image_n)
+            if rerank:
+                rtn_mat = jaccard_rerank_matrix_pair(image_n, text_n)
+                rvn_mat = jaccard_rerank_matrix_pair(text_n, image_n)
+            if save_data:
+                payload = dict(image_pid=image_pid.cpu().numpy(), text_pid=text_pid.cpu().numpy(),
+                               similarity=similarity.cpu().numpy())
+                if rerank:
+                    payload.update(rvn_mat=rvn_mat.cpu().numpy(), rtn_mat=rtn_mat.cpu().numpy())
+                np.savez(data_dir, **payload)
+        if rerank:
+            sim_t = similarity.t()
+            c, m, _ = rank(sim_t, image_pid, text_pid, topk_list, get_mAP=True)
+            results["i2t"], results["i2t_mAP"] = c, m
+            c, m, _ = rank(similarity, text_pid, image_pid, topk_list, get_mAP=True)
+            results["t2i"], results["t2i_mAP"] = c, m
+            c, m = jaccard_rerank_rank(rtn_mat, sim_t, image_pid, text_pid, topk_list)
+            results["re_i2t"], results["re_i2t_mAP"] = c, m
+            c, m = jaccard_rerank_rank(rvn_mat, similarity, text_pid, image_pid, topk_list)
+            results["re_t2i"], results["re_t2i_mAP"] = c, m
+        else:
+            results["t2i"], _ = rank(similarity, text_pid, image_pid, topk_list, get_mAP=False)
+            results["i2t"], _ = rank(similarity.t(), image_pid, text_pid, topk_list, get_mAP=False)
+
+    if rerank:
+        cols = ["t2i", "re_t2i", "i2t", "re_i2t"]
+        rows = [[k] + [float(results[c][j]) for c in cols] for j, k in enumerate(topk_list)]
+        rows.append(["mAP"] + [float(results[c + "_mAP"]) for c in cols])
+        logger.info("\n" + _table(rows, ["topk", "t2i", "re-t2i", "i2t", "re-i2t"]))
+    else:
+        rows = [[k, float(results["t2i"][j]), float(results["i2t"][j])] for j, k in enumerate(topk_list)]
+        logger.info("\n" + _table(rows, ["topk", "t2i", "i2t"]))
+    evaluation.last_results = results
+    return results["t2i"][0]
+
+
+def jaccard_rerank_matrix_pair(q_feats, g_feats):
+    from .rerank import jaccard_rerank_matrix
+    return jaccard_rerank_matrix(q_feats, g_feats)
+
+
+def compute_on_dataset(model, data_loader, device):
+    """lib/engine/inference.py:14-26, with the per-item dict kept for signature compatibility."""
+    model.eval()
+    results: Dict[int, list] = {}
+    for batch in data_loader:
+        images, captions, image_ids = batch
+        images = images.to(device)
+        captions = [c.to(device) for c in captions]
+        with torch.no_grad():
+            output = model(images, captions)
+        for result in output:
+            for img_id, pred in zip(image_ids, result):
+                results.setdefault(int(img_id), []).append(pred)
+    return results
+
+
+def inference(model, data_loader, dataset_name="cuhkpedes-test", device="cuda", output_folder="", save_data=True,
+              rerank=True):
+    """Drop-in for lib/engine/inference.py:48-96 (single process; the sharded multi-GPU evaluation lives in
+    textreid_b200.sharded)."""
+    logger = logging.getLogger("PersonSearch.inference")
+    dataset = data_loader.dataset
+    logger.info("Start evaluation on {} dataset({} images).".format(dataset_name, len(dataset)))
+    predictions = None
+    if not os.path.exists(os.path.join(output_folder, "inference_data.npz")):
+        predictions = compute_on_dataset(model, data_loader, torch.device(device))
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.barrier()
+            gathered = [None] * torch.distributed.get_world_size()
+            torch.distributed.all_gather_object(gathered, {k: [t.cpu() for t in v] for k, v in predictions.items()})
+            if torch.distributed.get_rank() != 0:
+                return None
+            predictions = {}
+            for part in gathered:
+                predictions.update(part)
+    return evaluation(dataset=dataset, predictions=predictions, output_folder=output_folder, save_data=save_data,
+                      rerank=rerank, topk=[1, 5, 10])

@@ -1,0 +1,205 @@
+"""MoCo loss dict on B200: host side of trb_moco_loss / trb_enqueue / trb_ema_update_*.
+
+Reference surface (lib/models/embeddings/moco_head/loss.py:21-39, lib/models/losses.py):
+the loss evaluator returns ``{"instance_loss", "infonce_loss", "global_align_loss"}`` of 0-d
+fp32 tensors that the trainer sums and back-propagates (lib/engine/trainer.py:82,90).  Here the
+three losses AND their gradients come out of one stream-ordered library call in ``forward``;
+``backward`` only scales by the upstream gradients (device-side, no host sync).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PRECISIONS = {"fp32": 0, "bf16": 1}
+LOSS_KEYS = ("instance_loss", "infonce_loss", "global_align_loss")
+_workspaces: Dict[Tuple, torch.Tensor] = {}
+
+
+def _workspace(shape: _lib.MocoShape, precision: int, device) -> torch.Tensor:
+    key = (shape.N, shape.D, shape.K, shape.C, precision, str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = _lib.load().trb_moco_loss_workspace_bytes(C.byref(shape), precision)
+        if nbytes < 0:
+            _lib.check(int(nbytes), "trb_moco_loss_workspace_bytes")
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().contiguous().float()
+
+
+class _MoCoLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v_embed, t_embed, v_qraw, t_qraw, projection, v_key, t_key, labels, v_queue, t_queue,
+                id_queue, hp, precision, normalize_keys, separate_q):
+        lib = _lib.load()
+        _lib.require_cuda(v_embed, t_embed, projection, v_key, t_key, labels, v_queue, t_queue, id_queue)
+        dev = v_embed.device
+        N, D = v_embed.shape
+        K = v_queue.shape[1]
+        Cn = projection.shape[1]
+        if v_queue.shape[0] != D or projection.shape[0] != D or t_embed.shape != v_embed.shape:
+            raise ValueError("inconsistent shapes for the MoCo loss")
+        shape = _lib.MocoShape(N, D, K, Cn)
+        ve, te = _f32c(v_embed), _f32c(t_embed)
+        vq, tq = (_f32c(v_qraw), _f32c(t_qraw)) if separate_q else (ve, te)
+        vk, tk = _f32c(v_key), _f32c(t_key)
+        vkn, tkn = torch.empty_like(vk), torch.empty_like(tk)
+        proj = _f32c(projection)
+        vqu, tqu = _f32c(v_queue), _f32c(t_queue)
+        lab = labels.detach().reshape(-1).to(torch.int64).contiguous()
+        idq = id_queue.detach().reshape(-1).to(torch.int64).contiguous()
+        need_grad = any(ctx.needs_input_grad[:5])
+        losses = torch.empty(3, dtype=torch.float32, device=dev)
+        d_inst = d_nce = d_ga = d_proj = None
+        if need_grad:
+            d_inst = torch.empty(2, N, D, dtype=torch.float32, device=dev)
+            d_nce = torch.empty(2, N, D, dtype=torch.float32, device=dev)
+            d_ga = torch.empty(2, N, D, dtype=torch.float32, device=dev)
+            d_proj = torch.empty(D, Cn, dtype=torch.float32, device=dev)
+        ws = _workspace(shape, precision, dev)
+        _lib.check(lib.trb_moco_loss(
+            _lib.ptr(ve), _lib.ptr(te), _lib.ptr(vq), _lib.ptr(tq), _lib.ptr(vk), _lib.ptr(tk), int(normalize_keys),
+            _lib.ptr(vkn), _lib.ptr(tkn), _lib.ptr(lab), _lib.ptr(vqu), _lib.ptr(tqu), _lib.ptr(idq), _lib.ptr(proj),
+            C.byref(shape), C.byref(hp), precision, _lib.ptr(losses), _lib.ptr(d_inst), _lib.ptr(d_nce), _lib.ptr(d_ga),
+            _lib.ptr(d_proj), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "trb_moco_loss")
+        ctx.separate_q = separate_q
+        ctx.grads = (d_inst, d_nce, d_ga, d_proj)
+        ctx.mark_non_differentiable(vkn, tkn)
+        return losses[0], losses[1], losses[2], vkn, tkn
+
+    @staticmethod
+    def backward(ctx, g_inst, g_nce, g_ga, _gvk, _gtk):
+        lib = _lib.load()
+        d_inst, d_nce, d_ga, d_proj = ctx.grads
+        dev = d_inst.device
+        st = _lib.stream_ptr(dev)
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        g = torch.stack([x.float() if x is not None else zero for x in (g_inst, g_nce, g_ga)]).contiguous()
+        n = d_inst[0].numel()
+
+        def comb(a, b, c):
+            out = torch.empty_like(d_inst[0])
+            _lib.check(lib.trb_combine3_f32(_lib.ptr(out), _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(g), n, st),
+                       "trb_combine3_f32")
+            return out
+
+        gvq = gtq = None
+        if ctx.separate_q:
+            gv, gt = comb(d_inst[0], None, d_ga[0]), comb(d_inst[1], None, d_ga[1])
+            gvq, gtq = comb(None, d_nce[0], None), comb(None, d_nce[1], None)
+        else:
+            gv, gt = comb(d_inst[0], d_nce[0], d_ga[0]), comb(d_inst[1], d_nce[1], d_ga[1])
+        gp = d_proj.clone() if ctx.needs_input_grad[4] else None
+        if gp is not None:
+            _lib.check(lib.trb_scale_inplace_f32(_lib.ptr(gp), _lib.ptr(g), gp.numel(), st), "trb_scale_inplace_f32")
+        return (gv, gt, gvq, gtq, gp) + (None,) * 10
+
+
+def moco_loss_dict(v_embed, t_embed, v_key, t_key, labels, v_queue, t_queue, id_queue, queue_ptr, projection, *,
+                   T: float = 0.07, epsilon: float = 0.0, alpha: float = 0.6, beta: float = 0.4, scale_pos: float = 10,
+                   scale_neg: float = 40, enqueue: bool = True, v_embed_q=None, t_embed_q=None,
+                   normalize_keys: bool = False, precision: str = "fp32") -> Dict[str, torch.Tensor]:
+    """Functional core of MoCoHead.forward's train branch (head.py:126-175) + LossComputation.forward
+    (moco_head/loss.py:21-39).
+
+    v_embed, t_embed [N, D]  post-Linear embeddings (un-normalised)
+    v_key, t_key     [N, D]  key embeddings; L2-normalised already unless ``normalize_keys``
+    v_embed_q/t_embed_q      InfoNCE query inputs of the FC=True variant (head.py:118-124); default = embeds
+    queues [D, K] fp32, id_queue [1, K] int64, queue_ptr [1] int64 are mutated in place when ``enqueue``.
+    """
+    if precision not in PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
+    separate_q = v_embed_q is not None or t_embed_q is not None
+    if separate_q and (v_embed_q is None or t_embed_q is None):
+        raise ValueError("v_embed_q and t_embed_q must be given together")
+    hp = _lib.MocoHParams(T, epsilon, alpha, beta, scale_pos, scale_neg)
+    li, ln, lg, vkn, tkn = _MoCoLossFunction.apply(
+        v_embed, t_embed, v_embed_q if separate_q else v_embed, t_embed_q if separate_q else t_embed, projection,
+        v_key, t_key, labels, v_queue, t_queue, id_queue, hp, PRECISIONS[precision], normalize_keys, separate_q)
+    if enqueue:
+        dequeue_and_enqueue(v_queue, t_queue, id_queue, queue_ptr, vkn, tkn, labels)
+    return {"instance_loss": li, "infonce_loss": ln, "global_align_loss": lg}
+
+
+@torch.no_grad()
+def dequeue_and_enqueue(v_queue, t_queue, id_queue, queue_ptr, v_keys, t_keys, ids) -> None:
+    """head.py:96-109 with the pointer kept on the device (no int(queue_ptr) sync)."""
+    _lib.require_cuda(v_queue, t_queue, id_queue, queue_ptr, v_keys, t_keys, ids)
+    for q in (v_queue, t_queue):
+        if q.dtype != torch.float32 or not q.is_contiguous():
+            raise ValueError("queues must be contiguous float32 [D, K] buffers")
+    if id_queue.dtype != torch.int64 or queue_ptr.dtype != torch.int64 or not id_queue.is_contiguous():
+        raise ValueError("id_queue / queue_ptr must be contiguous int64 buffers")
+    D, K = v_queue.shape
+    N = v_keys.shape[0]
+    if K % N != 0:
+        raise AssertionError("K %% batch_size != 0 (head.py:101)")
+    vk, tk = _f32c(v_keys), _f32c(t_keys)
+    ids = ids.detach().reshape(-1).to(torch.int64).contiguous()
+    _lib.check(_lib.load().trb_enqueue(_lib.ptr(v_queue), _lib.ptr(t_queue), _lib.ptr(id_queue), _lib.ptr(queue_ptr),
+                                       _lib.ptr(vk), _lib.ptr(tk), _lib.ptr(ids), N, D, K,
+                                       _lib.stream_ptr(v_queue.device)), "trb_enqueue")
+
+
+class MomentumUpdater:
+    """_momentum_update_key_encoder (head.py:73-94) as ONE launch over a device-resident chunk table
+    instead of ~3 elementwise launches per parameter tensor."""
+
+    CHUNK = 1 << 15
+
+    def __init__(self, m: float):
+        self.m = float(m)
+        self.one_minus_m = 1.0 - float(m)     # formed in double like the reference, rounded once to fp32
+        self._key = None
+        self._table = None
+        self._nchunks = 0
+
+    def _build(self, params_k: Sequence[torch.Tensor], params_q: Sequence[torch.Tensor]):
+        rows = []
+        for pk, pq in zip(params_k, params_q):
+            if pk.numel() == 0:
+                continue
+            if pk.dtype != torch.float32 or pq.dtype != torch.float32:
+                raise ValueError("momentum update expects float32 parameters")
+            if not (pk.is_contiguous() and pq.is_contiguous()) or pk.numel() != pq.numel():
+                raise ValueError("momentum update expects contiguous parameter pairs of equal size")
+            _lib.require_cuda(pk, pq)
+            n = pk.numel()
+            for off in range(0, n, self.CHUNK):
+                rows.append((pk.data_ptr() + 4 * off, pq.data_ptr() + 4 * off, min(self.CHUNK, n - off)))
+        arr = np.asarray(rows, dtype=np.uint64).reshape(-1, 3)
+        dev = params_k[0].device
+        self._table = torch.from_numpy(arr.view(np.int64)).to(dev)
+        self._nchunks = len(rows)
+
+    @torch.no_grad()
+    def __call__(self, params_k: Iterable[torch.Tensor], params_q: Iterable[torch.Tensor]) -> None:
+        pk = [p.data for p in params_k]
+        pq = [p.data for p in params_q]
+        if not pk:
+            return
+        key = tuple((a.data_ptr(), b.data_ptr(), a.numel()) for a, b in zip(pk, pq))
+        if key != self._key:
+            self._build(pk, pq)
+            self._key = key
+        _lib.check(_lib.load().trb_ema_update_chunks_f32(_lib.ptr(self._table), self._nchunks, self.CHUNK, self.m,
+                                                         self.one_minus_m, _lib.stream_ptr(pk[0].device)),
+                   "trb_ema_update_chunks_f32")
+
+
+@torch.no_grad()
+def ema_update_flat(p_k: torch.Tensor, p_q: torch.Tensor, m: float) -> None:
+    """Momentum update of one contiguous parameter arena."""
+    _lib.require_cuda(p_k, p_q)
+    _lib.check(_lib.load().trb_ema_update_f32(_lib.ptr(p_k), _lib.ptr(p_q), p_k.numel(), float(m), 1.0 - float(m),
+                                              _lib.stream_ptr(p_k.device)), "trb_ema_update_f32")

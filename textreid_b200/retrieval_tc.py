@@ -1,0 +1,60 @@
+"""Host side of the bf16 tensor-core retrieval path (trb_pack_rows_bf16 + trb_retrieval_stream_tc).
+
+Rows of both operands are gathered in pid order while they are packed, so that the relevant gallery
+items of a 128-query tile form one contiguous band of the packed gallery: the thresholds
+(similarities of relevant pairs) are then captured by a short banded run of the SAME tcgen05
+instruction sequence that the full stream uses, which makes them bit-identical to the streamed values.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .evaluation import RetrievalResult
+
+
+def pack_rows(x: torch.Tensor, perm: Optional[torch.Tensor] = None, normalize: bool = True, eps: float = 1e-12):
+    """[rows, D] fp32/bf16 -> packed pre-swizzled bf16 image (uint8 tensor) in tile-major order."""
+    _lib.require_cuda(x)
+    lib = _lib.load()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    rows, dim = x.shape
+    nbytes = lib.trb_packed_bytes(rows, dim)
+    if nbytes == 0 and rows > 0:
+        raise RuntimeError("tensor-core path needs an embedding size that is a multiple of 64 (got %d)" % dim)
+    packed = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+    if perm is not None:
+        perm = perm.to(torch.int64).contiguous()
+    _lib.check(lib.trb_pack_rows_bf16(_lib.ptr(x), int(x.dtype == torch.bfloat16), _lib.ptr(perm), int(normalize), eps,
+                                      _lib.ptr(packed), rows, dim, _lib.stream_ptr(x.device)), "trb_pack_rows_bf16")
+    return packed
+
+
+def choose_nsplit_tc(num_qtiles: int, num_gtiles: int, sms: int, a_load_tiles: float = 2.0) -> int:
+    """Number of gallery pieces per query tile: minimise waves x (tiles per unit + query-tile reload)."""
+    best, best_cost = 1, None
+    hi = max(1, min(64, num_gtiles // 4 if num_gtiles >= 8 else 1))
+    for ns in range(1, hi + 1):
+        units = num_qtiles * ns
+        waves = -(-units // sms)
+        cost = waves * (-(-num_gtiles // ns) + a_load_tiles)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = ns, cost
+    return best
+
+
+def retrieve_tc(text_embed, image_embed, q_pids, g_pids, topk=(1, 5, 10), get_mAP=True, normalized=False,
+                nsplit: Optional[int] = None) -> RetrievalResult:
+    """Single-GPU tensor-core evaluation = the sharded protocol with one shard and no collectives."""
+    from .sharded import CudaBackend, ShardWorker, _finish
+    backend = CudaBackend()
+    w = ShardWorker(text_embed, image_embed, q_pids, g_pids, 0, get_mAP, "bf16", backend, normalized=normalized)
+    thr = w.local_thresholds() if get_mAP else None
+    cand_sim, cand_idx, cnt = w.stream(thr, nsplit)
+    res = _finish(backend, [cand_sim], [cand_idx], q_pids, g_pids, w.rel, cnt, topk)
+    res.thresholds = thr[:w.rel.total] if get_mAP else None
+    return res
