@@ -148,11 +148,13 @@ int trb_pack_rows_bf16(const void* src, int src_is_bf16, const int64_t* perm, in
  * mode 1: threshold capture -- for packed query row i the gallery rows [band_lo[i], band_hi[i]) of
  *         this shard are its relevant items; writes thr[rel_ptr[q] + rel_off[i] + (g - band_lo[i])]
  *         and thr_gidx likewise, using the same MMA instruction sequence as mode 0 so that the
- *         captured values are bit-identical to the streamed ones. */
+ *         captured values are bit-identical to the streamed ones.
+ * max_rel: an upper bound on the relevant items of any query (selects how many thresholds stay in
+ *         registers, 4 or 8; rows with more take an exact slow path).  cand_* hold 2*nsplit lists per query. */
 int trb_retrieval_stream_tc(const void* q_packed, const void* g_packed, int64_t Q, int64_t G, int64_t D,
                             const int64_t* q_row_id, const int64_t* g_row_id, const int64_t* rel_ptr,
                             float* thr, int64_t* thr_gidx, const int32_t* band_lo, const int32_t* band_hi,
-                            const int32_t* rel_off, int mode, int nsplit, float* cand_sim,
+                            const int32_t* rel_off, int mode, int nsplit, int max_rel, float* cand_sim,
                             int64_t* cand_idx, int32_t* cnt, trb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -222,6 +222,7 @@ def rank(similarity: torch.Tensor, q_pids: torch.Tensor, g_pids: torch.Tensor,
             order = torch.topk(similarity, k=depth, dim=1, largest=True, sorted=True)[1]
     hit = g_pids[order] == q_pids.reshape(-1, 1)
 
+    depth = min(depth, hit.shape[1])
     reached = hit[:, :depth].cumsum(1).clamp(max=1)
     cmc = reached.float().mean(0) * 100
     cmc = cmc[topk_t - 1]

@@ -26,7 +26,6 @@ constexpr int STAGE_BYTES = 2 * BLOCK_BYTES;   // 256 gallery rows x 64 k  = 32 
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int RT = 8;                // thresholds kept in registers per query row
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_MAX = 232448;      // 227 KiB opt-in limit per CTA on sm_100
 
@@ -75,7 +74,153 @@ __device__ __forceinline__ UnitInfo unit_info(const Params& p, int64_t u) {
     return ui;
 }
 
-template <int MODE>
+// ---------------------------------------------------------------------------------------------
+// epilogue: per query row (= one TMEM lane = one thread) state and the per-chunk consumer
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t gid_of(const Params& p, int grow) { return p.g_row_id[grow]; }
+
+// v[j] for a run-time j without spilling v to local memory: 5-level select tree (31 FSEL)
+__device__ __forceinline__ float select32(const float (&v)[32], int j) {
+    float a[16], b[8], c[4];
+    const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8, b4 = j & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = b0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = b1 ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = b2 ? b[2 * i + 1] : b[2 * i];
+    const float d0 = b3 ? c[1] : c[0], d1 = b3 ? c[3] : c[2];
+    return b4 ? d1 : d0;
+}
+
+template <int RTN>
+struct RowState {
+    float ts[TRB_TOPK];      // best-first similarities
+    int tr[TRB_TOPK];        // their packed gallery rows (global index resolved lazily through g_row_id)
+    float thr[RTN];          // first RTN thresholds of the row (+inf = unused)
+    int cnt[RTN];
+    float thr_min;
+    int64_t s_lo, s_hi;      // slot range of the row in the CSR
+
+    __device__ __forceinline__ void init(const Params& p, int64_t q) {
+#pragma unroll
+        for (int k = 0; k < TRB_TOPK; ++k) { ts[k] = -CUDART_INF_F; tr[k] = -1; }
+#pragma unroll
+        for (int r = 0; r < RTN; ++r) { thr[r] = CUDART_INF_F; cnt[r] = 0; }
+        thr_min = CUDART_INF_F;
+        s_lo = s_hi = 0;
+        if (q >= 0 && p.rel_ptr != nullptr) {
+            s_lo = p.rel_ptr[q];
+            s_hi = p.rel_ptr[q + 1];
+#pragma unroll
+            for (int r = 0; r < RTN; ++r)
+                if (s_lo + r < s_hi) { thr[r] = p.thr[s_lo + r]; thr_min = fminf(thr_min, thr[r]); }
+            if (s_hi - s_lo > RTN) thr_min = -CUDART_INF_F;     // overflow thresholds: never skip
+        }
+    }
+
+    // (s, grow) ranks before (s2, grow2): similarity descending, ties by GLOBAL gallery index ascending
+    __device__ __forceinline__ bool before(const Params& p, float s, int grow, float s2, int grow2) const {
+        if (s > s2) return true;
+        if (s == s2 && grow2 >= 0) return gid_of(p, grow) < gid_of(p, grow2);     // rare: exact tie
+        return false;
+    }
+
+    __device__ __forceinline__ void insert(const Params& p, float s, int grow) {
+        if (!(s > -CUDART_INF_F) || !before(p, s, grow, ts[TRB_TOPK - 1], tr[TRB_TOPK - 1])) return;
+        bool placed = false;
+#pragma unroll
+        for (int k = TRB_TOPK - 1; k >= 1; --k) {
+            if (!placed) {
+                if (before(p, s, grow, ts[k - 1], tr[k - 1])) { ts[k] = ts[k - 1]; tr[k] = tr[k - 1]; }
+                else { ts[k] = s; tr[k] = grow; placed = true; }
+            }
+        }
+        if (!placed) { ts[0] = s; tr[0] = grow; }
+    }
+
+    __device__ __forceinline__ void flush(const Params& p, int64_t q, int64_t nlists, int64_t list) {
+        float* cs = p.cand_sim + (q * nlists + list) * TRB_TOPK;
+        int64_t* ci = p.cand_idx + (q * nlists + list) * TRB_TOPK;
+#pragma unroll
+        for (int k = 0; k < TRB_TOPK; ++k) { cs[k] = ts[k]; ci[k] = tr[k] >= 0 ? gid_of(p, tr[k]) : INT64_MAX; }
+#pragma unroll
+        for (int r = 0; r < RTN; ++r)
+            if (s_lo + r < s_hi && cnt[r]) atomicAdd(p.cnt + s_lo + r, cnt[r]);
+    }
+};
+
+// Cold path (exact ties with a threshold, or rows with more than RTN relevant items): works from a local
+// copy of the chunk and the thresholds in global memory, corrections go straight to the global counters.
+//   first_slot..s_hi : slots to process;  ties_only: the fast path already counted the strictly-greater items
+__device__ __noinline__ void cold_count(const Params& p, const float* lv, int g0, int64_t first_slot, int64_t last_slot,
+                                        bool ties_only) {
+    for (int64_t slot = first_slot; slot < last_slot; ++slot) {
+        const float th = p.thr[slot];
+        const int64_t ti = p.thr_gidx[slot];
+        int c = 0;
+        for (int j = 0; j < 32; ++j) {
+            const float s = lv[j];
+            if (s > th) c += ties_only ? 0 : 1;
+            else if (s == th) { const int64_t gi = gid_of(p, g0 + j); c += (gi >= 0 && gi < ti) ? 1 : 0; }
+        }
+        if (c) atomicAdd(p.cnt + slot, c);
+    }
+}
+
+template <int RTN>
+__device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st, const float (&v)[32], int g0, bool row_valid,
+                                             bool warp_has_thr) {
+    // chunk maximum (feeds both filters); ptxas folds this into 3-input FMNMX3
+    float m8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
+    const float cmax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+
+    // ---- top-10: candidates are rare after the first few tiles; handle them through a bit mask ----
+    if (row_valid && cmax >= st.ts[TRB_TOPK - 1]) {
+        const float kth = st.ts[TRB_TOPK - 1];
+        uint32_t cand = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cand |= (v[j] >= kth) ? (1u << j) : 0u;
+#pragma unroll 1
+        while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            st.insert(p, select32(v, j), g0 + j);
+        }
+    }
+
+    // ---- exact rank counts: #{s_g > thr} through the sign bit of (thr - s_g); exact ties detected by min|thr - s_g| ----
+    if (!warp_has_thr) return;
+    const bool need = row_valid && st.s_hi > st.s_lo && cmax >= st.thr_min;
+    if (!__any_sync(0xffffffffu, need)) return;
+    float dmin = CUDART_INF_F;
+#pragma unroll
+    for (int r = 0; r < RTN; ++r) {
+        const float th = st.thr[r];
+        int c = st.cnt[r];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const float d0 = th - v[j], d1 = th - v[j + 1];          // < 0  <=>  s_g > thr   (x - x = +0, never -0)
+            c += (int)(__float_as_uint(d0) >> 31);
+            c += (int)(__float_as_uint(d1) >> 31);
+            dmin = fminf(fminf(dmin, fabsf(d0)), fabsf(d1));
+        }
+        st.cnt[r] = c;
+    }
+    const bool tie = need && dmin == 0.0f;
+    const bool overflow = need && (st.s_hi - st.s_lo > RTN);
+    if (tie || overflow) {
+        float lv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lv[j] = v[j];
+        if (tie) cold_count(p, lv, g0, st.s_lo, min(st.s_lo + RTN, st.s_hi), true);
+        if (overflow) cold_count(p, lv, g0, st.s_lo + RTN, st.s_hi, false);
+    }
+}
+
+template <int MODE, int RTN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -172,6 +317,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         const int half = (warp - EPI_WARP0) >> 2;        // which 128 of the 256 accumulator columns
         const int row = quarter * 32 + lane;
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 128);
         int tbuf = 0;
         uint32_t tphase = 0;
         for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
@@ -179,123 +325,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
             if (ui.t_lo >= ui.t_hi) continue;
             const int64_t prow = ui.qt * TILE_M + row;                 // packed query row
             const int64_t q = prow < p.Q ? p.q_row_id[prow] : -1;      // original query number
-            // per-unit row state
-            TopK top;
-            float kth = -CUDART_INF_F, thr_min = CUDART_INF_F;
-            float thr[RT];
-            int64_t tgidx[RT];
-            int rcnt[RT];
-            int64_t s_lo = 0, s_hi = 0;
+            RowState<RTN> st;
             int32_t blo = 0, bhi = 0;
             int64_t slot_base = 0;
             if (MODE == 0) {
-                top.init();
-#pragma unroll
-                for (int r = 0; r < RT; ++r) { thr[r] = CUDART_INF_F; tgidx[r] = -1; rcnt[r] = 0; }
-                if (q >= 0 && p.rel_ptr != nullptr) {
-                    s_lo = p.rel_ptr[q];
-                    s_hi = p.rel_ptr[q + 1];
-#pragma unroll
-                    for (int r = 0; r < RT; ++r)
-                        if (s_lo + r < s_hi) { thr[r] = p.thr[s_lo + r]; tgidx[r] = p.thr_gidx[s_lo + r]; thr_min = fminf(thr_min, thr[r]); }
-                    if (s_hi - s_lo > RT) thr_min = -CUDART_INF_F;     // overflow thresholds: always take the exact path
-                }
+                st.init(p, q);
             } else if (q >= 0) {
                 blo = p.band_lo[prow];
                 bhi = p.band_hi[prow];
                 slot_base = p.rel_ptr[q] + p.rel_off[prow];
             }
+            const bool warp_has_thr = MODE == 0 && __any_sync(0xffffffffu, st.s_hi > st.s_lo);
 
             for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
                 mbar_wait(t_full + tbuf, tphase);
                 tc_fence_after();
+                const bool tail_tile = (t + 1) * TILE_N > p.G;         // only the last tile holds zero padding rows
 #pragma unroll 1
                 for (int chunk = 0; chunk < 4; ++chunk) {
                     float v[32];
                     __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tbuf * TILE_N + half * 128 + chunk * 32);
-                    tmem_ld32(taddr, v);
+                    tmem_ld32(lane_taddr + (uint32_t)(tbuf * TILE_N + chunk * 32), v);
                     if (chunk == 3) {                      // accumulator fully read by this warp: hand it back
                         tc_fence_before();
                         if (lane == 0) mbar_arrive(t_empty + tbuf);
                     }
-                    const int64_t g0 = t * TILE_N + half * 128 + chunk * 32;   // packed gallery row of v[0]
-                    if (q < 0) continue;
+                    const int g0 = (int)(t * TILE_N) + half * 128 + chunk * 32;   // packed gallery row of v[0]
                     if (MODE == 1) {
+                        if (q >= 0 && g0 < bhi && g0 + 32 > blo) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int64_t g = g0 + j;
-                            if (g >= blo && g < bhi) {
-                                p.thr[slot_base + (g - blo)] = v[j];
-                                p.thr_gidx[slot_base + (g - blo)] = p.g_row_id[g];
+                            for (int j = 0; j < 32; ++j) {
+                                const int g = g0 + j;
+                                if (g >= blo && g < bhi) {
+                                    p.thr[slot_base + (g - blo)] = v[j];
+                                    p.thr_gidx[slot_base + (g - blo)] = p.g_row_id[g];
+                                }
                             }
                         }
                         continue;
                     }
-                    if (g0 + 32 > p.G) {                   // padded gallery rows (zero vectors) never rank
+                    if (tail_tile) {                       // padded gallery rows (zero vectors) never rank
+                        const int gvalid = (int)p.G;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (g0 + j >= p.G) v[j] = -CUDART_INF_F;
+                            if (g0 + j >= gvalid) v[j] = -CUDART_INF_F;
                     }
-                    float cmax = v[0];
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
-                    if (cmax >= kth) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (v[j] >= top.s[TRB_TOPK - 1]) {
-                                const int64_t gi = p.g_row_id[g0 + j];
-                                if (gi >= 0) top.push(v[j], gi);
-                            }
-                        }
-                        kth = top.s[TRB_TOPK - 1];
-                    }
-                    if (s_hi > s_lo && cmax >= thr_min) {
-#pragma unroll
-                        for (int r = 0; r < RT; ++r) {
-                            const float th = thr[r];
-                            int c = 0;
-                            bool tie = false;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) { c += (v[j] > th) ? 1 : 0; tie |= (v[j] == th); }
-                            if (tie) {                     // exact ties are ordered by gallery index
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (v[j] == th) {
-                                        const int64_t gi = p.g_row_id[g0 + j];
-                                        c += (gi >= 0 && gi < tgidx[r]) ? 1 : 0;
-                                    }
-                            }
-                            rcnt[r] += c;
-                        }
-                        for (int64_t slot = s_lo + RT; slot < s_hi; ++slot) {    // rare: > RT relevant items
-                            const float th = p.thr[slot];
-                            const int64_t ti = p.thr_gidx[slot];
-                            int c = 0;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (v[j] > th) ++c;
-                                else if (v[j] == th) { const int64_t gi = p.g_row_id[g0 + j]; c += (gi >= 0 && gi < ti) ? 1 : 0; }
-                            }
-                            if (c) atomicAdd(p.cnt + slot, c);
-                        }
-                    }
+                    stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr);
                 }
                 tbuf ^= 1;
                 if (tbuf == 0) tphase ^= 1;
             }
 
-            if (MODE == 0 && q >= 0) {
-                const int64_t nlists = 2 * (int64_t)p.nsplit;
-                const int64_t list = ui.split * 2 + half;
-                float* cs = p.cand_sim + (q * nlists + list) * TRB_TOPK;
-                int64_t* ci = p.cand_idx + (q * nlists + list) * TRB_TOPK;
-#pragma unroll
-                for (int k = 0; k < TRB_TOPK; ++k) { cs[k] = top.s[k]; ci[k] = top.i[k]; }
-#pragma unroll
-                for (int r = 0; r < RT; ++r)
-                    if (s_lo + r < s_hi && rcnt[r]) atomicAdd(p.cnt + s_lo + r, rcnt[r]);
-            }
+            if (MODE == 0 && q >= 0) st.flush(p, q, 2 * (int64_t)p.nsplit, ui.split * 2 + half);
         }
     }
 
@@ -395,10 +476,10 @@ extern "C" int trb_pack_rows_bf16(const void* src, int src_is_bf16, const int64_
 extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packed, int64_t Q, int64_t G, int64_t D,
                                        const int64_t* q_row_id, const int64_t* g_row_id, const int64_t* rel_ptr, float* thr,
                                        int64_t* thr_gidx, const int32_t* band_lo, const int32_t* band_hi, const int32_t* rel_off,
-                                       int mode, int nsplit, float* cand_sim, int64_t* cand_idx, int32_t* cnt,
+                                       int mode, int nsplit, int max_rel, float* cand_sim, int64_t* cand_idx, int32_t* cnt,
                                        trb_stream_t stream) {
     TRB_REQUIRE(q_packed && g_packed && q_row_id && g_row_id, "stream_tc: null pointer");
-    TRB_REQUIRE(Q >= 0 && G >= 0, "stream_tc: bad shape");
+    TRB_REQUIRE(Q >= 0 && G >= 0 && G < (1LL << 31) - 512, "stream_tc: bad shape (a shard holds < 2^31 gallery rows)");
     TRB_REQUIRE(mode == 0 || mode == 1, "stream_tc: mode must be 0 (stream) or 1 (threshold capture)");
     if (D <= 0 || D % 64 != 0 || D > 512) {
         trb_set_error("stream_tc: D=%lld unsupported on the tensor-core path (needs a multiple of 64, <= 512)", (long long)D);
@@ -441,12 +522,15 @@ extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packe
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(p.num_units < sms ? p.num_units : sms);
-    if (mode == 0) {
-        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        retrieval_tc_kernel<0><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    if (mode == 0 && max_rel <= 4) {
+        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        retrieval_tc_kernel<0, 4><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    } else if (mode == 0) {
+        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        retrieval_tc_kernel<0, 8><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
     } else {
-        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        retrieval_tc_kernel<1><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        retrieval_tc_kernel<1, 4><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
     }
     TRB_LAUNCH_OK();
     return 0;

@@ -34,8 +34,9 @@ def pack_rows(x: torch.Tensor, perm: Optional[torch.Tensor] = None, normalize: b
     return packed
 
 
-def choose_nsplit_tc(num_qtiles: int, num_gtiles: int, sms: int, a_load_tiles: float = 2.0) -> int:
-    """Number of gallery pieces per query tile: minimise waves x (tiles per unit + query-tile reload)."""
+def choose_nsplit_tc(num_qtiles: int, num_gtiles: int, sms: int, a_load_tiles: float = 32.0) -> int:
+    """Number of gallery pieces per query tile: minimise waves x (tiles per unit + per-unit start-up), the start-up
+    being the query-tile reload plus the top-10 warm-up (most insertions happen in a unit's first tiles)."""
     best, best_cost = 1, None
     hi = max(1, min(64, num_gtiles // 4 if num_gtiles >= 8 else 1))
     for ns in range(1, hi + 1):

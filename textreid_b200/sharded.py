@@ -67,6 +67,10 @@ class ShardWorker:
         self.record_events = False       # bench.py: CUDA events around the stream kernel alone
         self.stream_events = None
         self.rel: Optional[RelevanceIndex] = build_relevance(q_pids, g_pids_all) if get_mAP else None
+        self.max_rel = 0
+        if get_mAP and self.rel.total > 0:
+            # one more host read next to build_relevance's: picks the 4- or 8-threshold kernel variant
+            self.max_rel = int((self.rel.rel_ptr[1:] - self.rel.rel_ptr[:-1]).max().item())
         if precision == "fp32":
             self.qn = text_embed.contiguous().float() if normalized else backend.normalize(text_embed)
             self.gn = image_shard.contiguous().float() if normalized else backend.normalize(image_shard)
@@ -122,7 +126,7 @@ class ShardWorker:
             _lib.check(_lib.load().trb_retrieval_stream_tc(
                 _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, D, _lib.ptr(self.q_row_id),
                 _lib.ptr(self.g_row_id), _lib.ptr(rel.rel_ptr), _lib.ptr(thr), _lib.ptr(scratch_gidx), _lib.ptr(self.band_lo),
-                _lib.ptr(self.band_hi), _lib.ptr(self.rel_off), 1, 1, None, None, None, _lib.stream_ptr(self.dev)),
+                _lib.ptr(self.band_hi), _lib.ptr(self.rel_off), 1, 1, self.max_rel, None, None, None, _lib.stream_ptr(self.dev)),
                 "trb_retrieval_stream_tc(mode=1)")
         return thr
 
@@ -156,7 +160,7 @@ class ShardWorker:
         _lib.check(lib.trb_retrieval_stream_tc(
             _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, D, _lib.ptr(self.q_row_id), _lib.ptr(self.g_row_id),
             _lib.ptr(rel.rel_ptr) if self.get_mAP else None, _lib.ptr(thr), _lib.ptr(gidx), None, None, None, 0, ns,
-            _lib.ptr(cand_sim), _lib.ptr(cand_idx), _lib.ptr(cnt), _lib.stream_ptr(self.dev)), "trb_retrieval_stream_tc(mode=0)")
+            self.max_rel, _lib.ptr(cand_sim), _lib.ptr(cand_idx), _lib.ptr(cnt), _lib.stream_ptr(self.dev)), "trb_retrieval_stream_tc(mode=0)")
         self._events(ev)
         return cand_sim, cand_idx, cnt
 
