@@ -141,6 +141,9 @@ int64_t trb_packed_bytes(int64_t rows, int64_t dim);   /* bytes of the packed im
 int trb_pack_rows_bf16(const void* src, int src_is_bf16, const int64_t* perm, int normalize, float eps,
                        void* packed, int64_t rows, int64_t dim, trb_stream_t stream);
 
+/* Candidate lists the tensor-core stream writes per query and gallery split (one per epilogue column group). */
+int trb_retrieval_tc_lists_per_split(void);
+
 /* Tensor-core stream over a packed gallery shard.  Rows of both packed operands may be permuted:
  * q_row_id [Qp] / g_row_id [Gp] give, per packed row, the query number (slot owner) and the GLOBAL
  * gallery index (-1 for padding rows).  Everything else as trb_retrieval_stream_f32.
@@ -150,7 +153,8 @@ int trb_pack_rows_bf16(const void* src, int src_is_bf16, const int64_t* perm, in
  *         and thr_gidx likewise, using the same MMA instruction sequence as mode 0 so that the
  *         captured values are bit-identical to the streamed ones.
  * max_rel: an upper bound on the relevant items of any query (selects how many thresholds stay in
- *         registers, 4 or 8; rows with more take an exact slow path).  cand_* hold 2*nsplit lists per query. */
+ *         registers, 4 or 8; rows with more take an exact slow path).  cand_* hold
+ *         trb_retrieval_tc_lists_per_split() * nsplit lists per query. */
 int trb_retrieval_stream_tc(const void* q_packed, const void* g_packed, int64_t Q, int64_t G, int64_t D,
                             const int64_t* q_row_id, const int64_t* g_row_id, const int64_t* rel_ptr,
                             float* thr, int64_t* thr_gidx, const int32_t* band_lo, const int32_t* band_hi,

@@ -88,7 +88,7 @@ def make_case(Q, G, D, n_ids, seed, exact=False, noise=1.0):
     return text, image, tpid, ipid
 
 
-def check_against_matrix(res, sim_cpu, tpid, ipid, topk=(1, 5, 10), exact_ap=False):
+def check_against_matrix(res, sim_cpu, tpid, ipid, topk=(1, 5, 10), exact_ap=False, ap_rtol=3e-7):
     """Ranking-stage exactness given a similarity matrix that is bit-identical to what the kernel saw."""
     Q, G = sim_cpu.shape
     cmc, mAP, order = O.rank(sim_cpu, tpid, ipid, topk, get_mAP=True, per_column_loop=False)
@@ -110,7 +110,7 @@ def check_against_matrix(res, sim_cpu, tpid, ipid, topk=(1, 5, 10), exact_ap=Fal
     if exact_ap:
         assert torch.equal(ap[~nan], ap_ref[~nan])
     else:
-        torch.testing.assert_close(ap[~nan], ap_ref[~nan], rtol=3e-7, atol=0)
+        torch.testing.assert_close(ap[~nan], ap_ref[~nan], rtol=ap_rtol, atol=0)
     if nan.any():
         assert torch.isnan(res.mAP.cpu())
     else:
@@ -173,7 +173,7 @@ def test_many_relevant_items_overflow_path():
     text, image, tpid, ipid = make_case(200, 700, 64, n_ids=20, seed=3)     # ~35 images per id
     res = trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "fp32")
     sim = similarity_matrix(trb.l2_normalize_rows(T(text)), trb.l2_normalize_rows(T(image))).cpu()
-    check_against_matrix(res, sim, tpid, ipid)
+    check_against_matrix(res, sim, tpid, ipid, ap_rtol=2e-6)     # ~35 terms per AP: summation order shows at a few ulp
     res2 = trb.rank_artifacts(sim.to(DEV), T(tpid), T(ipid), (1, 5, 10), True)     # > 64 slots per row path too
     assert torch.equal(res2.hit_ranks.cpu(), res.hit_ranks.cpu())
     assert torch.equal(res2.top_idx.cpu(), res.top_idx.cpu())

@@ -45,6 +45,7 @@ SIGNATURES = {
     "trb_similarity_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
     "trb_retrieval_finish": (_int, [_p, _p, _int, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "trb_retrieval_metrics": (_int, [_p, _p, _i64, C.POINTER(_i32), _int, _p, _p, _p]),
+    "trb_retrieval_tc_lists_per_split": (_int, []),
     "trb_packed_rows": (_i64, [_i64]),
     "trb_packed_bytes": (_i64, [_i64, _i64]),
     "trb_pack_rows_bf16": (_int, [_p, _int, _p, _int, _f, _p, _i64, _i64, _p]),

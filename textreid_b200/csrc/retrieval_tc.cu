@@ -7,13 +7,14 @@
 // Replaces (with evaluation.py:117-120 fused in by trb_pack_rows_bf16) the reference's
 //   similarity = text @ image.T ; argsort ; matches ; cumsum        lib/data/metrics/evaluation.py:11-37,120
 //
-// Warp roles (384 threads, one persistent CTA per SM):
+// Warp roles (640 threads, one persistent CTA per SM):
 //   warp 0 lane 0 : producer  - bulk copies: query tile (resident per work unit) + gallery k-chunk ring
 //   warp 1 lane 0 : MMA issuer - tcgen05.mma into TMEM buffer t&1, tcgen05.commit -> barriers
 //   warp 2        : TMEM allocator / deallocator
-//   warps 4..11   : epilogue  - warp w reads TMEM lanes 32*(w%4).. (its 32 query rows) and the
-//                   column half (w-4)/4 of the 256-column accumulator
+//   warps 4..19   : epilogue  - warp w reads TMEM lanes 32*(w%4).. (its 32 query rows) and the
+//                   64-column slice (w-4)/4 of the 256-column accumulator
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -23,9 +24,12 @@ constexpr int TILE_M = 128;          // queries per CTA tile (TMEM lanes)
 constexpr int TILE_N = 256;          // gallery rows per MMA tile (TMEM columns per buffer)
 constexpr int UMMA_K = 16;
 constexpr int STAGE_BYTES = 2 * BLOCK_BYTES;   // 256 gallery rows x 64 k  = 32 KiB
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 640;
 constexpr int EPI_WARP0 = 4;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int COLS_PER_WARP = TILE_N / (NUM_EPI_WARPS / 4);   // 64 accumulator columns per epilogue warp
+constexpr int CHUNKS_PER_WARP = COLS_PER_WARP / 32;
+constexpr int LISTS_PER_SPLIT = NUM_EPI_WARPS / 4;            // candidate lists a query gets per gallery split
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_MAX = 232448;      // 227 KiB opt-in limit per CTA on sm_100
 
@@ -44,10 +48,11 @@ struct Params {
     const int32_t* band_hi;
     const int32_t* rel_off;
     int nsplit;
-    float* cand_sim;         // [Qorig, 2*nsplit, 10]
+    float* cand_sim;         // [Qorig, LISTS_PER_SPLIT*nsplit, 10]
     int64_t* cand_idx;
     int32_t* cnt;            // [total]
     int64_t num_qtiles, num_gtiles, num_units;
+    uint32_t two;            // the constant 2 as a kernel argument (see madhi2)
 };
 
 struct UnitInfo {
@@ -168,7 +173,16 @@ __device__ __noinline__ void cold_count(const Params& p, const float* lv, int g0
     }
 }
 
-template <int RTN>
+// c + (bits(d) >> 31) as one multiply-add on the FMA pipe; the multiplier is a run-time register so that
+// neither nvcc nor ptxas strength-reduces it back to LEA.HI (ALU pipe)
+__device__ __forceinline__ uint32_t madhi2_r(float d, uint32_t c, uint32_t two) {
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(__float_as_uint(d)), "r"(two), "r"(c));
+    return r;
+}
+#define madhi2(d, c) madhi2_r(d, c, two)
+
+template <int RTN, bool IMAD_COUNT>
 __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st, const float (&v)[32], int g0, bool row_valid,
                                              bool warp_has_thr) {
     // chunk maximum (feeds both filters); ptxas folds this into 3-input FMNMX3
@@ -195,20 +209,35 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
     if (!warp_has_thr) return;
     const bool need = row_valid && st.s_hi > st.s_lo && cmax >= st.thr_min;
     if (!__any_sync(0xffffffffu, need)) return;
-    float dmin = CUDART_INF_F;
+    // four independent accumulator chains per quantity: the counting is latency-bound otherwise
+    float dm0 = CUDART_INF_F, dm1 = CUDART_INF_F, dm2 = CUDART_INF_F, dm3 = CUDART_INF_F;
+    const uint32_t two = IMAD_COUNT ? p.two : 2u;
 #pragma unroll
     for (int r = 0; r < RTN; ++r) {
         const float th = st.thr[r];
-        int c = st.cnt[r];
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            const float d0 = th - v[j], d1 = th - v[j + 1];          // < 0  <=>  s_g > thr   (x - x = +0, never -0)
-            c += (int)(__float_as_uint(d0) >> 31);
-            c += (int)(__float_as_uint(d1) >> 31);
-            dmin = fminf(fminf(dmin, fabsf(d0)), fabsf(d1));
+        for (int j = 0; j < 32; j += 8) {
+            // d < 0  <=>  s_g > thr   (x - x = +0, never -0);  d == 0  <=>  exact tie
+            const float d0 = th - v[j], d1 = th - v[j + 1], d2 = th - v[j + 2], d3 = th - v[j + 3];
+            const float d4 = th - v[j + 4], d5 = th - v[j + 5], d6 = th - v[j + 6], d7 = th - v[j + 7];
+            if (IMAD_COUNT && (r & 1)) {     // odd thresholds count on the FMA pipe: mad.hi(d, 2, c) = c + (d >> 31)
+                c0 = madhi2(d0, c0); c1 = madhi2(d1, c1); c2 = madhi2(d2, c2); c3 = madhi2(d3, c3);
+                c0 = madhi2(d4, c0); c1 = madhi2(d5, c1); c2 = madhi2(d6, c2); c3 = madhi2(d7, c3);
+            } else {
+                c0 += __float_as_uint(d0) >> 31; c1 += __float_as_uint(d1) >> 31;
+                c2 += __float_as_uint(d2) >> 31; c3 += __float_as_uint(d3) >> 31;
+                c0 += __float_as_uint(d4) >> 31; c1 += __float_as_uint(d5) >> 31;
+                c2 += __float_as_uint(d6) >> 31; c3 += __float_as_uint(d7) >> 31;
+            }
+            dm0 = fminf(fminf(dm0, fabsf(d0)), fabsf(d4));
+            dm1 = fminf(fminf(dm1, fabsf(d1)), fabsf(d5));
+            dm2 = fminf(fminf(dm2, fabsf(d2)), fabsf(d6));
+            dm3 = fminf(fminf(dm3, fabsf(d3)), fabsf(d7));
         }
-        st.cnt[r] = c;
+        st.cnt[r] += (int)((c0 + c1) + (c2 + c3));
     }
+    const float dmin = fminf(fminf(dm0, dm1), fminf(dm2, dm3));
     const bool tie = need && dmin == 0.0f;
     const bool overflow = need && (st.s_hi - st.s_lo > RTN);
     if (tie || overflow) {
@@ -220,7 +249,7 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
     }
 }
 
-template <int MODE, int RTN>
+template <int MODE, int RTN, bool IMAD_COUNT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -315,9 +344,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
     } else if (warp >= EPI_WARP0) {
         // ------------------------------- epilogue -------------------------------------------
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
-        const int half = (warp - EPI_WARP0) >> 2;        // which 128 of the 256 accumulator columns
+        const int colgrp = (warp - EPI_WARP0) >> 2;      // which COLS_PER_WARP slice of the 256 accumulator columns
         const int row = quarter * 32 + lane;
-        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 128);
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colgrp * COLS_PER_WARP);
         int tbuf = 0;
         uint32_t tphase = 0;
         for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
@@ -342,15 +371,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 tc_fence_after();
                 const bool tail_tile = (t + 1) * TILE_N > p.G;         // only the last tile holds zero padding rows
 #pragma unroll 1
-                for (int chunk = 0; chunk < 4; ++chunk) {
+                for (int chunk = 0; chunk < CHUNKS_PER_WARP; ++chunk) {
                     float v[32];
                     __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
                     tmem_ld32(lane_taddr + (uint32_t)(tbuf * TILE_N + chunk * 32), v);
-                    if (chunk == 3) {                      // accumulator fully read by this warp: hand it back
+                    if (chunk == CHUNKS_PER_WARP - 1) {    // accumulator fully read by this warp: hand it back
                         tc_fence_before();
                         if (lane == 0) mbar_arrive(t_empty + tbuf);
                     }
-                    const int g0 = (int)(t * TILE_N) + half * 128 + chunk * 32;   // packed gallery row of v[0]
+                    const int g0 = (int)(t * TILE_N) + colgrp * COLS_PER_WARP + chunk * 32;   // packed gallery row of v[0]
                     if (MODE == 1) {
                         if (q >= 0 && g0 < bhi && g0 + 32 > blo) {
 #pragma unroll
@@ -370,13 +399,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                         for (int j = 0; j < 32; ++j)
                             if (g0 + j >= gvalid) v[j] = -CUDART_INF_F;
                     }
-                    stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr);
+                    stream_chunk<RTN, IMAD_COUNT>(p, st, v, g0, q >= 0, warp_has_thr);
                 }
                 tbuf ^= 1;
                 if (tbuf == 0) tphase ^= 1;
             }
 
-            if (MODE == 0 && q >= 0) st.flush(p, q, 2 * (int64_t)p.nsplit, ui.split * 2 + half);
+            if (MODE == 0 && q >= 0) st.flush(p, q, LISTS_PER_SPLIT * (int64_t)p.nsplit, ui.split * LISTS_PER_SPLIT + colgrp);
         }
     }
 
@@ -449,6 +478,8 @@ pack_rows_kernel(const void* __restrict__ src, const int64_t* __restrict__ perm,
 
 }  // namespace
 
+extern "C" int trb_retrieval_tc_lists_per_split(void) { return LISTS_PER_SPLIT; }
+
 extern "C" int64_t trb_packed_rows(int64_t rows) { return rows <= 0 ? 0 : ((rows + TILE_N - 1) / TILE_N) * TILE_N; }
 
 extern "C" int64_t trb_packed_bytes(int64_t rows, int64_t dim) {
@@ -512,6 +543,7 @@ extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packe
     p.q_row_id = q_row_id; p.g_row_id = g_row_id; p.rel_ptr = rel_ptr; p.thr = thr; p.thr_gidx = thr_gidx;
     p.band_lo = band_lo; p.band_hi = band_hi; p.rel_off = rel_off;
     p.nsplit = nsplit; p.cand_sim = cand_sim; p.cand_idx = cand_idx; p.cnt = cnt;
+    p.two = 2u;
     p.num_qtiles = trb_ceil_div(Q, TILE_M);
     p.num_gtiles = trb_ceil_div(G, TILE_N);
     TRB_REQUIRE(nsplit <= p.num_gtiles, "stream_tc: nsplit=%d exceeds the number of gallery tiles %lld", nsplit, (long long)p.num_gtiles);
@@ -522,16 +554,20 @@ extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packe
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(p.num_units < sms ? p.num_units : sms);
-    if (mode == 0 && max_rel <= 4) {
-        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        retrieval_tc_kernel<0, 4><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
-    } else if (mode == 0) {
-        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        retrieval_tc_kernel<0, 8><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
-    } else {
-        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        retrieval_tc_kernel<1, 4><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
-    }
+    // TRB_TC_VARIANT=1 counts half of the thresholds with IMAD.HI (FMA pipe) instead of LEA.HI (ALU pipe); A/B switch.
+    static const int variant = getenv("TRB_TC_VARIANT") ? atoi(getenv("TRB_TC_VARIANT")) : 0;
+#define TRB_LAUNCH_TC(MODE_, RTN_, IMAD_)                                                                                    \
+    do {                                                                                                                     \
+        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<MODE_, RTN_, IMAD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         smem_bytes));                                                                       \
+        retrieval_tc_kernel<MODE_, RTN_, IMAD_><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                  \
+    } while (0)
+    if (mode == 1) TRB_LAUNCH_TC(1, 4, false);
+    else if (max_rel <= 4 && variant == 1) TRB_LAUNCH_TC(0, 4, true);
+    else if (max_rel <= 4) TRB_LAUNCH_TC(0, 4, false);
+    else if (variant == 1) TRB_LAUNCH_TC(0, 8, true);
+    else TRB_LAUNCH_TC(0, 8, false);
+#undef TRB_LAUNCH_TC
     TRB_LAUNCH_OK();
     return 0;
 }

@@ -38,6 +38,10 @@ class RelevanceIndex:
     rel_ptr: torch.Tensor      # [Q+1] int64, CSR offsets (one slot per (query, relevant gallery item))
     rel_col: torch.Tensor      # [total] int64, global gallery index of every slot, ascending per query
     total: int
+    store: Optional[torch.Tensor] = None   # backing buffer of rel_col with >= 1 element (never a NULL device pointer)
+
+    def col_ptr(self):
+        return _lib.ptr(self.store if self.store is not None else self.rel_col)
 
 
 def build_relevance(q_pids: torch.Tensor, g_pids: torch.Tensor) -> RelevanceIndex:
@@ -48,7 +52,8 @@ def build_relevance(q_pids: torch.Tensor, g_pids: torch.Tensor) -> RelevanceInde
     dev = q_pids.device
     if g_pids.numel() == 0:
         z = torch.zeros(q_pids.numel() + 1, dtype=torch.int64, device=dev)
-        return RelevanceIndex(z, torch.zeros(1, dtype=torch.int64, device=dev)[:0], 0)
+        st = torch.zeros(1, dtype=torch.int64, device=dev)
+        return RelevanceIndex(z, st[:0], 0, st)
     sorted_pid, order = torch.sort(g_pids, stable=True)
     lo = torch.searchsorted(sorted_pid, q_pids, right=False)
     hi = torch.searchsorted(sorted_pid, q_pids, right=True)
@@ -60,7 +65,7 @@ def build_relevance(q_pids: torch.Tensor, g_pids: torch.Tensor) -> RelevanceInde
     within = torch.arange(total, device=dev) - rel_ptr[:-1][slot_q]
     store = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)   # never a NULL device pointer
     store[:total] = order[lo[slot_q] + within]   # stable sort => ascending gallery index inside a pid group
-    return RelevanceIndex(rel_ptr, store[:total], total)
+    return RelevanceIndex(rel_ptr, store[:total], total, store)
 
 
 # --------------------------------------------------------------------------------------------
@@ -168,7 +173,7 @@ def rank_artifacts(similarity: torch.Tensor, q_pids: torch.Tensor, g_pids: torch
     cnt = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=dev) if get_mAP else None
     _lib.check(lib.trb_rank_similarity_f32(
         _lib.ptr(similarity), similarity.stride(0), similarity.stride(1), Q, G,
-        _lib.ptr(rel.rel_ptr) if get_mAP else None, _lib.ptr(rel.rel_col) if get_mAP else None,
+        _lib.ptr(rel.rel_ptr) if get_mAP else None, rel.col_ptr() if get_mAP else None,
         _lib.ptr(cand_sim), _lib.ptr(cand_idx), _lib.ptr(cnt), _lib.stream_ptr(dev)), "trb_rank_similarity_f32")
     return _finish_and_metrics(cand_sim, cand_idx, 1, q_pids, g_pids, rel, cnt, topk)
 
@@ -259,12 +264,12 @@ def retrieve(text_embed: torch.Tensor, image_embed: torch.Tensor, text_pid: torc
         thr = torch.zeros(max(rel.total, 1), dtype=torch.float32, device=dev)
         cnt = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=dev)
         _lib.check(lib.trb_retrieval_thresholds_f32(_lib.ptr(qn), _lib.ptr(gn), _lib.ptr(rel.rel_ptr),
-                                                    _lib.ptr(rel.rel_col), _lib.ptr(thr), Q, D,
+                                                    rel.col_ptr(), _lib.ptr(thr), Q, D,
                                                     _lib.stream_ptr(dev)), "trb_retrieval_thresholds_f32")
     if nsplit is None:
         nsplit = _choose_nsplit(Q, G, 128, 128, _sm_count(dev))
     cand_sim, cand_idx = _stream_fp32(qn, gn, 0, rel.rel_ptr if get_mAP else None, thr,
-                                      rel.rel_col if get_mAP else None, cnt, nsplit)
+                                      rel.store if get_mAP else None, cnt, nsplit)
     return _finish_and_metrics(cand_sim, cand_idx, nsplit, q_pids, g_pids, rel, cnt, topk)
 
 

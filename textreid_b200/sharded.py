@@ -137,9 +137,7 @@ class ShardWorker:
         Q = self.q_pids.numel()
         if self.precision == "fp32":
             ns = nsplit or self.backend.nsplit(Q, self.Gs, self.dev)
-            gidx = rel.rel_col if self.get_mAP else None
-            if self.get_mAP and gidx.numel() == 0:
-                gidx = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            gidx = rel.store if self.get_mAP else None
             ev = self._events()
             cand_sim, cand_idx = self.backend.stream_fp32(self.qn, self.gn, self.g_base, rel.rel_ptr if self.get_mAP else None,
                                                           thr, gidx, cnt, ns)
@@ -151,11 +149,12 @@ class ShardWorker:
         num_gtiles = -(-self.Gs // 256)
         ns = nsplit or choose_nsplit_tc(-(-Q // 128), num_gtiles, _sm_count(self.dev))
         ns = max(1, min(ns, num_gtiles))
-        cand_sim = torch.empty(Q, 2 * ns, TOPK_DEPTH, dtype=torch.float32, device=self.dev)
-        cand_idx = torch.empty(Q, 2 * ns, TOPK_DEPTH, dtype=torch.int64, device=self.dev)
+        lists = int(lib.trb_retrieval_tc_lists_per_split()) * ns
+        cand_sim = torch.empty(Q, lists, TOPK_DEPTH, dtype=torch.float32, device=self.dev)
+        cand_idx = torch.empty(Q, lists, TOPK_DEPTH, dtype=torch.int64, device=self.dev)
         gidx = None
         if self.get_mAP:
-            gidx = rel.rel_col if rel.rel_col.numel() else torch.zeros(1, dtype=torch.int64, device=self.dev)
+            gidx = rel.store
         ev = self._events()
         _lib.check(lib.trb_retrieval_stream_tc(
             _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, D, _lib.ptr(self.q_row_id), _lib.ptr(self.g_row_id),
