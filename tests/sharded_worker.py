@@ -1,0 +1,146 @@
+"""Rank worker for the sharded-evaluation tests (launched by torch.multiprocessing / torchrun).
+
+backend == "oracle": CPU stand-in for the device kernels (gloo) -- exercises only the HOST logic of
+textreid_b200.sharded (CSR bookkeeping, slot offsets, collectives, merge orchestration).
+backend == "cuda": the real library over NCCL, one GPU per rank.
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import textreid_oracle as O
+from textreid_b200.evaluation import RetrievalResult
+
+
+class OracleBackend:
+    """Same contracts as the CUDA kernels (include/textreid_b200.h), computed with torch on the CPU."""
+    name = "oracle"
+
+    def normalize(self, x):
+        return O.normalize_rows(x.float())
+
+    def thresholds_fp32(self, qn, gn, rel_ptr, rel_row, thr):
+        counts = rel_ptr[1:] - rel_ptr[:-1]
+        qidx = torch.repeat_interleave(torch.arange(qn.shape[0]), counts)
+        rows = rel_row[:qidx.numel()]
+        ok = rows >= 0
+        thr[:qidx.numel()][ok] = (qn[qidx[ok]] * gn[rows[ok]]).sum(1)
+
+    def nsplit(self, Q, G, device):
+        return 2 if G >= 4 else 1
+
+    def stream_fp32(self, qn, gn, g_base, rel_ptr, thr, thr_gidx, cnt, nsplit):
+        Q, G = qn.shape[0], gn.shape[0]
+        sim = qn @ gn.t()
+        gidx = torch.arange(G) + g_base
+        cand_sim = torch.full((Q, nsplit, 10), float("-inf"))
+        cand_idx = torch.full((Q, nsplit, 10), torch.iinfo(torch.int64).max, dtype=torch.int64)
+        for s in range(nsplit):
+            lo, hi = G * s // nsplit, G * (s + 1) // nsplit
+            if hi > lo:
+                order = torch.argsort(sim[:, lo:hi], dim=1, descending=True, stable=True)[:, :10]
+                k = order.shape[1]
+                cand_sim[:, s, :k] = torch.gather(sim[:, lo:hi], 1, order)
+                cand_idx[:, s, :k] = gidx[lo:hi][order]
+        if rel_ptr is not None:
+            counts = rel_ptr[1:] - rel_ptr[:-1]
+            qidx = torch.repeat_interleave(torch.arange(Q), counts)
+            n = qidx.numel()
+            s_rows = sim[qidx]                                   # [n, G]
+            t, ti = thr[:n].unsqueeze(1), thr_gidx[:n].unsqueeze(1)
+            before = (s_rows > t) | ((s_rows == t) & (gidx.unsqueeze(0) < ti))
+            cnt[:n] += before.sum(1).to(torch.int32)
+        return cand_sim, cand_idx
+
+    def finish(self, cand_sim, cand_idx, nlists, q_pids, g_pids, rel, cnt, topk):
+        Q = q_pids.numel()
+        cs, ci = cand_sim.reshape(Q, -1), cand_idx.reshape(Q, -1)
+        key = torch.argsort(ci, dim=1, stable=True)              # ties by index, then stable by similarity
+        cs, ci = torch.gather(cs, 1, key), torch.gather(ci, 1, key)
+        order = torch.argsort(cs, dim=1, descending=True, stable=True)[:, :10]
+        top_sim, top_idx = torch.gather(cs, 1, order), torch.gather(ci, 1, order)
+        top_idx = torch.where(top_sim == float("-inf"), torch.full_like(top_idx, -1), top_idx)
+        topk = list(topk)
+        if rel is None:
+            hit = (g_pids[top_idx.clamp(min=0)] == q_pids.view(-1, 1)) & (top_idx >= 0)
+            first = torch.where(hit.any(1), hit.float().argmax(1), torch.full((Q,), 2 ** 31 - 1)).to(torch.int32)
+            cmc = torch.stack([(first < k).float().mean() * 100 for k in topk])
+            return RetrievalResult(cmc, None, top_idx, top_sim, first, None, None, None)
+        ranks, ap, first = [], [], []
+        for q in range(Q):
+            r = torch.sort(cnt[rel.rel_ptr[q]:rel.rel_ptr[q + 1]])[0]
+            ranks.append(r)
+            first.append(int(r[0]) if r.numel() else 2 ** 31 - 1)
+            s = torch.tensor(0.0)
+            for j, x in enumerate(r.tolist()):
+                s = s + torch.tensor(float(j + 1)) / torch.tensor(float(x + 1))
+            ap.append(s / torch.tensor(float(r.numel())) if r.numel() else torch.tensor(float("nan")))
+        first = torch.tensor(first, dtype=torch.int32)
+        ap = torch.stack(ap)
+        cmc = torch.stack([(first < k).float().sum() / Q * 100 for k in topk])
+        return RetrievalResult(cmc, ap.double().mean().float() * 100, top_idx, top_sim, first, ap,
+                               torch.cat(ranks).to(torch.int32) if ranks else None, rel.rel_ptr)
+
+
+def make_case(Q, G, D, n_ids, seed, exact=False):
+    """exact=True: +-1/8 Rademacher rows with D=64 (unit norm, every dot product exact in fp32 under any
+    summation order, many ties) so that shard-local and global arithmetic agree bit for bit."""
+    g = torch.Generator().manual_seed(seed)
+    ipid = torch.randint(0, n_ids, (G,), generator=g)
+    src = torch.randint(0, G, (Q,), generator=g)
+    tpid = ipid[src].clone()
+    if exact:
+        assert D == 64
+        image = (torch.randint(0, 2, (G, D), generator=g).float() * 2 - 1) / 8.0
+        text = (torch.randint(0, 2, (Q, D), generator=g).float() * 2 - 1) / 8.0
+    else:
+        image = torch.randn(G, D, generator=g)
+        text = 0.5 * image[src] + torch.randn(Q, D, generator=g)
+    return text, image, tpid, ipid
+
+
+def shard_slices(G, world, uneven=True):
+    cuts = [0]
+    for r in range(world):
+        share = G // world + (37 if (uneven and r == 0) else 0)
+        cuts.append(min(G, cuts[-1] + share))
+    cuts[-1] = G
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def worker(rank, world, backend_name, port, out_dir, precision="fp32", Q=150, G=700, D=64, exact=True):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if backend_name == "cuda":
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        dev = torch.device("cuda", rank)
+        backend = None
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dev = torch.device("cpu")
+        backend = OracleBackend()
+    from textreid_b200.sharded import retrieve_sharded
+    text, image, tpid, ipid = make_case(Q, G, D, max(G // 5, 1), seed=5, exact=exact)
+    lo, hi = shard_slices(G, world)[rank]
+    res = retrieve_sharded(text.to(dev), image[lo:hi].to(dev), tpid.to(dev), ipid[lo:hi].to(dev), (1, 5, 10), True,
+                           precision, backend=backend)
+    res_topk = retrieve_sharded(text.to(dev), image[lo:hi].to(dev), tpid.to(dev), ipid[lo:hi].to(dev), (1, 5, 10), False,
+                                precision, backend=backend)
+    torch.save({"cmc": res.cmc.cpu(), "mAP": res.mAP.cpu(), "top_idx": res.top_idx.cpu(), "top_sim": res.top_sim.cpu(),
+                "hit_ranks": res.hit_ranks.cpu(), "rel_ptr": res.rel_ptr.cpu(), "ap": res.ap.cpu(),
+                "cmc_topk": res_topk.cmc.cpu(), "top_idx_topk": res_topk.top_idx.cpu()},
+               os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":      # torchrun entry: python tests/sharded_worker.py <backend> <out_dir> <precision>
+    worker(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), sys.argv[1], int(os.environ.get("MASTER_PORT", "29511")),
+           sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "fp32", Q=300, G=3000, D=64, exact=False)

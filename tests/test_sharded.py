@@ -1,0 +1,74 @@
+"""Gallery-sharded evaluation (the N>1 path): world_size-2 gloo run of the host logic on CPU with an
+oracle-backed stand-in for the device kernels, and (GPU boxes with >= 2 devices) the real NCCL run."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import textreid_oracle as O
+from tests.sharded_worker import make_case, worker
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def check_outputs(out_dir, world, Q, G, D, exact_sim):
+    text, image, tpid, ipid = make_case(Q, G, D, max(G // 5, 1), seed=5, exact=exact_sim)
+    sim = O.similarity_matrix(text, image)
+    cmc, mAP, order = O.rank(sim, tpid, ipid, (1, 5, 10), True, per_column_loop=False)
+    ranks = O.hit_ranks(sim, tpid, ipid)
+    outs = [torch.load(os.path.join(out_dir, "rank%d.pt" % r)) for r in range(world)]
+    for o in outs[1:]:                                    # every rank ends with the same result
+        for k in outs[0]:
+            assert torch.equal(o[k], outs[0][k]) or (o[k].dtype.is_floating_point and torch.allclose(o[k], outs[0][k], equal_nan=True)), k
+    o = outs[0]
+    if exact_sim:
+        assert torch.equal(o["top_idx"], order[:, :10])
+        assert torch.equal(o["top_idx_topk"], order[:, :10])
+        for q in range(Q):
+            assert torch.equal(o["hit_ranks"][o["rel_ptr"][q]:o["rel_ptr"][q + 1]].long(), ranks[q])
+        assert torch.equal(o["cmc"], cmc) and torch.equal(o["cmc_topk"], cmc)
+        torch.testing.assert_close(o["mAP"], mAP, rtol=2e-6, atol=0)
+    else:
+        agree = (o["top_idx"] == order[:, :10]).float().mean()
+        assert agree > 0.97
+        assert (o["cmc"] - cmc).abs().max() <= 100.0 * 3 / Q
+        assert abs(float(o["mAP"]) - float(mAP)) < 0.5
+
+
+def test_sharded_host_logic_gloo_world2(tmp_path):
+    port = free_port()
+    mp.spawn(worker, args=(2, "oracle", port, str(tmp_path)), nprocs=2, join=True)
+    check_outputs(str(tmp_path), 2, 150, 700, 64, exact_sim=True)
+
+
+def test_sharded_host_logic_gloo_world3_uneven(tmp_path):
+    port = free_port()
+    mp.spawn(worker, args=(3, "oracle", port, str(tmp_path)), nprocs=3, join=True)
+    check_outputs(str(tmp_path), 3, 150, 700, 64, exact_sim=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sharded_nccl(tmp_path, precision):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "tests", "sharded_worker.py"), "cuda",
+           str(tmp_path), precision]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    check_outputs(str(tmp_path), world, 300, 3000, 64, exact_sim=False)
