@@ -35,6 +35,8 @@ class OracleBackend:
     def nsplit(self, Q, G, device):
         return 2 if G >= 4 else 1
 
+    # no merge_lists(): the driver then takes the variable-list-count gather path, which the gloo tests cover
+
     def stream_fp32(self, qn, gn, g_base, rel_ptr, thr, thr_gidx, cnt, nsplit):
         Q, G = qn.shape[0], gn.shape[0]
         sim = qn @ gn.t()

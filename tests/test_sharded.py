@@ -23,9 +23,12 @@ def free_port():
     return p
 
 
-def check_outputs(out_dir, world, Q, G, D, exact_sim):
+def check_outputs(out_dir, world, Q, G, D, exact_sim, precision="fp32"):
     text, image, tpid, ipid = make_case(Q, G, D, max(G // 5, 1), seed=5, exact=exact_sim)
-    sim = O.similarity_matrix(text, image)
+    if precision == "bf16":     # the kernel sees bf16-rounded normalised operands
+        sim = (O.normalize_rows(text).bfloat16().double() @ O.normalize_rows(image).bfloat16().double().t()).float()
+    else:
+        sim = O.similarity_matrix(text, image)
     cmc, mAP, order = O.rank(sim, tpid, ipid, (1, 5, 10), True, per_column_loop=False)
     ranks = O.hit_ranks(sim, tpid, ipid)
     outs = [torch.load(os.path.join(out_dir, "rank%d.pt" % r)) for r in range(world)]
@@ -71,4 +74,4 @@ def test_sharded_nccl(tmp_path, precision):
            str(tmp_path), precision]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    check_outputs(str(tmp_path), world, 300, 3000, 64, exact_sim=False)
+    check_outputs(str(tmp_path), world, 300, 3000, 64, exact_sim=False, precision=precision)

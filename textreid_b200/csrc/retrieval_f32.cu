@@ -356,7 +356,8 @@ retrieval_finish_kernel(const float* __restrict__ cand_sim, const int64_t* __res
         int64_t bi = INT64_MAX;
         for (int p = lane; p < n; p += 32) {
             const float s = cs[p];
-            const int64_t i = ci[p];
+            int64_t i = ci[p];
+            if (i < 0) i = INT64_MAX;     // padding of an already-merged list
             // strictly after the previous winner, and better than the running best
             if (ranks_before(last_s, last_i, s, i) && ranks_before(s, i, bs, bi)) { bs = s; bi = i; }
         }

@@ -51,6 +51,19 @@ class CudaBackend:
     def finish(self, cand_sim, cand_idx, nlists, q_pids, g_pids, rel, cnt, topk):
         return _finish_and_metrics(cand_sim, cand_idx, nlists, q_pids, g_pids, rel, cnt, topk)
 
+    def merge_lists(self, cand_sim, cand_idx, q_pids, g_pids):
+        """[Q, L, 10] candidate lists -> [Q, 1, 10]: the rank-local merge that keeps the all-gather at 120 B/query."""
+        Q, L, K = cand_sim.shape
+        if L == 1:
+            return cand_sim, cand_idx
+        dev = cand_sim.device
+        top_sim = torch.empty(Q, 1, K, dtype=torch.float32, device=dev)
+        top_idx = torch.empty(Q, 1, K, dtype=torch.int64, device=dev)
+        _lib.check(_lib.load().trb_retrieval_finish(
+            _lib.ptr(cand_sim), _lib.ptr(cand_idx), L, Q, _lib.ptr(q_pids), _lib.ptr(g_pids), g_pids.numel(), None, None,
+            _lib.ptr(top_sim), _lib.ptr(top_idx), None, None, None, _lib.stream_ptr(dev)), "trb_retrieval_finish")
+        return top_sim, top_idx
+
 
 class ShardWorker:
     """State of one gallery shard between the exchange steps."""
@@ -238,10 +251,18 @@ def retrieve_sharded(text_embed, image_shard, text_pid, image_pid_shard, topk=(1
     cand_sim, cand_idx, cnt = w.stream(thr, nsplit)
     if get_mAP:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
-    # candidate lists: [Q, L, 10] per rank, L may differ -> gather along a leading L axis
-    sims = _all_gather_varlen(cand_sim.permute(1, 0, 2).contiguous(), group)
-    idxs = _all_gather_varlen(cand_idx.permute(1, 0, 2).contiguous(), group)
-    res = _finish(backend, [s.permute(1, 0, 2) for s in sims], [i.permute(1, 0, 2) for i in idxs], q_pids, g_pids_all,
-                  w.rel, cnt, topk)
+    # candidate lists: merge this rank's L lists to one per query, then all-gather [Q, 10] x (fp32, int64)
+    world = dist.get_world_size(group)
+    if hasattr(backend, "merge_lists"):
+        cand_sim, cand_idx = backend.merge_lists(cand_sim, cand_idx, q_pids, g_pids_all)
+        sims = torch.empty((world,) + tuple(cand_sim.shape), dtype=cand_sim.dtype, device=cand_sim.device)
+        idxs = torch.empty((world,) + tuple(cand_idx.shape), dtype=cand_idx.dtype, device=cand_idx.device)
+        dist.all_gather_into_tensor(sims, cand_sim.contiguous(), group=group)
+        dist.all_gather_into_tensor(idxs, cand_idx.contiguous(), group=group)
+        sim_parts, idx_parts = [sims[r] for r in range(world)], [idxs[r] for r in range(world)]
+    else:   # stand-in backends (tests): list counts may differ per rank -> gather along a leading list axis
+        sim_parts = [x.permute(1, 0, 2) for x in _all_gather_varlen(cand_sim.permute(1, 0, 2).contiguous(), group)]
+        idx_parts = [x.permute(1, 0, 2) for x in _all_gather_varlen(cand_idx.permute(1, 0, 2).contiguous(), group)]
+    res = _finish(backend, sim_parts, idx_parts, q_pids, g_pids_all, w.rel, cnt, topk)
     res.thresholds = thr[:w.rel.total] if get_mAP else None
     return res
