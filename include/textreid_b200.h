@@ -144,19 +144,23 @@ int trb_pack_rows_bf16(const void* src, int src_is_bf16, const int64_t* perm, in
 /* Candidate lists the tensor-core stream writes per query and gallery split (one per epilogue column group). */
 int trb_retrieval_tc_lists_per_split(void);
 
-/* Tensor-core stream over a packed gallery shard.  Rows of both packed operands may be permuted:
- * q_row_id [Qp] / g_row_id [Gp] give, per packed row, the query number (slot owner) and the GLOBAL
- * gallery index (-1 for padding rows).  Everything else as trb_retrieval_stream_f32.
- * mode 0: top-10 candidates + counts against thr (thr may be NULL -> top-k only)
- * mode 1: threshold capture -- for packed query row i the gallery rows [band_lo[i], band_hi[i]) of
- *         this shard are its relevant items; writes thr[rel_ptr[q] + rel_off[i] + (g - band_lo[i])]
- *         and thr_gidx likewise, using the same MMA instruction sequence as mode 0 so that the
- *         captured values are bit-identical to the streamed ones.
- * max_rel: an upper bound on the relevant items of any query (selects how many thresholds stay in
- *         registers, 4 or 8; rows with more take an exact slow path).  cand_* hold
- *         trb_retrieval_tc_lists_per_split() * nsplit lists per query. */
+/* Tensor-core pass over a packed gallery shard (G local rows; a shard holds < 2^31 rows).
+ * q_row_id [Qp]: original query number of every packed query row (-1 = padding); queries may be packed in any order.
+ *
+ * mode 0 -- stream: the gallery MUST be packed in index order (perm = NULL); the global index of packed row g is
+ *   g_base + g.  Produces top-10 candidate lists (trb_retrieval_tc_lists_per_split() * nsplit per query, best first,
+ *   global int64 indices, unused lists padded with -inf / INT64_MAX) and, when rel_ptr/thr/thr_gidx/cnt are given,
+ *   cnt[slot] += #{local g : (s_g, g) ranks before (thr[slot], thr_gidx[slot])}.  Because the stream is in index order,
+ *   ties are resolved by position: chunks before the relevant item compare with >=, chunks after it with >.
+ *   nsplit: gallery pieces for the query tiles of the last, partial wave of the persistent grid (whole waves are
+ *   never split); max_rel: upper bound on the relevant items of a query (4 or 8 thresholds stay in registers, rows
+ *   with more take an exact slow path).
+ * mode 1 -- threshold capture: queries AND gallery packed in pid order (perm = argsort of the pids), g_row_id [Gp] gives
+ *   the global index of every packed gallery row (-1 = padding).  For packed query row i the packed gallery rows
+ *   [band_lo[i], band_hi[i]) are its relevant items; writes thr[rel_ptr[q] + rel_off[i] + (g - band_lo[i])] and
+ *   thr_gidx likewise, with the same tcgen05.mma sequence as mode 0 so the values are bit-identical to the streamed ones. */
 int trb_retrieval_stream_tc(const void* q_packed, const void* g_packed, int64_t Q, int64_t G, int64_t D,
-                            const int64_t* q_row_id, const int64_t* g_row_id, const int64_t* rel_ptr,
+                            const int64_t* q_row_id, const int64_t* g_row_id, int64_t g_base, const int64_t* rel_ptr,
                             float* thr, int64_t* thr_gidx, const int32_t* band_lo, const int32_t* band_hi,
                             const int32_t* rel_off, int mode, int nsplit, int max_rel, float* cand_sim,
                             int64_t* cand_idx, int32_t* cnt, trb_stream_t stream);

@@ -99,9 +99,10 @@ def test_first_occurrence_matches_reference_semantics():
 
 
 def test_work_split_choices():
-    assert choose_nsplit_tc(782, 3907, 148) * 782 >= 148
+    assert choose_nsplit_tc(782, 3907, 148) == 3        # 782 = 5*148 + 42 -> the 42 remainder tiles are cut in 3
+    assert choose_nsplit_tc(296, 3907, 148) == 1        # whole waves only
     assert choose_nsplit_tc(1, 1, 148) == 1
-    assert 1 <= choose_nsplit_tc(49, 13, 148) <= 3
+    assert choose_nsplit_tc(49, 13, 148) == 3
     assert _choose_nsplit(6156, 3074, 128, 128, 148) >= 1
     assert _choose_nsplit(10, 5, 128, 128, 148) == 1
 

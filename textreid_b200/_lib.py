@@ -49,7 +49,7 @@ SIGNATURES = {
     "trb_packed_rows": (_i64, [_i64]),
     "trb_packed_bytes": (_i64, [_i64, _i64]),
     "trb_pack_rows_bf16": (_int, [_p, _int, _p, _int, _f, _p, _i64, _i64, _p]),
-    "trb_retrieval_stream_tc": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _int, _int, _int,
+    "trb_retrieval_stream_tc": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _int, _int, _int,
                                        _p, _p, _p, _p]),
     "trb_moco_loss_workspace_bytes": (_i64, [C.POINTER(MocoShape), _int]),
     "trb_moco_loss": (_int, [_p, _p, _p, _p, _p, _p, _int, _p, _p, _p, _p, _p, _p, _p, C.POINTER(MocoShape),

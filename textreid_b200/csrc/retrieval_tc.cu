@@ -40,7 +40,8 @@ struct Params {
     int kchunks;             // D / 64
     int nstages;
     const int64_t* q_row_id; // [Qp] original query number per packed row, -1 = padding
-    const int64_t* g_row_id; // [Gp] global gallery index per packed row, -1 = padding
+    const int64_t* g_row_id; // mode 1: [Gp] global gallery index per (pid-sorted) packed row, -1 = padding
+    int64_t g_base;          // mode 0: the gallery is packed in index order; global index = g_base + packed row
     const int64_t* rel_ptr;  // [Qorig+1]
     float* thr;              // [total]  (mode 0: read, mode 1: written)
     int64_t* thr_gidx;       // [total]
@@ -52,7 +53,9 @@ struct Params {
     int64_t* cand_idx;
     int32_t* cnt;            // [total]
     int64_t num_qtiles, num_gtiles, num_units;
-    uint32_t two;            // the constant 2 as a kernel argument (see madhi2)
+    int64_t full_qtiles;     // mode 0: query tiles [0, full_qtiles) stream the whole gallery in one unit (whole waves of the
+                             // persistent grid); the remaining tiles are cut into nsplit gallery pieces to balance the last wave
+    int debug;               // TRB_TC_DEBUG (probing only): 1 = epilogue reads TMEM but skips the arithmetic, 2 = skips the TMEM read too
 };
 
 struct UnitInfo {
@@ -63,10 +66,18 @@ template <int MODE>
 __device__ __forceinline__ UnitInfo unit_info(const Params& p, int64_t u) {
     UnitInfo ui;
     if (MODE == 0) {
-        ui.split = u / p.num_qtiles;
-        ui.qt = u % p.num_qtiles;
-        ui.t_lo = p.num_gtiles * ui.split / p.nsplit;
-        ui.t_hi = p.num_gtiles * (ui.split + 1) / p.nsplit;
+        if (u < p.full_qtiles) {
+            ui.split = -1;                   // unsplit: writes list group 0 and pads the others
+            ui.qt = u;
+            ui.t_lo = 0;
+            ui.t_hi = p.num_gtiles;
+        } else {
+            const int64_t r = u - p.full_qtiles, rem = p.num_qtiles - p.full_qtiles;
+            ui.split = r / rem;              // split-major: concurrent CTAs stream the same gallery range
+            ui.qt = p.full_qtiles + r % rem;
+            ui.t_lo = p.num_gtiles * ui.split / p.nsplit;
+            ui.t_hi = p.num_gtiles * (ui.split + 1) / p.nsplit;
+        }
     } else {
         ui.split = 0;
         ui.qt = u;
@@ -81,8 +92,19 @@ __device__ __forceinline__ UnitInfo unit_info(const Params& p, int64_t u) {
 
 // ---------------------------------------------------------------------------------------------
 // epilogue: per query row (= one TMEM lane = one thread) state and the per-chunk consumer
+//
+// The stream (mode 0) walks the gallery in GLOBAL INDEX order.  The pinned ranking order is (similarity desc, index asc),
+// so for a relevant item r with similarity thr: an item g ranks before r  <=>  s_g > thr, or s_g == thr and g < r
+//   <=>  s_g >= thr for g < r  and  s_g > thr for g > r.
+// Chunks that lie entirely before r therefore count against nextbelow(thr) (">=" as a strict compare), chunks after r
+// against thr itself, and only the one chunk that contains r needs a correction.  No per-value tie detection, no index
+// look-ups: 2 instructions per (value, threshold): d = t - v (FADD), count += bits(d) >> 31 (LEA.HI).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int64_t gid_of(const Params& p, int grow) { return p.g_row_id[grow]; }
+__device__ __forceinline__ float next_below(float x) {        // largest float < x (x finite or +inf)
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t r = (x > 0.0f) ? b - 1u : (((b << 1) == 0u) ? 0x80000001u : b + 1u);
+    return __uint_as_float(r);
+}
 
 // v[j] for a run-time j without spilling v to local memory: 5-level select tree (31 FSEL)
 __device__ __forceinline__ float select32(const float (&v)[32], int j) {
@@ -101,43 +123,39 @@ __device__ __forceinline__ float select32(const float (&v)[32], int j) {
 template <int RTN>
 struct RowState {
     float ts[TRB_TOPK];      // best-first similarities
-    int tr[TRB_TOPK];        // their packed gallery rows (global index resolved lazily through g_row_id)
+    int tr[TRB_TOPK];        // their packed (= local) gallery rows
     float thr[RTN];          // first RTN thresholds of the row (+inf = unused)
+    int rloc[RTN];           // local row of the relevant item: < 0 lives on a lower shard, >= G on a higher one
     int cnt[RTN];
-    float thr_min;
     int64_t s_lo, s_hi;      // slot range of the row in the CSR
 
     __device__ __forceinline__ void init(const Params& p, int64_t q) {
 #pragma unroll
         for (int k = 0; k < TRB_TOPK; ++k) { ts[k] = -CUDART_INF_F; tr[k] = -1; }
 #pragma unroll
-        for (int r = 0; r < RTN; ++r) { thr[r] = CUDART_INF_F; cnt[r] = 0; }
-        thr_min = CUDART_INF_F;
+        for (int r = 0; r < RTN; ++r) { thr[r] = CUDART_INF_F; rloc[r] = INT32_MAX; cnt[r] = 0; }
         s_lo = s_hi = 0;
         if (q >= 0 && p.rel_ptr != nullptr) {
             s_lo = p.rel_ptr[q];
             s_hi = p.rel_ptr[q + 1];
 #pragma unroll
             for (int r = 0; r < RTN; ++r)
-                if (s_lo + r < s_hi) { thr[r] = p.thr[s_lo + r]; thr_min = fminf(thr_min, thr[r]); }
-            if (s_hi - s_lo > RTN) thr_min = -CUDART_INF_F;     // overflow thresholds: never skip
+                if (s_lo + r < s_hi) {
+                    thr[r] = p.thr[s_lo + r];
+                    const int64_t l = p.thr_gidx[s_lo + r] - p.g_base;
+                    rloc[r] = l < 0 ? -1 : (l >= p.G ? INT32_MAX : (int)l);
+                }
         }
     }
 
-    // (s, grow) ranks before (s2, grow2): similarity descending, ties by GLOBAL gallery index ascending
-    __device__ __forceinline__ bool before(const Params& p, float s, int grow, float s2, int grow2) const {
-        if (s > s2) return true;
-        if (s == s2 && grow2 >= 0) return gid_of(p, grow) < gid_of(p, grow2);     // rare: exact tie
-        return false;
-    }
-
-    __device__ __forceinline__ void insert(const Params& p, float s, int grow) {
-        if (!(s > -CUDART_INF_F) || !before(p, s, grow, ts[TRB_TOPK - 1], tr[TRB_TOPK - 1])) return;
+    // the stream is in ascending index order, so a later value only displaces strictly smaller entries
+    __device__ __forceinline__ void insert(float s, int grow) {
+        if (!(s > ts[TRB_TOPK - 1])) return;
         bool placed = false;
 #pragma unroll
         for (int k = TRB_TOPK - 1; k >= 1; --k) {
             if (!placed) {
-                if (before(p, s, grow, ts[k - 1], tr[k - 1])) { ts[k] = ts[k - 1]; tr[k] = tr[k - 1]; }
+                if (s > ts[k - 1]) { ts[k] = ts[k - 1]; tr[k] = tr[k - 1]; }
                 else { ts[k] = s; tr[k] = grow; placed = true; }
             }
         }
@@ -148,108 +166,107 @@ struct RowState {
         float* cs = p.cand_sim + (q * nlists + list) * TRB_TOPK;
         int64_t* ci = p.cand_idx + (q * nlists + list) * TRB_TOPK;
 #pragma unroll
-        for (int k = 0; k < TRB_TOPK; ++k) { cs[k] = ts[k]; ci[k] = tr[k] >= 0 ? gid_of(p, tr[k]) : INT64_MAX; }
+        for (int k = 0; k < TRB_TOPK; ++k) { cs[k] = ts[k]; ci[k] = tr[k] >= 0 ? p.g_base + tr[k] : INT64_MAX; }
 #pragma unroll
         for (int r = 0; r < RTN; ++r)
             if (s_lo + r < s_hi && cnt[r]) atomicAdd(p.cnt + s_lo + r, cnt[r]);
     }
 };
 
-// Cold path (exact ties with a threshold, or rows with more than RTN relevant items): works from a local
-// copy of the chunk and the thresholds in global memory, corrections go straight to the global counters.
-//   first_slot..s_hi : slots to process;  ties_only: the fast path already counted the strictly-greater items
-__device__ __noinline__ void cold_count(const Params& p, const float* lv, int g0, int64_t first_slot, int64_t last_slot,
-                                        bool ties_only) {
-    for (int64_t slot = first_slot; slot < last_slot; ++slot) {
+__device__ __forceinline__ void pad_list(const Params& p, int64_t q, int64_t nlists, int64_t list) {
+    float* cs = p.cand_sim + (q * nlists + list) * TRB_TOPK;
+    int64_t* ci = p.cand_idx + (q * nlists + list) * TRB_TOPK;
+#pragma unroll
+    for (int k = 0; k < TRB_TOPK; ++k) { cs[k] = -CUDART_INF_F; ci[k] = INT64_MAX; }
+}
+
+// Cold paths, working from a local copy of the chunk and the thresholds in global memory; corrections go straight to
+// the global counters.
+//  fix_own_chunk : the chunk contains relevant items of this row; the fast path compared it against thr itself (">"),
+//                  values equal to thr that precede the item must be added.
+//  count_overflow: rows with more than RTN relevant items -- exact count of the extra slots for this chunk.
+__device__ __noinline__ void fix_own_chunk(const Params& p, const float* lv, int g0, int64_t s_lo, int64_t s_end) {
+    for (int64_t slot = s_lo; slot < s_end; ++slot) {
+        const int64_t l = p.thr_gidx[slot] - p.g_base - g0;        // position of the item inside this chunk
+        if (l < 0 || l >= 32) continue;
         const float th = p.thr[slot];
-        const int64_t ti = p.thr_gidx[slot];
         int c = 0;
-        for (int j = 0; j < 32; ++j) {
-            const float s = lv[j];
-            if (s > th) c += ties_only ? 0 : 1;
-            else if (s == th) { const int64_t gi = gid_of(p, g0 + j); c += (gi >= 0 && gi < ti) ? 1 : 0; }
-        }
+        for (int j = 0; j < (int)l; ++j) c += (lv[j] == th) ? 1 : 0;
+        if (c) atomicAdd(p.cnt + slot, c);
+    }
+}
+__device__ __noinline__ void count_overflow(const Params& p, const float* lv, int g0, int64_t s_first, int64_t s_hi) {
+    for (int64_t slot = s_first; slot < s_hi; ++slot) {
+        const float th = p.thr[slot];
+        const int64_t ti = p.thr_gidx[slot] - p.g_base - g0;
+        int c = 0;
+        for (int j = 0; j < 32; ++j) c += (lv[j] > th || (lv[j] == th && j < ti)) ? 1 : 0;
         if (c) atomicAdd(p.cnt + slot, c);
     }
 }
 
-// c + (bits(d) >> 31) as one multiply-add on the FMA pipe; the multiplier is a run-time register so that
-// neither nvcc nor ptxas strength-reduces it back to LEA.HI (ALU pipe)
-__device__ __forceinline__ uint32_t madhi2_r(float d, uint32_t c, uint32_t two) {
-    uint32_t r;
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(__float_as_uint(d)), "r"(two), "r"(c));
-    return r;
-}
-#define madhi2(d, c) madhi2_r(d, c, two)
-
-template <int RTN, bool IMAD_COUNT>
+template <int RTN>
 __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st, const float (&v)[32], int g0, bool row_valid,
                                              bool warp_has_thr) {
-    // chunk maximum (feeds both filters); ptxas folds this into 3-input FMNMX3
+    // chunk maximum for the top-10 filter; ptxas folds this into 3-input FMNMX3
     float m8[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
     const float cmax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
 
-    // ---- top-10: candidates are rare after the first few tiles; handle them through a bit mask ----
-    if (row_valid && cmax >= st.ts[TRB_TOPK - 1]) {
+    // ---- top-10: candidates are rare after the first tiles; only 4-value groups whose maximum beats the current
+    //      10th best are scanned, and the hits go through a bit mask + select tree (keeps the hot loop compact) ----
+    if (row_valid && cmax > st.ts[TRB_TOPK - 1]) {
         const float kth = st.ts[TRB_TOPK - 1];
         uint32_t cand = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) cand |= (v[j] >= kth) ? (1u << j) : 0u;
+        for (int i = 0; i < 8; ++i) {
+            if (m8[i] > kth) {
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m |= (v[4 * i + j] > kth) ? (1u << j) : 0u;
+                cand |= m << (4 * i);
+            }
+        }
 #pragma unroll 1
         while (cand) {
             const int j = __ffs(cand) - 1;
             cand &= cand - 1;
-            st.insert(p, select32(v, j), g0 + j);
+            st.insert(select32(v, j), g0 + j);
         }
     }
 
-    // ---- exact rank counts: #{s_g > thr} through the sign bit of (thr - s_g); exact ties detected by min|thr - s_g| ----
+    // ---- exact rank counts ----
     if (!warp_has_thr) return;
-    const bool need = row_valid && st.s_hi > st.s_lo && cmax >= st.thr_min;
-    if (!__any_sync(0xffffffffu, need)) return;
-    // four independent accumulator chains per quantity: the counting is latency-bound otherwise
-    float dm0 = CUDART_INF_F, dm1 = CUDART_INF_F, dm2 = CUDART_INF_F, dm3 = CUDART_INF_F;
-    const uint32_t two = IMAD_COUNT ? p.two : 2u;
+    bool own = false;
 #pragma unroll
     for (int r = 0; r < RTN; ++r) {
-        const float th = st.thr[r];
+        const int rl = st.rloc[r];
+        // whole chunk precedes the item -> ties count (>= thr as > nextbelow(thr)); otherwise strict
+        const float te = (g0 + 32 <= rl) ? next_below(st.thr[r]) : st.thr[r];
+        own |= (rl >= g0) & (rl < g0 + 32);
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            // d < 0  <=>  s_g > thr   (x - x = +0, never -0);  d == 0  <=>  exact tie
-            const float d0 = th - v[j], d1 = th - v[j + 1], d2 = th - v[j + 2], d3 = th - v[j + 3];
-            const float d4 = th - v[j + 4], d5 = th - v[j + 5], d6 = th - v[j + 6], d7 = th - v[j + 7];
-            if (IMAD_COUNT && (r & 1)) {     // odd thresholds count on the FMA pipe: mad.hi(d, 2, c) = c + (d >> 31)
-                c0 = madhi2(d0, c0); c1 = madhi2(d1, c1); c2 = madhi2(d2, c2); c3 = madhi2(d3, c3);
-                c0 = madhi2(d4, c0); c1 = madhi2(d5, c1); c2 = madhi2(d6, c2); c3 = madhi2(d7, c3);
-            } else {
-                c0 += __float_as_uint(d0) >> 31; c1 += __float_as_uint(d1) >> 31;
-                c2 += __float_as_uint(d2) >> 31; c3 += __float_as_uint(d3) >> 31;
-                c0 += __float_as_uint(d4) >> 31; c1 += __float_as_uint(d5) >> 31;
-                c2 += __float_as_uint(d6) >> 31; c3 += __float_as_uint(d7) >> 31;
-            }
-            dm0 = fminf(fminf(dm0, fabsf(d0)), fabsf(d4));
-            dm1 = fminf(fminf(dm1, fabsf(d1)), fabsf(d5));
-            dm2 = fminf(fminf(dm2, fabsf(d2)), fabsf(d6));
-            dm3 = fminf(fminf(dm3, fabsf(d3)), fabsf(d7));
+        for (int j = 0; j < 32; j += 4) {
+            c0 += __float_as_uint(te - v[j]) >> 31;           // te - v < 0  <=>  v > te   (x - x = +0, never -0)
+            c1 += __float_as_uint(te - v[j + 1]) >> 31;
+            c2 += __float_as_uint(te - v[j + 2]) >> 31;
+            c3 += __float_as_uint(te - v[j + 3]) >> 31;
         }
         st.cnt[r] += (int)((c0 + c1) + (c2 + c3));
     }
-    const float dmin = fminf(fminf(dm0, dm1), fminf(dm2, dm3));
-    const bool tie = need && dmin == 0.0f;
-    const bool overflow = need && (st.s_hi - st.s_lo > RTN);
-    if (tie || overflow) {
+    const bool overflow = row_valid && (st.s_hi - st.s_lo > RTN);
+    own = own && row_valid;
+    if (own || overflow) {
         float lv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) lv[j] = v[j];
-        if (tie) cold_count(p, lv, g0, st.s_lo, min(st.s_lo + RTN, st.s_hi), true);
-        if (overflow) cold_count(p, lv, g0, st.s_lo + RTN, st.s_hi, false);
+        if (own) fix_own_chunk(p, lv, g0, st.s_lo, min(st.s_lo + RTN, st.s_hi));
+        if (overflow) count_overflow(p, lv, g0, st.s_lo + RTN, st.s_hi);
     }
 }
 
-template <int MODE, int RTN, bool IMAD_COUNT>
+template <int MODE, int RTN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -374,12 +391,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 for (int chunk = 0; chunk < CHUNKS_PER_WARP; ++chunk) {
                     float v[32];
                     __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
-                    tmem_ld32(lane_taddr + (uint32_t)(tbuf * TILE_N + chunk * 32), v);
+                    if (!(p.debug & 2)) tmem_ld32(lane_taddr + (uint32_t)(tbuf * TILE_N + chunk * 32), v);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
                     if (chunk == CHUNKS_PER_WARP - 1) {    // accumulator fully read by this warp: hand it back
                         tc_fence_before();
                         if (lane == 0) mbar_arrive(t_empty + tbuf);
                     }
                     const int g0 = (int)(t * TILE_N) + colgrp * COLS_PER_WARP + chunk * 32;   // packed gallery row of v[0]
+                    if (p.debug & 3) { if (v[5] == 12345.678f) p.cand_sim[0] = v[7]; continue; }
                     if (MODE == 1) {
                         if (q >= 0 && g0 < bhi && g0 + 32 > blo) {
 #pragma unroll
@@ -399,13 +421,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                         for (int j = 0; j < 32; ++j)
                             if (g0 + j >= gvalid) v[j] = -CUDART_INF_F;
                     }
-                    stream_chunk<RTN, IMAD_COUNT>(p, st, v, g0, q >= 0, warp_has_thr);
+                    stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr);
                 }
                 tbuf ^= 1;
                 if (tbuf == 0) tphase ^= 1;
             }
 
-            if (MODE == 0 && q >= 0) st.flush(p, q, LISTS_PER_SPLIT * (int64_t)p.nsplit, ui.split * LISTS_PER_SPLIT + colgrp);
+            if (MODE == 0 && q >= 0) {
+                const int64_t nlists = LISTS_PER_SPLIT * (int64_t)p.nsplit;
+                st.flush(p, q, nlists, (ui.split < 0 ? 0 : ui.split) * LISTS_PER_SPLIT + colgrp);
+                if (ui.split < 0)            // unsplit unit: the list groups of the other splits stay empty
+                    for (int64_t l = LISTS_PER_SPLIT + colgrp; l < nlists; l += LISTS_PER_SPLIT)
+                        pad_list(p, q, nlists, l);
+            }
         }
     }
 
@@ -505,11 +533,12 @@ extern "C" int trb_pack_rows_bf16(const void* src, int src_is_bf16, const int64_
 }
 
 extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packed, int64_t Q, int64_t G, int64_t D,
-                                       const int64_t* q_row_id, const int64_t* g_row_id, const int64_t* rel_ptr, float* thr,
+                                       const int64_t* q_row_id, const int64_t* g_row_id, int64_t g_base, const int64_t* rel_ptr, float* thr,
                                        int64_t* thr_gidx, const int32_t* band_lo, const int32_t* band_hi, const int32_t* rel_off,
                                        int mode, int nsplit, int max_rel, float* cand_sim, int64_t* cand_idx, int32_t* cnt,
                                        trb_stream_t stream) {
-    TRB_REQUIRE(q_packed && g_packed && q_row_id && g_row_id, "stream_tc: null pointer");
+    TRB_REQUIRE(q_packed && g_packed && q_row_id, "stream_tc: null pointer");
+    TRB_REQUIRE(mode == 0 || g_row_id != nullptr, "stream_tc: mode 1 needs g_row_id (global index of the pid-sorted packed rows)");
     TRB_REQUIRE(Q >= 0 && G >= 0 && G < (1LL << 31) - 512, "stream_tc: bad shape (a shard holds < 2^31 gallery rows)");
     TRB_REQUIRE(mode == 0 || mode == 1, "stream_tc: mode must be 0 (stream) or 1 (threshold capture)");
     if (D <= 0 || D % 64 != 0 || D > 512) {
@@ -540,33 +569,31 @@ extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packe
     int ns = (SMEM_MAX - fixed_bytes - a_bytes) / STAGE_BYTES;
     p.nstages = ns > MAX_STAGES ? MAX_STAGES : ns;
     TRB_REQUIRE(p.nstages >= 2, "stream_tc: not enough shared memory for a 2-stage ring at D=%lld", (long long)D);
-    p.q_row_id = q_row_id; p.g_row_id = g_row_id; p.rel_ptr = rel_ptr; p.thr = thr; p.thr_gidx = thr_gidx;
+    p.q_row_id = q_row_id; p.g_row_id = g_row_id; p.g_base = g_base; p.rel_ptr = rel_ptr; p.thr = thr; p.thr_gidx = thr_gidx;
     p.band_lo = band_lo; p.band_hi = band_hi; p.rel_off = rel_off;
     p.nsplit = nsplit; p.cand_sim = cand_sim; p.cand_idx = cand_idx; p.cnt = cnt;
-    p.two = 2u;
+    p.debug = getenv("TRB_TC_DEBUG") ? atoi(getenv("TRB_TC_DEBUG")) : 0;
     p.num_qtiles = trb_ceil_div(Q, TILE_M);
     p.num_gtiles = trb_ceil_div(G, TILE_N);
     TRB_REQUIRE(nsplit <= p.num_gtiles, "stream_tc: nsplit=%d exceeds the number of gallery tiles %lld", nsplit, (long long)p.num_gtiles);
-    p.num_units = mode == 0 ? p.num_qtiles * nsplit : p.num_qtiles;
-
-    const int smem_bytes = a_bytes + p.nstages * STAGE_BYTES + fixed_bytes;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // whole waves of the persistent grid take unsplit query tiles; only the remainder is split (nsplit pieces each)
+    p.full_qtiles = (mode == 0 && nsplit > 1) ? (p.num_qtiles / sms) * sms : (mode == 0 ? p.num_qtiles : 0);
+    p.num_units = mode == 0 ? p.full_qtiles + (p.num_qtiles - p.full_qtiles) * nsplit : p.num_qtiles;
+
+    const int smem_bytes = a_bytes + p.nstages * STAGE_BYTES + fixed_bytes;
     const unsigned grid = (unsigned)(p.num_units < sms ? p.num_units : sms);
-    // TRB_TC_VARIANT=1 counts half of the thresholds with IMAD.HI (FMA pipe) instead of LEA.HI (ALU pipe); A/B switch.
-    static const int variant = getenv("TRB_TC_VARIANT") ? atoi(getenv("TRB_TC_VARIANT")) : 0;
-#define TRB_LAUNCH_TC(MODE_, RTN_, IMAD_)                                                                                    \
-    do {                                                                                                                     \
-        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<MODE_, RTN_, IMAD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         smem_bytes));                                                                       \
-        retrieval_tc_kernel<MODE_, RTN_, IMAD_><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                  \
+#define TRB_LAUNCH_TC(MODE_, RTN_)                                                                                     \
+    do {                                                                                                               \
+        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<MODE_, RTN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         smem_bytes));                                                                 \
+        retrieval_tc_kernel<MODE_, RTN_><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                   \
     } while (0)
-    if (mode == 1) TRB_LAUNCH_TC(1, 4, false);
-    else if (max_rel <= 4 && variant == 1) TRB_LAUNCH_TC(0, 4, true);
-    else if (max_rel <= 4) TRB_LAUNCH_TC(0, 4, false);
-    else if (variant == 1) TRB_LAUNCH_TC(0, 8, true);
-    else TRB_LAUNCH_TC(0, 8, false);
+    if (mode == 1) TRB_LAUNCH_TC(1, 4);
+    else if (max_rel <= 4) TRB_LAUNCH_TC(0, 4);
+    else TRB_LAUNCH_TC(0, 8);
 #undef TRB_LAUNCH_TC
     TRB_LAUNCH_OK();
     return 0;

@@ -34,18 +34,17 @@ def pack_rows(x: torch.Tensor, perm: Optional[torch.Tensor] = None, normalize: b
     return packed
 
 
-def choose_nsplit_tc(num_qtiles: int, num_gtiles: int, sms: int, a_load_tiles: float = 32.0) -> int:
-    """Number of gallery pieces per query tile: minimise waves x (tiles per unit + per-unit start-up), the start-up
-    being the query-tile reload plus the top-10 warm-up (most insertions happen in a unit's first tiles)."""
-    best, best_cost = 1, None
-    hi = max(1, min(64, num_gtiles // 4 if num_gtiles >= 8 else 1))
-    for ns in range(1, hi + 1):
-        units = num_qtiles * ns
-        waves = -(-units // sms)
-        cost = waves * (-(-num_gtiles // ns) + a_load_tiles)
-        if best_cost is None or cost < best_cost - 1e-9:
-            best, best_cost = ns, cost
-    return best
+def choose_nsplit_tc(num_qtiles: int, num_gtiles: int, sms: int) -> int:
+    """Gallery split factor for the query tiles of the LAST (partial) wave of the persistent grid.
+
+    The kernel gives whole waves (multiples of the SM count) of query tiles one unit each -- a unit then streams the
+    entire gallery, which keeps the per-unit start-up (query tile load, top-10 warm-up) negligible -- and cuts only the
+    remaining ``num_qtiles % sms`` tiles into ``nsplit`` gallery pieces so that the last wave is short instead of
+    leaving most SMs idle.  With fewer query tiles than SMs every tile is split."""
+    rem = num_qtiles % sms
+    if rem == 0:
+        return 1
+    return int(max(1, min(sms // rem, max(1, num_gtiles // 4), 32)))
 
 
 def retrieve_tc(text_embed, image_embed, q_pids, g_pids, topk=(1, 5, 10), get_mAP=True, normalized=False,

@@ -92,24 +92,28 @@ class ShardWorker:
         else:
             raise ValueError("precision must be 'fp32' or 'bf16'")
 
-    # ---- bf16 tensor-core preparation: pid-sorted packed operands and band bookkeeping ----
+    # ---- bf16 tensor-core preparation: packed operands and band bookkeeping ----
     def _prepare_tc(self, text_embed, image_shard, normalized):
+        """Queries are packed once, in pid order.  The gallery is packed in INDEX order for the stream (ties are then
+        resolved by position) and, when ranks are wanted, a second time in pid order for the threshold capture, where the
+        relevant items of a 128-query tile form one contiguous band."""
         from .retrieval_tc import pack_rows
         lib = _lib.load()
         dev = self.dev
         Q = text_embed.shape[0]
         self.Qp, self.Gp = int(lib.trb_packed_rows(Q)), int(lib.trb_packed_rows(self.Gs))
-        g_pids_local = self.g_pids_all[self.g_base:self.g_base + self.Gs]
         q_sorted, q_order = torch.sort(self.q_pids, stable=True)
-        g_sorted, g_order = torch.sort(g_pids_local, stable=True)
         self.q_packed = pack_rows(text_embed, q_order, normalize=not normalized)
-        self.g_packed = pack_rows(image_shard, g_order, normalize=not normalized)
         self.q_row_id = torch.full((self.Qp,), -1, dtype=torch.int64, device=dev)
         self.q_row_id[:Q] = q_order
-        self.g_row_id = torch.full((self.Gp,), -1, dtype=torch.int64, device=dev)
-        self.g_row_id[:self.Gs] = g_order + self.g_base
+        self.g_packed = pack_rows(image_shard, None, normalize=not normalized)
         if self.get_mAP:
             rel = self.rel
+            g_pids_local = self.g_pids_all[self.g_base:self.g_base + self.Gs]
+            g_sorted, g_order = torch.sort(g_pids_local, stable=True)
+            self.g_packed_pid = pack_rows(image_shard, g_order, normalize=not normalized)
+            self.g_row_id = torch.full((self.Gp,), -1, dtype=torch.int64, device=dev)
+            self.g_row_id[:self.Gs] = g_order + self.g_base
             self.band_lo = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
             self.band_hi = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
             self.band_lo[:Q] = torch.searchsorted(g_sorted, q_sorted, right=False).to(torch.int32)
@@ -137,8 +141,8 @@ class ShardWorker:
             Q = self.q_pids.numel()
             D = self.q_packed.numel() // (2 * self.Qp)
             _lib.check(_lib.load().trb_retrieval_stream_tc(
-                _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, D, _lib.ptr(self.q_row_id),
-                _lib.ptr(self.g_row_id), _lib.ptr(rel.rel_ptr), _lib.ptr(thr), _lib.ptr(scratch_gidx), _lib.ptr(self.band_lo),
+                _lib.ptr(self.q_packed), _lib.ptr(self.g_packed_pid), Q, self.Gs, D, _lib.ptr(self.q_row_id),
+                _lib.ptr(self.g_row_id), self.g_base, _lib.ptr(rel.rel_ptr), _lib.ptr(thr), _lib.ptr(scratch_gidx), _lib.ptr(self.band_lo),
                 _lib.ptr(self.band_hi), _lib.ptr(self.rel_off), 1, 1, self.max_rel, None, None, None, _lib.stream_ptr(self.dev)),
                 "trb_retrieval_stream_tc(mode=1)")
         return thr
@@ -170,7 +174,7 @@ class ShardWorker:
             gidx = rel.store
         ev = self._events()
         _lib.check(lib.trb_retrieval_stream_tc(
-            _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, D, _lib.ptr(self.q_row_id), _lib.ptr(self.g_row_id),
+            _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, D, _lib.ptr(self.q_row_id), None, self.g_base,
             _lib.ptr(rel.rel_ptr) if self.get_mAP else None, _lib.ptr(thr), _lib.ptr(gidx), None, None, None, 0, ns,
             self.max_rel, _lib.ptr(cand_sim), _lib.ptr(cand_idx), _lib.ptr(cnt), _lib.stream_ptr(self.dev)), "trb_retrieval_stream_tc(mode=0)")
         self._events(ev)
