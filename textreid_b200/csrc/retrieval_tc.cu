@@ -55,7 +55,8 @@ struct Params {
     int64_t num_qtiles, num_gtiles, num_units;
     int64_t full_qtiles;     // mode 0: query tiles [0, full_qtiles) stream the whole gallery in one unit (whole waves of the
                              // persistent grid); the remaining tiles are cut into nsplit gallery pieces to balance the last wave
-    int debug;               // TRB_TC_DEBUG (probing only): 1 = epilogue reads TMEM but skips the arithmetic, 2 = skips the TMEM read too
+    uint32_t wait_hint_ns;   // suspend-time hint of the epilogue warps' accumulator waits
+    int debug;               // builds with -DTRB_TC_PROBE only (TRB_TC_DEBUG env): 1 = epilogue skips the arithmetic, 2 = and the TMEM read
 };
 
 struct UnitInfo {
@@ -384,24 +385,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
             const bool warp_has_thr = MODE == 0 && __any_sync(0xffffffffu, st.s_hi > st.s_lo);
 
             for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
-                mbar_wait(t_full + tbuf, tphase);
+                mbar_wait_sleepy(t_full + tbuf, tphase, p.wait_hint_ns);
                 tc_fence_after();
                 const bool tail_tile = (t + 1) * TILE_N > p.G;         // only the last tile holds zero padding rows
 #pragma unroll 1
                 for (int chunk = 0; chunk < CHUNKS_PER_WARP; ++chunk) {
                     float v[32];
                     __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
+#ifdef TRB_TC_PROBE
                     if (!(p.debug & 2)) tmem_ld32(lane_taddr + (uint32_t)(tbuf * TILE_N + chunk * 32), v);
                     else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = 0.f;
                     }
+#else
+                    tmem_ld32(lane_taddr + (uint32_t)(tbuf * TILE_N + chunk * 32), v);
+#endif
                     if (chunk == CHUNKS_PER_WARP - 1) {    // accumulator fully read by this warp: hand it back
                         tc_fence_before();
                         if (lane == 0) mbar_arrive(t_empty + tbuf);
                     }
                     const int g0 = (int)(t * TILE_N) + colgrp * COLS_PER_WARP + chunk * 32;   // packed gallery row of v[0]
+#ifdef TRB_TC_PROBE
                     if (p.debug & 3) { if (v[5] == 12345.678f) p.cand_sim[0] = v[7]; continue; }
+#endif
                     if (MODE == 1) {
                         if (q >= 0 && g0 < bhi && g0 + 32 > blo) {
 #pragma unroll
@@ -572,6 +579,7 @@ extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packe
     p.q_row_id = q_row_id; p.g_row_id = g_row_id; p.g_base = g_base; p.rel_ptr = rel_ptr; p.thr = thr; p.thr_gidx = thr_gidx;
     p.band_lo = band_lo; p.band_hi = band_hi; p.rel_off = rel_off;
     p.nsplit = nsplit; p.cand_sim = cand_sim; p.cand_idx = cand_idx; p.cnt = cnt;
+    p.wait_hint_ns = getenv("TRB_TC_WAIT_NS") ? (uint32_t)atoi(getenv("TRB_TC_WAIT_NS")) : 1000u;
     p.debug = getenv("TRB_TC_DEBUG") ? atoi(getenv("TRB_TC_DEBUG")) : 0;
     p.num_qtiles = trb_ceil_div(Q, TILE_M);
     p.num_gtiles = trb_ceil_div(G, TILE_N);
