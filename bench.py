@@ -294,6 +294,13 @@ def main():
         ev1.record()
         barrier()
     launches = _lib.launch_count()
+    if os.environ.get("TRB_PROFILE_PHASES") and world > 1:     # every rank takes part in the collectives
+        from textreid_b200.sharded import PhaseTimer
+        PhaseTimer.marks = []
+        step(text, image, q_pid, g_pid)
+        rep = PhaseTimer.report()
+        if rank == 0:
+            sys.stderr.write("PHASES " + rep + "\n")
     ms = ev0.elapsed_time(ev1) / args.steps
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:

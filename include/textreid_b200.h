@@ -105,7 +105,7 @@ int trb_similarity_f32(const float* qn, const float* gn, float* sim, int64_t Q, 
 /* Merge `nlists` candidate lists per query into the final top-10 and derive the per-query
  * ranking artefacts.
  *   cand_sim/cand_idx [Q, nlists, 10]
- *   q_pids [Q], g_pids [G_total] (global gallery pids)
+ *   q_pids [Q], g_pids [G_total] (global gallery pids): only read for the top-k-only first hit; may be NULL otherwise
  *   rel_ptr/cnt       NULL in top-k-only mode (rank(get_mAP=False), evaluation.py:16-19)
  * outputs
  *   top_sim/top_idx [Q,10]  best-first; idx int64 global

@@ -350,7 +350,7 @@ retrieval_finish_kernel(const float* __restrict__ cand_sim, const int64_t* __res
     float last_s = CUDART_INF_F;
     int64_t last_i = -1;
     int first_in_top = INT32_MAX;
-    const int64_t qpid = q_pids[q];
+    const int64_t qpid = (q_pids != nullptr) ? q_pids[q] : -1;
     for (int round = 0; round < TRB_TOPK; ++round) {
         float bs = -CUDART_INF_F;
         int64_t bi = INT64_MAX;
@@ -370,7 +370,7 @@ retrieval_finish_kernel(const float* __restrict__ cand_sim, const int64_t* __res
         if (lane == 0) {
             top_sim[q * TRB_TOPK + round] = bs;
             top_idx[q * TRB_TOPK + round] = (bi == INT64_MAX) ? -1 : bi;
-            if (first_in_top == INT32_MAX && bi != INT64_MAX && bi >= 0 && bi < G_total && g_pids[bi] == qpid)
+            if (first_in_top == INT32_MAX && g_pids != nullptr && bi != INT64_MAX && bi >= 0 && bi < G_total && g_pids[bi] == qpid)
                 first_in_top = round;
         }
         last_s = bs;
@@ -423,7 +423,9 @@ extern "C" int trb_retrieval_finish(const float* cand_sim, const int64_t* cand_i
                                     const int64_t* q_pids, const int64_t* g_pids, int64_t G_total,
                                     const int64_t* rel_ptr, const int32_t* cnt, float* top_sim, int64_t* top_idx,
                                     int32_t* first_hit, int32_t* hit_ranks, float* ap, trb_stream_t stream) {
-    TRB_REQUIRE(cand_sim && cand_idx && q_pids && g_pids && top_sim && top_idx, "retrieval_finish: null pointer");
+    TRB_REQUIRE(cand_sim && cand_idx && top_sim && top_idx, "retrieval_finish: null pointer");
+    TRB_REQUIRE(rel_ptr != nullptr || first_hit == nullptr || (q_pids && g_pids),
+                "retrieval_finish: top-k-only first hits need q_pids and g_pids");
     TRB_REQUIRE(nlists >= 1 && Q >= 0, "retrieval_finish: bad shape");
     TRB_REQUIRE((rel_ptr == nullptr) == (cnt == nullptr), "retrieval_finish: rel_ptr and cnt must be given together");
     if (Q == 0) return 0;

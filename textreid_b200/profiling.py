@@ -7,19 +7,20 @@ import torch
 from .sharded import CudaBackend, ShardWorker
 
 
-def time_stream_kernel(text, image, q_pid, g_pid, precision, iters=5, flush=None, g_base=0, g_pids_all=None):
-    """Median duration (ms) of the gallery stream kernel alone, thresholds already captured."""
+def time_stream_kernel(text, image, q_pid, g_pid, precision, iters=5, flush=None):
+    """Median duration (ms) of the gallery stream kernel alone (single shard), thresholds already captured."""
     q_pids = q_pid.reshape(-1).to(torch.int64).contiguous()
-    g_all = (g_pid if g_pids_all is None else g_pids_all).reshape(-1).to(torch.int64).contiguous()
-    w = ShardWorker(text, image, q_pids, g_all, g_base, True, precision, CudaBackend())
-    thr = w.local_thresholds()
-    w.stream(thr)                       # warm-up
+    g_pids = g_pid.reshape(-1).to(torch.int64).contiguous()
+    w = ShardWorker(text, image, q_pids, g_pids, 0, True, precision, CudaBackend())
+    w.set_layout(w.local_counts().unsqueeze(0), 0)
+    w.set_thresholds(*w.local_thresholds())
+    w.stream()                          # warm-up
     w.record_events = True
     times = []
     for _ in range(iters):
         if flush is not None:
             flush.fill_(1)
-        w.stream(thr)
+        w.stream()
         torch.cuda.synchronize()
         a, b = w.stream_events
         times.append(a.elapsed_time(b))

@@ -50,11 +50,5 @@ def choose_nsplit_tc(num_qtiles: int, num_gtiles: int, sms: int) -> int:
 def retrieve_tc(text_embed, image_embed, q_pids, g_pids, topk=(1, 5, 10), get_mAP=True, normalized=False,
                 nsplit: Optional[int] = None) -> RetrievalResult:
     """Single-GPU tensor-core evaluation = the sharded protocol with one shard and no collectives."""
-    from .sharded import CudaBackend, ShardWorker, _finish
-    backend = CudaBackend()
-    w = ShardWorker(text_embed, image_embed, q_pids, g_pids, 0, get_mAP, "bf16", backend, normalized=normalized)
-    thr = w.local_thresholds() if get_mAP else None
-    cand_sim, cand_idx, cnt = w.stream(thr, nsplit)
-    res = _finish(backend, [cand_sim], [cand_idx], q_pids, g_pids, w.rel, cnt, topk)
-    res.thresholds = thr[:w.rel.total] if get_mAP else None
-    return res
+    from .sharded import retrieve_sharded_local
+    return retrieve_sharded_local(text_embed, [image_embed], q_pids, [g_pids], topk, get_mAP, "bf16", None, nsplit, normalized)

@@ -29,6 +29,30 @@ from .evaluation import (RelevanceIndex, RetrievalResult, TOPK_DEPTH, _choose_ns
                          _stream_fp32, build_relevance, l2_normalize_rows)
 
 
+class PhaseTimer:
+    """Optional CUDA-event phase marks (TRB_PROFILE_PHASES=1): where a step's time goes besides the stream kernel."""
+    enabled = bool(int(__import__("os").environ.get("TRB_PROFILE_PHASES", "0")))
+    marks: list = []
+
+    @classmethod
+    def mark(cls, name):
+        if cls.enabled and torch.cuda.is_available():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            cls.marks.append((name, e, __import__("time").perf_counter()))
+
+    @classmethod
+    def report(cls):
+        if not cls.marks:
+            return ""
+        torch.cuda.synchronize()
+        out = []
+        for (n0, e0, t0), (n1, e1, t1) in zip(cls.marks[:-1], cls.marks[1:]):
+            out.append("%s: gpu %.3f ms host %.3f ms" % (n1, e0.elapsed_time(e1), (t1 - t0) * 1e3))
+        cls.marks = []
+        return "; ".join(out)
+
+
 class CudaBackend:
     """Device work of one shard, served by libtextreid_b200.so."""
 
@@ -51,7 +75,7 @@ class CudaBackend:
     def finish(self, cand_sim, cand_idx, nlists, q_pids, g_pids, rel, cnt, topk):
         return _finish_and_metrics(cand_sim, cand_idx, nlists, q_pids, g_pids, rel, cnt, topk)
 
-    def merge_lists(self, cand_sim, cand_idx, q_pids, g_pids):
+    def merge_lists(self, cand_sim, cand_idx):
         """[Q, L, 10] candidate lists -> [Q, 1, 10]: the rank-local merge that keeps the all-gather at 120 B/query."""
         Q, L, K = cand_sim.shape
         if L == 1:
@@ -60,101 +84,130 @@ class CudaBackend:
         top_sim = torch.empty(Q, 1, K, dtype=torch.float32, device=dev)
         top_idx = torch.empty(Q, 1, K, dtype=torch.int64, device=dev)
         _lib.check(_lib.load().trb_retrieval_finish(
-            _lib.ptr(cand_sim), _lib.ptr(cand_idx), L, Q, _lib.ptr(q_pids), _lib.ptr(g_pids), g_pids.numel(), None, None,
+            _lib.ptr(cand_sim), _lib.ptr(cand_idx), L, Q, None, None, 0, None, None,
             _lib.ptr(top_sim), _lib.ptr(top_idx), None, None, None, _lib.stream_ptr(dev)), "trb_retrieval_finish")
         return top_sim, top_idx
 
 
 class ShardWorker:
-    """State of one gallery shard between the exchange steps."""
+    """State of one gallery shard between the exchange steps.
 
-    def __init__(self, text_embed, image_shard, q_pids, g_pids_all, g_base, get_mAP, precision, backend, normalized=False):
+    Slot layout of the relevance CSR (one slot per (query, relevant gallery item)): the slots of query q are ordered by
+    global gallery index, i.e. by (owning rank, position in the rank's pid-sorted shard).  A rank therefore only needs
+    every rank's per-query COUNT of relevant items to place its own slots: no global pid gather, no global sort."""
+
+    def __init__(self, text_embed, image_shard, q_pids, g_pids_local, g_base, get_mAP, precision, backend, normalized=False):
         self.backend = backend
         self.precision = precision
         self.get_mAP = get_mAP
         self.g_base = int(g_base)
         self.q_pids = q_pids
-        self.g_pids_all = g_pids_all
+        self.g_pids_local = g_pids_local
         self.Gs = image_shard.shape[0]
+        self.Q = q_pids.numel()
         self.dev = text_embed.device
         self.record_events = False       # bench.py: CUDA events around the stream kernel alone
         self.stream_events = None
-        self.rel: Optional[RelevanceIndex] = build_relevance(q_pids, g_pids_all) if get_mAP else None
+        self.rel: Optional[RelevanceIndex] = None
         self.max_rel = 0
-        if get_mAP and self.rel.total > 0:
-            # one more host read next to build_relevance's: picks the 4- or 8-threshold kernel variant
-            self.max_rel = int((self.rel.rel_ptr[1:] - self.rel.rel_ptr[:-1]).max().item())
+        dev = self.dev
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        need_sorted_queries = precision == "bf16" or get_mAP
+        if need_sorted_queries:
+            self.q_sorted, self.q_order = torch.sort(q_pids, stable=True)
+        if get_mAP:
+            self.g_sorted, self.g_order = torch.sort(g_pids_local, stable=True)   # stable: ascending index inside a pid
+            self.lo_s = torch.searchsorted(self.g_sorted, self.q_sorted, right=False)   # per pid-sorted query row
+            self.hi_s = torch.searchsorted(self.g_sorted, self.q_sorted, right=True)
         if precision == "fp32":
             self.qn = text_embed.contiguous().float() if normalized else backend.normalize(text_embed)
             self.gn = image_shard.contiguous().float() if normalized else backend.normalize(image_shard)
-        elif precision == "bf16":
-            self._prepare_tc(text_embed, image_shard, normalized)
         else:
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+            from .retrieval_tc import pack_rows
+            lib = _lib.load()
+            self.Qp, self.Gp = int(lib.trb_packed_rows(self.Q)), int(lib.trb_packed_rows(self.Gs))
+            self.D = text_embed.shape[1]
+            # queries once, in pid order; gallery in INDEX order for the stream (ties resolved by position) and, when
+            # ranks are wanted, again in pid order for the threshold capture (relevant items form a contiguous band)
+            self.q_packed = pack_rows(text_embed, self.q_order, normalize=not normalized)
+            self.q_row_id = torch.full((self.Qp,), -1, dtype=torch.int64, device=dev)
+            self.q_row_id[:self.Q] = self.q_order
+            self.g_packed = pack_rows(image_shard, None, normalize=not normalized)
+            if get_mAP:
+                self.g_packed_pid = pack_rows(image_shard, self.g_order, normalize=not normalized)
+                self.g_row_id = torch.full((self.Gp,), -1, dtype=torch.int64, device=dev)
+                self.g_row_id[:self.Gs] = self.g_order + self.g_base
+                self.band_lo = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
+                self.band_hi = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
+                self.band_lo[:self.Q] = self.lo_s.to(torch.int32)
+                self.band_hi[:self.Q] = self.hi_s.to(torch.int32)
 
-    # ---- bf16 tensor-core preparation: packed operands and band bookkeeping ----
-    def _prepare_tc(self, text_embed, image_shard, normalized):
-        """Queries are packed once, in pid order.  The gallery is packed in INDEX order for the stream (ties are then
-        resolved by position) and, when ranks are wanted, a second time in pid order for the threshold capture, where the
-        relevant items of a 128-query tile form one contiguous band."""
-        from .retrieval_tc import pack_rows
-        lib = _lib.load()
+    # ---- step 0: how many relevant items of every query live on this shard ----
+    def local_counts(self) -> torch.Tensor:
+        counts = torch.zeros(self.Q, dtype=torch.int32, device=self.dev)
+        counts[self.q_order] = (self.hi_s - self.lo_s).to(torch.int32)
+        return counts
+
+    def set_layout(self, counts_all: torch.Tensor, rank: int) -> None:
+        """counts_all [P, Q] int32 (rank-major).  Fixes the CSR and this rank's offsets; ONE host read."""
         dev = self.dev
-        Q = text_embed.shape[0]
-        self.Qp, self.Gp = int(lib.trb_packed_rows(Q)), int(lib.trb_packed_rows(self.Gs))
-        q_sorted, q_order = torch.sort(self.q_pids, stable=True)
-        self.q_packed = pack_rows(text_embed, q_order, normalize=not normalized)
-        self.q_row_id = torch.full((self.Qp,), -1, dtype=torch.int64, device=dev)
-        self.q_row_id[:Q] = q_order
-        self.g_packed = pack_rows(image_shard, None, normalize=not normalized)
-        if self.get_mAP:
-            rel = self.rel
-            g_pids_local = self.g_pids_all[self.g_base:self.g_base + self.Gs]
-            g_sorted, g_order = torch.sort(g_pids_local, stable=True)
-            self.g_packed_pid = pack_rows(image_shard, g_order, normalize=not normalized)
-            self.g_row_id = torch.full((self.Gp,), -1, dtype=torch.int64, device=dev)
-            self.g_row_id[:self.Gs] = g_order + self.g_base
-            self.band_lo = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
-            self.band_hi = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
-            self.band_lo[:Q] = torch.searchsorted(g_sorted, q_sorted, right=False).to(torch.int32)
-            self.band_hi[:Q] = torch.searchsorted(g_sorted, q_sorted, right=True).to(torch.int32)
-            # slots of a query are ordered by global gallery index: this shard's items start after the
-            # items that live on lower shards
-            below = torch.zeros(rel.total + 1, dtype=torch.int64, device=dev)
-            torch.cumsum((rel.rel_col < self.g_base).to(torch.int64), 0, out=below[1:])
-            off = below[rel.rel_ptr[1:]] - below[rel.rel_ptr[:-1]]
+        c64 = counts_all.to(torch.int64)
+        per_q = c64.sum(0)
+        rel_ptr = torch.zeros(self.Q + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(per_q, 0, out=rel_ptr[1:])
+        off = c64[:rank].sum(0) if rank > 0 else torch.zeros(self.Q, dtype=torch.int64, device=dev)
+        local = c64[rank]
+        host = torch.stack([rel_ptr[-1], per_q.max() if self.Q else rel_ptr[-1], local.sum()]).cpu()
+        total, self.max_rel, self.total_local = int(host[0]), int(host[1]), int(host[2])
+        self.gidx_store = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)
+        self.rel = RelevanceIndex(rel_ptr, self.gidx_store[:total], total, self.gidx_store)
+        self.off_q = off                                   # [Q] slots of lower ranks, original query order
+        if self.precision == "bf16":
             self.rel_off = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
-            self.rel_off[:Q] = off[q_order].to(torch.int32)
+            self.rel_off[:self.Q] = off[self.q_order].to(torch.int32)
 
-    # ---- step 1 ----
-    def local_thresholds(self) -> torch.Tensor:
+    # ---- step 1: similarities (and global indices) of this shard's relevant items; zeros elsewhere ----
+    def local_thresholds(self):
         rel = self.rel
-        thr = torch.zeros(max(rel.total, 1), dtype=torch.float32, device=self.dev)
+        dev = self.dev
+        thr = torch.zeros(max(rel.total, 1), dtype=torch.float32, device=dev)
+        gidx = torch.zeros(max(rel.total, 1), dtype=torch.int64, device=dev)
         if self.precision == "fp32":
-            local = rel.rel_col - self.g_base
-            rel_row = torch.where((local >= 0) & (local < self.Gs), local, torch.full_like(local, -1)).contiguous()
-            if rel_row.numel() == 0:
-                rel_row = torch.full((1,), -1, dtype=torch.int64, device=self.dev)
+            # local slots: query (pid-sorted row i) owns sorted-gallery rows [lo_s[i], hi_s[i])
+            cnt_s = self.hi_s - self.lo_s
+            row_i = torch.repeat_interleave(torch.arange(self.Q, device=dev), cnt_s, output_size=self.total_local)
+            start = torch.cumsum(cnt_s, 0) - cnt_s
+            within = torch.arange(self.total_local, device=dev) - start[row_i]
+            q = self.q_order[row_i]
+            slot = rel.rel_ptr[q] + self.off_q[q] + within
+            rows = self.g_order[self.lo_s[row_i] + within]
+            rel_row = torch.full((max(rel.total, 1),), -1, dtype=torch.int64, device=dev)
+            rel_row[slot] = rows
+            gidx[slot] = rows + self.g_base
             self.backend.thresholds_fp32(self.qn, self.gn, rel.rel_ptr, rel_row, thr)
         else:
-            scratch_gidx = torch.zeros(max(rel.total, 1), dtype=torch.int64, device=self.dev)
-            Q = self.q_pids.numel()
-            D = self.q_packed.numel() // (2 * self.Qp)
             _lib.check(_lib.load().trb_retrieval_stream_tc(
-                _lib.ptr(self.q_packed), _lib.ptr(self.g_packed_pid), Q, self.Gs, D, _lib.ptr(self.q_row_id),
-                _lib.ptr(self.g_row_id), self.g_base, _lib.ptr(rel.rel_ptr), _lib.ptr(thr), _lib.ptr(scratch_gidx), _lib.ptr(self.band_lo),
-                _lib.ptr(self.band_hi), _lib.ptr(self.rel_off), 1, 1, self.max_rel, None, None, None, _lib.stream_ptr(self.dev)),
+                _lib.ptr(self.q_packed), _lib.ptr(self.g_packed_pid), self.Q, self.Gs, self.D, _lib.ptr(self.q_row_id),
+                _lib.ptr(self.g_row_id), self.g_base, _lib.ptr(rel.rel_ptr), _lib.ptr(thr), _lib.ptr(gidx), _lib.ptr(self.band_lo),
+                _lib.ptr(self.band_hi), _lib.ptr(self.rel_off), 1, 1, self.max_rel, None, None, None, _lib.stream_ptr(dev)),
                 "trb_retrieval_stream_tc(mode=1)")
-        return thr
+        return thr, gidx
+
+    def set_thresholds(self, thr: torch.Tensor, gidx: torch.Tensor) -> None:
+        """Thresholds / item indices of ALL shards (after the exchange)."""
+        self.thr = thr
+        self.gidx_store.copy_(gidx)
 
     # ---- step 2 ----
-    def stream(self, thr: Optional[torch.Tensor], nsplit: Optional[int] = None):
+    def stream(self, nsplit: Optional[int] = None):
         rel = self.rel
         cnt = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=self.dev) if self.get_mAP else None
-        Q = self.q_pids.numel()
+        thr = self.thr if self.get_mAP else None
+        gidx = self.gidx_store if self.get_mAP else None
+        Q = self.Q
         if self.precision == "fp32":
             ns = nsplit or self.backend.nsplit(Q, self.Gs, self.dev)
-            gidx = rel.store if self.get_mAP else None
             ev = self._events()
             cand_sim, cand_idx = self.backend.stream_fp32(self.qn, self.gn, self.g_base, rel.rel_ptr if self.get_mAP else None,
                                                           thr, gidx, cnt, ns)
@@ -162,19 +215,15 @@ class ShardWorker:
             return cand_sim, cand_idx, cnt
         from .retrieval_tc import choose_nsplit_tc
         lib = _lib.load()
-        D = self.q_packed.numel() // (2 * self.Qp)
         num_gtiles = -(-self.Gs // 256)
         ns = nsplit or choose_nsplit_tc(-(-Q // 128), num_gtiles, _sm_count(self.dev))
         ns = max(1, min(ns, num_gtiles))
         lists = int(lib.trb_retrieval_tc_lists_per_split()) * ns
         cand_sim = torch.empty(Q, lists, TOPK_DEPTH, dtype=torch.float32, device=self.dev)
         cand_idx = torch.empty(Q, lists, TOPK_DEPTH, dtype=torch.int64, device=self.dev)
-        gidx = None
-        if self.get_mAP:
-            gidx = rel.store
         ev = self._events()
         _lib.check(lib.trb_retrieval_stream_tc(
-            _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, D, _lib.ptr(self.q_row_id), None, self.g_base,
+            _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, self.D, _lib.ptr(self.q_row_id), None, self.g_base,
             _lib.ptr(rel.rel_ptr) if self.get_mAP else None, _lib.ptr(thr), _lib.ptr(gidx), None, None, None, 0, ns,
             self.max_rel, _lib.ptr(cand_sim), _lib.ptr(cand_idx), _lib.ptr(cnt), _lib.stream_ptr(self.dev)), "trb_retrieval_stream_tc(mode=0)")
         self._events(ev)
@@ -192,32 +241,53 @@ class ShardWorker:
 
 
 def _finish(backend, cand_sims, cand_idxs, q_pids, g_pids_all, rel, cnt, topk):
-    cand_sim = torch.cat(cand_sims, dim=1).contiguous()
-    cand_idx = torch.cat(cand_idxs, dim=1).contiguous()
+    cand_sim = torch.cat(cand_sims, dim=1).contiguous() if len(cand_sims) > 1 else cand_sims[0].contiguous()
+    cand_idx = torch.cat(cand_idxs, dim=1).contiguous() if len(cand_idxs) > 1 else cand_idxs[0].contiguous()
+    if g_pids_all is None:      # ranks come from the counts; candidate pids are not needed
+        g_pids_all = torch.zeros(1, dtype=torch.int64, device=q_pids.device)[:0]
     return backend.finish(cand_sim, cand_idx, cand_sim.shape[1], q_pids, g_pids_all, rel, cnt, topk)
 
 
 def retrieve_sharded_local(text_embed, image_shards: Sequence[torch.Tensor], text_pid, image_pid_shards, topk=(1, 5, 10),
-                           get_mAP=True, precision="fp32", backend=None, nsplit=None) -> RetrievalResult:
+                           get_mAP=True, precision="fp32", backend=None, nsplit=None, normalized=False) -> RetrievalResult:
     """All shards processed by ONE process, with the collectives replaced by local sums / concatenation.
-    Same code path per shard as the distributed driver; used to validate the exchange protocol."""
+    Same code path per shard as the distributed driver; used to validate the exchange protocol (and, with a single
+    shard, as the single-GPU tensor-core entry)."""
     backend = backend or CudaBackend()
     q_pids = text_pid.reshape(-1).to(torch.int64).contiguous()
-    g_pids_all = torch.cat([p.reshape(-1).to(torch.int64) for p in image_pid_shards]).contiguous()
+    pids = [p.reshape(-1).to(torch.int64).contiguous() for p in image_pid_shards]
     bases, b = [], 0
     for s in image_shards:
         bases.append(b)
         b += s.shape[0]
-    workers = [ShardWorker(text_embed, s, q_pids, g_pids_all, base, get_mAP, precision, backend)
-               for s, base in zip(image_shards, bases)]
-    thr = None
+    workers = [ShardWorker(text_embed, s, q_pids, p, base, get_mAP, precision, backend, normalized)
+               for s, p, base in zip(image_shards, pids, bases)]
+    g_pids_all = None
     if get_mAP:
-        thr = torch.stack([w.local_thresholds() for w in workers]).sum(0)
-    outs = [w.stream(thr, nsplit) for w in workers]
+        counts_all = torch.stack([w.local_counts() for w in workers])
+        for r, w in enumerate(workers):
+            w.set_layout(counts_all, r)
+        parts = [w.local_thresholds() for w in workers]
+        thr = torch.stack([p[0] for p in parts]).sum(0)
+        gidx = torch.stack([p[1] for p in parts]).sum(0)
+        for w in workers:
+            w.set_thresholds(thr, gidx)
+    else:
+        g_pids_all = torch.cat(pids).contiguous()
+    outs = [w.stream(nsplit) for w in workers]
     cnt = torch.stack([o[2] for o in outs]).sum(0).to(torch.int32) if get_mAP else None
     res = _finish(backend, [o[0] for o in outs], [o[1] for o in outs], q_pids, g_pids_all, workers[0].rel, cnt, topk)
     res.thresholds = thr[:workers[0].rel.total] if get_mAP else None
     return res
+
+
+def _all_gather_stack(t: torch.Tensor, group=None) -> torch.Tensor:
+    """all_gather of equally-shaped tensors into one [world, *shape] tensor (flat buffers: works on NCCL and gloo)."""
+    world = dist.get_world_size(group)
+    flat = t.contiguous().reshape(-1)
+    out = torch.empty(world * flat.numel(), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.reshape((world,) + tuple(t.shape))
 
 
 def _all_gather_varlen(t: torch.Tensor, group=None) -> List[torch.Tensor]:
@@ -236,37 +306,53 @@ def _all_gather_varlen(t: torch.Tensor, group=None) -> List[torch.Tensor]:
 
 
 def retrieve_sharded(text_embed, image_shard, text_pid, image_pid_shard, topk=(1, 5, 10), get_mAP=True, precision="fp32",
-                     group=None, backend=None, nsplit=None) -> RetrievalResult:
+                     group=None, backend=None, nsplit=None, shard_sizes: Optional[Sequence[int]] = None) -> RetrievalResult:
     """Distributed driver: call on every rank with the full query set and this rank's gallery slice
-    (slices are contiguous and ordered by rank).  Returns the same RetrievalResult on every rank."""
+    (slices are contiguous and ordered by rank).  Returns the same RetrievalResult on every rank.
+    ``shard_sizes`` (rows per rank) saves the size exchange when the caller knows the split."""
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("retrieve_sharded needs an initialised torch.distributed process group")
     backend = backend or CudaBackend()
-    rank = dist.get_rank(group)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = text_embed.device
+    PhaseTimer.mark("start")
     q_pids = text_pid.reshape(-1).to(torch.int64).contiguous()
-    pid_parts = _all_gather_varlen(image_pid_shard.reshape(-1).to(torch.int64).contiguous(), group)
-    g_pids_all = torch.cat(pid_parts).contiguous()
-    g_base = sum(p.numel() for p in pid_parts[:rank])
-    w = ShardWorker(text_embed, image_shard, q_pids, g_pids_all, g_base, get_mAP, precision, backend)
-    thr = None
+    g_pids_local = image_pid_shard.reshape(-1).to(torch.int64).contiguous()
+    if shard_sizes is None:
+        n = torch.tensor([g_pids_local.numel()], dtype=torch.int64, device=dev)
+        shard_sizes = _all_gather_stack(n, group).reshape(-1).tolist()      # one host read
+    g_base = int(sum(shard_sizes[:rank]))
+    w = ShardWorker(text_embed, image_shard, q_pids, g_pids_local, g_base, get_mAP, precision, backend)
+    PhaseTimer.mark("prepare(sort,pack)")
+    g_pids_all = None
     if get_mAP:
-        thr = w.local_thresholds()
+        counts = w.local_counts()
+        w.set_layout(_all_gather_stack(counts, group), rank)
+        PhaseTimer.mark("layout(allgather counts)")
+        thr, gidx = w.local_thresholds()
+        PhaseTimer.mark("thresholds")
         dist.all_reduce(thr, op=dist.ReduceOp.SUM, group=group)      # one non-zero contributor per slot: exact
-    cand_sim, cand_idx, cnt = w.stream(thr, nsplit)
+        dist.all_reduce(gidx, op=dist.ReduceOp.SUM, group=group)
+        w.set_thresholds(thr, gidx)
+        PhaseTimer.mark("allreduce_thr")
+    else:
+        g_pids_all = torch.cat(_all_gather_varlen(g_pids_local, group)).contiguous()   # pids of the top-10 candidates
+    cand_sim, cand_idx, cnt = w.stream(nsplit)
+    PhaseTimer.mark("stream")
     if get_mAP:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    PhaseTimer.mark("allreduce_cnt")
     # candidate lists: merge this rank's L lists to one per query, then all-gather [Q, 10] x (fp32, int64)
-    world = dist.get_world_size(group)
     if hasattr(backend, "merge_lists"):
-        cand_sim, cand_idx = backend.merge_lists(cand_sim, cand_idx, q_pids, g_pids_all)
-        sims = torch.empty((world,) + tuple(cand_sim.shape), dtype=cand_sim.dtype, device=cand_sim.device)
-        idxs = torch.empty((world,) + tuple(cand_idx.shape), dtype=cand_idx.dtype, device=cand_idx.device)
-        dist.all_gather_into_tensor(sims, cand_sim.contiguous(), group=group)
-        dist.all_gather_into_tensor(idxs, cand_idx.contiguous(), group=group)
-        sim_parts, idx_parts = [sims[r] for r in range(world)], [idxs[r] for r in range(world)]
+        cand_sim, cand_idx = backend.merge_lists(cand_sim, cand_idx)
+        sims, idxs = _all_gather_stack(cand_sim, group), _all_gather_stack(cand_idx, group)
+        sim_parts, idx_parts = [sims.permute(1, 0, 2, 3).reshape(cand_sim.shape[0], -1, cand_sim.shape[2])], \
+                               [idxs.permute(1, 0, 2, 3).reshape(cand_idx.shape[0], -1, cand_idx.shape[2])]
     else:   # stand-in backends (tests): list counts may differ per rank -> gather along a leading list axis
         sim_parts = [x.permute(1, 0, 2) for x in _all_gather_varlen(cand_sim.permute(1, 0, 2).contiguous(), group)]
         idx_parts = [x.permute(1, 0, 2) for x in _all_gather_varlen(cand_idx.permute(1, 0, 2).contiguous(), group)]
+    PhaseTimer.mark("merge+allgather_cand")
     res = _finish(backend, sim_parts, idx_parts, q_pids, g_pids_all, w.rel, cnt, topk)
-    res.thresholds = thr[:w.rel.total] if get_mAP else None
+    PhaseTimer.mark("finish+metrics")
+    res.thresholds = w.thr[:w.rel.total] if get_mAP else None
     return res

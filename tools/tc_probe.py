@@ -9,12 +9,14 @@ from textreid_b200.sharded import ShardWorker, CudaBackend
 def run(Q, G, D, get_map, n_ids, iters=3, nsplit=None):
     text, q_pid, image, g_pid = eval_data(Q, G, D, n_ids, 0, G, "cuda", torch.bfloat16)
     w = ShardWorker(text, image, q_pid.long(), g_pid.long(), 0, get_map, "bf16", CudaBackend())
-    thr = w.local_thresholds() if get_map else None
-    w.stream(thr, nsplit)
+    if get_map:
+        w.set_layout(w.local_counts().unsqueeze(0), 0)
+        w.set_thresholds(*w.local_thresholds())
+    w.stream(nsplit)
     w.record_events = True
     ts = []
     for _ in range(iters):
-        w.stream(thr, nsplit)
+        w.stream(nsplit)
         torch.cuda.synchronize()
         a, b = w.stream_events
         ts.append(a.elapsed_time(b))
