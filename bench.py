@@ -270,7 +270,8 @@ def main():
 
     def step(text_d, image_d, q_pid_d, g_pid_d):
         if world > 1:
-            return retrieve_sharded(text_d, image_d, q_pid_d, g_pid_d, (1, 5, 10), True, args.precision)
+            sizes = [shard_bounds(G, world, r)[1] - shard_bounds(G, world, r)[0] for r in range(world)]
+            return retrieve_sharded(text_d, image_d, q_pid_d, g_pid_d, (1, 5, 10), True, args.precision, shard_sizes=sizes)
         return trb.retrieve(text_d, image_d, q_pid_d, g_pid_d, (1, 5, 10), True, args.precision)
 
     def barrier():

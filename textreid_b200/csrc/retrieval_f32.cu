@@ -347,38 +347,77 @@ retrieval_finish_kernel(const float* __restrict__ cand_sim, const int64_t* __res
     const float* cs = cand_sim + q * n;
     const int64_t* ci = cand_idx + q * n;
 
-    float last_s = CUDART_INF_F;
-    int64_t last_i = -1;
     int first_in_top = INT32_MAX;
     const int64_t qpid = (q_pids != nullptr) ? q_pids[q] : -1;
-    for (int round = 0; round < TRB_TOPK; ++round) {
-        float bs = -CUDART_INF_F;
-        int64_t bi = INT64_MAX;
-        for (int p = lane; p < n; p += 32) {
-            const float s = cs[p];
-            int64_t i = ci[p];
-            if (i < 0) i = INT64_MAX;     // padding of an already-merged list
-            // strictly after the previous winner, and better than the running best
-            if (ranks_before(last_s, last_i, s, i) && ranks_before(s, i, bs, bi)) { bs = s; bi = i; }
-        }
+    constexpr int CPL = 8;                       // candidates per lane kept in registers (n <= 256)
+    if (n <= 32 * CPL) {
+        float rs[CPL];
+        int64_t ri[CPL];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-            const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ranks_before(os, oi, bs, bi)) { bs = os; bi = oi; }
+        for (int c = 0; c < CPL; ++c) {
+            const int p = lane + 32 * c;
+            rs[c] = -CUDART_INF_F;
+            ri[c] = INT64_MAX;
+            if (p < n) {
+                rs[c] = cs[p];
+                ri[c] = ci[p];
+                if (ri[c] < 0) ri[c] = INT64_MAX;            // padding of an already-merged list
+            }
         }
-        if (lane == 0) {
-            top_sim[q * TRB_TOPK + round] = bs;
-            top_idx[q * TRB_TOPK + round] = (bi == INT64_MAX) ? -1 : bi;
-            if (first_in_top == INT32_MAX && g_pids != nullptr && bi != INT64_MAX && bi >= 0 && bi < G_total && g_pids[bi] == qpid)
-                first_in_top = round;
+        for (int round = 0; round < TRB_TOPK; ++round) {
+            float bs = -CUDART_INF_F;
+            int64_t bi = INT64_MAX;
+            int bc = -1;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+                if (ranks_before(rs[c], ri[c], bs, bi)) { bs = rs[c]; bi = ri[c]; bc = c; }
+            float ws = bs;
+            int64_t wi = bi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+                const int64_t oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                if (ranks_before(os, oi, ws, wi)) { ws = os; wi = oi; }
+            }
+            if (bc >= 0 && bs == ws && bi == wi) {           // this lane owned the winner: consume it
+#pragma unroll
+                for (int c = 0; c < CPL; ++c)
+                    if (c == bc) { rs[c] = -CUDART_INF_F; ri[c] = INT64_MAX; }
+            }
+            if (lane == 0) {
+                top_sim[q * TRB_TOPK + round] = ws;
+                top_idx[q * TRB_TOPK + round] = (wi == INT64_MAX) ? -1 : wi;
+                if (first_in_top == INT32_MAX && g_pids != nullptr && wi != INT64_MAX && wi >= 0 && wi < G_total && g_pids[wi] == qpid)
+                    first_in_top = round;
+            }
         }
-        last_s = bs;
-        last_i = bi;
-        if (bi == INT64_MAX) {   // fewer than 10 gallery items: pad the remainder
-            if (lane == 0)
-                for (int r = round + 1; r < TRB_TOPK; ++r) { top_sim[q * TRB_TOPK + r] = -CUDART_INF_F; top_idx[q * TRB_TOPK + r] = -1; }
-            break;
+    } else {
+        float last_s = CUDART_INF_F;
+        int64_t last_i = -1;
+        for (int round = 0; round < TRB_TOPK; ++round) {
+            float bs = -CUDART_INF_F;
+            int64_t bi = INT64_MAX;
+            for (int p = lane; p < n; p += 32) {
+                const float s = cs[p];
+                int64_t i = ci[p];
+                if (i < 0) i = INT64_MAX;
+                // strictly after the previous winner, and better than the running best
+                if (ranks_before(last_s, last_i, s, i) && ranks_before(s, i, bs, bi)) { bs = s; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+                const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ranks_before(os, oi, bs, bi)) { bs = os; bi = oi; }
+            }
+            if (lane == 0) {
+                top_sim[q * TRB_TOPK + round] = bs;
+                top_idx[q * TRB_TOPK + round] = (bi == INT64_MAX) ? -1 : bi;
+                if (first_in_top == INT32_MAX && g_pids != nullptr && bi != INT64_MAX && bi >= 0 && bi < G_total && g_pids[bi] == qpid)
+                    first_in_top = round;
+            }
+            last_s = bs;
+            last_i = bi;
         }
     }
 

@@ -26,7 +26,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .evaluation import (RelevanceIndex, RetrievalResult, TOPK_DEPTH, _choose_nsplit, _finish_and_metrics, _sm_count,
-                         _stream_fp32, build_relevance, l2_normalize_rows)
+                         _stream_fp32, _topk_host_array, build_relevance, l2_normalize_rows)
 
 
 class PhaseTimer:
@@ -74,6 +74,49 @@ class CudaBackend:
 
     def finish(self, cand_sim, cand_idx, nlists, q_pids, g_pids, rel, cnt, topk):
         return _finish_and_metrics(cand_sim, cand_idx, nlists, q_pids, g_pids, rel, cnt, topk)
+
+    def finish_scattered(self, cand_sim, cand_idx, rel, cnt, topk, group):
+        """Finish with the queries partitioned over the ranks: an all-to-all hands every rank the candidate lists of
+        ITS Q/P queries (120 B/query/rank instead of an all-gather of everything), each rank derives top-10 / hit
+        ranks / AP for them, and the small per-query results are gathered back so that every rank ends identical."""
+        lib = _lib.load()
+        dev = cand_sim.device
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        Q, K = cand_sim.shape[0], cand_sim.shape[2]
+        Qc = -(-Q // world)
+        Qp = Qc * world
+        sim_pad = torch.full((Qp, K), float("-inf"), dtype=torch.float32, device=dev)
+        idx_pad = torch.full((Qp, K), -1, dtype=torch.int64, device=dev)
+        sim_pad[:Q], idx_pad[:Q] = cand_sim[:, 0], cand_idx[:, 0]
+        sim_rx, idx_rx = torch.empty_like(sim_pad), torch.empty_like(idx_pad)       # [P, Qc, K]: lists of my queries
+        dist.all_to_all_single(sim_rx, sim_pad, group=group)
+        dist.all_to_all_single(idx_rx, idx_pad, group=group)
+        sim_my = sim_rx.reshape(world, Qc, K).permute(1, 0, 2).contiguous()          # [Qc, P, K]
+        idx_my = idx_rx.reshape(world, Qc, K).permute(1, 0, 2).contiguous()
+        rel_ptr_pad = torch.full((Qp + 1,), rel.total, dtype=torch.int64, device=dev)
+        rel_ptr_pad[:Q + 1] = rel.rel_ptr
+        my_ptr = rel_ptr_pad[rank * Qc: (rank + 1) * Qc + 1].contiguous()
+        # packed per-query results: top_sim | top_idx | first_hit | ap, gathered with one collective per dtype
+        top_sim = torch.empty(Qc, K, dtype=torch.float32, device=dev)
+        top_idx = torch.empty(Qc, K, dtype=torch.int64, device=dev)
+        first_hit = torch.empty(Qc, dtype=torch.int32, device=dev)
+        ap = torch.empty(Qc, dtype=torch.float32, device=dev)
+        hit_ranks = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=dev)   # each rank fills its queries' slots
+        _lib.check(lib.trb_retrieval_finish(
+            _lib.ptr(sim_my), _lib.ptr(idx_my), world, Qc, None, None, 0, _lib.ptr(my_ptr), _lib.ptr(cnt),
+            _lib.ptr(top_sim), _lib.ptr(top_idx), _lib.ptr(first_hit), _lib.ptr(hit_ranks), _lib.ptr(ap),
+            _lib.stream_ptr(dev)), "trb_retrieval_finish")
+        f32 = _all_gather_stack(torch.cat([top_sim, ap.unsqueeze(1)], dim=1), group).reshape(Qp, K + 1)[:Q]
+        i64 = _all_gather_stack(torch.cat([top_idx, first_hit.to(torch.int64).unsqueeze(1)], dim=1), group).reshape(Qp, K + 1)[:Q]
+        dist.all_reduce(hit_ranks, op=dist.ReduceOp.SUM, group=group)               # disjoint slots: exact
+        top_sim, ap = f32[:, :K].contiguous(), f32[:, K].contiguous()
+        top_idx, first_hit = i64[:, :K].contiguous(), i64[:, K].to(torch.int32).contiguous()
+        arr, n, _ = _topk_host_array(topk)
+        cmc = torch.empty(n, dtype=torch.float32, device=dev)
+        mAP = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.check(lib.trb_retrieval_metrics(_lib.ptr(first_hit), _lib.ptr(ap), Q, arr, n, _lib.ptr(cmc), _lib.ptr(mAP),
+                                             _lib.stream_ptr(dev)), "trb_retrieval_metrics")
+        return RetrievalResult(cmc, mAP, top_idx, top_sim, first_hit, ap, hit_ranks[:rel.total], rel.rel_ptr)
 
     def merge_lists(self, cand_sim, cand_idx):
         """[Q, L, 10] candidate lists -> [Q, 1, 10]: the rank-local merge that keeps the all-gather at 120 B/query."""
@@ -343,6 +386,13 @@ def retrieve_sharded(text_embed, image_shard, text_pid, image_pid_shard, topk=(1
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     PhaseTimer.mark("allreduce_cnt")
     # candidate lists: merge this rank's L lists to one per query, then all-gather [Q, 10] x (fp32, int64)
+    if get_mAP and hasattr(backend, "finish_scattered") and world > 1:
+        cand_sim, cand_idx = backend.merge_lists(cand_sim, cand_idx)
+        PhaseTimer.mark("local_merge")
+        res = backend.finish_scattered(cand_sim, cand_idx, w.rel, cnt, topk, group)
+        PhaseTimer.mark("scattered_finish+metrics")
+        res.thresholds = w.thr[:w.rel.total]
+        return res
     if hasattr(backend, "merge_lists"):
         cand_sim, cand_idx = backend.merge_lists(cand_sim, cand_idx)
         sims, idxs = _all_gather_stack(cand_sim, group), _all_gather_stack(cand_idx, group)

@@ -2,12 +2,12 @@
 # Scaling sweep on one box: bench.py at N = 1, 2, 4, 8 (whatever the box has).
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
-for n in 1 2 4 8; do
+for n in ${SCALE_NS:-1 2 4 8}; do
   if [ $n -le $NG ]; then
     if [ $n -eq 1 ]; then
-      timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 --no-secondary --no-cpu-baseline > gpurun_out/scale_n$n.log 2> gpurun_out/scale_n$n.err
+      timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --no-secondary --no-cpu-baseline > gpurun_out/scale_n$n.log 2> gpurun_out/scale_n$n.err
     else
-      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 5 --warmup 3 > gpurun_out/scale_n$n.log 2> gpurun_out/scale_n$n.err
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/scale_n$n.log 2> gpurun_out/scale_n$n.err
     fi
     python - <<PY
 import json
