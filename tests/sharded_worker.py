@@ -35,7 +35,39 @@ class OracleBackend:
     def nsplit(self, Q, G, device):
         return 2 if G >= 4 else 1
 
-    # no merge_lists(): the driver then takes the variable-list-count gather path, which the gloo tests cover
+    def merge_lists(self, cand_sim, cand_idx):
+        Q = cand_sim.shape[0]
+        cs, ci = cand_sim.reshape(Q, -1), cand_idx.reshape(Q, -1)
+        key = torch.argsort(ci, dim=1, stable=True)
+        cs, ci = torch.gather(cs, 1, key), torch.gather(ci, 1, key)
+        order = torch.argsort(cs, dim=1, descending=True, stable=True)[:, :10]
+        ts, ti = torch.gather(cs, 1, order), torch.gather(ci, 1, order)
+        ti = torch.where(ts == float("-inf"), torch.full_like(ti, -1), ti)
+        return ts.unsqueeze(1).contiguous(), ti.unsqueeze(1).contiguous()
+
+    def finish_partial(self, sim_my, idx_my, my_ptr, cnt, total):
+        Qc = sim_my.shape[0]
+        idx_my = torch.where(idx_my < 0, torch.full_like(idx_my, torch.iinfo(torch.int64).max), idx_my)
+        ts, ti = self.merge_lists(sim_my, idx_my)
+        ts, ti = ts[:, 0], ti[:, 0]
+        ti = torch.where(ti == torch.iinfo(torch.int64).max, torch.full_like(ti, -1), ti)
+        hit_ranks = torch.zeros(max(total, 1), dtype=torch.int32)
+        first, ap = [], []
+        for q in range(Qc):
+            lo, hi = int(my_ptr[q]), int(my_ptr[q + 1])
+            r = torch.sort(cnt[lo:hi])[0]
+            hit_ranks[lo:hi] = r
+            first.append(int(r[0]) if r.numel() else 2 ** 31 - 1)
+            s = torch.tensor(0.0)
+            for j, x in enumerate(r.tolist()):
+                s = s + torch.tensor(float(j + 1)) / torch.tensor(float(x + 1))
+            ap.append(s / torch.tensor(float(r.numel())) if r.numel() else torch.tensor(float("nan")))
+        return ts, ti, torch.tensor(first, dtype=torch.int32), torch.stack(ap), hit_ranks
+
+    def metrics(self, first_hit, ap, topk):
+        Q = first_hit.numel()
+        cmc = torch.stack([(first_hit < k).float().sum() / Q * 100 for k in topk])
+        return cmc, ap.double().mean().float() * 100
 
     def stream_fp32(self, qn, gn, g_base, rel_ptr, thr, thr_gidx, cnt, nsplit):
         Q, G = qn.shape[0], gn.shape[0]
@@ -116,7 +148,7 @@ def shard_slices(G, world, uneven=True):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def worker(rank, world, backend_name, port, out_dir, precision="fp32", Q=150, G=700, D=64, exact=True):
+def worker(rank, world, backend_name, port, out_dir, precision="fp32", Q=151, G=700, D=64, exact=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     if backend_name == "cuda":
@@ -132,7 +164,7 @@ def worker(rank, world, backend_name, port, out_dir, precision="fp32", Q=150, G=
     text, image, tpid, ipid = make_case(Q, G, D, max(G // 5, 1), seed=5, exact=exact)
     lo, hi = shard_slices(G, world)[rank]
     res = retrieve_sharded(text.to(dev), image[lo:hi].to(dev), tpid.to(dev), ipid[lo:hi].to(dev), (1, 5, 10), True,
-                           precision, backend=backend)
+                           precision, backend=backend, return_hit_ranks=True)
     res_topk = retrieve_sharded(text.to(dev), image[lo:hi].to(dev), tpid.to(dev), ipid[lo:hi].to(dev), (1, 5, 10), False,
                                 precision, backend=backend)
     torch.save({"cmc": res.cmc.cpu(), "mAP": res.mAP.cpu(), "top_idx": res.top_idx.cpu(), "top_sim": res.top_sim.cpu(),

@@ -53,13 +53,13 @@ def check_outputs(out_dir, world, Q, G, D, exact_sim, precision="fp32"):
 def test_sharded_host_logic_gloo_world2(tmp_path):
     port = free_port()
     mp.spawn(worker, args=(2, "oracle", port, str(tmp_path)), nprocs=2, join=True)
-    check_outputs(str(tmp_path), 2, 150, 700, 64, exact_sim=True)
+    check_outputs(str(tmp_path), 2, 151, 700, 64, exact_sim=True)
 
 
 def test_sharded_host_logic_gloo_world3_uneven(tmp_path):
     port = free_port()
     mp.spawn(worker, args=(3, "oracle", port, str(tmp_path)), nprocs=3, join=True)
-    check_outputs(str(tmp_path), 3, 150, 700, 64, exact_sim=True)
+    check_outputs(str(tmp_path), 3, 151, 700, 64, exact_sim=True)
 
 
 @pytest.mark.gpu

@@ -75,48 +75,31 @@ class CudaBackend:
     def finish(self, cand_sim, cand_idx, nlists, q_pids, g_pids, rel, cnt, topk):
         return _finish_and_metrics(cand_sim, cand_idx, nlists, q_pids, g_pids, rel, cnt, topk)
 
-    def finish_scattered(self, cand_sim, cand_idx, rel, cnt, topk, group):
-        """Finish with the queries partitioned over the ranks: an all-to-all hands every rank the candidate lists of
-        ITS Q/P queries (120 B/query/rank instead of an all-gather of everything), each rank derives top-10 / hit
-        ranks / AP for them, and the small per-query results are gathered back so that every rank ends identical."""
+    def finish_partial(self, sim_my, idx_my, my_ptr, cnt, total):
+        """top-10 / first hit / AP (and the sorted hit ranks, written into a zeroed full-size buffer) for a block of
+        queries whose candidate lists are [Qc, L, 10] and whose CSR slice is my_ptr [Qc+1] (global slot numbers)."""
         lib = _lib.load()
-        dev = cand_sim.device
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        Q, K = cand_sim.shape[0], cand_sim.shape[2]
-        Qc = -(-Q // world)
-        Qp = Qc * world
-        sim_pad = torch.full((Qp, K), float("-inf"), dtype=torch.float32, device=dev)
-        idx_pad = torch.full((Qp, K), -1, dtype=torch.int64, device=dev)
-        sim_pad[:Q], idx_pad[:Q] = cand_sim[:, 0], cand_idx[:, 0]
-        sim_rx, idx_rx = torch.empty_like(sim_pad), torch.empty_like(idx_pad)       # [P, Qc, K]: lists of my queries
-        dist.all_to_all_single(sim_rx, sim_pad, group=group)
-        dist.all_to_all_single(idx_rx, idx_pad, group=group)
-        sim_my = sim_rx.reshape(world, Qc, K).permute(1, 0, 2).contiguous()          # [Qc, P, K]
-        idx_my = idx_rx.reshape(world, Qc, K).permute(1, 0, 2).contiguous()
-        rel_ptr_pad = torch.full((Qp + 1,), rel.total, dtype=torch.int64, device=dev)
-        rel_ptr_pad[:Q + 1] = rel.rel_ptr
-        my_ptr = rel_ptr_pad[rank * Qc: (rank + 1) * Qc + 1].contiguous()
-        # packed per-query results: top_sim | top_idx | first_hit | ap, gathered with one collective per dtype
+        dev = sim_my.device
+        Qc, L, K = sim_my.shape
         top_sim = torch.empty(Qc, K, dtype=torch.float32, device=dev)
         top_idx = torch.empty(Qc, K, dtype=torch.int64, device=dev)
         first_hit = torch.empty(Qc, dtype=torch.int32, device=dev)
         ap = torch.empty(Qc, dtype=torch.float32, device=dev)
-        hit_ranks = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=dev)   # each rank fills its queries' slots
+        hit_ranks = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)
         _lib.check(lib.trb_retrieval_finish(
-            _lib.ptr(sim_my), _lib.ptr(idx_my), world, Qc, None, None, 0, _lib.ptr(my_ptr), _lib.ptr(cnt),
+            _lib.ptr(sim_my), _lib.ptr(idx_my), L, Qc, None, None, 0, _lib.ptr(my_ptr), _lib.ptr(cnt),
             _lib.ptr(top_sim), _lib.ptr(top_idx), _lib.ptr(first_hit), _lib.ptr(hit_ranks), _lib.ptr(ap),
             _lib.stream_ptr(dev)), "trb_retrieval_finish")
-        f32 = _all_gather_stack(torch.cat([top_sim, ap.unsqueeze(1)], dim=1), group).reshape(Qp, K + 1)[:Q]
-        i64 = _all_gather_stack(torch.cat([top_idx, first_hit.to(torch.int64).unsqueeze(1)], dim=1), group).reshape(Qp, K + 1)[:Q]
-        dist.all_reduce(hit_ranks, op=dist.ReduceOp.SUM, group=group)               # disjoint slots: exact
-        top_sim, ap = f32[:, :K].contiguous(), f32[:, K].contiguous()
-        top_idx, first_hit = i64[:, :K].contiguous(), i64[:, K].to(torch.int32).contiguous()
+        return top_sim, top_idx, first_hit, ap, hit_ranks
+
+    def metrics(self, first_hit, ap, topk):
         arr, n, _ = _topk_host_array(topk)
+        dev = first_hit.device
         cmc = torch.empty(n, dtype=torch.float32, device=dev)
         mAP = torch.empty((), dtype=torch.float32, device=dev)
-        _lib.check(lib.trb_retrieval_metrics(_lib.ptr(first_hit), _lib.ptr(ap), Q, arr, n, _lib.ptr(cmc), _lib.ptr(mAP),
-                                             _lib.stream_ptr(dev)), "trb_retrieval_metrics")
-        return RetrievalResult(cmc, mAP, top_idx, top_sim, first_hit, ap, hit_ranks[:rel.total], rel.rel_ptr)
+        _lib.check(_lib.load().trb_retrieval_metrics(_lib.ptr(first_hit), _lib.ptr(ap), first_hit.numel(), arr, n, _lib.ptr(cmc),
+                                                     _lib.ptr(mAP), _lib.stream_ptr(dev)), "trb_retrieval_metrics")
+        return cmc, mAP
 
     def merge_lists(self, cand_sim, cand_idx):
         """[Q, L, 10] candidate lists -> [Q, 1, 10]: the rank-local merge that keeps the all-gather at 120 B/query."""
@@ -324,6 +307,52 @@ def retrieve_sharded_local(text_embed, image_shards: Sequence[torch.Tensor], tex
     return res
 
 
+def _pack_f32_i32(f: torch.Tensor, i: torch.Tensor) -> torch.Tensor:
+    """(fp32, index < 2^31) -> one int64 per pair, so that one collective moves both."""
+    return (i.to(torch.int64) << 32) | (f.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF)
+
+
+def _unpack_f32_i32(p: torch.Tensor):
+    f = (p & 0xFFFFFFFF).to(torch.int32).view(torch.float32)
+    return f, p >> 32
+
+
+def _finish_scattered(backend, cand_sim, cand_idx, rel, cnt, topk, group, want_hit_ranks):
+    """Finish with the queries partitioned over the ranks: an all-to-all hands every rank the candidate list of ITS
+    Q/P queries from every rank (8 B per candidate), each rank derives top-10 / first hit / AP for them, and the small
+    per-query results are gathered back, so every rank ends with identical results.  Indices travel as 31-bit values
+    packed next to the fp32 similarity (the caller checks the gallery size)."""
+    dev = cand_sim.device
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    Q, K = cand_sim.shape[0], cand_sim.shape[2]
+    Qc = -(-Q // world)
+    Qp = Qc * world
+    tx = torch.full((Qp, K), -1 << 32, dtype=torch.int64, device=dev)
+    tx[:, :] = _pack_f32_i32(torch.full((1,), float("-inf"), device=dev), torch.full((1,), -1, dtype=torch.int64, device=dev))
+    tx[:Q] = _pack_f32_i32(cand_sim[:, 0], cand_idx[:, 0].clamp(min=-1))
+    rx = torch.empty_like(tx)                                              # [P, Qc, K]: lists of my queries
+    dist.all_to_all_single(rx.reshape(-1), tx.reshape(-1), group=group)
+    sim_my, idx_my = _unpack_f32_i32(rx.reshape(world, Qc, K).permute(1, 0, 2).contiguous())   # [Qc, P, K]
+    rel_ptr_pad = torch.full((Qp + 1,), rel.total, dtype=torch.int64, device=dev)
+    rel_ptr_pad[:Q + 1] = rel.rel_ptr
+    my_ptr = rel_ptr_pad[rank * Qc: (rank + 1) * Qc + 1].contiguous()
+    top_sim, top_idx, first_hit, ap, hit_ranks = backend.finish_partial(sim_my.contiguous(), idx_my.contiguous(), my_ptr, cnt,
+                                                                         rel.total)
+    # per-query results -> one int64 block: 10 x (sim, idx) pairs + (ap, first_hit)
+    block = torch.cat([_pack_f32_i32(top_sim, top_idx), _pack_f32_i32(ap, first_hit.to(torch.int64)).unsqueeze(1)], dim=1)
+    allb = _all_gather_stack(block, group).reshape(Qp, K + 1)[:Q]
+    top_sim, top_idx = _unpack_f32_i32(allb[:, :K].contiguous())
+    ap, first_hit = _unpack_f32_i32(allb[:, K].contiguous())
+    first_hit = first_hit.to(torch.int32)
+    if want_hit_ranks:
+        dist.all_reduce(hit_ranks, op=dist.ReduceOp.SUM, group=group)      # disjoint slots per rank: exact
+        hit_ranks = hit_ranks[:rel.total]
+    else:
+        hit_ranks = None
+    cmc, mAP = backend.metrics(first_hit.contiguous(), ap.contiguous(), topk)
+    return RetrievalResult(cmc, mAP, top_idx.contiguous(), top_sim.contiguous(), first_hit, ap, hit_ranks, rel.rel_ptr)
+
+
 def _all_gather_stack(t: torch.Tensor, group=None) -> torch.Tensor:
     """all_gather of equally-shaped tensors into one [world, *shape] tensor (flat buffers: works on NCCL and gloo)."""
     world = dist.get_world_size(group)
@@ -349,10 +378,12 @@ def _all_gather_varlen(t: torch.Tensor, group=None) -> List[torch.Tensor]:
 
 
 def retrieve_sharded(text_embed, image_shard, text_pid, image_pid_shard, topk=(1, 5, 10), get_mAP=True, precision="fp32",
-                     group=None, backend=None, nsplit=None, shard_sizes: Optional[Sequence[int]] = None) -> RetrievalResult:
+                     group=None, backend=None, nsplit=None, shard_sizes: Optional[Sequence[int]] = None,
+                     return_hit_ranks: bool = False) -> RetrievalResult:
     """Distributed driver: call on every rank with the full query set and this rank's gallery slice
     (slices are contiguous and ordered by rank).  Returns the same RetrievalResult on every rank.
-    ``shard_sizes`` (rows per rank) saves the size exchange when the caller knows the split."""
+    ``shard_sizes`` (rows per rank) saves the size exchange when the caller knows the split; ``return_hit_ranks``
+    additionally gathers the per-slot hit ranks (a diagnostic; R@k / AP / mAP do not need it)."""
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("retrieve_sharded needs an initialised torch.distributed process group")
     backend = backend or CudaBackend()
@@ -374,8 +405,14 @@ def retrieve_sharded(text_embed, image_shard, text_pid, image_pid_shard, topk=(1
         PhaseTimer.mark("layout(allgather counts)")
         thr, gidx = w.local_thresholds()
         PhaseTimer.mark("thresholds")
-        dist.all_reduce(thr, op=dist.ReduceOp.SUM, group=group)      # one non-zero contributor per slot: exact
-        dist.all_reduce(gidx, op=dist.ReduceOp.SUM, group=group)
+        if int(sum(shard_sizes)) < (1 << 31) - 1:
+            packed = _pack_f32_i32(thr, gidx)             # one contributor per slot, zeros elsewhere: the sum is exact
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+            thr, gidx = _unpack_f32_i32(packed)
+            thr, gidx = thr.contiguous(), gidx.contiguous()
+        else:
+            dist.all_reduce(thr, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(gidx, op=dist.ReduceOp.SUM, group=group)
         w.set_thresholds(thr, gidx)
         PhaseTimer.mark("allreduce_thr")
     else:
@@ -386,10 +423,11 @@ def retrieve_sharded(text_embed, image_shard, text_pid, image_pid_shard, topk=(1
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     PhaseTimer.mark("allreduce_cnt")
     # candidate lists: merge this rank's L lists to one per query, then all-gather [Q, 10] x (fp32, int64)
-    if get_mAP and hasattr(backend, "finish_scattered") and world > 1:
+    g_total = int(sum(shard_sizes))
+    if get_mAP and hasattr(backend, "finish_partial") and world > 1 and g_total < (1 << 31) - 1:
         cand_sim, cand_idx = backend.merge_lists(cand_sim, cand_idx)
         PhaseTimer.mark("local_merge")
-        res = backend.finish_scattered(cand_sim, cand_idx, w.rel, cnt, topk, group)
+        res = _finish_scattered(backend, cand_sim, cand_idx, w.rel, cnt, topk, group, return_hit_ranks)
         PhaseTimer.mark("scattered_finish+metrics")
         res.thresholds = w.thr[:w.rel.total]
         return res
