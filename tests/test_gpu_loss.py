@@ -199,3 +199,28 @@ def test_ema_bit_exact(golden_dir, n):
     kd = T(g2["k"]).clone()
     trb.ema_update_flat(kd, T(g2["q"]), float(g2["m"]))
     assert torch.equal(kd.cpu(), torch.from_numpy(g2["k1"]))
+
+
+@pytest.mark.parametrize("N,D,K,C,masked", [(128, 256, 2048, 11003, "some"), (32, 64, 128, 1000, "empty"), (20, 48, 60, 77, "some"),
+                                              (256, 256, 4096, 11003, "some")])
+def test_loss_dict_bf16_tensor_core_path(N, D, K, C, masked):
+    """precision="bf16": every contraction runs on tcgen05 with bf16 operands / fp32 accumulation (row-wise softmax math
+    stays fp32).  Losses within 1e-3 of the fp64 oracle (north star: 1e-3 on the bf16 path); gradients carry the bf16
+    operand rounding (2^-9 relative per element) and are compared at that level."""
+    inp = synth_loss_inputs(N, D, K, C, seed=N + K, masked=masked)
+    d, gv, gt, gp = run_fused(inp, 0.1, precision="bf16")
+    args = [inp[k].double() if inp[k].dtype.is_floating_point else inp[k]
+            for k in ("v_embed", "t_embed", "v_key", "t_key", "labels", "v_queue", "t_queue", "id_queue", "projection")]
+    losses, rv, rt, rp = O.moco_loss_dict_with_grads(*args, epsilon=0.1)
+    for k in KEYS:
+        torch.testing.assert_close(d[k].cpu().double(), losses[k], rtol=1e-3, atol=1e-4)
+    for got, ref in ((gv, rv), (gt, rt), (gp, rp)):
+        got = got.cpu().double()
+        err = (got - ref).abs().max() / ref.abs().max()
+        assert float(err) < 2e-2, float(err)
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0)
+        assert float(cos) > 0.9995, float(cos)
+    # and the two precisions agree with each other far inside the bf16 budget
+    d32, gv32, _, gp32 = run_fused(inp, 0.1, precision="fp32")
+    for k in KEYS:
+        torch.testing.assert_close(d[k], d32[k], rtol=1e-3, atol=1e-4)

@@ -10,6 +10,7 @@
 // The bf16 tcgen05 path (precision = 1) lives in loss_tc.cu and keeps them on chip instead.
 #include "common.cuh"
 #include "sgemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace {
 
@@ -222,12 +223,23 @@ struct Workspace {
     float *E2, *en, *qn, *inv_e, *inv_q, *pos, *dpos, *S_nce, *Z, *inv_c, *S_ga, *dq_nce, *dq_ga, *part, *rows_inst,
         *rows_nce, *rows_ga;
     uint8_t* mask;
+    uint8_t *pkA, *pkB;       // packed bf16 operand scratch of the tensor-core path
     int64_t bytes;
 };
 
 constexpr int SPLIT_NCE = 8, SPLIT_INST = 32;
 
-Workspace carve(void* base, int N, int D, int K, int C) {
+// One contraction, on the FFMA pipe (precision 0) or on the tensor cores (precision 1: both operands are first
+// rounded to bf16 into the packed tile-major layout, then tcgen05.mma accumulates in fp32).
+int run_gemm(const GemmArgs& g, bool use_tc, const Workspace& w, cudaStream_t st) {
+    if (!use_tc) return launch_gemm(g, st);
+    int rc;
+    if ((rc = tc_pack_strided(g.A, g.a_sm, g.a_sk, g.M, g.K, g.kscale, nullptr, w.pkA, st))) return rc;
+    if ((rc = tc_pack_strided(g.B, g.b_sn, g.b_sk, g.N, g.K, nullptr, nullptr, w.pkB, st))) return rc;
+    return tc_gemm_launch(w.pkA, w.pkB, g.C, g.c_sm, g.c_split, g.M, g.N, g.K, g.splitk, g.nscale, st);
+}
+
+Workspace carve(void* base, int N, int D, int K, int C, bool use_tc) {
     Workspace w;
     char* p = static_cast<char*>(base);
     auto take = [&](int64_t nfloats) {
@@ -247,6 +259,18 @@ Workspace carve(void* base, int N, int D, int K, int C) {
     w.part = take(part);
     w.rows_inst = take(2 * N); w.rows_nce = take(2 * N); w.rows_ga = take(N);
     w.mask = reinterpret_cast<uint8_t*>(take((K + 3) / 4));
+    w.pkA = w.pkB = nullptr;
+    if (use_tc) {
+        // largest packed operands: A = dZ [2N x C], B = projection^T [C x D] / dZ^T [C x 2N] / queues [K x D]
+        int64_t a = tc_gemm_packed_bytes(2 * N, C), b = tc_gemm_packed_bytes(C, D);
+        const int64_t cand[] = {tc_gemm_packed_bytes(2 * N, D), tc_gemm_packed_bytes(2 * N, K), tc_gemm_packed_bytes(D, 2 * N)};
+        for (int64_t x : cand) a = x > a ? x : a;
+        const int64_t candb[] = {tc_gemm_packed_bytes(C, 2 * N), tc_gemm_packed_bytes(K, D), tc_gemm_packed_bytes(D, K),
+                                 tc_gemm_packed_bytes(D, C), tc_gemm_packed_bytes(D, N), tc_gemm_packed_bytes(N, D)};
+        for (int64_t x : candb) b = x > b ? x : b;
+        w.pkA = reinterpret_cast<uint8_t*>(take(a / 4 + 64));
+        w.pkB = reinterpret_cast<uint8_t*>(take(b / 4 + 64));
+    }
     w.bytes = p - static_cast<char*>(base);
     return w;
 }
@@ -254,17 +278,20 @@ Workspace carve(void* base, int N, int D, int K, int C) {
 }  // namespace
 
 int64_t trb_moco_loss_workspace_bytes_f32(const trb_moco_shape* s) {
-    return carve(nullptr, s->N, s->D, s->K, s->C).bytes;
+    return carve(nullptr, s->N, s->D, s->K, s->C, false).bytes;
+}
+int64_t trb_moco_loss_workspace_bytes_tc(const trb_moco_shape* s) {
+    return carve(nullptr, s->N, s->D, s->K, s->C, true).bytes;
 }
 
-int trb_moco_loss_f32(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
-                      const float* v_key, const float* t_key, int normalize_keys, float* v_key_n, float* t_key_n,
-                      const int64_t* labels, const float* v_queue, const float* t_queue, const int64_t* id_queue,
-                      const float* projection, const trb_moco_shape* shape, const trb_moco_hparams* hp, float* losses,
-                      float* d_inst, float* d_nce, float* d_ga, float* d_projection, void* workspace,
-                      int64_t workspace_bytes, cudaStream_t st) {
+static int moco_loss_impl(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
+                          const float* v_key, const float* t_key, int normalize_keys, float* v_key_n, float* t_key_n,
+                          const int64_t* labels, const float* v_queue, const float* t_queue, const int64_t* id_queue,
+                          const float* projection, const trb_moco_shape* shape, const trb_moco_hparams* hp, float* losses,
+                          float* d_inst, float* d_nce, float* d_ga, float* d_projection, void* workspace,
+                          int64_t workspace_bytes, cudaStream_t st, bool use_tc) {
     const int N = shape->N, D = shape->D, K = shape->K, C = shape->C;
-    Workspace w = carve(workspace, N, D, K, C);
+    Workspace w = carve(workspace, N, D, K, C, use_tc);
     if (workspace_bytes < w.bytes) {
         trb_set_error("moco_loss: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)w.bytes);
         return TRB_ERR_WORKSPACE;
@@ -285,7 +312,7 @@ int trb_moco_loss_f32(const float* v_embed, const float* t_embed, const float* v
     for (int mod = 0; mod < 2; ++mod) {
         GemmArgs g{w.qn + (int64_t)mod * N * D, D, 1, mod ? v_queue : t_queue, K, 1,
                    w.S_nce + (int64_t)mod * N * K, K, 0, N, K, D, nullptr, nullptr, 1};
-        if ((rc = launch_gemm(g, st))) return rc;
+        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
     }
     nce_rows_kernel<<<rows, 256, 0, st>>>(w.S_nce, w.pos, w.mask, hp->T, N, K, w.rows_nce, w.dpos, grads);
     TRB_LAUNCH_OK();
@@ -293,7 +320,7 @@ int trb_moco_loss_f32(const float* v_embed, const float* t_embed, const float* v
     // ---- instance logits for both modalities at once (losses.py:53-54)
     {
         GemmArgs g{w.E2, D, 1, projection, C, 1, w.Z, C, 0, rows, C, D, nullptr, w.inv_c, 1};
-        if ((rc = launch_gemm(g, st))) return rc;
+        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
     }
     instance_rows_kernel<<<rows, 256, 0, st>>>(w.Z, labels, hp->epsilon, N, C, w.rows_inst, grads);
     TRB_LAUNCH_OK();
@@ -301,7 +328,7 @@ int trb_moco_loss_f32(const float* v_embed, const float* t_embed, const float* v
     // ---- global align similarity (losses.py:114)
     {
         GemmArgs g{w.en, D, 1, w.en + (int64_t)N * D, 1, D, w.S_ga, N, 0, N, N, D, nullptr, nullptr, 1};
-        if ((rc = launch_gemm(g, st))) return rc;
+        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
     }
     align_rows_kernel<<<N, 128, 0, st>>>(w.S_ga, labels, hp->alpha, hp->beta, hp->scale_pos, hp->scale_neg, N, w.rows_ga, grads);
     TRB_LAUNCH_OK();
@@ -315,7 +342,7 @@ int trb_moco_loss_f32(const float* v_embed, const float* t_embed, const float* v
     for (int mod = 0; mod < 2; ++mod) {
         GemmArgs g{w.S_nce + (int64_t)mod * N * K, K, 1, mod ? v_queue : t_queue, 1, K,
                    w.part, D, ND, N, D, K, nullptr, nullptr, SPLIT_NCE};
-        if ((rc = launch_gemm(g, st))) return rc;
+        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
         reduce_partials_kernel<<<(unsigned)((ND + 255) / 256), 256, 0, st>>>(w.dq_nce + mod * ND, w.part, SPLIT_NCE, ND);
         TRB_LAUNCH_OK();
     }
@@ -325,13 +352,13 @@ int trb_moco_loss_f32(const float* v_embed, const float* t_embed, const float* v
     // ---- instance backward: dE = dZ @ What^T (split over classes), dWhat = E^T @ dZ
     {
         GemmArgs g{w.Z, C, 1, projection, 1, C, w.part, D, 2 * ND, rows, D, C, w.inv_c, nullptr, SPLIT_INST};
-        if ((rc = launch_gemm(g, st))) return rc;
+        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
         reduce_partials_kernel<<<(unsigned)((2 * ND + 255) / 256), 256, 0, st>>>(d_inst, w.part, SPLIT_INST, 2 * ND);
         TRB_LAUNCH_OK();
     }
     if (d_projection) {
         GemmArgs g{w.E2, 1, D, w.Z, C, 1, d_projection, C, 0, D, C, rows, nullptr, nullptr, 1};
-        if ((rc = launch_gemm(g, st))) return rc;
+        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
         projection_backward_kernel<<<(C + 255) / 256, 256, 0, st>>>(d_projection, projection, w.inv_c, D, C);
         TRB_LAUNCH_OK();
     }
@@ -339,11 +366,24 @@ int trb_moco_loss_f32(const float* v_embed, const float* t_embed, const float* v
     // ---- global align backward: dq_v = dS @ q_t, dq_t = dS^T @ q_v, through the normalisation
     {
         GemmArgs gv{w.S_ga, N, 1, w.en + ND, D, 1, w.dq_ga, D, 0, N, D, N, nullptr, nullptr, 1};
-        if ((rc = launch_gemm(gv, st))) return rc;
+        if ((rc = run_gemm(gv, use_tc, w, st))) return rc;
         GemmArgs gt{w.S_ga, 1, N, w.en, D, 1, w.dq_ga + ND, D, 0, N, D, N, nullptr, nullptr, 1};
-        if ((rc = launch_gemm(gt, st))) return rc;
+        if ((rc = run_gemm(gt, use_tc, w, st))) return rc;
     }
     normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w.dq_ga, nullptr, nullptr, nullptr, w.en, w.inv_e, d_ga, N, D);
     TRB_LAUNCH_OK();
     return 0;
 }
+
+#define TRB_LOSS_ARGS                                                                                                          \
+    const float *v_embed, const float *t_embed, const float *v_qraw, const float *t_qraw, const float *v_key,                  \
+        const float *t_key, int normalize_keys, float *v_key_n, float *t_key_n, const int64_t *labels, const float *v_queue,   \
+        const float *t_queue, const int64_t *id_queue, const float *projection, const trb_moco_shape *shape,                    \
+        const trb_moco_hparams *hp, float *losses, float *d_inst, float *d_nce, float *d_ga, float *d_projection,              \
+        void *workspace, int64_t workspace_bytes, cudaStream_t st
+#define TRB_LOSS_PASS                                                                                                          \
+    v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, normalize_keys, v_key_n, t_key_n, labels, v_queue, t_queue, id_queue,      \
+        projection, shape, hp, losses, d_inst, d_nce, d_ga, d_projection, workspace, workspace_bytes, st
+
+int trb_moco_loss_f32(TRB_LOSS_ARGS) { return moco_loss_impl(TRB_LOSS_PASS, false); }
+int trb_moco_loss_tc(TRB_LOSS_ARGS) { return moco_loss_impl(TRB_LOSS_PASS, true); }
