@@ -217,10 +217,36 @@ def test_loss_dict_bf16_tensor_core_path(N, D, K, C, masked):
     for got, ref in ((gv, rv), (gt, rt), (gp, rp)):
         got = got.cpu().double()
         err = (got - ref).abs().max() / ref.abs().max()
-        assert float(err) < 2e-2, float(err)
+        assert float(err) < (2e-2 if N >= 32 else 4e-2), float(err)
         cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0)
         assert float(cos) > 0.9995, float(cos)
     # and the two precisions agree with each other far inside the bf16 budget
     d32, gv32, _, gp32 = run_fused(inp, 0.1, precision="fp32")
     for k in KEYS:
         torch.testing.assert_close(d[k], d32[k], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replay_matches_eager(precision):
+    """cuda_graph=True replays loss + gradients + enqueue as one graph: same numbers, same queue evolution."""
+    inp = synth_loss_inputs(32, 64, 128, 257, seed=7)
+    def fresh():
+        a = {k: v.clone().to(DEV) for k, v in inp.items()}
+        a["ptr"] = torch.zeros(1, dtype=torch.int64, device=DEV)
+        return a
+    runs = {}
+    for graph in (False, True):
+        a = fresh()
+        ve, te, pr = a["v_embed"].requires_grad_(True), a["t_embed"].requires_grad_(True), a["projection"].requires_grad_(True)
+        hist = []
+        for step in range(5):                      # 128 / 32 = 4 slots: the pointer wraps
+            d = trb.moco_loss_dict(ve, te, a["v_key"], a["t_key"], a["labels"], a["v_queue"], a["t_queue"], a["id_queue"],
+                                   a["ptr"], pr, epsilon=0.1, enqueue=True, precision=precision, cuda_graph=graph)
+            ve.grad = te.grad = pr.grad = None
+            sum(d.values()).backward()
+            hist.append(([float(d[k]) for k in KEYS], ve.grad.clone(), pr.grad.clone(), int(a["ptr"]), a["v_queue"].clone(),
+                         a["id_queue"].clone()))
+        runs[graph] = hist
+    for e, g in zip(runs[False], runs[True]):
+        assert e[0] == g[0] and e[3] == g[3]
+        assert torch.equal(e[1], g[1]) and torch.equal(e[2], g[2]) and torch.equal(e[4], g[4]) and torch.equal(e[5], g[5])

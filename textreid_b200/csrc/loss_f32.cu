@@ -77,13 +77,23 @@ queue_mask_kernel(const int64_t* __restrict__ id_queue, const int64_t* __restric
     mask[k] = hit ? 1 : 0;
 }
 
+// 32 columns x 8 row-groups per CTA: coalesced along the class dimension, 8-way split of the D-long column walk
 __global__ void __launch_bounds__(256)
 column_inv_norm_kernel(const float* __restrict__ W, float* __restrict__ inv_c, int D, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ float part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float ss = 0.f;
-    for (int d = 0; d < D; ++d) { const float w = W[(int64_t)d * C + c]; ss = fmaf(w, w, ss); }
-    inv_c[c] = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));
+    if (c < C)
+        for (int d = ty; d < D; d += 8) { const float w = W[(int64_t)d * C + c]; ss = fmaf(w, w, ss); }
+    part[ty][tx] = ss;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][tx];
+        inv_c[c] = __fdiv_rn(1.0f, fmaxf(sqrtf(t), 1e-12f));
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -189,18 +199,26 @@ normalize_backward_kernel(const float* __restrict__ dq, const float* __restrict_
     }
 }
 
-// dW = (dWhat - <dWhat, What>_col What) / ||W||_col, What = W * inv_c   (thread per column, in place)
+// dW = (dWhat - <dWhat, What>_col What) / ||W||_col, What = W * inv_c   (in place; 32 columns x 8 row-groups per CTA)
 __global__ void __launch_bounds__(256)
 projection_backward_kernel(float* __restrict__ dW, const float* __restrict__ W, const float* __restrict__ inv_c, int D, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const float ic = inv_c[c];
+    __shared__ float part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const float ic = c < C ? inv_c[c] : 0.f;
     float dot = 0.f;
-    for (int d = 0; d < D; ++d) dot = fmaf(dW[(int64_t)d * C + c], W[(int64_t)d * C + c] * ic, dot);
-    for (int d = 0; d < D; ++d) {
-        const int64_t o = (int64_t)d * C + c;
-        dW[o] = (dW[o] - dot * (W[o] * ic)) * ic;
-    }
+    if (c < C)
+        for (int d = ty; d < D; d += 8) dot = fmaf(dW[(int64_t)d * C + c], W[(int64_t)d * C + c] * ic, dot);
+    part[ty][tx] = dot;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    if (c < C)
+        for (int d = ty; d < D; d += 8) {
+            const int64_t o = (int64_t)d * C + c;
+            dW[o] = (dW[o] - t * (W[o] * ic)) * ic;
+        }
 }
 
 // losses[0] = sum(inst rows)/N ; losses[1] = sum(nce rows)/N ; losses[2] = sum(align rows)*2/N
@@ -228,6 +246,12 @@ struct Workspace {
 };
 
 constexpr int SPLIT_NCE = 8, SPLIT_INST = 32;
+
+// split-K factor actually used: the tensor-core kernel cannot split finer than one 64-wide k-chunk per part
+static inline int eff_split(int split, int K, bool use_tc) {
+    const int chunks = use_tc ? (K + 63) / 64 : (K + GK - 1) / GK;
+    return split < chunks ? split : (chunks < 1 ? 1 : chunks);
+}
 
 // One contraction, on the FFMA pipe (precision 0) or on the tensor cores (precision 1: both operands are first
 // rounded to bf16 into the packed tile-major layout, then tcgen05.mma accumulates in fp32).
@@ -304,7 +328,7 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     TRB_LAUNCH_OK();
     queue_mask_kernel<<<(K + 255) / 256, 256, N * sizeof(int64_t), st>>>(id_queue, labels, w.mask, N, K);
     TRB_LAUNCH_OK();
-    column_inv_norm_kernel<<<(C + 255) / 256, 256, 0, st>>>(projection, w.inv_c, D, C);
+    column_inv_norm_kernel<<<(C + 31) / 32, 256, 0, st>>>(projection, w.inv_c, D, C);
     TRB_LAUNCH_OK();
 
     int rc;
@@ -339,11 +363,12 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
 
     const int64_t ND = (int64_t)N * D;
     // ---- InfoNCE backward: dq = dS @ queue^T (+ dpos * key), through the normalisation
+    const int split_nce = eff_split(SPLIT_NCE, K, use_tc), split_inst = eff_split(SPLIT_INST, C, use_tc);
     for (int mod = 0; mod < 2; ++mod) {
         GemmArgs g{w.S_nce + (int64_t)mod * N * K, K, 1, mod ? v_queue : t_queue, 1, K,
-                   w.part, D, ND, N, D, K, nullptr, nullptr, SPLIT_NCE};
+                   w.part, D, ND, N, D, K, nullptr, nullptr, split_nce};
         if ((rc = run_gemm(g, use_tc, w, st))) return rc;
-        reduce_partials_kernel<<<(unsigned)((ND + 255) / 256), 256, 0, st>>>(w.dq_nce + mod * ND, w.part, SPLIT_NCE, ND);
+        reduce_partials_kernel<<<(unsigned)((ND + 255) / 256), 256, 0, st>>>(w.dq_nce + mod * ND, w.part, split_nce, ND);
         TRB_LAUNCH_OK();
     }
     normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w.dq_nce, w.dpos, v_key_n, t_key_n, w.qn, w.inv_q, d_nce, N, D);
@@ -351,15 +376,15 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
 
     // ---- instance backward: dE = dZ @ What^T (split over classes), dWhat = E^T @ dZ
     {
-        GemmArgs g{w.Z, C, 1, projection, 1, C, w.part, D, 2 * ND, rows, D, C, w.inv_c, nullptr, SPLIT_INST};
+        GemmArgs g{w.Z, C, 1, projection, 1, C, w.part, D, 2 * ND, rows, D, C, w.inv_c, nullptr, split_inst};
         if ((rc = run_gemm(g, use_tc, w, st))) return rc;
-        reduce_partials_kernel<<<(unsigned)((2 * ND + 255) / 256), 256, 0, st>>>(d_inst, w.part, SPLIT_INST, 2 * ND);
+        reduce_partials_kernel<<<(unsigned)((2 * ND + 255) / 256), 256, 0, st>>>(d_inst, w.part, split_inst, 2 * ND);
         TRB_LAUNCH_OK();
     }
     if (d_projection) {
         GemmArgs g{w.E2, 1, D, w.Z, C, 1, d_projection, C, 0, D, C, rows, nullptr, nullptr, 1};
         if ((rc = run_gemm(g, use_tc, w, st))) return rc;
-        projection_backward_kernel<<<(C + 255) / 256, 256, 0, st>>>(d_projection, projection, w.inv_c, D, C);
+        projection_backward_kernel<<<(C + 31) / 32, 256, 0, st>>>(d_projection, projection, w.inv_c, D, C);
         TRB_LAUNCH_OK();
     }
 

@@ -17,6 +17,8 @@ import torch
 from . import _lib
 
 PRECISIONS = {"fp32": 0, "bf16": 1}
+_GRAPHS: Dict[Tuple, tuple] = {}       # pointer-keyed CUDA graphs of the loss step (see moco_loss_dict(cuda_graph=True))
+_GRAPH_CAP = 8
 LOSS_KEYS = ("instance_loss", "infonce_loss", "global_align_loss")
 _workspaces: Dict[Tuple, torch.Tensor] = {}
 
@@ -40,7 +42,7 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 class _MoCoLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, v_embed, t_embed, v_qraw, t_qraw, projection, v_key, t_key, labels, v_queue, t_queue,
-                id_queue, hp, precision, normalize_keys, separate_q):
+                id_queue, hp, precision, normalize_keys, separate_q, queue_ptr, enqueue, cuda_graph):
         lib = _lib.load()
         _lib.require_cuda(v_embed, t_embed, projection, v_key, t_key, labels, v_queue, t_queue, id_queue)
         dev = v_embed.device
@@ -53,29 +55,74 @@ class _MoCoLossFunction(torch.autograd.Function):
         ve, te = _f32c(v_embed), _f32c(t_embed)
         vq, tq = (_f32c(v_qraw), _f32c(t_qraw)) if separate_q else (ve, te)
         vk, tk = _f32c(v_key), _f32c(t_key)
-        vkn, tkn = torch.empty_like(vk), torch.empty_like(tk)
         proj = _f32c(projection)
-        vqu, tqu = _f32c(v_queue), _f32c(t_queue)
         lab = labels.detach().reshape(-1).to(torch.int64).contiguous()
-        idq = id_queue.detach().reshape(-1).to(torch.int64).contiguous()
         need_grad = any(ctx.needs_input_grad[:5])
-        losses = torch.empty(3, dtype=torch.float32, device=dev)
-        d_inst = d_nce = d_ga = d_proj = None
-        if need_grad:
-            d_inst = torch.empty(2, N, D, dtype=torch.float32, device=dev)
-            d_nce = torch.empty(2, N, D, dtype=torch.float32, device=dev)
-            d_ga = torch.empty(2, N, D, dtype=torch.float32, device=dev)
-            d_proj = torch.empty(D, Cn, dtype=torch.float32, device=dev)
-        ws = _workspace(shape, precision, dev)
-        _lib.check(lib.trb_moco_loss(
-            _lib.ptr(ve), _lib.ptr(te), _lib.ptr(vq), _lib.ptr(tq), _lib.ptr(vk), _lib.ptr(tk), int(normalize_keys),
-            _lib.ptr(vkn), _lib.ptr(tkn), _lib.ptr(lab), _lib.ptr(vqu), _lib.ptr(tqu), _lib.ptr(idq), _lib.ptr(proj),
-            C.byref(shape), C.byref(hp), precision, _lib.ptr(losses), _lib.ptr(d_inst), _lib.ptr(d_nce), _lib.ptr(d_ga),
-            _lib.ptr(d_proj), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "trb_moco_loss")
+        if enqueue:
+            for q in (v_queue, t_queue):
+                if q.dtype != torch.float32 or not q.is_contiguous():
+                    raise ValueError("queues must be contiguous float32 [D, K] buffers")
+            if id_queue.dtype != torch.int64 or queue_ptr.dtype != torch.int64 or not id_queue.is_contiguous():
+                raise ValueError("id_queue / queue_ptr must be contiguous int64 buffers")
+            if K % N != 0:
+                raise AssertionError("K %% batch_size != 0 (head.py:101)")
+            vqu, tqu, idq = v_queue, t_queue, id_queue.reshape(-1)
+        else:
+            vqu, tqu = _f32c(v_queue), _f32c(t_queue)
+            idq = id_queue.detach().reshape(-1).to(torch.int64).contiguous()
+
+        def allocate():
+            out = dict(losses=torch.empty(3, dtype=torch.float32, device=dev), vkn=torch.empty_like(vk), tkn=torch.empty_like(tk))
+            if need_grad:
+                for name in ("d_inst", "d_nce", "d_ga"):
+                    out[name] = torch.empty(2, N, D, dtype=torch.float32, device=dev)
+                out["d_proj"] = torch.empty(D, Cn, dtype=torch.float32, device=dev)
+            return out
+
+        def launch(out, ws, do_enqueue):
+            _lib.check(lib.trb_moco_loss(
+                _lib.ptr(ve), _lib.ptr(te), _lib.ptr(vq), _lib.ptr(tq), _lib.ptr(vk), _lib.ptr(tk), int(normalize_keys),
+                _lib.ptr(out["vkn"]), _lib.ptr(out["tkn"]), _lib.ptr(lab), _lib.ptr(vqu), _lib.ptr(tqu), _lib.ptr(idq),
+                _lib.ptr(proj), C.byref(shape), C.byref(hp), precision, _lib.ptr(out["losses"]), _lib.ptr(out.get("d_inst")),
+                _lib.ptr(out.get("d_nce")), _lib.ptr(out.get("d_ga")), _lib.ptr(out.get("d_proj")), _lib.ptr(ws), ws.numel(),
+                _lib.stream_ptr(dev)), "trb_moco_loss")
+            if do_enqueue:   # head.py:175 -- after the logits were taken from the old queue contents
+                _lib.check(lib.trb_enqueue(_lib.ptr(vqu), _lib.ptr(tqu), _lib.ptr(idq), _lib.ptr(queue_ptr), _lib.ptr(out["vkn"]),
+                                           _lib.ptr(out["tkn"]), _lib.ptr(lab), N, D, K, _lib.stream_ptr(dev)), "trb_enqueue")
+
+        if cuda_graph:
+            # The whole step is a fixed launch sequence on fixed addresses: replay it as one CUDA graph.  Graphs are keyed
+            # by the input pointers (steady-state training loops hand back the same addresses from the caching allocator);
+            # the outputs of a replay are valid until the next replay of the same graph.
+            key = (ve.data_ptr(), te.data_ptr(), vq.data_ptr(), tq.data_ptr(), vk.data_ptr(), tk.data_ptr(), lab.data_ptr(),
+                   vqu.data_ptr(), tqu.data_ptr(), idq.data_ptr(), proj.data_ptr(), queue_ptr.data_ptr() if enqueue else 0,
+                   N, D, K, Cn, precision, bool(normalize_keys), need_grad, bool(enqueue),
+                   hp.T, hp.epsilon, hp.alpha, hp.beta, hp.scale_pos, hp.scale_neg)
+            entry = _GRAPHS.get(key)
+            if entry is None:
+                if len(_GRAPHS) >= _GRAPH_CAP:
+                    _GRAPHS.pop(next(iter(_GRAPHS)))
+                out = allocate()
+                nbytes = lib.trb_moco_loss_workspace_bytes(C.byref(shape), precision)
+                if nbytes < 0:
+                    _lib.check(int(nbytes), "trb_moco_loss_workspace_bytes")
+                ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+                launch(out, ws, False)                   # eager warm-up (validates arguments, sets kernel attributes)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    launch(out, ws, enqueue)
+                entry = (graph, out, ws, (ve, te, vq, tq, vk, tk, lab, vqu, tqu, idq, proj))   # keep the addresses alive
+                _GRAPHS[key] = entry
+            entry[0].replay()
+            out = entry[1]
+        else:
+            out = allocate()
+            launch(out, _workspace(shape, precision, dev), enqueue)
         ctx.separate_q = separate_q
-        ctx.grads = (d_inst, d_nce, d_ga, d_proj)
-        ctx.mark_non_differentiable(vkn, tkn)
-        return losses[0], losses[1], losses[2], vkn, tkn
+        ctx.grads = (out.get("d_inst"), out.get("d_nce"), out.get("d_ga"), out.get("d_proj"))
+        ctx.mark_non_differentiable(out["vkn"], out["tkn"])
+        losses = out["losses"]
+        return losses[0], losses[1], losses[2], out["vkn"], out["tkn"]
 
     @staticmethod
     def backward(ctx, g_inst, g_nce, g_ga, _gvk, _gtk):
@@ -102,13 +149,13 @@ class _MoCoLossFunction(torch.autograd.Function):
         gp = d_proj.clone() if ctx.needs_input_grad[4] else None
         if gp is not None:
             _lib.check(lib.trb_scale_inplace_f32(_lib.ptr(gp), _lib.ptr(g), gp.numel(), st), "trb_scale_inplace_f32")
-        return (gv, gt, gvq, gtq, gp) + (None,) * 10
+        return (gv, gt, gvq, gtq, gp) + (None,) * 13
 
 
 def moco_loss_dict(v_embed, t_embed, v_key, t_key, labels, v_queue, t_queue, id_queue, queue_ptr, projection, *,
                    T: float = 0.07, epsilon: float = 0.0, alpha: float = 0.6, beta: float = 0.4, scale_pos: float = 10,
                    scale_neg: float = 40, enqueue: bool = True, v_embed_q=None, t_embed_q=None,
-                   normalize_keys: bool = False, precision: str = "fp32") -> Dict[str, torch.Tensor]:
+                   normalize_keys: bool = False, precision: str = "fp32", cuda_graph: bool = False) -> Dict[str, torch.Tensor]:
     """Functional core of MoCoHead.forward's train branch (head.py:126-175) + LossComputation.forward
     (moco_head/loss.py:21-39).
 
@@ -116,6 +163,9 @@ def moco_loss_dict(v_embed, t_embed, v_key, t_key, labels, v_queue, t_queue, id_
     v_key, t_key     [N, D]  key embeddings; L2-normalised already unless ``normalize_keys``
     v_embed_q/t_embed_q      InfoNCE query inputs of the FC=True variant (head.py:118-124); default = embeds
     queues [D, K] fp32, id_queue [1, K] int64, queue_ptr [1] int64 are mutated in place when ``enqueue``.
+    ``cuda_graph=True`` replays the whole step (loss, gradients, enqueue) as one CUDA graph keyed by the input addresses;
+    the returned losses / saved gradients then live in graph-owned buffers that the next replay overwrites (fine for the
+    reference's loop: ``backward()`` runs before the next ``forward()``, trainer.py:81-91).
     """
     if precision not in PRECISIONS:
         raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
@@ -125,9 +175,8 @@ def moco_loss_dict(v_embed, t_embed, v_key, t_key, labels, v_queue, t_queue, id_
     hp = _lib.MocoHParams(T, epsilon, alpha, beta, scale_pos, scale_neg)
     li, ln, lg, vkn, tkn = _MoCoLossFunction.apply(
         v_embed, t_embed, v_embed_q if separate_q else v_embed, t_embed_q if separate_q else t_embed, projection,
-        v_key, t_key, labels, v_queue, t_queue, id_queue, hp, PRECISIONS[precision], normalize_keys, separate_q)
-    if enqueue:
-        dequeue_and_enqueue(v_queue, t_queue, id_queue, queue_ptr, vkn, tkn, labels)
+        v_key, t_key, labels, v_queue, t_queue, id_queue, hp, PRECISIONS[precision], normalize_keys, separate_q,
+        queue_ptr, bool(enqueue), bool(cuda_graph))
     return {"instance_loss": li, "infonce_loss": ln, "global_align_loss": lg}
 
 

@@ -39,13 +39,14 @@ def make_loss_evaluator(cfg):
 
 
 class FusedMoCoHead(nn.Module):
-    def __init__(self, cfg, visual_model, textual_model, precision: str = "fp32"):
+    def __init__(self, cfg, visual_model, textual_model, precision: str = "fp32", cuda_graph: bool = False):
         super().__init__()
         self.embed_size = cfg.MODEL.EMBEDDING.FEATURE_SIZE
         self.K = cfg.MODEL.MOCO.K
         self.m = cfg.MODEL.MOCO.M
         self.fc = cfg.MODEL.MOCO.FC
         self.precision = precision
+        self.cuda_graph = cuda_graph
 
         self.v_encoder_q = visual_model
         self.t_encoder_q = textual_model
@@ -123,7 +124,8 @@ class FusedMoCoHead(nn.Module):
         ev = self.loss_evaluator
         return moco_loss_dict(v_embed, t_embed, v_k, t_k, id_q, self.v_queue, self.t_queue, self.id_queue,
                               self.queue_ptr, ev.projection, T=ev.T, epsilon=ev.epsilon, enqueue=True,
-                              v_embed_q=v_q, t_embed_q=t_q, normalize_keys=True, precision=self.precision)
+                              v_embed_q=v_q, t_embed_q=t_q, normalize_keys=True, precision=self.precision,
+                              cuda_graph=self.cuda_graph)
 
 
 def build_moco_head(cfg, visual_model, textual_model):

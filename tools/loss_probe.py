@@ -12,7 +12,8 @@ def main(N=128, D=256, K=2048, C=11003, iters=20):
     ptr = torch.zeros(1, dtype=torch.int64, device=dev)
     def step():
         d = trb.moco_loss_dict(ve, te, inp["v_key"], inp["t_key"], inp["labels"], inp["v_queue"], inp["t_queue"], inp["id_queue"],
-                               ptr, pr, epsilon=0.1, enqueue=True, precision=os.environ.get("TRB_LOSS_PRECISION", "fp32"))
+                               ptr, pr, epsilon=0.1, enqueue=True, precision=os.environ.get("TRB_LOSS_PRECISION", "fp32"),
+                               cuda_graph=bool(int(os.environ.get("TRB_LOSS_GRAPH", "0"))))
         ve.grad = te.grad = pr.grad = None
         (d["instance_loss"] + d["infonce_loss"] + d["global_align_loss"]).backward()
         return d
