@@ -176,26 +176,33 @@ def secondary_measurements(pk, device):
     def flush():
         flush_buf.fill_(1)
 
-    # ---- MoCo loss dict fwd+bwd, configs[1]: N=128, K=2048, D=256, C=11003 ----
+    # ---- MoCo loss dict fwd+bwd (+ enqueue), configs[1]: N=128, K=2048, D=256, C=11003 ----
+    # one step = what trainer.py:81-90 does with the head's output: loss dict -> sum -> backward.  Labels change every step
+    # (device-side) so that the queue never degenerates into "every slot masked".
     N, D, K, C = 128, 256, 2048, 11003
-    inp = {k: v.to(device) for k, v in synth_loss_inputs(N, D, K, C, seed=0).items()}
-    ve, te, pr = inp["v_embed"].requires_grad_(True), inp["t_embed"].requires_grad_(True), inp["projection"].requires_grad_(True)
-    ptr = torch.zeros(1, dtype=torch.int64, device=device)
-
-    def loss_step():
-        d = trb.moco_loss_dict(ve, te, inp["v_key"], inp["t_key"], inp["labels"], inp["v_queue"], inp["t_queue"], inp["id_queue"],
-                               ptr, pr, epsilon=0.1, enqueue=True, precision="fp32")
-        ve.grad = te.grad = pr.grad = None
-        (d["instance_loss"] + d["infonce_loss"] + d["global_align_loss"]).backward()
-
-    med, best = time_cuda(loss_step, 30, 5, flush)
     bytes_alg = 27.8e6            # queues + projection read + dProjection write + embeddings
-    out["moco_loss_fp32"] = {
-        "metric": "MoCo loss steps/s (loss dict fwd+bwd + enqueue, bs128, queue 2048, D=256, C=11003)", "value": 1e3 / med,
-        "unit": "steps/s", "ms_per_step": med, "dtype": "f32", "l2_flushed": True,
-        "roofline": {"bound": "hbm", "achieved": bytes_alg / (med * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                     "frac": bytes_alg / (med * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
-                     "note": "whole step (host launches included), algorithmic 27.8 MB; fp32 parity path"}}
+    for prec in ("bf16", "fp32"):
+        for graph in (True, False):
+            inp = {k: v.to(device) for k, v in synth_loss_inputs(N, D, K, C, seed=0).items()}
+            ve, te, pr = inp["v_embed"].requires_grad_(True), inp["t_embed"].requires_grad_(True), inp["projection"].requires_grad_(True)
+            ptr = torch.zeros(1, dtype=torch.int64, device=device)
+            labels = inp["labels"]
+
+            def loss_step():
+                labels.add_(97).remainder_(C)
+                d = trb.moco_loss_dict(ve, te, inp["v_key"], inp["t_key"], labels, inp["v_queue"], inp["t_queue"], inp["id_queue"],
+                                       ptr, pr, epsilon=0.1, enqueue=True, precision=prec, cuda_graph=graph)
+                ve.grad = te.grad = pr.grad = None
+                (d["instance_loss"] + d["infonce_loss"] + d["global_align_loss"]).backward()
+
+            med, best = time_cuda(loss_step, 40, 8, flush)
+            key = "moco_loss_%s%s" % (prec, "_graph" if graph else "")
+            out[key] = {
+                "metric": "MoCo loss steps/s (loss dict fwd+bwd + enqueue, bs128, queue 2048, D=256, C=11003)", "value": 1e3 / med,
+                "unit": "steps/s", "ms_per_step": med, "dtype": "bf16" if prec == "bf16" else "f32", "cuda_graph": graph, "l2_flushed": True,
+                "roofline": {"bound": "hbm", "achieved": bytes_alg / (med * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": bytes_alg / (med * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+                             "note": "whole step incl. host-side autograd, algorithmic 27.8 MB"}}
     # ---- EMA over an RN50+GRU-sized arena: 41,755,488 fp32 parameters ----
     P = 41_755_488
     pk_, pq_ = torch.randn(P, device=device), torch.randn(P, device=device)

@@ -97,6 +97,27 @@ int trb_rank_similarity_f32(const float* sim, int64_t row_stride, int64_t col_st
                             int64_t G, const int64_t* rel_ptr, const int64_t* rel_col,
                             float* cand_sim, int64_t* cand_idx, int32_t* cnt, trb_stream_t stream);
 
+/* k-reciprocal re-ranking (evaluation.py:40-65, 151-156): rank the float64 scores
+ *   alpha * |N(q) & N(g)| / |N(q) | N(g)|  +  sim[q,g]
+ * where N(q) = q_nn[q, 0:n] are the n best gallery items of query q and N(g) = g_nn[g, 0:n] the n best gallery items
+ * of gallery item g (n = 5, alpha = 0.05 in the reference).  Same outputs as trb_rank_similarity_f32; the scores are
+ * formed on the fly in float64 (the reference's jaccard matrix is float64), the matrix is not materialised. */
+int trb_rank_rerank_f64(const float* sim, int64_t row_stride, int64_t col_stride, int64_t Q, int64_t G,
+                        const int64_t* q_nn, const int64_t* g_nn, int n_neighbors, double alpha,
+                        const int64_t* rel_ptr, const int64_t* rel_col, float* cand_sim, int64_t* cand_idx,
+                        int32_t* cnt, trb_stream_t stream);
+
+/* Same as trb_rank_similarity_f32 for a materialised FLOAT64 score matrix (re-ranked scores rebuilt from the
+ * rvn_mat / rtn_mat arrays of a cached inference_data.npz, evaluation.py:85-95). */
+int trb_rank_scores_f64(const double* scores, int64_t row_stride, int64_t col_stride, int64_t Q, int64_t G,
+                        const int64_t* rel_ptr, const int64_t* rel_col, float* cand_sim, int64_t* cand_idx,
+                        int32_t* cnt, trb_stream_t stream);
+
+/* out[Q,G] (float64) = alpha * Jaccard(N(q), N(g)): the rvn_mat / rtn_mat arrays of inference_data.npz
+ * (evaluation.py:126-142).  Compatibility only. */
+int trb_jaccard_f64(const int64_t* q_nn, const int64_t* g_nn, int n_neighbors, double alpha, double* out, int64_t Q,
+                    int64_t G, trb_stream_t stream);
+
 /* sim[Q,G] = qn @ gn^T, materialised (evaluation.py:120).  Compatibility only: the npz cache
  * (evaluation.py:126-142), re-ranking, and callers of rank().  Same k-ascending FFMA order as above. */
 int trb_similarity_f32(const float* qn, const float* gn, float* sim, int64_t Q, int64_t G, int64_t D,

@@ -276,3 +276,57 @@ def test_sharded_gallery_merge_single_device():
             one = trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "bf16")
             assert torch.equal(parts.top_idx, one.top_idx)
             assert torch.equal(parts.hit_ranks, one.hit_ranks)
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation(): the reference entry point incl. k-reciprocal re-ranking and the npz cache
+# ----------------------------------------------------------------------------------------------
+class _DS:
+    def __init__(self, image_ids, pids):
+        self.image_ids, self.pids = image_ids, pids
+
+    def __len__(self):
+        return len(self.pids)
+
+    def get_id_info(self, idx):
+        return self.image_ids[idx], self.pids[idx]
+
+
+def test_evaluation_entry_matches_reference_golden(golden_dir, tmp_path):
+    """evaluation(dataset, predictions, output_folder, topk, save_data, rerank) against the fixture recorded from the
+    unmodified reference: R@1 return value, every logged ranking, and the npz cache it writes."""
+    from textreid_b200.evaluation import evaluation
+    g = load(golden_dir, "evaluation_small")
+    v, t = T(g["v"]), T(g["t"])
+    ds = _DS([int(x) for x in g["image_ids"]], [int(x) for x in g["pids"]])
+    preds = {i: [v[i], t[i]] for i in range(v.shape[0])}
+    # plain (trainer path, rerank=False) with and without the cache
+    out = tmp_path / "plain"; out.mkdir()
+    r1 = evaluation(ds, preds, str(out), [1, 5, 10], save_data=True, rerank=False)
+    assert torch.equal(r1.cpu(), torch.from_numpy(g["plain.r1"]))
+    assert torch.equal(evaluation.last_results["t2i"].cpu(), torch.from_numpy(g["plain.t2i_cmc"]))
+    assert torch.equal(evaluation.last_results["i2t"].cpu(), torch.from_numpy(g["plain.i2t_cmc"]))
+    data = np.load(out / "inference_data.npz")
+    assert set(data.files) == {"image_pid", "text_pid", "similarity"}
+    assert np.array_equal(data["image_pid"], g["plain.npz.image_pid"])
+    np.testing.assert_allclose(data["similarity"], g["plain.npz.similarity"], rtol=1e-5, atol=1e-6)
+    r1b = evaluation(ds, preds, str(tmp_path), [1, 5, 10], save_data=False, rerank=False)     # fused path, no matrix
+    assert torch.equal(r1b.cpu(), torch.from_numpy(g["plain.r1"]))
+    # re-rank (test_net.py path)
+    out = tmp_path / "rerank"; out.mkdir()
+    r1 = evaluation(ds, preds, str(out), [1, 5, 10], save_data=True, rerank=True)
+    res = evaluation.last_results
+    assert torch.equal(r1.cpu(), torch.from_numpy(g["rerank.r1"]))
+    for key in ("t2i", "i2t", "re_t2i", "re_i2t"):
+        assert torch.equal(res[key].cpu(), torch.from_numpy(g["rerank.%s_cmc" % key])), key
+        torch.testing.assert_close(res[key + "_mAP"].cpu(), torch.from_numpy(g["rerank.%s_mAP" % key]), rtol=2e-6, atol=0)
+    data = np.load(out / "inference_data.npz")
+    assert data["rvn_mat"].dtype == np.float64
+    np.testing.assert_allclose(data["rvn_mat"], g["rerank.npz.rvn_mat"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(data["rtn_mat"], g["rerank.npz.rtn_mat"], rtol=0, atol=1e-12)
+    # predictions=None: read the cache the reference itself would have written
+    np.savez(tmp_path / "inference_data.npz", **{k[len("rerank.npz."):]: g[k] for k in g if k.startswith("rerank.npz.")})
+    r1c = evaluation(ds, None, str(tmp_path), [1, 5, 10], save_data=False, rerank=True)
+    assert torch.equal(r1c.cpu(), torch.from_numpy(g["rerank.r1"]))
+    for key in ("re_t2i", "re_i2t"):
+        assert torch.equal(evaluation.last_results[key].cpu(), torch.from_numpy(g["rerank.%s_cmc" % key])), key

@@ -42,6 +42,9 @@ SIGNATURES = {
     "trb_retrieval_thresholds_f32": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _p]),
     "trb_retrieval_stream_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _int, _p, _p, _p, _p]),
     "trb_rank_similarity_f32": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "trb_rank_rerank_f64": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _int, C.c_double, _p, _p, _p, _p, _p, _p]),
+    "trb_rank_scores_f64": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "trb_jaccard_f64": (_int, [_p, _p, _int, C.c_double, _p, _i64, _i64, _p]),
     "trb_similarity_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
     "trb_retrieval_finish": (_int, [_p, _p, _int, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "trb_retrieval_metrics": (_int, [_p, _p, _i64, C.POINTER(_i32), _int, _p, _p, _p]),
@@ -85,7 +88,7 @@ def load() -> C.CDLL:
 # kernels launched per successful library call (bench.py reports the sum as "gpu_launches")
 KERNELS_PER_CALL = {
     "trb_l2_normalize_rows_f32": 1, "trb_retrieval_thresholds_f32": 1, "trb_retrieval_stream_f32": 1,
-    "trb_rank_similarity_f32": 1, "trb_similarity_f32": 1, "trb_retrieval_finish": 1, "trb_retrieval_metrics": 1,
+    "trb_rank_similarity_f32": 1, "trb_rank_rerank_f64": 1, "trb_rank_scores_f64": 1, "trb_jaccard_f64": 1, "trb_similarity_f32": 1, "trb_retrieval_finish": 1, "trb_retrieval_metrics": 1,
     "trb_pack_rows_bf16": 1, "trb_retrieval_stream_tc": 1, "trb_moco_loss": 24, "trb_combine3_f32": 1,
     "trb_scale_inplace_f32": 1, "trb_ema_update_f32": 1, "trb_ema_update_chunks_f32": 1, "trb_enqueue": 2,
 }

@@ -80,32 +80,39 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 }
 
 // Ranking order pinned by the north star: similarity descending, gallery index ascending.
-__device__ __forceinline__ bool ranks_before(float s_a, int64_t i_a, float s_b, int64_t i_b) {
+template <typename T>
+__device__ __forceinline__ bool ranks_before(T s_a, int64_t i_a, T s_b, int64_t i_b) {
     return (s_a > s_b) || (s_a == s_b && i_a < i_b);
 }
 
+template <typename T> __device__ __forceinline__ T neg_inf();
+template <> __device__ __forceinline__ float neg_inf<float>() { return -CUDART_INF_F; }
+template <> __device__ __forceinline__ double neg_inf<double>() { return -CUDART_INF; }
+
 // Per-thread best-TRB_TOPK list kept sorted (best first) in registers.  All indexing is static
 // after unrolling, so the arrays stay in registers.
-struct TopK {
-    float s[TRB_TOPK];
+template <typename T>
+struct TopKT {
+    T s[TRB_TOPK];
     int64_t i[TRB_TOPK];
     __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int k = 0; k < TRB_TOPK; ++k) { s[k] = -CUDART_INF_F; i[k] = INT64_MAX; }
+        for (int k = 0; k < TRB_TOPK; ++k) { s[k] = neg_inf<T>(); i[k] = INT64_MAX; }
     }
-    __device__ __forceinline__ bool admits(float v, int64_t idx) const {
+    __device__ __forceinline__ bool admits(T v, int64_t idx) const {
         return ranks_before(v, idx, s[TRB_TOPK - 1], i[TRB_TOPK - 1]);
     }
-    __device__ __forceinline__ void push(float v, int64_t idx) {
+    __device__ __forceinline__ void push(T v, int64_t idx) {
         if (!admits(v, idx)) return;
         s[TRB_TOPK - 1] = v;
         i[TRB_TOPK - 1] = idx;
 #pragma unroll
         for (int k = TRB_TOPK - 1; k > 0; --k) {
             if (ranks_before(s[k], i[k], s[k - 1], i[k - 1])) {
-                float ts = s[k]; s[k] = s[k - 1]; s[k - 1] = ts;
+                T ts = s[k]; s[k] = s[k - 1]; s[k - 1] = ts;
                 int64_t ti = i[k]; i[k] = i[k - 1]; i[k - 1] = ti;
             }
         }
     }
 };
+using TopK = TopKT<float>;

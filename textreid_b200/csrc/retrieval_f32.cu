@@ -233,32 +233,76 @@ extern "C" int trb_retrieval_stream_f32(const float* qn, const float* gn, int64_
 }
 
 // ---------------------------------------------------------------------------
-// rank from a materialised similarity matrix: one CTA per query row
+// rank from materialised scores: one CTA per query row.  The score of (q, g) comes from a loader:
+//   SimLoader    : the fp32 similarity matrix itself                    (rank(similarity, ...), evaluation.py:11)
+//   RerankLoader : float64  alpha * Jaccard(top-n(q), top-n(g)) + sim   (k-reciprocal re-ranking, evaluation.py:40-65,
+//                  151-156: "rvn_mat + similarity" is float64 because jaccard_mat comes from np.zeros)
 // ---------------------------------------------------------------------------
 namespace {
 constexpr int RS_THREADS = 256, RS_SLOTS = 64;
-}
 
+struct SimLoader {
+    using T = float;
+    const float* sim;
+    int64_t row_stride, col_stride;
+    const float* row;
+    __device__ __forceinline__ void init(int64_t q) { row = sim + q * row_stride; }
+    __device__ __forceinline__ float operator()(int64_t g) const { return row[g * col_stride]; }
+};
+
+struct F64Loader {           // a materialised float64 score matrix (re-ranked scores read back from inference_data.npz)
+    using T = double;
+    const double* m;
+    int64_t row_stride, col_stride;
+    const double* row;
+    __device__ __forceinline__ void init(int64_t q) { row = m + q * row_stride; }
+    __device__ __forceinline__ double operator()(int64_t g) const { return row[g * col_stride]; }
+};
+
+struct RerankLoader {
+    using T = double;
+    const float* sim;
+    int64_t row_stride, col_stride;
+    const int64_t* q_nn;     // [Q, n] neighbours of every query among the gallery
+    const int64_t* g_nn;     // [G, n] neighbours of every gallery item among the gallery
+    int n;
+    double alpha;
+    const float* row;
+    const int64_t* qn;
+    __device__ __forceinline__ void init(int64_t q) { row = sim + q * row_stride; qn = q_nn + q * n; }
+    __device__ __forceinline__ double operator()(int64_t g) const {
+        int inter = 0;
+        for (int a = 0; a < n; ++a) {
+            const int64_t x = qn[a];
+            for (int b = 0; b < n; ++b) inter += (g_nn[g * n + b] == x) ? 1 : 0;
+        }
+        const double jac = (double)inter / (double)(2 * n - inter);        // |A & B| / |A | B| with |A| = |B| = n
+        return alpha * jac + (double)row[g * col_stride];
+    }
+};
+}  // namespace
+
+template <class Loader>
 __global__ void __launch_bounds__(RS_THREADS)
-rank_similarity_kernel(const float* __restrict__ sim, int64_t row_stride, int64_t col_stride, int64_t Q, int64_t G,
-                       const int64_t* __restrict__ rel_ptr, const int64_t* __restrict__ rel_col,
-                       float* __restrict__ cand_sim, int64_t* __restrict__ cand_idx, int32_t* __restrict__ cnt) {
-    __shared__ float p_s[RS_THREADS * TRB_TOPK];
+rank_scores_kernel(Loader ld, int64_t Q, int64_t G, const int64_t* __restrict__ rel_ptr, const int64_t* __restrict__ rel_col,
+                   float* __restrict__ cand_sim, int64_t* __restrict__ cand_idx, int32_t* __restrict__ cnt) {
+    using T = typename Loader::T;
+    __shared__ T p_s[RS_THREADS * TRB_TOPK];
     __shared__ int64_t p_i[RS_THREADS * TRB_TOPK];
-    __shared__ float th_s[RS_SLOTS];
+    __shared__ T th_s[RS_SLOTS];
     __shared__ int64_t th_i[RS_SLOTS];
     __shared__ int th_c[RS_SLOTS];
-    __shared__ float w_s[RS_THREADS / 32];
+    __shared__ T w_s[RS_THREADS / 32];
     __shared__ int64_t w_i[RS_THREADS / 32];
     __shared__ int w_p[RS_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t q = blockIdx.x;
-    const float* row = sim + q * row_stride;
+    ld.init(q);
 
-    TopK top;
+    TopKT<T> top;
     top.init();
-    for (int64_t g = tid; g < G; g += RS_THREADS) top.push(row[g * col_stride], g);
+    for (int64_t g = tid; g < G; g += RS_THREADS) top.push(ld(g), g);
 
     // ranks of the relevant items, RS_SLOTS thresholds at a time
     if (rel_ptr != nullptr) {
@@ -269,17 +313,23 @@ rank_similarity_kernel(const float* __restrict__ sim, int64_t row_stride, int64_
             if (tid < n) {
                 const int64_t g = rel_col[base + tid];
                 th_i[tid] = g;
-                th_s[tid] = row[g * col_stride];
+                th_s[tid] = ld(g);
                 th_c[tid] = 0;
             }
             __syncthreads();
-            for (int r = 0; r < n; ++r) {
-                const float th = th_s[r];
-                const int64_t ti = th_i[r];
-                int c = 0;
-                for (int64_t g = tid; g < G; g += RS_THREADS) c += ranks_before(row[g * col_stride], g, th, ti) ? 1 : 0;
-                c = warp_sum_i(c);
-                if (lane == 0 && c) atomicAdd(&th_c[r], c);
+            for (int r0 = 0; r0 < n; r0 += 8) {          // 8 thresholds per sweep: one score evaluation serves all of them
+                int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int64_t g = tid; g < G; g += RS_THREADS) {
+                    const T s = ld(g);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (r0 + j < n) c[j] += ranks_before(s, g, th_s[r0 + j], th_i[r0 + j]) ? 1 : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int t = warp_sum_i(c[j]);
+                    if (lane == 0 && t && r0 + j < n) atomicAdd(&th_c[r0 + j], t);
+                }
             }
             __syncthreads();
             if (tid < n) cnt[base + tid] = th_c[tid];
@@ -291,7 +341,7 @@ rank_similarity_kernel(const float* __restrict__ sim, int64_t row_stride, int64_
     for (int k = 0; k < TRB_TOPK; ++k) { p_s[tid * TRB_TOPK + k] = top.s[k]; p_i[tid * TRB_TOPK + k] = top.i[k]; }
     __syncthreads();
     for (int round = 0; round < TRB_TOPK; ++round) {
-        float bs = -CUDART_INF_F;
+        T bs = neg_inf<T>();
         int64_t bi = INT64_MAX;
         int bp = -1;
         for (int p = tid; p < RS_THREADS * TRB_TOPK; p += RS_THREADS) {
@@ -299,7 +349,7 @@ rank_similarity_kernel(const float* __restrict__ sim, int64_t row_stride, int64_
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const T os = __shfl_xor_sync(0xffffffffu, bs, o);
             const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
             const int op = __shfl_xor_sync(0xffffffffu, bp, o);
             if (ranks_before(os, oi, bs, bi)) { bs = os; bi = oi; bp = op; }
@@ -309,9 +359,9 @@ rank_similarity_kernel(const float* __restrict__ sim, int64_t row_stride, int64_
         if (tid == 0) {
             for (int w = 1; w < RS_THREADS / 32; ++w)
                 if (ranks_before(w_s[w], w_i[w], bs, bi)) { bs = w_s[w]; bi = w_i[w]; bp = w_p[w]; }
-            cand_sim[q * TRB_TOPK + round] = bs;
+            cand_sim[q * TRB_TOPK + round] = (float)bs;
             cand_idx[q * TRB_TOPK + round] = bi;
-            if (bp >= 0) { p_s[bp] = -CUDART_INF_F; p_i[bp] = INT64_MAX; }
+            if (bp >= 0) { p_s[bp] = neg_inf<T>(); p_i[bp] = INT64_MAX; }
         }
         __syncthreads();
     }
@@ -325,8 +375,60 @@ extern "C" int trb_rank_similarity_f32(const float* sim, int64_t row_stride, int
     TRB_REQUIRE((rel_ptr == nullptr) == (rel_col == nullptr) && (rel_ptr == nullptr) == (cnt == nullptr),
                 "rank_similarity: rel_ptr, rel_col and cnt must be given together");
     if (Q == 0) return 0;
-    rank_similarity_kernel<<<(unsigned)Q, RS_THREADS, 0, (cudaStream_t)stream>>>(sim, row_stride, col_stride, Q, G, rel_ptr,
-                                                                                rel_col, cand_sim, cand_idx, cnt);
+    SimLoader ld{sim, row_stride, col_stride, nullptr};
+    rank_scores_kernel<SimLoader><<<(unsigned)Q, RS_THREADS, 0, (cudaStream_t)stream>>>(ld, Q, G, rel_ptr, rel_col, cand_sim, cand_idx, cnt);
+    TRB_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int trb_rank_scores_f64(const double* scores, int64_t row_stride, int64_t col_stride, int64_t Q, int64_t G,
+                                   const int64_t* rel_ptr, const int64_t* rel_col, float* cand_sim, int64_t* cand_idx,
+                                   int32_t* cnt, trb_stream_t stream) {
+    TRB_REQUIRE(scores && cand_sim && cand_idx, "rank_scores_f64: null pointer");
+    TRB_REQUIRE(Q >= 0 && G >= 0, "rank_scores_f64: bad shape");
+    TRB_REQUIRE((rel_ptr == nullptr) == (rel_col == nullptr) && (rel_ptr == nullptr) == (cnt == nullptr),
+                "rank_scores_f64: rel_ptr, rel_col and cnt must be given together");
+    if (Q == 0) return 0;
+    F64Loader ld{scores, row_stride, col_stride, nullptr};
+    rank_scores_kernel<F64Loader><<<(unsigned)Q, RS_THREADS, 0, (cudaStream_t)stream>>>(ld, Q, G, rel_ptr, rel_col, cand_sim, cand_idx, cnt);
+    TRB_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int trb_rank_rerank_f64(const float* sim, int64_t row_stride, int64_t col_stride, int64_t Q, int64_t G,
+                                   const int64_t* q_nn, const int64_t* g_nn, int n_neighbors, double alpha,
+                                   const int64_t* rel_ptr, const int64_t* rel_col, float* cand_sim, int64_t* cand_idx,
+                                   int32_t* cnt, trb_stream_t stream) {
+    TRB_REQUIRE(sim && q_nn && g_nn && cand_sim && cand_idx, "rank_rerank: null pointer");
+    TRB_REQUIRE(Q >= 0 && G >= 0 && n_neighbors >= 1 && n_neighbors <= TRB_TOPK, "rank_rerank: bad shape (1 <= neighbours <= 10)");
+    TRB_REQUIRE((rel_ptr == nullptr) == (rel_col == nullptr) && (rel_ptr == nullptr) == (cnt == nullptr),
+                "rank_rerank: rel_ptr, rel_col and cnt must be given together");
+    if (Q == 0) return 0;
+    RerankLoader ld{sim, row_stride, col_stride, q_nn, g_nn, n_neighbors, alpha, nullptr, nullptr};
+    rank_scores_kernel<RerankLoader><<<(unsigned)Q, RS_THREADS, 0, (cudaStream_t)stream>>>(ld, Q, G, rel_ptr, rel_col, cand_sim, cand_idx, cnt);
+    TRB_LAUNCH_OK();
+    return 0;
+}
+
+// alpha * Jaccard matrix in float64, materialised (the rvn_mat / rtn_mat arrays of inference_data.npz, evaluation.py:126-142)
+__global__ void __launch_bounds__(256)
+jaccard_f64_kernel(const int64_t* __restrict__ q_nn, const int64_t* __restrict__ g_nn, int n, double alpha, double* __restrict__ out,
+                   int64_t Q, int64_t G) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Q * G) return;
+    const int64_t q = e / G, g = e % G;
+    int inter = 0;
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) inter += (q_nn[q * n + a] == g_nn[g * n + b]) ? 1 : 0;
+    out[e] = alpha * ((double)inter / (double)(2 * n - inter));
+}
+
+extern "C" int trb_jaccard_f64(const int64_t* q_nn, const int64_t* g_nn, int n_neighbors, double alpha, double* out, int64_t Q,
+                               int64_t G, trb_stream_t stream) {
+    TRB_REQUIRE(q_nn && g_nn && out, "jaccard: null pointer");
+    TRB_REQUIRE(Q >= 0 && G >= 0 && n_neighbors >= 1, "jaccard: bad shape");
+    if (Q * G == 0) return 0;
+    jaccard_f64_kernel<<<(unsigned)trb_ceil_div(Q * G, 256), 256, 0, (cudaStream_t)stream>>>(q_nn, g_nn, n_neighbors, alpha, out, Q, G);
     TRB_LAUNCH_OK();
     return 0;
 }
@@ -350,7 +452,21 @@ retrieval_finish_kernel(const float* __restrict__ cand_sim, const int64_t* __res
     int first_in_top = INT32_MAX;
     const int64_t qpid = (q_pids != nullptr) ? q_pids[q] : -1;
     constexpr int CPL = 8;                       // candidates per lane kept in registers (n <= 256)
-    if (n <= 32 * CPL) {
+    if (nlists == 1) {
+        // already best-first (possibly ordered by float64 scores that the fp32 copies cannot distinguish): pass through
+        if (lane < TRB_TOPK) {
+            int64_t i = ci[lane];
+            if (i == INT64_MAX) i = -1;
+            top_sim[q * TRB_TOPK + lane] = cs[lane];
+            top_idx[q * TRB_TOPK + lane] = i;
+        }
+        if (g_pids != nullptr) {
+            for (int r = 0; r < TRB_TOPK; ++r) {
+                const int64_t i = ci[r];
+                if (i >= 0 && i < G_total && g_pids[i] == qpid) { first_in_top = r; break; }
+            }
+        }
+    } else if (n <= 32 * CPL) {
         float rs[CPL];
         int64_t ri[CPL];
 #pragma unroll

@@ -301,7 +301,6 @@ def evaluation(dataset, predictions, output_folder, topk, save_data=True, rerank
     ``inference_data.npz`` from ``output_folder`` like the reference.  Re-ranking (k-reciprocal,
     evaluation.py:40-65) is applied when ``rerank`` is True.
     """
-    from .rerank import jaccard_rerank_rank
     logger = logging.getLogger("PersonSearch.inference")
     data_dir = os.path.join(output_folder, "inference_data.npz")
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -333,23 +332,25 @@ def evaluation(dataset, predictions, output_folder, topk, save_data=True, rerank
         similarity = rvn_mat = rtn_mat = None
 
     results = {}
+    from .rerank import jaccard_rerank_matrix, neighbor_lists, rerank_rank, similarity_matrix
     if similarity is None and not save_data and not rerank:
         # fast path (trainer.py:124): nothing needs the matrix
         t2i = retrieve(text_n, image_n, text_pid, image_pid, topk_list, get_mAP=False, precision=precision, normalized=True)
         i2t = retrieve(image_n, text_n, image_pid, text_pid, topk_list, get_mAP=False, precision=precision, normalized=True)
         results["t2i"], results["i2t"] = t2i.cmc, i2t.cmc
     else:
+        nn_t2i = nn_i2t = None
         if similarity is None:
-            from .rerank import similarity_matrix
             similarity = similarity_matrix(text_n, image_n)
             if rerank:
-                rtn_mat = jaccard_rerank_matrix_pair(image_n, text_n)
-                rvn_mat = jaccard_rerank_matrix_pair(text_n, image_n)
+                nn_t2i = neighbor_lists(text_n, image_n)      # (text -> image, image -> image)
+                nn_i2t = neighbor_lists(image_n, text_n)      # (image -> text, text -> text)
             if save_data:
                 payload = dict(image_pid=image_pid.cpu().numpy(), text_pid=text_pid.cpu().numpy(),
                                similarity=similarity.cpu().numpy())
                 if rerank:
-                    payload.update(rvn_mat=rvn_mat.cpu().numpy(), rtn_mat=rtn_mat.cpu().numpy())
+                    payload.update(rvn_mat=jaccard_rerank_matrix(text_n, image_n).cpu().numpy(),
+                                   rtn_mat=jaccard_rerank_matrix(image_n, text_n).cpu().numpy())
                 np.savez(data_dir, **payload)
         if rerank:
             sim_t = similarity.t()
@@ -357,10 +358,15 @@ def evaluation(dataset, predictions, output_folder, topk, save_data=True, rerank
             results["i2t"], results["i2t_mAP"] = c, m
             c, m, _ = rank(similarity, text_pid, image_pid, topk_list, get_mAP=True)
             results["t2i"], results["t2i_mAP"] = c, m
-            c, m = jaccard_rerank_rank(rtn_mat, sim_t, image_pid, text_pid, topk_list)
-            results["re_i2t"], results["re_i2t_mAP"] = c, m
-            c, m = jaccard_rerank_rank(rvn_mat, similarity, text_pid, image_pid, topk_list)
-            results["re_t2i"], results["re_t2i_mAP"] = c, m
+            if nn_t2i is not None:
+                r = rerank_rank(sim_t, nn_i2t[0], nn_i2t[1], image_pid, text_pid, topk_list)
+                results["re_i2t"], results["re_i2t_mAP"] = r.cmc, r.mAP
+                r = rerank_rank(similarity, nn_t2i[0], nn_t2i[1], text_pid, image_pid, topk_list)
+                results["re_t2i"], results["re_t2i_mAP"] = r.cmc, r.mAP
+            else:   # cached npz: the float64 matrices were loaded; their sum with the similarity is ranked as float64 scores
+                for key, mat, s_, qp, gp in (("re_i2t", rtn_mat, sim_t, image_pid, text_pid), ("re_t2i", rvn_mat, similarity, text_pid, image_pid)):
+                    c, m = _rank_float64_matrix(mat + s_, qp, gp, topk_list)
+                    results[key], results[key + "_mAP"] = c, m
         else:
             results["t2i"], _ = rank(similarity, text_pid, image_pid, topk_list, get_mAP=False)
             results["i2t"], _ = rank(similarity.t(), image_pid, text_pid, topk_list, get_mAP=False)
@@ -377,9 +383,21 @@ def evaluation(dataset, predictions, output_folder, topk, save_data=True, rerank
     return results["t2i"][0]
 
 
-def jaccard_rerank_matrix_pair(q_feats, g_feats):
-    from .rerank import jaccard_rerank_matrix
-    return jaccard_rerank_matrix(q_feats, g_feats)
+def _rank_float64_matrix(scores: torch.Tensor, q_pids, g_pids, topk):
+    """Cached-npz path: rank an already materialised float64 score matrix (evaluation.py:85-95, 151-156)."""
+    dev = scores.device
+    Q, G = scores.shape
+    q_pids = q_pids.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+    g_pids = g_pids.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+    rel = build_relevance(q_pids, g_pids)
+    cand_sim = torch.empty(Q, TOPK_DEPTH, dtype=torch.float32, device=dev)
+    cand_idx = torch.empty(Q, TOPK_DEPTH, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().trb_rank_scores_f64(_lib.ptr(scores), scores.stride(0), scores.stride(1), Q, G, _lib.ptr(rel.rel_ptr),
+                                               rel.col_ptr(), _lib.ptr(cand_sim), _lib.ptr(cand_idx), _lib.ptr(cnt),
+                                               _lib.stream_ptr(dev)), "trb_rank_scores_f64")
+    res = _finish_and_metrics(cand_sim, cand_idx, 1, q_pids, g_pids, rel, cnt, topk)
+    return res.cmc, res.mAP
 
 
 def compute_on_dataset(model, data_loader, device):

@@ -27,3 +27,20 @@ def main(N=128, D=256, K=2048, C=11003, iters=20):
 
 if __name__ == "__main__":
     main()
+
+def graph_only(iters=200):
+    """GPU time of the captured step alone (loss + gradients + enqueue), replayed back to back."""
+    from textreid_b200.losses import _GRAPHS
+    if not _GRAPHS:
+        return
+    g = next(iter(_GRAPHS.values()))[0]
+    for _ in range(10): g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters): g.replay()
+    b.record(); torch.cuda.synchronize()
+    print("graph replay alone: %.1f us/step" % (a.elapsed_time(b) * 1e3 / iters))
+
+if __name__ == "__main__":
+    graph_only()
