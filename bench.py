@@ -353,8 +353,11 @@ def main():
         roof = None
         if kern_ms:
             ach = flops / (kern_ms * 1e-3) / 1e12
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+            # (profiles/r01_ncu_retrieval_tc_final.md: 100k x 1M x 256 on one GPU); algorithmic bytes are 563 MB
+            traffic = 4.24e9 if (world == 1 and args.workload == "retrieval_1m" and args.precision == "bf16") else None
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": None, "kernel": "retrieval_tc_kernel<0>" if args.precision == "bf16" else "stream_f32_kernel",
+                    "traffic": traffic, "kernel": "retrieval_tc_kernel<0>" if args.precision == "bf16" else "stream_f32_kernel",
                     "kernel_ms": kern_ms, "peak_source": pk["source"] + " bf16 sustained (kernel timed back to back inside a long step)",
                     "algorithmic_flops_per_launch": flops}
             if args.precision == "fp32":

@@ -14,5 +14,5 @@ if [ "${1:-}" != "nobench" ]; then
   timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
   echo "bench exit $?" | tee -a gpurun_out/summary.txt
 fi
-tail -5 gpurun_out/pytest_simt.log gpurun_out/pytest_tc.log gpurun_out/smoke.log
-tail -c 3000 gpurun_out/bench.log 2>/dev/null
+for f in gpurun_out/pytest_simt.log gpurun_out/pytest_tc.log gpurun_out/smoke.log; do tail -n 3 $f; done
+tail -c 3000 gpurun_out/bench.log 2>/dev/null; true
