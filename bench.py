@@ -51,10 +51,12 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, enabled=True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:       # one sampler per job (rank 0): N concurrent nvidia-smi loops perturb the timed region
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -291,7 +293,7 @@ def main():
         res = step(text, image, q_pid, g_pid)
     barrier()
     _lib.reset_launch_count()
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
