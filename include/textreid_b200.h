@@ -221,7 +221,11 @@ int64_t trb_moco_loss_workspace_bytes(const trb_moco_shape* shape, int precision
  *   losses [3]               instance, infonce, global_align (each with upstream grad 1)
  *   d_inst, d_nce, d_ga      [2,N,D] per-loss gradients w.r.t. (v,t) embeds / qraw; NULL skips bwd
  *   d_projection [D,C]       gradient of instance_loss w.r.t. projection
- * The queue column mask (head.py:148-157) is evaluated on the device; no host sync. */
+ * The queue column mask (head.py:148-157) is evaluated on the device; no host sync.
+ * The three losses are independent between the shared prologue and the final reduction: the call forks two
+ * internal helper streams off `stream` (created once per device, joined back before the call's last launch), so the
+ * work is ordered after / before everything else on `stream` as usual and a CUDA-graph capture of the call yields a
+ * 3-wide DAG.  One trb_moco_loss call may be in flight per device at a time. */
 int trb_moco_loss(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
                   const float* v_key, const float* t_key, int normalize_keys, float* v_key_n,
                   float* t_key_n, const int64_t* labels, const float* v_queue, const float* t_queue,

@@ -237,15 +237,17 @@ loss_reduce_kernel(const float* __restrict__ inst_rows, const float* __restrict_
     }
 }
 
+constexpr int SPLIT_NCE = 8, SPLIT_INST = 32;
+
 struct Workspace {
     float *E2, *en, *qn, *inv_e, *inv_q, *pos, *dpos, *S_nce, *Z, *inv_c, *S_ga, *dq_nce, *dq_ga, *part, *rows_inst,
         *rows_nce, *rows_ga;
     uint8_t* mask;
-    uint8_t *pkA, *pkB;       // packed bf16 operand scratch of the tensor-core path
+    uint8_t *pkA, *pkB;       // packed bf16 operand scratch of the tensor-core path (instance branch)
+    uint8_t *pkA_nce, *pkB_nce, *pkA_ga, *pkB_ga;
+    float* part_nce;          // split-K partials of the InfoNCE branch
     int64_t bytes;
 };
-
-constexpr int SPLIT_NCE = 8, SPLIT_INST = 32;
 
 // split-K factor actually used: the tensor-core kernel cannot split finer than one 64-wide k-chunk per part
 static inline int eff_split(int split, int K, bool use_tc) {
@@ -255,12 +257,34 @@ static inline int eff_split(int split, int K, bool use_tc) {
 
 // One contraction, on the FFMA pipe (precision 0) or on the tensor cores (precision 1: both operands are first
 // rounded to bf16 into the packed tile-major layout, then tcgen05.mma accumulates in fp32).
-int run_gemm(const GemmArgs& g, bool use_tc, const Workspace& w, cudaStream_t st) {
+struct Scratch { uint8_t* pkA; uint8_t* pkB; };
+int run_gemm(const GemmArgs& g, bool use_tc, const Scratch& sc, cudaStream_t st) {
     if (!use_tc) return launch_gemm(g, st);
     int rc;
-    if ((rc = tc_pack_strided(g.A, g.a_sm, g.a_sk, g.M, g.K, g.kscale, nullptr, w.pkA, st))) return rc;
-    if ((rc = tc_pack_strided(g.B, g.b_sn, g.b_sk, g.N, g.K, nullptr, nullptr, w.pkB, st))) return rc;
-    return tc_gemm_launch(w.pkA, w.pkB, g.C, g.c_sm, g.c_split, g.M, g.N, g.K, g.splitk, g.nscale, st);
+    if ((rc = tc_pack_strided(g.A, g.a_sm, g.a_sk, g.M, g.K, g.kscale, nullptr, sc.pkA, st))) return rc;
+    if ((rc = tc_pack_strided(g.B, g.b_sn, g.b_sk, g.N, g.K, nullptr, nullptr, sc.pkB, st))) return rc;
+    return tc_gemm_launch(sc.pkA, sc.pkB, g.C, g.c_sm, g.c_split, g.M, g.N, g.K, g.splitk, g.nscale, st);
+}
+
+// The three loss branches (instance / InfoNCE / global-align) are independent between the prologue and the final
+// reduction; they run on the caller's stream plus two helper streams, forked and joined with events, so that a
+// captured CUDA graph becomes a 3-wide DAG instead of a chain of ~45 dependent small launches.  The helper streams and
+// events are process-level, created on first use (per device), and carry no data between calls.
+struct Fork { cudaStream_t s1, s2; cudaEvent_t fork, j1, j2; bool ok; };
+static Fork* helper_streams() {
+    static Fork pool[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    Fork& f = pool[dev];
+    if (!f.ok) {
+        if (cudaStreamCreateWithFlags(&f.s1, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&f.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.j1, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.j2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        f.ok = true;
+    }
+    return &f;
 }
 
 Workspace carve(void* base, int N, int D, int K, int C, bool use_tc) {
@@ -294,7 +318,18 @@ Workspace carve(void* base, int N, int D, int K, int C, bool use_tc) {
         for (int64_t x : candb) b = x > b ? x : b;
         w.pkA = reinterpret_cast<uint8_t*>(take(a / 4 + 64));
         w.pkB = reinterpret_cast<uint8_t*>(take(b / 4 + 64));
+        const int64_t an = tc_gemm_packed_bytes(N, K) > tc_gemm_packed_bytes(N, D) ? tc_gemm_packed_bytes(N, K) : tc_gemm_packed_bytes(N, D);
+        const int64_t bn = tc_gemm_packed_bytes(K, D) > tc_gemm_packed_bytes(D, K) ? tc_gemm_packed_bytes(K, D) : tc_gemm_packed_bytes(D, K);
+        w.pkA_nce = reinterpret_cast<uint8_t*>(take(an / 4 + 64));
+        w.pkB_nce = reinterpret_cast<uint8_t*>(take(bn / 4 + 64));
+        const int64_t ag = tc_gemm_packed_bytes(N, N) > tc_gemm_packed_bytes(N, D) ? tc_gemm_packed_bytes(N, N) : tc_gemm_packed_bytes(N, D);
+        const int64_t bg = tc_gemm_packed_bytes(N, D) > tc_gemm_packed_bytes(D, N) ? tc_gemm_packed_bytes(N, D) : tc_gemm_packed_bytes(D, N);
+        w.pkA_ga = reinterpret_cast<uint8_t*>(take(ag / 4 + 64));
+        w.pkB_ga = reinterpret_cast<uint8_t*>(take(bg / 4 + 64));
+    } else {
+        w.pkA_nce = w.pkB_nce = w.pkA_ga = w.pkB_ga = nullptr;
     }
+    w.part_nce = take((int64_t)SPLIT_NCE * N * D);
     w.bytes = p - static_cast<char*>(base);
     return w;
 }
@@ -323,79 +358,90 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     const bool grads = d_inst != nullptr;
     const int rows = 2 * N;
 
+    Fork* fk = helper_streams();
+    if (fk == nullptr) { trb_set_error("moco_loss: could not create helper streams"); return TRB_ERR_INVALID; }
+    cudaStream_t s_nce = fk->s1, s_ga = fk->s2;          // the instance branch stays on the caller's stream
+    const Scratch sc_inst{w.pkA, w.pkB}, sc_nce{w.pkA_nce, w.pkB_nce}, sc_ga{w.pkA_ga, w.pkB_ga};
+    const int64_t ND = (int64_t)N * D;
+    const int split_nce = eff_split(SPLIT_NCE, K, use_tc), split_inst = eff_split(SPLIT_INST, C, use_tc);
+    int rc;
+
+    // ---- shared prologue on the caller's stream
     prologue_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, normalize_keys,
                                                           v_key_n, t_key_n, w.E2, w.en, w.inv_e, w.qn, w.inv_q, w.pos, N, D);
     TRB_LAUNCH_OK();
-    queue_mask_kernel<<<(K + 255) / 256, 256, N * sizeof(int64_t), st>>>(id_queue, labels, w.mask, N, K);
-    TRB_LAUNCH_OK();
-    column_inv_norm_kernel<<<(C + 31) / 32, 256, 0, st>>>(projection, w.inv_c, D, C);
-    TRB_LAUNCH_OK();
+    TRB_CUDA_OK(cudaEventRecord(fk->fork, st));
+    TRB_CUDA_OK(cudaStreamWaitEvent(s_nce, fk->fork, 0));
+    TRB_CUDA_OK(cudaStreamWaitEvent(s_ga, fk->fork, 0));
 
-    int rc;
-    // ---- InfoNCE logits: v queries x text queue, t queries x image queue (head.py:164,170)
+    // ---- InfoNCE branch (helper stream 1): mask, logits of v queries x text queue and t queries x image queue
+    //      (head.py:148-170), row-wise CE (losses.py:206-217), dq = dS @ queue^T + dpos * key, normalise backward
+    queue_mask_kernel<<<(K + 255) / 256, 256, N * sizeof(int64_t), s_nce>>>(id_queue, labels, w.mask, N, K);
+    TRB_LAUNCH_OK();
     for (int mod = 0; mod < 2; ++mod) {
         GemmArgs g{w.qn + (int64_t)mod * N * D, D, 1, mod ? v_queue : t_queue, K, 1,
                    w.S_nce + (int64_t)mod * N * K, K, 0, N, K, D, nullptr, nullptr, 1};
-        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
+        if ((rc = run_gemm(g, use_tc, sc_nce, s_nce))) return rc;
     }
-    nce_rows_kernel<<<rows, 256, 0, st>>>(w.S_nce, w.pos, w.mask, hp->T, N, K, w.rows_nce, w.dpos, grads);
+    nce_rows_kernel<<<rows, 256, 0, s_nce>>>(w.S_nce, w.pos, w.mask, hp->T, N, K, w.rows_nce, w.dpos, grads);
     TRB_LAUNCH_OK();
+    if (grads) {
+        for (int mod = 0; mod < 2; ++mod) {
+            GemmArgs g{w.S_nce + (int64_t)mod * N * K, K, 1, mod ? v_queue : t_queue, 1, K,
+                       w.part_nce, D, ND, N, D, K, nullptr, nullptr, split_nce};
+            if ((rc = run_gemm(g, use_tc, sc_nce, s_nce))) return rc;
+            reduce_partials_kernel<<<(unsigned)((ND + 255) / 256), 256, 0, s_nce>>>(w.dq_nce + mod * ND, w.part_nce, split_nce, ND);
+            TRB_LAUNCH_OK();
+        }
+        normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, s_nce>>>(w.dq_nce, w.dpos, v_key_n, t_key_n, w.qn, w.inv_q, d_nce, N, D);
+        TRB_LAUNCH_OK();
+    }
+    TRB_CUDA_OK(cudaEventRecord(fk->j1, s_nce));
 
-    // ---- instance logits for both modalities at once (losses.py:53-54)
+    // ---- global-align branch (helper stream 2): S = q_v q_t^T (losses.py:114), pair losses, dq_v = dS q_t, dq_t = dS^T q_v
+    {
+        GemmArgs g{w.en, D, 1, w.en + ND, 1, D, w.S_ga, N, 0, N, N, D, nullptr, nullptr, 1};
+        if ((rc = run_gemm(g, use_tc, sc_ga, s_ga))) return rc;
+    }
+    align_rows_kernel<<<N, 128, 0, s_ga>>>(w.S_ga, labels, hp->alpha, hp->beta, hp->scale_pos, hp->scale_neg, N, w.rows_ga, grads);
+    TRB_LAUNCH_OK();
+    if (grads) {
+        GemmArgs gv{w.S_ga, N, 1, w.en + ND, D, 1, w.dq_ga, D, 0, N, D, N, nullptr, nullptr, 1};
+        if ((rc = run_gemm(gv, use_tc, sc_ga, s_ga))) return rc;
+        GemmArgs gt{w.S_ga, 1, N, w.en, D, 1, w.dq_ga + ND, D, 0, N, D, N, nullptr, nullptr, 1};
+        if ((rc = run_gemm(gt, use_tc, sc_ga, s_ga))) return rc;
+        normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, s_ga>>>(w.dq_ga, nullptr, nullptr, nullptr, w.en, w.inv_e, d_ga, N, D);
+        TRB_LAUNCH_OK();
+    }
+    TRB_CUDA_OK(cudaEventRecord(fk->j2, s_ga));
+
+    // ---- instance branch (caller's stream): column norms, logits of both modalities at once (losses.py:51-54),
+    //      label-smoothed CE rows, dE = dZ @ What^T (split over classes), dWhat = E^T @ dZ, column-normalisation Jacobian
+    column_inv_norm_kernel<<<(C + 31) / 32, 256, 0, st>>>(projection, w.inv_c, D, C);
+    TRB_LAUNCH_OK();
     {
         GemmArgs g{w.E2, D, 1, projection, C, 1, w.Z, C, 0, rows, C, D, nullptr, w.inv_c, 1};
-        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
+        if ((rc = run_gemm(g, use_tc, sc_inst, st))) return rc;
     }
     instance_rows_kernel<<<rows, 256, 0, st>>>(w.Z, labels, hp->epsilon, N, C, w.rows_inst, grads);
     TRB_LAUNCH_OK();
-
-    // ---- global align similarity (losses.py:114)
-    {
-        GemmArgs g{w.en, D, 1, w.en + (int64_t)N * D, 1, D, w.S_ga, N, 0, N, N, D, nullptr, nullptr, 1};
-        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
-    }
-    align_rows_kernel<<<N, 128, 0, st>>>(w.S_ga, labels, hp->alpha, hp->beta, hp->scale_pos, hp->scale_neg, N, w.rows_ga, grads);
-    TRB_LAUNCH_OK();
-
-    loss_reduce_kernel<<<1, 256, 0, st>>>(w.rows_inst, w.rows_nce, w.rows_ga, N, losses);
-    TRB_LAUNCH_OK();
-    if (!grads) return 0;
-
-    const int64_t ND = (int64_t)N * D;
-    // ---- InfoNCE backward: dq = dS @ queue^T (+ dpos * key), through the normalisation
-    const int split_nce = eff_split(SPLIT_NCE, K, use_tc), split_inst = eff_split(SPLIT_INST, C, use_tc);
-    for (int mod = 0; mod < 2; ++mod) {
-        GemmArgs g{w.S_nce + (int64_t)mod * N * K, K, 1, mod ? v_queue : t_queue, 1, K,
-                   w.part, D, ND, N, D, K, nullptr, nullptr, split_nce};
-        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
-        reduce_partials_kernel<<<(unsigned)((ND + 255) / 256), 256, 0, st>>>(w.dq_nce + mod * ND, w.part, split_nce, ND);
-        TRB_LAUNCH_OK();
-    }
-    normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w.dq_nce, w.dpos, v_key_n, t_key_n, w.qn, w.inv_q, d_nce, N, D);
-    TRB_LAUNCH_OK();
-
-    // ---- instance backward: dE = dZ @ What^T (split over classes), dWhat = E^T @ dZ
-    {
+    if (grads) {
         GemmArgs g{w.Z, C, 1, projection, 1, C, w.part, D, 2 * ND, rows, D, C, w.inv_c, nullptr, split_inst};
-        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
+        if ((rc = run_gemm(g, use_tc, sc_inst, st))) return rc;
         reduce_partials_kernel<<<(unsigned)((2 * ND + 255) / 256), 256, 0, st>>>(d_inst, w.part, split_inst, 2 * ND);
         TRB_LAUNCH_OK();
-    }
-    if (d_projection) {
-        GemmArgs g{w.E2, 1, D, w.Z, C, 1, d_projection, C, 0, D, C, rows, nullptr, nullptr, 1};
-        if ((rc = run_gemm(g, use_tc, w, st))) return rc;
-        projection_backward_kernel<<<(C + 31) / 32, 256, 0, st>>>(d_projection, projection, w.inv_c, D, C);
-        TRB_LAUNCH_OK();
+        if (d_projection) {
+            GemmArgs g2{w.E2, 1, D, w.Z, C, 1, d_projection, C, 0, D, C, rows, nullptr, nullptr, 1};
+            if ((rc = run_gemm(g2, use_tc, sc_inst, st))) return rc;
+            projection_backward_kernel<<<(C + 31) / 32, 256, 0, st>>>(d_projection, projection, w.inv_c, D, C);
+            TRB_LAUNCH_OK();
+        }
     }
 
-    // ---- global align backward: dq_v = dS @ q_t, dq_t = dS^T @ q_v, through the normalisation
-    {
-        GemmArgs gv{w.S_ga, N, 1, w.en + ND, D, 1, w.dq_ga, D, 0, N, D, N, nullptr, nullptr, 1};
-        if ((rc = run_gemm(gv, use_tc, w, st))) return rc;
-        GemmArgs gt{w.S_ga, 1, N, w.en, D, 1, w.dq_ga + ND, D, 0, N, D, N, nullptr, nullptr, 1};
-        if ((rc = run_gemm(gt, use_tc, w, st))) return rc;
-    }
-    normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w.dq_ga, nullptr, nullptr, nullptr, w.en, w.inv_e, d_ga, N, D);
+    // ---- join, then the three loss scalars in a fixed reduction order
+    TRB_CUDA_OK(cudaStreamWaitEvent(st, fk->j1, 0));
+    TRB_CUDA_OK(cudaStreamWaitEvent(st, fk->j2, 0));
+    loss_reduce_kernel<<<1, 256, 0, st>>>(w.rows_inst, w.rows_nce, w.rows_ga, N, losses);
     TRB_LAUNCH_OK();
     return 0;
 }
