@@ -25,8 +25,7 @@ descending sort.  ``rank(..., stable=True)`` is therefore the default.
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence
 
 import torch
 

@@ -1,7 +1,6 @@
 """CPU-side tests: the C-ABI library loads and exports every symbol the header declares, and the
 host-side index logic (relevance CSR, first-occurrence dedup, work splitting, packed layout) is right.
 No compute call is made here (no GPU in the build container)."""
-import ctypes
 import os
 import re
 

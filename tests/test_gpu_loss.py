@@ -1,6 +1,5 @@
 """GPU parity tests of the MoCo loss step (loss dict + gradients, EMA, enqueue) against the golden
 fixtures of the unmodified reference and against the CPU oracle.  `pytest -m gpu` on a B200."""
-import copy
 import os
 from types import SimpleNamespace
 

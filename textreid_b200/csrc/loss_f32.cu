@@ -125,7 +125,8 @@ nce_rows_kernel(float* __restrict__ S, const float* __restrict__ pos, const uint
     if (threadIdx.x == 0) dpos[row] = (expf(z0 - lse) - 1.0f) * gscale;
 }
 
-// instance loss with label smoothing (losses.py:26-39, 53-60).  Z row [C].
+// instance loss with label smoothing (losses.py:26-39, 53-60).  Z row [C].  One sweep gathers (max, sum exp, sum z)
+// with the online-softmax recurrence, a second sweep writes the logit gradient in place.
 __global__ void __launch_bounds__(256)
 instance_rows_kernel(float* __restrict__ Z, const int64_t* __restrict__ labels, float eps, int N, int C,
                      float* __restrict__ loss_row, int want_grad) {
@@ -133,13 +134,16 @@ instance_rows_kernel(float* __restrict__ Z, const int64_t* __restrict__ labels, 
     const int row = blockIdx.x;
     float* z = Z + (int64_t)row * C;
     const int y = (int)labels[row % N];
-    float mx = -CUDART_INF_F, sz = 0.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) { const float v = z[c]; mx = fmaxf(mx, v); sz += v; }
-    mx = block_max(mx, red);
+    float m = -CUDART_INF_F, se = 0.f, sz = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = z[c];
+        sz += v;
+        if (v > m) { se = se * expf(m - v) + 1.0f; m = v; }
+        else se += expf(v - m);
+    }
+    const float mx = block_max(m, red);
+    se = block_sum(se * expf(m - mx), red);       // threads with no element carry m = -inf, se = 0 -> contribute 0
     sz = block_sum(sz, red);
-    float se = 0.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) se += expf(z[c] - mx);
-    se = block_sum(se, red);
     const float lse = mx + logf(se);
     const float zy = z[y];
     __syncthreads();
@@ -244,7 +248,7 @@ struct Workspace {
         *rows_nce, *rows_ga;
     uint8_t* mask;
     uint8_t *pkA, *pkB;       // packed bf16 operand scratch of the tensor-core path (instance branch)
-    uint8_t *pkA_nce, *pkB_nce, *pkA_ga, *pkB_ga;
+    uint8_t *pkA_nce, *pkB_nce, *pkA_ga, *pkB_ga, *pkA_dw, *pkB_dw;
     float* part_nce;          // split-K partials of the InfoNCE branch
     int64_t bytes;
 };
@@ -270,7 +274,7 @@ int run_gemm(const GemmArgs& g, bool use_tc, const Scratch& sc, cudaStream_t st)
 // reduction; they run on the caller's stream plus two helper streams, forked and joined with events, so that a
 // captured CUDA graph becomes a 3-wide DAG instead of a chain of ~45 dependent small launches.  The helper streams and
 // events are process-level, created on first use (per device), and carry no data between calls.
-struct Fork { cudaStream_t s1, s2; cudaEvent_t fork, j1, j2; bool ok; };
+struct Fork { cudaStream_t s1, s2, s3; cudaEvent_t fork, fork3, j1, j2, j3; bool ok; };
 static Fork* helper_streams() {
     static Fork pool[16] = {};
     int dev = 0;
@@ -279,6 +283,9 @@ static Fork* helper_streams() {
     if (!f.ok) {
         if (cudaStreamCreateWithFlags(&f.s1, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithFlags(&f.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&f.s3, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.fork3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.j3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&f.j1, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&f.j2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -326,8 +333,10 @@ Workspace carve(void* base, int N, int D, int K, int C, bool use_tc) {
         const int64_t bg = tc_gemm_packed_bytes(N, D) > tc_gemm_packed_bytes(D, N) ? tc_gemm_packed_bytes(N, D) : tc_gemm_packed_bytes(D, N);
         w.pkA_ga = reinterpret_cast<uint8_t*>(take(ag / 4 + 64));
         w.pkB_ga = reinterpret_cast<uint8_t*>(take(bg / 4 + 64));
+        w.pkA_dw = reinterpret_cast<uint8_t*>(take(tc_gemm_packed_bytes(D, 2 * N) / 4 + 64));
+        w.pkB_dw = reinterpret_cast<uint8_t*>(take(tc_gemm_packed_bytes(C, 2 * N) / 4 + 64));
     } else {
-        w.pkA_nce = w.pkB_nce = w.pkA_ga = w.pkB_ga = nullptr;
+        w.pkA_nce = w.pkB_nce = w.pkA_ga = w.pkB_ga = w.pkA_dw = w.pkB_dw = nullptr;
     }
     w.part_nce = take((int64_t)SPLIT_NCE * N * D);
     w.bytes = p - static_cast<char*>(base);
@@ -361,7 +370,7 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     Fork* fk = helper_streams();
     if (fk == nullptr) { trb_set_error("moco_loss: could not create helper streams"); return TRB_ERR_INVALID; }
     cudaStream_t s_nce = fk->s1, s_ga = fk->s2;          // the instance branch stays on the caller's stream
-    const Scratch sc_inst{w.pkA, w.pkB}, sc_nce{w.pkA_nce, w.pkB_nce}, sc_ga{w.pkA_ga, w.pkB_ga};
+    const Scratch sc_inst{w.pkA, w.pkB}, sc_nce{w.pkA_nce, w.pkB_nce}, sc_ga{w.pkA_ga, w.pkB_ga}, sc_dw{w.pkA_dw, w.pkB_dw};
     const int64_t ND = (int64_t)N * D;
     const int split_nce = eff_split(SPLIT_NCE, K, use_tc), split_inst = eff_split(SPLIT_INST, C, use_tc);
     int rc;
@@ -426,16 +435,21 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     instance_rows_kernel<<<rows, 256, 0, st>>>(w.Z, labels, hp->epsilon, N, C, w.rows_inst, grads);
     TRB_LAUNCH_OK();
     if (grads) {
+        // the two contractions with dZ are independent: dWhat goes to helper stream 3
+        if (d_projection) {
+            TRB_CUDA_OK(cudaEventRecord(fk->fork3, st));
+            TRB_CUDA_OK(cudaStreamWaitEvent(fk->s3, fk->fork3, 0));
+            GemmArgs g2{w.E2, 1, D, w.Z, C, 1, d_projection, C, 0, D, C, rows, nullptr, nullptr, 1};
+            if ((rc = run_gemm(g2, use_tc, sc_dw, fk->s3))) return rc;
+            projection_backward_kernel<<<(C + 31) / 32, 256, 0, fk->s3>>>(d_projection, projection, w.inv_c, D, C);
+            TRB_LAUNCH_OK();
+            TRB_CUDA_OK(cudaEventRecord(fk->j3, fk->s3));
+        }
         GemmArgs g{w.Z, C, 1, projection, 1, C, w.part, D, 2 * ND, rows, D, C, w.inv_c, nullptr, split_inst};
         if ((rc = run_gemm(g, use_tc, sc_inst, st))) return rc;
         reduce_partials_kernel<<<(unsigned)((2 * ND + 255) / 256), 256, 0, st>>>(d_inst, w.part, split_inst, 2 * ND);
         TRB_LAUNCH_OK();
-        if (d_projection) {
-            GemmArgs g2{w.E2, 1, D, w.Z, C, 1, d_projection, C, 0, D, C, rows, nullptr, nullptr, 1};
-            if ((rc = run_gemm(g2, use_tc, sc_inst, st))) return rc;
-            projection_backward_kernel<<<(C + 31) / 32, 256, 0, st>>>(d_projection, projection, w.inv_c, D, C);
-            TRB_LAUNCH_OK();
-        }
+        if (d_projection) TRB_CUDA_OK(cudaStreamWaitEvent(st, fk->j3, 0));
     }
 
     // ---- join, then the three loss scalars in a fixed reduction order

@@ -603,11 +603,22 @@ retrieval_metrics_kernel(const int32_t* __restrict__ first_hit, const float* __r
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double s = 0.0;
-    for (int64_t q = tid; q < Q; q += 1024) {
-        const int32_t fh = first_hit[q];
+    // fixed assignment q = tid + 1024*j, four independent loads in flight per thread
+    for (int64_t q0 = tid; q0 < Q; q0 += 4096) {
+        int32_t fh[4];
+        float a[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) c[i] += (i < cuts.n && fh < cuts.k[i]) ? 1 : 0;
-        if (ap) s += (double)ap[q];
+        for (int u = 0; u < 4; ++u) {
+            const int64_t q = q0 + 1024 * u;
+            fh[u] = q < Q ? first_hit[q] : INT32_MAX;
+            a[u] = (ap && q < Q) ? ap[q] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] += (i < cuts.n && fh[u] < cuts.k[i]) ? 1 : 0;
+            s += (double)a[u];
+        }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

@@ -9,7 +9,7 @@ three losses AND their gradients come out of one stream-ordered library call in 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, Iterable, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -26,7 +26,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .evaluation import (RelevanceIndex, RetrievalResult, TOPK_DEPTH, _choose_nsplit, _finish_and_metrics, _sm_count,
-                         _stream_fp32, _topk_host_array, build_relevance, l2_normalize_rows)
+                         _stream_fp32, _topk_host_array, l2_normalize_rows)
 
 
 class PhaseTimer:

@@ -18,7 +18,6 @@ import argparse
 import os
 import sys
 import tempfile
-import types
 from types import SimpleNamespace
 
 import numpy as np

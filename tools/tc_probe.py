@@ -1,8 +1,7 @@
 """Probe of the tensor-core stream kernel: where does the time go? (run on the GPU box)"""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import textreid_b200 as trb
 from textreid_b200.synthetic import eval_data
 from textreid_b200.sharded import ShardWorker, CudaBackend
 
