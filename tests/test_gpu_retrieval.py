@@ -330,3 +330,45 @@ def test_evaluation_entry_matches_reference_golden(golden_dir, tmp_path):
     assert torch.equal(r1c.cpu(), torch.from_numpy(g["rerank.r1"]))
     for key in ("re_t2i", "re_i2t"):
         assert torch.equal(evaluation.last_results[key].cpu(), torch.from_numpy(g["rerank.%s_cmc" % key])), key
+
+
+def test_inference_entry_runs_model_and_evaluates(golden_dir, tmp_path):
+    """inference(model, data_loader, ...) (lib/engine/inference.py:48-96): encode with the model's eval branch, evaluate,
+    return t2i R@1 -- here with a stub model that replays the golden embeddings."""
+    from textreid_b200.evaluation import inference
+    g = load(golden_dir, "evaluation_small")
+    v, t = torch.from_numpy(g["v"]), torch.from_numpy(g["t"])
+    n = v.shape[0]
+
+    class Cap:
+        def __init__(self, i): self.i = i
+        def to(self, device): return self
+
+    class Loader:
+        dataset = _DS([int(x) for x in g["image_ids"]], [int(x) for x in g["pids"]])
+        def __iter__(self):
+            for b0 in range(0, n, 16):
+                idx = list(range(b0, min(b0 + 16, n)))
+                yield torch.tensor(idx, dtype=torch.float32).unsqueeze(1), [Cap(i) for i in idx], tuple(idx)
+
+    class Model(torch.nn.Module):
+        def forward(self, images, captions):
+            idx = images[:, 0].long().cpu()
+            return [v[idx].to(images.device), t[idx].to(images.device)]
+
+    r1 = inference(Model(), Loader(), device=DEV, output_folder=str(tmp_path), save_data=False, rerank=False)
+    assert torch.equal(r1.cpu(), torch.from_numpy(g["plain.r1"]))
+    r1 = inference(Model(), Loader(), device=DEV, output_folder=str(tmp_path), save_data=True, rerank=True)
+    assert torch.equal(r1.cpu(), torch.from_numpy(g["rerank.r1"]))
+    assert os.path.exists(os.path.join(str(tmp_path), "inference_data.npz"))
+    r1 = inference(Model(), Loader(), device=DEV, output_folder=str(tmp_path), save_data=False, rerank=True)   # cached npz path
+    assert torch.equal(r1.cpu(), torch.from_numpy(g["rerank.r1"]))
+
+
+def test_tensor_core_path_rejects_unsupported_embedding_size():
+    text, image, tpid, ipid = make_case(64, 300, 1024, n_ids=50, seed=2)
+    with pytest.raises(RuntimeError, match="unsupported|multiple of 64"):
+        trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "bf16")
+    text, image, tpid, ipid = make_case(64, 300, 40, n_ids=50, seed=2)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "bf16")
