@@ -372,3 +372,22 @@ def test_tensor_core_path_rejects_unsupported_embedding_size():
     text, image, tpid, ipid = make_case(64, 300, 40, n_ids=50, seed=2)
     with pytest.raises(RuntimeError, match="multiple of 64"):
         trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "bf16")
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_sharded_tie_heavy_exact_fixture(precision):
+    """Three uneven gallery shards on the tie-heavy exact-arithmetic fixture: ties that straddle shard boundaries must still
+    be ordered by global gallery index (position-based >= / > thresholds in the tensor-core stream)."""
+    from textreid_b200.sharded import retrieve_sharded_local
+    gen = torch.Generator().manual_seed(123)
+    Q, G, D = 200, 1500, 256
+    image = (torch.randint(0, 2, (G, D), generator=gen).float() * 2 - 1) / 16.0
+    text = (torch.randint(0, 2, (Q, D), generator=gen).float() * 2 - 1) / 16.0
+    ipid = torch.randint(0, 60, (G,), generator=gen)          # ~25 relevant items per query: register + overflow slots
+    tpid = ipid[torch.randint(0, G, (Q,), generator=gen)].clone()
+    cuts = [0, 300, 301, 1100, G]                              # includes a one-row shard
+    shards = [T(image[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    pids = [T(ipid[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    res = retrieve_sharded_local(T(text), shards, T(tpid), pids, (1, 5, 10), True, precision)
+    sim = O.similarity_matrix(text, image)
+    check_against_matrix(res, sim, tpid, ipid, ap_rtol=2e-6)
