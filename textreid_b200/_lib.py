@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtextreid_b200.so")
+LIB_PATH = os.environ.get("TRB_LIB") or os.path.join(_HERE, "libtextreid_b200.so")   # TRB_LIB: A/B tuning builds
 
 TOPK_DEPTH = 10
 

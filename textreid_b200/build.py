@@ -47,6 +47,27 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def build_variant(defs, out_name: str) -> str:
+    """A/B builds for tuning: same sources with extra -D defines, linked to a differently named library that
+    TRB_LIB=<path> makes the loader pick up."""
+    nvcc = _nvcc()
+    out_dir = os.path.join(OBJ_DIR, out_name)
+    os.makedirs(out_dir, exist_ok=True)
+    objs = []
+    for src in sources():
+        obj = os.path.join(out_dir, os.path.basename(src)[:-3] + ".o")
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *defs, "-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr)
+        objs.append(obj)
+    path = os.path.join(HERE, out_name + ".so")
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", path, *objs, "-Xcompiler", "-fPIC",
+                        "-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    return path
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]

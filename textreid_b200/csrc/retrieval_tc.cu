@@ -24,9 +24,12 @@ constexpr int TILE_M = 128;          // queries per CTA tile (TMEM lanes)
 constexpr int TILE_N = 256;          // gallery rows per MMA tile (TMEM columns per buffer)
 constexpr int UMMA_K = 16;
 constexpr int STAGE_BYTES = 2 * BLOCK_BYTES;   // 256 gallery rows x 64 k  = 32 KiB
-constexpr int NUM_THREADS = 640;
+#ifndef TRB_EPI_WARPS
+#define TRB_EPI_WARPS 16
+#endif
+constexpr int NUM_THREADS = 128 + 32 * TRB_EPI_WARPS;
 constexpr int EPI_WARP0 = 4;
-constexpr int NUM_EPI_WARPS = 16;
+constexpr int NUM_EPI_WARPS = TRB_EPI_WARPS;
 constexpr int COLS_PER_WARP = TILE_N / (NUM_EPI_WARPS / 4);   // 64 accumulator columns per epilogue warp
 constexpr int CHUNKS_PER_WARP = COLS_PER_WARP / 32;
 constexpr int LISTS_PER_SPLIT = NUM_EPI_WARPS / 4;            // candidate lists a query gets per gallery split
