@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "sgemm.cuh"
 #include "tc_gemm.cuh"
+#include "loss_fused.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -250,8 +252,19 @@ struct Workspace {
     uint8_t *pkA, *pkB;       // packed bf16 operand scratch of the tensor-core path (instance branch)
     uint8_t *pkA_nce, *pkB_nce, *pkA_ga, *pkB_ga, *pkA_dw, *pkB_dw;
     float* part_nce;          // split-K partials of the InfoNCE branch
+    uint8_t* fused;           // scratch of the fused cooperative kernel (loss_fused.cu); null when the shape does not fit it
     int64_t bytes;
 };
+
+// SM count of the current device (148 when there is none, e.g. a size query in a CPU-only build container)
+static int sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+        cudaGetLastError();
+        return 148;
+    }
+    return sms;
+}
 
 // split-K factor actually used: the tensor-core kernel cannot split finer than one 64-wide k-chunk per part
 static inline int eff_split(int split, int K, bool use_tc) {
@@ -339,6 +352,9 @@ Workspace carve(void* base, int N, int D, int K, int C, bool use_tc) {
         w.pkA_nce = w.pkB_nce = w.pkA_ga = w.pkB_ga = w.pkA_dw = w.pkB_dw = nullptr;
     }
     w.part_nce = take((int64_t)SPLIT_NCE * N * D);
+    w.fused = nullptr;
+    if (use_tc && fused_loss_supported(N, D, K, C, sm_count()))
+        w.fused = reinterpret_cast<uint8_t*>(take(fused_loss_scratch_bytes(N, D, K, C) / 4 + 64));
     w.bytes = p - static_cast<char*>(base);
     return w;
 }
@@ -375,16 +391,40 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     const int split_nce = eff_split(SPLIT_NCE, K, use_tc), split_inst = eff_split(SPLIT_INST, C, use_tc);
     int rc;
 
-    // ---- shared prologue on the caller's stream
-    prologue_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, normalize_keys,
-                                                          v_key_n, t_key_n, w.E2, w.en, w.inv_e, w.qn, w.inv_q, w.pos, N, D);
-    TRB_LAUNCH_OK();
+    // ---- fused path: when the shape fits, the prologue plus ONE cooperative tcgen05 kernel (loss_fused.cu) replace the
+    //      branches named in `roles` (bit 0 instance, 1 InfoNCE, 2 align; TRB_FUSED_ROLES narrows it for debugging)
+    int roles = 0;
+    FusedLossArgs fa;
+    if (w.fused != nullptr) {
+        roles = 7;
+        if (const char* e = getenv("TRB_FUSED_ROLES")) roles = atoi(e) & 7;
+    }
+    if (roles) {
+        fa.N = N; fa.D = D; fa.K = K; fa.C = C;
+        fa.T = hp->T; fa.eps = hp->epsilon; fa.alpha = hp->alpha; fa.beta = hp->beta; fa.sp = hp->scale_pos; fa.sn = hp->scale_neg;
+        fa.v_embed = v_embed; fa.t_embed = t_embed; fa.v_qraw = v_qraw; fa.t_qraw = t_qraw; fa.v_key = v_key; fa.t_key = t_key;
+        fa.normalize_keys = normalize_keys; fa.labels = labels; fa.id_queue = id_queue;
+        fa.v_queue = v_queue; fa.t_queue = t_queue; fa.projection = projection;
+        fa.v_key_n = v_key_n; fa.t_key_n = t_key_n; fa.E2 = w.E2; fa.en = w.en; fa.qn = w.qn; fa.inv_e = w.inv_e; fa.inv_q = w.inv_q;
+        fa.pos = w.pos; fa.dpos = w.dpos; fa.rows_inst = w.rows_inst; fa.rows_nce = w.rows_nce; fa.rows_ga = w.rows_ga;
+        fa.losses = losses; fa.d_inst = d_inst; fa.d_nce = d_nce; fa.d_ga = d_ga; fa.d_proj = d_projection;
+        fa.scratch = w.fused; fa.roles = roles; fa.reduce_losses = roles == 7;
+        if ((rc = fused_loss_prologue(fa, st))) return rc;
+        if (roles == 7) return fused_loss_launch(fa, st);       // the whole step: two launches, no helper streams
+    } else {
+        // ---- shared prologue on the caller's stream
+        prologue_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, normalize_keys,
+                                                              v_key_n, t_key_n, w.E2, w.en, w.inv_e, w.qn, w.inv_q, w.pos, N, D);
+        TRB_LAUNCH_OK();
+    }
     TRB_CUDA_OK(cudaEventRecord(fk->fork, st));
     TRB_CUDA_OK(cudaStreamWaitEvent(s_nce, fk->fork, 0));
     TRB_CUDA_OK(cudaStreamWaitEvent(s_ga, fk->fork, 0));
+    if (roles && (rc = fused_loss_launch(fa, st))) return rc;
 
     // ---- InfoNCE branch (helper stream 1): mask, logits of v queries x text queue and t queries x image queue
     //      (head.py:148-170), row-wise CE (losses.py:206-217), dq = dS @ queue^T + dpos * key, normalise backward
+    if (!(roles & 2)) {
     queue_mask_kernel<<<(K + 255) / 256, 256, N * sizeof(int64_t), s_nce>>>(id_queue, labels, w.mask, N, K);
     TRB_LAUNCH_OK();
     for (int mod = 0; mod < 2; ++mod) {
@@ -405,9 +445,11 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
         normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, s_nce>>>(w.dq_nce, w.dpos, v_key_n, t_key_n, w.qn, w.inv_q, d_nce, N, D);
         TRB_LAUNCH_OK();
     }
+    }
     TRB_CUDA_OK(cudaEventRecord(fk->j1, s_nce));
 
     // ---- global-align branch (helper stream 2): S = q_v q_t^T (losses.py:114), pair losses, dq_v = dS q_t, dq_t = dS^T q_v
+    if (!(roles & 4)) {
     {
         GemmArgs g{w.en, D, 1, w.en + ND, 1, D, w.S_ga, N, 0, N, N, D, nullptr, nullptr, 1};
         if ((rc = run_gemm(g, use_tc, sc_ga, s_ga))) return rc;
@@ -422,10 +464,12 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
         normalize_backward_kernel<<<(rows + 7) / 8, 256, 0, s_ga>>>(w.dq_ga, nullptr, nullptr, nullptr, w.en, w.inv_e, d_ga, N, D);
         TRB_LAUNCH_OK();
     }
+    }
     TRB_CUDA_OK(cudaEventRecord(fk->j2, s_ga));
 
     // ---- instance branch (caller's stream): column norms, logits of both modalities at once (losses.py:51-54),
     //      label-smoothed CE rows, dE = dZ @ What^T (split over classes), dWhat = E^T @ dZ, column-normalisation Jacobian
+    if (!(roles & 1)) {
     column_inv_norm_kernel<<<(C + 31) / 32, 256, 0, st>>>(projection, w.inv_c, D, C);
     TRB_LAUNCH_OK();
     {
@@ -450,6 +494,7 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
         reduce_partials_kernel<<<(unsigned)((2 * ND + 255) / 256), 256, 0, st>>>(d_inst, w.part, split_inst, 2 * ND);
         TRB_LAUNCH_OK();
         if (d_projection) TRB_CUDA_OK(cudaStreamWaitEvent(st, fk->j3, 0));
+    }
     }
 
     // ---- join, then the three loss scalars in a fixed reduction order
