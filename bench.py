@@ -183,28 +183,58 @@ def secondary_measurements(pk, device):
     # (device-side) so that the queue never degenerates into "every slot masked".
     N, D, K, C = 128, 256, 2048, 11003
     bytes_alg = 27.8e6            # queues + projection read + dProjection write + embeddings
+    launches = {}
     for prec in ("bf16", "fp32"):
-        for graph in (True, False):
+        for mode in ("stepgraph", "graph", "eager"):
             inp = {k: v.to(device) for k, v in synth_loss_inputs(N, D, K, C, seed=0).items()}
             ve, te, pr = inp["v_embed"].requires_grad_(True), inp["t_embed"].requires_grad_(True), inp["projection"].requires_grad_(True)
             ptr = torch.zeros(1, dtype=torch.int64, device=device)
             labels = inp["labels"]
 
-            def loss_step():
+            def loss_step(inner_graph):
                 labels.add_(97).remainder_(C)
                 d = trb.moco_loss_dict(ve, te, inp["v_key"], inp["t_key"], labels, inp["v_queue"], inp["t_queue"], inp["id_queue"],
-                                       ptr, pr, epsilon=0.1, enqueue=True, precision=prec, cuda_graph=graph)
-                ve.grad = te.grad = pr.grad = None
+                                       ptr, pr, epsilon=0.1, enqueue=True, precision=prec, cuda_graph=inner_graph)
                 (d["instance_loss"] + d["infonce_loss"] + d["global_align_loss"]).backward()
 
-            med, best = time_cuda(loss_step, 40, 8, flush)
-            key = "moco_loss_%s%s" % (prec, "_graph" if graph else "")
+            if mode == "stepgraph":
+                # the whole trainer-style step (loss dict -> sum -> backward -> enqueue) captured once with torch.cuda.graph and
+                # replayed: the way a production loop removes the host from the path; gradients land in static .grad tensors
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        ve.grad = te.grad = pr.grad = None
+                        loss_step(False)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                ve.grad = te.grad = pr.grad = None
+                whole = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(whole):
+                    loss_step(False)
+                fn = whole.replay
+            else:
+                def fn(inner=(mode == "graph")):
+                    ve.grad = te.grad = pr.grad = None
+                    loss_step(inner)
+
+            med, best = time_cuda(fn, 40, 8, flush)
+            key = "moco_loss_%s_%s" % (prec, mode)
             out[key] = {
                 "metric": "MoCo loss steps/s (loss dict fwd+bwd + enqueue, bs128, queue 2048, D=256, C=11003)", "value": 1e3 / med,
-                "unit": "steps/s", "ms_per_step": med, "dtype": "bf16" if prec == "bf16" else "f32", "cuda_graph": graph, "l2_flushed": True,
+                "unit": "steps/s", "ms_per_step": med, "ms_best": best, "dtype": "bf16" if prec == "bf16" else "f32",
+                "mode": {"stepgraph": "whole step captured in one CUDA graph (torch.cuda.graph around loss dict + backward)",
+                         "graph": "library call replayed from its own CUDA graph, autograd glue eager",
+                         "eager": "every launch issued from Python"}[mode],
+                "l2_flushed": True,
                 "roofline": {"bound": "hbm", "achieved": bytes_alg / (med * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                              "frac": bytes_alg / (med * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
-                             "note": "whole step incl. host-side autograd, algorithmic 27.8 MB"}}
+                             "note": "whole step (two label kernels, loss dict + gradients, loss sum, backward combine, enqueue); "
+                                     "algorithmic 27.8 MB"}}
+            del fn
+        shape = trb._lib.MocoShape(N, D, K, C)
+        launches[prec] = int(trb._lib.load().trb_moco_loss_launches(__import__("ctypes").byref(shape), 1 if prec == "bf16" else 0))
+    out["moco_loss_kernel_launches"] = launches
     # ---- EMA over an RN50+GRU-sized arena: 41,755,488 fp32 parameters ----
     P = 41_755_488
     pk_, pq_ = torch.randn(P, device=device), torch.randn(P, device=device)

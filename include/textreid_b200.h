@@ -207,6 +207,11 @@ typedef struct trb_moco_hparams {
 
 int64_t trb_moco_loss_workspace_bytes(const trb_moco_shape* shape, int precision);
 
+/* Kernel launches one trb_moco_loss call issues for this shape on the current device: 2 when precision = 1 takes the fused
+ * path (prologue + one cooperative tcgen05 kernel; needs N <= 128, D a multiple of 64 up to 256 and
+ * ceil(C/128) + 2*ceil(K/128) + 1 <= #SMs), otherwise the length of the unfused launch sequence. */
+int trb_moco_loss_launches(const trb_moco_shape* shape, int precision);
+
 /* Loss dict and its gradients in one stream-ordered call (fwd and bwd fused: the softmax
  * statistics are consumed where they are produced, nothing is saved for a later backward).
  *   v_embed, t_embed [N,D]   post-Linear, un-normalised (instance + global-align inputs)
@@ -216,7 +221,9 @@ int64_t trb_moco_loss_workspace_bytes(const trb_moco_shape* shape, int precision
  *                            (head.py:139,145) and written to v_key_n / t_key_n [N,D]
  *   labels [N] int64; v_queue, t_queue [D,K]; id_queue [K] int64 (-1 = empty slot)
  *   projection [D,C]
- *   precision: 0 = fp32 FFMA path (parity, 1e-5); 1 = bf16 tcgen05 path (1e-3)
+ *   precision: 0 = fp32 FFMA path (parity, 1e-5); 1 = bf16 tcgen05 path (1e-3): operands rounded once to bf16, fp32
+ *              accumulation in TMEM, softmax / loss math in fp32.  Shapes that fit (trb_moco_loss_launches == 2) run as ONE
+ *              cooperative kernel in which logits, softmax statistics and logit gradients never leave the SM.
  * outputs
  *   losses [3]               instance, infonce, global_align (each with upstream grad 1)
  *   d_inst, d_nce, d_ga      [2,N,D] per-loss gradients w.r.t. (v,t) embeds / qraw; NULL skips bwd
@@ -238,6 +245,17 @@ int trb_moco_loss(const float* v_embed, const float* t_embed, const float* v_qra
  * be NULL).  Backward of the loss dict without a host sync (trainer.py:82,90 uses g = 1,1,1). */
 int trb_combine3_f32(float* out, const float* a, const float* b, const float* c, const float* g,
                      int64_t n, trb_stream_t stream);
+
+/* Whole backward of the loss dict in ONE launch: the per-loss gradients saved by trb_moco_loss times the three upstream
+ * gradients (DEVICE scalars; NULL = that loss did not take part in the backward pass, trainer.py:82,90 passes 1,1,1):
+ *   out_v / out_t [N,D]   = g_inst * d_inst[m] + g_nce * d_nce[m] + g_ga * d_ga[m]          (m = 0 image, 1 text)
+ *   separate_q (cfg.MODEL.MOCO.FC, head.py:118-124): the InfoNCE term goes to out_vq / out_tq instead
+ *   out_proj [D,C]        = g_inst * d_proj   (NULL skips it; g_inst == 1 is a plain copy)
+ * nd = N*D, dc = D*C. */
+int trb_moco_grad_combine(const float* d_inst, const float* d_nce, const float* d_ga, const float* d_proj,
+                          const float* g_inst, const float* g_nce, const float* g_ga, int separate_q, int64_t nd,
+                          int64_t dc, float* out_v, float* out_t, float* out_vq, float* out_tq, float* out_proj,
+                          trb_stream_t stream);
 
 /* x *= g[0] unless g[0] == 1 (then no memory traffic). */
 int trb_scale_inplace_f32(float* x, const float* g, int64_t n, trb_stream_t stream);

@@ -249,3 +249,144 @@ def test_cuda_graph_replay_matches_eager(precision):
     for e, g in zip(runs[False], runs[True]):
         assert e[0] == g[0] and e[3] == g[3]
         assert torch.equal(e[1], g[1]) and torch.equal(e[2], g[2]) and torch.equal(e[4], g[4]) and torch.equal(e[5], g[5])
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused cooperative kernel (csrc/loss_fused.cu): precision="bf16" takes it whenever the shape fits
+# ---------------------------------------------------------------------------------------------------
+import ctypes as C
+
+from textreid_b200 import _lib
+
+ARGS = ("v_embed", "t_embed", "v_key", "t_key", "labels", "v_queue", "t_queue", "id_queue", "projection")
+
+
+def _launches(N, D, K, Cn, precision):
+    shape = _lib.MocoShape(N, D, K, Cn)
+    return int(_lib.load().trb_moco_loss_launches(C.byref(shape), precision))
+
+
+def test_fused_shape_gate():
+    """Two launches (prologue + cooperative kernel) exactly where the fused path applies."""
+    assert _launches(128, 256, 2048, 11003, 1) == 2          # BASELINE configs[1]
+    assert _launches(32, 64, 128, 257, 1) == 2               # D padded to 128
+    assert _launches(100, 192, 200, 257, 1) == 2             # ragged K and C tiles
+    assert _launches(256, 256, 4096, 11003, 1) > 2           # N > 128: generic launch sequence
+    assert _launches(20, 48, 60, 77, 1) > 2                  # D not a multiple of 64
+    assert _launches(128, 256, 2048, 40000, 1) > 2           # more tiles than SMs
+    assert _launches(128, 256, 2048, 11003, 0) > 2           # fp32 path is never fused
+
+
+@pytest.mark.parametrize("N,D,K,Cn,masked", [(128, 256, 2048, 11003, "some"), (100, 192, 200, 257, "some"), (32, 64, 128, 1000, "empty"),
+                                              (8, 128, 384, 130, "some")])
+def test_fused_matches_unfused_bf16(monkeypatch, N, D, K, Cn, masked):
+    """The fused kernel and the generic bf16 launch sequence round the same operands to bf16: losses agree to fp32 level,
+    gradients far inside the bf16 budget.  Both are checked against the fp64 oracle."""
+    assert _launches(N, D, K, Cn, 1) == 2
+    inp = synth_loss_inputs(N, D, K, Cn, seed=N + K, masked=masked)
+    fused = run_fused(inp, 0.1, precision="bf16")
+    monkeypatch.setenv("TRB_FUSED_ROLES", "0")
+    plain = run_fused(inp, 0.1, precision="bf16")
+    monkeypatch.delenv("TRB_FUSED_ROLES")
+    for k in KEYS:
+        torch.testing.assert_close(fused[0][k], plain[0][k], rtol=2e-5, atol=1e-5)
+    for a, b in zip(fused[1:], plain[1:]):
+        err = (a - b).abs().max() / b.abs().max()
+        assert float(err) < 1e-2, float(err)
+    args = [inp[k].double() if inp[k].dtype.is_floating_point else inp[k] for k in ARGS]
+    losses, rv, rt, rp = O.moco_loss_dict_with_grads(*args, epsilon=0.1)
+    for k in KEYS:
+        torch.testing.assert_close(fused[0][k].cpu().double(), losses[k], rtol=1e-3, atol=1e-4)
+    for got, ref in zip(fused[1:], (rv, rt, rp)):
+        cos = torch.nn.functional.cosine_similarity(got.cpu().double().flatten(), ref.flatten(), dim=0)
+        assert float(cos) > 0.9995, float(cos)
+
+
+def test_fused_edge_cases_all_masked_and_eps0():
+    """Every queue slot masked (K' = 0: only the positive logit is left, infonce = 0) and label smoothing off."""
+    N, D, K, Cn = 16, 64, 128, 300
+    inp = synth_loss_inputs(N, D, K, Cn, seed=5, masked="some")
+    inp["id_queue"][:] = inp["labels"][0]
+    d, gv, gt, gp = run_fused(inp, 0.0, precision="bf16")
+    args = [inp[k].double() if inp[k].dtype.is_floating_point else inp[k] for k in ARGS]
+    losses, rv, rt, rp = O.moco_loss_dict_with_grads(*args, epsilon=0.0)
+    assert float(d["infonce_loss"]) == 0.0 and float(losses["infonce_loss"]) == 0.0
+    for k in KEYS:
+        torch.testing.assert_close(d[k].cpu().double(), losses[k], rtol=1e-3, atol=1e-4)
+    for got, ref in ((gv, rv), (gt, rt), (gp, rp)):
+        assert float((got.cpu().double() - ref).abs().max() / ref.abs().max()) < 4e-2
+    assert torch.isfinite(gv).all() and torch.isfinite(gp).all()
+
+
+def test_fused_separate_queries_and_key_normalisation():
+    """cfg.MODEL.MOCO.FC = True (head.py:118-124): InfoNCE queries come from their own head; keys arrive un-normalised."""
+    N, D, K, Cn = 64, 256, 512, 2000
+    inp = {k: v.to(DEV) for k, v in synth_loss_inputs(N, D, K, Cn, seed=11).items()}
+    g = torch.Generator().manual_seed(3)
+    vq_raw, tq_raw = torch.randn(N, D, generator=g).to(DEV), torch.randn(N, D, generator=g).to(DEV)
+    vk_raw, tk_raw = 3.0 * inp["v_key"], 0.5 * inp["t_key"]
+    leaves = [inp["v_embed"].clone().requires_grad_(True), inp["t_embed"].clone().requires_grad_(True),
+              vq_raw.clone().requires_grad_(True), tq_raw.clone().requires_grad_(True), inp["projection"].clone().requires_grad_(True)]
+    ptr = torch.zeros(1, dtype=torch.int64, device=DEV)
+    d = trb.moco_loss_dict(leaves[0], leaves[1], vk_raw, tk_raw, inp["labels"], inp["v_queue"].clone(), inp["t_queue"].clone(),
+                           inp["id_queue"].clone(), ptr, leaves[4], epsilon=0.1, enqueue=False, v_embed_q=leaves[2], t_embed_q=leaves[3],
+                           normalize_keys=True, precision="bf16")
+    sum(d.values()).backward()
+    ref_leaves = [x.detach().cpu().double().requires_grad_(True) for x in leaves]
+    c = {k: (v.cpu().double() if v.dtype.is_floating_point else v.cpu()) for k, v in inp.items()}
+    rd = O.moco_loss_dict(ref_leaves[0], ref_leaves[1], c["v_key"], c["t_key"], c["labels"], c["v_queue"], c["t_queue"], c["id_queue"],
+                          ref_leaves[4], epsilon=0.1, v_embed_q=ref_leaves[2], t_embed_q=ref_leaves[3])
+    sum(rd.values()).backward()
+    for k in KEYS:
+        torch.testing.assert_close(d[k].detach().cpu().double(), rd[k].detach(), rtol=1e-3, atol=1e-4)
+    for got, ref in zip(leaves, ref_leaves):
+        err = (got.grad.cpu().double() - ref.grad).abs().max() / ref.grad.abs().max()
+        assert float(err) < 2e-2, float(err)
+
+
+def test_fused_forward_only_and_repeatability():
+    """No tensor requires grad -> the library skips the backward half; repeated calls are bit-identical (fixed-order reductions,
+    no atomics)."""
+    inp = {k: v.to(DEV) for k, v in synth_loss_inputs(128, 256, 2048, 11003, seed=9).items()}
+    ptr = torch.zeros(1, dtype=torch.int64, device=DEV)
+
+    def call(grad):
+        ve, te, pr = (inp[k].clone().requires_grad_(grad) for k in ("v_embed", "t_embed", "projection"))
+        d = trb.moco_loss_dict(ve, te, inp["v_key"], inp["t_key"], inp["labels"], inp["v_queue"], inp["t_queue"], inp["id_queue"],
+                               ptr, pr, epsilon=0.1, enqueue=False, precision="bf16")
+        if grad:
+            sum(d.values()).backward()
+        return [d[k].detach().clone() for k in KEYS], ([ve.grad.clone(), te.grad.clone(), pr.grad.clone()] if grad else None)
+
+    l0, _ = call(False)
+    l1, g1 = call(True)
+    l2, g2 = call(True)
+    for a, b, c in zip(l0, l1, l2):
+        assert torch.equal(a, b) and torch.equal(b, c)
+    for a, b in zip(g1, g2):
+        assert torch.equal(a, b)
+
+
+def test_grad_combine_single_launch_backward():
+    """trb_moco_grad_combine = g_inst * d_inst + g_nce * d_nce + g_ga * d_ga (+ projection), upstream scalars read on the device."""
+    lib = _lib.load()
+    N, D, Cn = 24, 64, 131
+    g = torch.Generator().manual_seed(0)
+    d_inst, d_nce, d_ga = (torch.randn(2, N, D, generator=g).to(DEV) for _ in range(3))
+    d_proj = torch.randn(D, Cn, generator=g).to(DEV)
+    gs = [torch.tensor(x, device=DEV) for x in (0.5, -2.0, 3.0)]
+    for separate in (0, 1):
+        for g_inst in (gs[0], torch.tensor(1.0, device=DEV), None):
+            ov, ot, ovq, otq = (torch.full((N, D), float("nan"), device=DEV) for _ in range(4))
+            op = torch.full((D, Cn), float("nan"), device=DEV)
+            _lib.check(lib.trb_moco_grad_combine(_lib.ptr(d_inst), _lib.ptr(d_nce), _lib.ptr(d_ga), _lib.ptr(d_proj), _lib.ptr(g_inst),
+                                                 _lib.ptr(gs[1]), _lib.ptr(gs[2]), separate, N * D, D * Cn, _lib.ptr(ov), _lib.ptr(ot),
+                                                 _lib.ptr(ovq) if separate else None, _lib.ptr(otq) if separate else None, _lib.ptr(op),
+                                                 _lib.stream_ptr(DEV)), "trb_moco_grad_combine")
+            gi = 0.0 if g_inst is None else float(g_inst)
+            for m, (o, oq) in enumerate(((ov, ovq), (ot, otq))):
+                want = gi * d_inst[m] + 3.0 * d_ga[m] + (0 if separate else -2.0 * d_nce[m])
+                torch.testing.assert_close(o, want, rtol=1e-6, atol=1e-6)
+                if separate:
+                    torch.testing.assert_close(oq, -2.0 * d_nce[m], rtol=0, atol=0)
+            torch.testing.assert_close(op, gi * d_proj, rtol=0, atol=0)

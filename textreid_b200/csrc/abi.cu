@@ -38,6 +38,12 @@ extern "C" int64_t trb_moco_loss_workspace_bytes(const trb_moco_shape* shape, in
     return TRB_ERR_INVALID;
 }
 
+int trb_moco_loss_launches_impl(const trb_moco_shape* s, int precision);
+extern "C" int trb_moco_loss_launches(const trb_moco_shape* shape, int precision) {
+    if (check_shape(shape)) return TRB_ERR_INVALID;
+    return trb_moco_loss_launches_impl(shape, precision);
+}
+
 extern "C" int trb_moco_loss(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
                              const float* v_key, const float* t_key, int normalize_keys, float* v_key_n, float* t_key_n,
                              const int64_t* labels, const float* v_queue, const float* t_queue, const int64_t* id_queue,

@@ -368,6 +368,15 @@ int64_t trb_moco_loss_workspace_bytes_tc(const trb_moco_shape* s) {
     return carve(nullptr, s->N, s->D, s->K, s->C, true).bytes;
 }
 
+// launches of one call (grads and d_projection requested); mirrors the sequence below
+int trb_moco_loss_launches_impl(const trb_moco_shape* s, int precision) {
+    const bool use_tc = precision == 1;
+    if (use_tc && fused_loss_supported(s->N, s->D, s->K, s->C, sm_count()) && !getenv("TRB_FUSED_ROLES")) return 2;
+    const int per_gemm = use_tc ? 3 : 1;
+    // prologue, mask, column norms, 3 row kernels, 2 normalise-backward, projection backward, loss reduce, 3 partial reductions
+    return 13 + 10 * per_gemm;
+}
+
 static int moco_loss_impl(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
                           const float* v_key, const float* t_key, int normalize_keys, float* v_key_n, float* t_key_n,
                           const int64_t* labels, const float* v_queue, const float* t_queue, const int64_t* id_queue,

@@ -30,7 +30,7 @@ constexpr int F_DZ_BYTES = 2 * BLOCK_BYTES;         // 32 KiB   logit gradient o
 constexpr int F_WB_BYTES = 2 * 256 * 128;           // 64 KiB   W / queue tile: [2 column chunks][256 d][128 B]
 constexpr int F_WB_CHUNK = 256 * 128;
 constexpr int F_OFF_E = 0, F_OFF_DZ = F_E_BYTES, F_OFF_WB = F_OFF_DZ + F_DZ_BYTES, F_OFF_MISC = F_OFF_WB + F_WB_BYTES;
-constexpr int F_MISC_BYTES = 1024;
+constexpr int F_MISC_BYTES = 2048;
 constexpr int F_SMEM = F_OFF_MISC + F_MISC_BYTES + 1024;   // + alignment slack
 
 struct FP {
@@ -41,8 +41,10 @@ struct FP {
     const float* key_n[2];          // positive key of modality m: [0] = t_key_n, [1] = v_key_n            (head.py:160,166)
     const int64_t *labels, *id_queue;
     const uint8_t *Ep, *ENp, *QNp;
+    const uint8_t* QUp;             // bf16 tile images of the two queues [modality][tile][64 KiB], written by the prologue
     const float *en, *qn, *inv_e, *inv_q, *pos;
-    float4 *st_inst, *st_nce;
+    float2 *ms_inst, *zz_inst, *ms_nce;     // per-tile softmax statistics [tile][256 rows]: (max, sum exp) and (sum z, z_y)
+    unsigned long long* dbg;                // optional phase timestamps [cta][16] (TRB_FUSED_DEBUG)
     float *part_inst, *part_nce, *dpos, *rows_inst, *rows_nce, *rows_ga, *losses, *d_inst, *d_nce, *d_ga, *d_proj;
     unsigned* bar;
 };
@@ -97,59 +99,138 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// fp32 tile src[d, c0 + c] (d < nrows, c < 128) -> bf16 image in shared memory; per-column sums of squares -> red[8][128]
+// Column order of warp w's rows (d = w mod 8): columns are rotated by `head` so that every warp-wide access of 32 consecutive
+// floats starts on a 32-byte sector of the row-major [*, ld] matrix (rows are only 4-byte aligned when ld is odd); the one
+// access that wraps around holds the two ragged tile edges.
+__device__ __forceinline__ int sector_head(int w, int64_t ld, int c0) { return (8 - (int)(((int64_t)w * ld + c0) & 7)) & 7; }
+
+// fp32 tile src[d, c0 + c] (d < nrows, c < 128) -> bf16 image in shared memory; per-column sums of squares -> red[8][128].
+// Warp w takes rows d = w + 8 i, so (d & 7) == w and (d >> 3) == i: the swizzled column part of the address is a per-thread
+// constant.  All loads of the tile are issued before the first use; `rot` staggers the row order between CTAs so that CTAs
+// sweeping the same rows of a power-of-two-pitched matrix do not hit the same DRAM channels in lock step.
 __device__ __forceinline__ void load_tile_bf16(const float* __restrict__ src, int64_t ld, int nrows, int rows_pad, int c0,
-                                               int ncols, uint8_t* wb, float* red) {
+                                               int ncols, int rot, bool use_head, uint8_t* wb, float* red) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = use_head ? sector_head(w, ld, c0) : 0;
+    const int groups = rows_pad >> 3;                      // 16 or 32 row groups
     float ss[4] = {0.f, 0.f, 0.f, 0.f};
     bool cv[4];
+    int cc[4];
+    uint8_t* dst[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cv[j] = c0 + lane + 32 * j < ncols;
-    for (int i0 = 0; i0 < rows_pad / 8; i0 += 4) {
-        float v[4][4];
+    for (int j = 0; j < 4; ++j) {
+        const int c = (head + lane + 32 * j) & 127;
+        cc[j] = c;
+        cv[j] = c0 + c < ncols;
+        dst[j] = wb + (c >> 6) * F_WB_CHUNK + w * 128 + ((((c & 63) >> 3) ^ w) << 4) + (c & 7) * 2;
+    }
+    const float* base = src + (int64_t)w * ld + c0;
+    float v[32][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int d = w + 8 * (i0 + u);
+    for (int u = 0; u < 32; ++u) {
+        const int i = (u + rot) & (groups - 1);
+        const bool rv = u < groups && w + 8 * i < nrows;
+        const float* r = base + (int64_t)(8 * i) * ld;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                v[u][j] = (d < nrows && cv[j]) ? __ldg(src + (int64_t)d * ld + c0 + lane + 32 * j) : 0.f;
-        }
+        for (int j = 0; j < 4; ++j) v[u][j] = (rv && cv[j]) ? __ldcg(r + cc[j]) : 0.f;   // L2 only: with a power-of-two pitch
+                                                                                          // every row of the tile maps to the same L1 sets
+    }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int d = w + 8 * (i0 + u);
+    for (int u = 0; u < 32; ++u) {
+        const int i = (u + rot) & (groups - 1);
+        if (u < groups) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 ss[j] = fmaf(v[u][j], v[u][j], ss[j]);
-                *reinterpret_cast<__nv_bfloat16*>(wb + wb_offset(d, lane + 32 * j)) = __float2bfloat16_rn(v[u][j]);
+                *reinterpret_cast<__nv_bfloat16*>(dst[j] + i * 1024) = __float2bfloat16_rn(v[u][j]);
             }
         }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[w * 128 + lane + 32 * j] = ss[j];
+    for (int j = 0; j < 4; ++j) red[w * 128 + cc[j]] = ss[j];
 }
 
 struct Smem {
     uint8_t *E, *DZ, *WB;
-    float* inv;            // [128] column scale: 1/||w_c|| (instance) or 1/T (InfoNCE); 0 for excluded columns
-    uint32_t* valid;       // [4]   bit c: column takes part in the softmax
-    uint64_t *bar_load, *bar_mma;
+    float2* col;           // [128] per column: (scale * log2(e), 0 or F_NEG); scale = 1/||w_c|| (instance) or 1/T (InfoNCE), 0 if excluded
+    uint64_t *bar_load, *bar_mma, *bar_dw;
     uint32_t* tmem_slot;
     float* red32;          // [32]  block_sum scratch
 };
 
-// combine the per-tile softmax statistics of one row: returns lse; sz / zy = sums of the 3rd / 4th statistic
-__device__ __forceinline__ float combine_stats(const float4* __restrict__ st, int tiles, float m0, float s0, float& sz, float& zy) {
-    float M = m0, S = s0;
-    sz = 0.f; zy = 0.f;
-    for (int t = 0; t < tiles; ++t) {
-        const float4 a = __ldcg(st + t);
-        sz += a.z; zy += a.w;
-        if (a.y > 0.f) {
-            if (a.x > M) { S = S * expf(M - a.x) + a.y; M = a.x; }
-            else S += a.y * expf(a.x - M);
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define F_STAMP(k)                                                                                     \
+    do {                                                                                               \
+        if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + (k)] = globaltimer_ns();     \
+    } while (0)
+
+constexpr float F_NEG = -1e30f;
+constexpr float F_LOG2E = 1.4426950408889634f, F_LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2(float x) {      // 2^x, MUFU.EX2; underflows to exactly 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// one full 32-byte sector per lane: no partial-sector writes (which cost a read-modify-write in L2 on ECC memory)
+__device__ __forceinline__ void st_v8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}      // finite stand-in for -inf in the running maxima (exp underflows to exactly 0)
+
+// base-2 log-sum-exp of one row from the per-tile statistics ms[tile][256] = (max2, sum 2^(z2 - max2)); (M, S) = running start.
+// 32 independent loads in flight per batch: the loop is latency-, not bandwidth-bound.
+__device__ __forceinline__ float lse2_of_row(const float2* __restrict__ ms, int row, int tiles, float M, float S) {
+    for (int t0 = 0; t0 < tiles; t0 += 48) {
+        float2 a[48];
+#pragma unroll
+        for (int i = 0; i < 48; ++i) a[i] = __ldcg(ms + (size_t)min(t0 + i, tiles - 1) * 256 + row);
+        asm volatile("" ::: "memory");
+        float mb = M;
+#pragma unroll
+        for (int i = 0; i < 48; ++i) {
+            if (t0 + i >= tiles) a[i] = make_float2(F_NEG, 0.f);
+            a[i].x = fmaxf(a[i].x, F_NEG);
+            mb = fmaxf(mb, a[i].x);
+        }
+        float acc = S * ex2(M - mb);
+#pragma unroll
+        for (int i = 0; i < 48; ++i) acc += a[i].y * ex2(a[i].x - mb);
+        M = mb; S = acc;
+    }
+    return M + log2f(S);
+}
+__device__ __forceinline__ float2 sum_of_row(const float2* __restrict__ zz, int row, int tiles) {
+    float sx = 0.f, sy = 0.f;
+    for (int t0 = 0; t0 < tiles; t0 += 32) {
+        float2 a[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = (t0 + i < tiles) ? __ldcg(zz + (size_t)(t0 + i) * 256 + row) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { sx += a[i].x; sy += a[i].y; }
+    }
+    return make_float2(sx, sy);
+}
+
+// u[i] of lane L = value of column i held by row L.  Returns, in lane L, the sum over the 32 rows of column L
+// (butterfly transpose-reduce: 31 shuffles, fixed order).
+__device__ __forceinline__ float lane_transpose_sum(float (&u)[32], int lane) {
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const bool up = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < step; ++i) {
+            const float send = up ? u[i] : u[i + step];
+            const float keep = up ? u[i + step] : u[i];
+            u[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
         }
     }
-    return M + logf(S);
+    return u[0];
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -166,42 +247,56 @@ __device__ void tile_program(const FP& p, const Smem& sm, uint32_t tmem, int mod
     const int tiles = INST ? p.T_inst : p.T_k;
     const uint32_t lanes = (uint32_t)(q * 32) << 16;
     uint32_t mma_phase = 0;
-    float* red = reinterpret_cast<float*>(sm.DZ);      // [8][128] + [128]: free whenever no logit gradient is staged
+    // scratch inside the logit-gradient region while no gradient is staged there
+    float* red = reinterpret_cast<float*>(sm.DZ);                        // [8][128] column partials
+    int64_t* s_lab = reinterpret_cast<int64_t*>(sm.DZ + 8192);           // [128] batch ids (InfoNCE mask)
+    float* s_lse2 = reinterpret_cast<float*>(sm.DZ + 16384);             // [256] base-2 row log-sum-exp
 
-    // ---- operand rows: packed bf16 image written by the prologue (instance: raw embeds, both modalities; InfoNCE: q rows)
+    // ---- operand rows: packed bf16 image written by the prologue (instance: raw embeds, both modalities; InfoNCE: q rows).
+    //      InfoNCE also bulk-loads its queue tile: the prologue re-packed the fp32 [D, K] queues (whose power-of-two row pitch
+    //      makes a strided 128-column tile read crawl) into contiguous bf16 tile images.
     if (tid == 0) {
         const uint8_t* src = INST ? p.Ep : p.QNp + (size_t)mod * p.KC * BLOCK_BYTES;
         const int blocks = MT * p.KC;
-        mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES);
+        mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES + (INST ? 0u : (uint32_t)F_WB_BYTES));
         for (int b = 0; b < blocks; ++b) bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, src + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
+        if (!INST) {
+            const uint8_t* qsrc = p.QUp + ((size_t)mod * p.T_k + tile) * F_WB_BYTES;
+            for (int b = 0; b < F_WB_BYTES / BLOCK_BYTES; ++b)
+                bulk_g2s(sm.WB + (size_t)b * BLOCK_BYTES, qsrc + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
+        }
+    }
+    int64_t slot_id = -1;
+    if (!INST && tid < 128) {
+        s_lab[tid] = tid < N ? p.labels[tid] : INT64_MIN;
+        if (c0 + tid < ncols) slot_id = p.id_queue[c0 + tid];
     }
 
-    // ---- W / queue tile: HBM -> bf16 shared image, column statistics
-    load_tile_bf16(INST ? p.W : p.queue[mod], ncols, p.D, Dp, c0, ncols, sm.WB, red);
+    // ---- instance: W tile HBM -> bf16 shared image, column norms
+    if (INST) load_tile_bf16(p.W, ncols, p.D, Dp, c0, ncols, (p.variant & 2) ? 0 : ((tile * 7) & 31), !(p.variant & 4), sm.WB, red);
     __syncthreads();
     if (tid < 128) {
-        float tot = 0.f;
-#pragma unroll
-        for (int ww = 0; ww < 8; ++ww) tot += red[ww * 128 + tid];
         bool ok = c0 + tid < ncols;
-        float inv = 0.f;
+        float scale = 0.f;
         if (INST) {
-            if (ok) inv = __fdiv_rn(1.0f, fmaxf(sqrtf(tot), 1e-12f));           // losses.py:51
+            float tot = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) tot += red[ww * 128 + tid];
+            if (ok) scale = __fdiv_rn(1.0f, fmaxf(sqrtf(tot), 1e-12f));         // losses.py:51
         } else {
             if (ok) {                                                           // head.py:148-157: drop slots holding a batch id
-                const int64_t id = p.id_queue[c0 + tid];
                 bool hit = false;
-                for (int i = 0; i < N; ++i) hit |= (p.labels[i] == id);
+#pragma unroll 8
+                for (int i = 0; i < 128; ++i) hit |= (s_lab[i] == slot_id);
                 ok = !hit;
             }
-            if (ok) inv = __fdiv_rn(1.0f, p.T);
+            if (ok) scale = __fdiv_rn(1.0f, p.T);
         }
-        sm.inv[tid] = inv;
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) sm.valid[w] = bal;
+        sm.col[tid] = make_float2(scale * F_LOG2E, ok ? 0.f : F_NEG);
     }
     fence_async_smem();
     __syncthreads();
+    F_STAMP(1);
 
     // ---- forward logits: z[mt] = E[mt] . Wb   (M = 128 rows, N = 128 columns, K = Dp)
     if (tid == 0) {
@@ -218,162 +313,197 @@ __device__ void tile_program(const FP& p, const Smem& sm, uint32_t tmem, int mod
     mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
     mma_phase ^= 1;
     tc_fence_after();
+    F_STAMP(2);
 
-    // ---- per-row partial softmax statistics of this tile (thread = row n of block h)
+    // ---- per-row partial softmax statistics of this tile, base 2 (thread = row n of block h): z2 = acc * scale * log2(e)
+    const int y = INST ? (int)p.labels[n < N ? n : 0] - c0 : -1;
     if (h < MT) {
-        const int y = INST ? (int)p.labels[n < N ? n : 0] - c0 : -1;
-        float m = -CUDART_INF_F, s = 0.f, sz = 0.f, zy = 0.f;
+        float m = F_NEG, s = 0.f, sz2 = 0.f, zy2 = 0.f;
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             float v[32];
             tmem_ld32(tmem + lanes + (uint32_t)(h * 128 + j * 32), v);
-            const uint32_t vm = sm.valid[j];
-            float cm = -CUDART_INF_F;
+            float cm = F_NEG;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float z = v[i] * sm.inv[j * 32 + i];
-                const bool ok = (vm >> i) & 1u;
-                sz += ok ? z : 0.f;
-                if (INST && j * 32 + i == y) zy = z;
-                v[i] = ok ? z : -CUDART_INF_F;
+                const float2 cc = sm.col[j * 32 + i];
+                sz2 = fmaf(v[i], cc.x, sz2);                       // excluded columns have scale 0
+                v[i] = fmaf(v[i], cc.x, cc.y);                     // ... and bias F_NEG
                 cm = fmaxf(cm, v[i]);
             }
-            if (cm > -CUDART_INF_F) {
-                const float nm = fmaxf(m, cm);
-                float acc = 0.f;
+            if (INST && (unsigned)(y - j * 32) < 32u) {            // rare: this row's label lies in this chunk
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc += expf(v[i] - nm);
-                s = s * expf(m - nm) + acc;
-                m = nm;
+                for (int i = 0; i < 32; ++i)
+                    if (i == y - j * 32) zy2 = v[i];
             }
+            const float nm = fmaxf(m, cm);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc += ex2(v[i] - nm);
+            s = s * ex2(m - nm) + acc;
+            m = nm;
         }
         if (n < N) {
-            float4* st = (INST ? p.st_inst : p.st_nce) + (size_t)((INST ? h : mod) * 128 + n) * tiles + tile;
-            *st = make_float4(m, s, sz, zy);
+            const size_t at = (size_t)tile * 256 + (INST ? h : mod) * 128 + n;
+            (INST ? p.ms_inst : p.ms_nce)[at] = make_float2(m, s);
+            if (INST) p.zz_inst[at] = make_float2(sz2 * F_LN2, zy2 * F_LN2);
         }
     }
+    F_STAMP(3);
 
     grid_barrier(p.bar, gridDim.x);
+    F_STAMP(4);
 
-    // ---- row log-sum-exp over all tiles; the first tile of a row set also writes the row losses
-    float lse[MT];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-        lse[mt] = 0.f;
-        if (n < N) {
-            const int rb = INST ? mt : mod;
-            const float4* st = (INST ? p.st_inst : p.st_nce) + (size_t)(rb * 128 + n) * tiles;
-            float sz, zy;
-            if (INST) {
-                lse[mt] = combine_stats(st, tiles, -CUDART_INF_F, 0.f, sz, zy);
-                if (tile == 0 && h == mt)                                       // losses.py:26-39 with label smoothing
-                    p.rows_inst[mt * N + n] = lse[mt] - (1.0f - p.eps) * zy - (p.eps / (float)p.C) * sz;
-            } else {
-                const float z0 = __fdiv_rn(p.pos[mod * N + n], p.T);            // column 0 of the reference's logits
-                lse[mt] = combine_stats(st, tiles, z0, 1.0f, sz, zy);
-                if (tile == 0 && h == 0) {                                      // losses.py:206-217, target 0
-                    p.rows_nce[mod * N + n] = lse[mt] - z0;
-                    p.dpos[mod * N + n] = (expf(z0 - lse[mt]) - 1.0f) / ((float)N * p.T);
-                }
+    // ---- row log-sum-exp over all tiles (one thread per row, shared through shared memory); the first tile writes the row losses
+    if (h < MT && n < N) {
+        if (INST) {
+            const int row = h * 128 + n;
+            const float l2 = lse2_of_row(p.ms_inst, row, tiles, F_NEG, 0.f);
+            s_lse2[row] = l2;
+            if (tile == 0) {                                                    // losses.py:26-39 with label smoothing
+                const float2 zz = sum_of_row(p.zz_inst, row, tiles);
+                p.rows_inst[h * N + n] = l2 * F_LN2 - (1.0f - p.eps) * zz.y - (p.eps / (float)p.C) * zz.x;
+            }
+        } else {
+            const float z02 = __fdiv_rn(p.pos[mod * N + n], p.T) * F_LOG2E;     // column 0 of the reference's logits (base 2)
+            const float l2 = lse2_of_row(p.ms_nce, mod * 128 + n, tiles, z02, 1.0f);
+            s_lse2[n] = l2;
+            if (tile == 0) {                                                    // losses.py:206-217, target 0
+                p.rows_nce[mod * N + n] = (l2 - z02) * F_LN2;                   // exactly 0 when only the positive is left
+                p.dpos[mod * N + n] = (exp2f(z02 - l2) - 1.0f) / ((float)N * p.T);
             }
         }
     }
+    __syncthreads();
+    float lse2[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) lse2[mt] = n < N ? s_lse2[mt * 128 + n] : 0.f;
+    __syncthreads();                                    // the region is rewritten with logit gradients below
+    F_STAMP(5);
 
     if (p.want_grad) {
-        const float invN = 1.0f / (float)N;
-        const float onehot = INST ? 1.0f - p.eps : 0.f, uni = INST ? p.eps / (float)p.C : 0.f;
+        const float rs = n < N ? F_LN2 / (float)N : 0.f;          // dz' = (softmax - target) / N * scale, scale = col.x * ln 2
+        const float uni = INST ? p.eps / (float)p.C : 0.f;
+        const float uni_hot = uni + (INST ? 1.0f - p.eps : 0.f);
         const bool do_dw = INST && p.d_proj != nullptr;
         const int NH = Dp / 128;
-#pragma unroll 1
+        float csum[2] = {0.f, 0.f};                    // <dz', z2>_rows of this thread's two 32-column chunks (column = lane)
+        // TMEM columns: Z0 = [0,128) and Z1 = [128,256) hold the logits of row blocks 0 / 1, W0|W1 = [256,512) the dWs accumulator.
+        // Row block 0: dE halves go to Z0 (its logits are consumed) and W0 (dWs has not started); once they are drained, dWs(0)
+        // is issued and runs under the gradient math of row block 1.  Row block 1: dE halves go to Z1 and Z0, dWs(1)
+        // accumulates on top; one wait, one drain.
+#pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-            // -- logit gradient of row block mt -> bf16 shared image (thread = row n, 64 columns of chunk h)
-            const int y = INST ? (int)p.labels[n < N ? n : 0] - c0 : -1;
-            const float lse_row = (mt == 0) ? lse[0] : lse[MT - 1];
-#pragma unroll 1
+            // -- logit gradient of row block mt -> bf16 (thread = row n, 64 columns of chunk h), staged in registers
+            uint4 o[2][4];
+#pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int j = h * 2 + jj;
-                float v[32];
+                const int yy = y - j * 32;
+                float v[32], u[32];
                 tmem_ld32(tmem + lanes + (uint32_t)(mt * 128 + j * 32), v);
-                const uint32_t vm = sm.valid[j];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int c = j * 32 + i;
-                    const float sc = sm.inv[c];
-                    const float z = v[i] * sc;
-                    const float g = expf(z - lse_row) - ((c == y) ? onehot : 0.f) - uni;
-                    const bool ok = ((vm >> i) & 1u) && (n < N);
-                    v[i] = ok ? g * invN * sc : 0.f;
+                    const float sc2 = sm.col[j * 32 + i].x;
+                    const float z2 = v[i] * sc2;
+                    const float g = ex2(z2 - lse2[mt]) - ((i == yy) ? uni_hot : uni);
+                    v[i] = g * (sc2 * rs);                         // exactly 0 for excluded columns and padding rows
+                    u[i] = v[i] * z2;
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    uint4 o;
-                    o.x = pack2(v[8 * k + 0], v[8 * k + 1]); o.y = pack2(v[8 * k + 2], v[8 * k + 3]);
-                    o.z = pack2(v[8 * k + 4], v[8 * k + 5]); o.w = pack2(v[8 * k + 6], v[8 * k + 7]);
-                    *reinterpret_cast<uint4*>(sm.DZ + dz_offset(h, n, jj * 4 + k)) = o;
+                    o[jj][k].x = pack2(v[8 * k + 0], v[8 * k + 1]); o[jj][k].y = pack2(v[8 * k + 2], v[8 * k + 3]);
+                    o[jj][k].z = pack2(v[8 * k + 4], v[8 * k + 5]); o[jj][k].w = pack2(v[8 * k + 6], v[8 * k + 7]);
                 }
+                // <dWs, What>_col = sum_rows dz'[row, c] * z[row, c]  (dWs = E^T dz', z = E What): the column-normalisation
+                // Jacobian needs no second pass over W
+                if (do_dw) csum[jj] += lane_transpose_sum(u, lane);
             }
+            if (mt == 1 && do_dw) {                    // dWs(0) still reads the previous image
+                mbar_wait_sleepy(sm.bar_dw, 0, 32);
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sm.DZ + dz_offset(h, n, jj * 4 + k)) = o[jj][k];
             tc_fence_before();
             fence_async_smem();
             __syncthreads();
+            F_STAMP(10 + 2 * mt);
 
-            const int rounds = INST ? NH : 1;          // instance: dE in 128-column rounds that reuse z[mt]'s TMEM columns
-            for (int r = 0; r < rounds; ++r) {
-                if (tid == 0) {
-                    tc_fence_after();
-                    const uint32_t e0 = smem_u32(sm.E), wb0 = smem_u32(sm.WB), dz0 = smem_u32(sm.DZ);
-                    if (do_dw && r == 0) {
-                        // dWs[d, c] += sum_rows E[row, d] * dz'[row, c]   (M = 128 d per half, N = 128 columns, K = 128 rows)
-                        const uint32_t id_w = idesc(128, 128, 1, 1);
-                        for (int hh = 0; hh < NH; ++hh)
-                            for (int ks = 0; ks < 8; ++ks)
-                                umma_bf16(tmem + 256 + hh * 128,
-                                          desc_mn(e0 + (mt * p.KC + 2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES, p.variant),
-                                          desc_mn(dz0 + ks * 2048, BLOCK_BYTES, p.variant), id_w, (uint32_t)((mt > 0) | (ks > 0)));
-                    }
-                    // dE[row, d] = sum_c dz'[row, c] * Wb[d, c]           (M = 128 rows, N = d, K = 128 columns)
-                    const int nd = INST ? 128 : Dp;
-                    const uint32_t id_e = idesc(128, nd, 0, 0);
-                    const uint32_t dcol = INST ? (uint32_t)(mt * 128) : 256u;
+            const bool two = INST && NH == 2;          // dE has two 128-column halves
+            const uint32_t colA = INST ? (uint32_t)(mt * 128) : 256u;            // half a (InfoNCE: all Dp columns)
+            const uint32_t colB = mt == 0 ? 256u : 0u;                           // half b
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t e0 = smem_u32(sm.E), wb0 = smem_u32(sm.WB), dz0 = smem_u32(sm.DZ);
+                // dE[row, d] = sum_c dz'[row, c] * Wb[d, c]           (M = 128 rows, N = d, K = 128 columns)
+                const uint32_t id_e = idesc(128, INST ? 128 : Dp, 0, 0);
+                for (int r = 0; r < (two ? 2 : 1); ++r)
                     for (int ks = 0; ks < 8; ++ks)
-                        umma_bf16(tmem + dcol, umma_desc_sw128(dz0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
+                        umma_bf16(tmem + (r ? colB : colA), umma_desc_sw128(dz0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
                                   umma_desc_sw128(wb0 + (ks >> 2) * F_WB_CHUNK + r * (128 * 128) + (ks & 3) * 32), id_e,
                                   (uint32_t)(ks > 0));
-                    umma_commit(sm.bar_mma);
+                if (do_dw && mt == 1) {
+                    // dWs[d, c] += sum_rows E[row, d] * dz'[row, c]   (M = 128 d per half, N = 128 columns, K = 128 rows)
+                    const uint32_t id_w = idesc(128, 128, 1, 1);
+                    for (int hh = 0; hh < NH; ++hh)
+                        for (int ks = 0; ks < 8; ++ks)
+                            umma_bf16(tmem + 256 + hh * 128,
+                                      desc_mn(e0 + (p.KC + 2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES, p.variant),
+                                      desc_mn(dz0 + ks * 2048, BLOCK_BYTES, p.variant), id_w, 1u);
                 }
-                mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
-                mma_phase ^= 1;
-                tc_fence_after();
-                // -- drain the partial dE of this tile to global (reduced over tiles after the second grid barrier)
-                if (INST) {
-                    float* dst = p.part_inst + ((size_t)tile * 256 + mt * 128 + n) * Dp + r * 128 + h * 64;
-#pragma unroll 1
+                umma_commit(sm.bar_mma);
+            }
+            mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
+            mma_phase ^= 1;
+            tc_fence_after();
+            // -- drain the partial dE of this tile to global (reduced over tiles after the second grid barrier)
+            // partial layout [tile][row block][8-column chunk][128 rows][8]: the 32 rows of a warp write 1 KiB contiguous
+            if (INST) {
+                float* dst = p.part_inst + ((size_t)(tile * 2 + mt) * (Dp / 8) * 128 + n) * 8;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (r == 1 && !two) break;
+#pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         float v[32];
-                        tmem_ld32(tmem + lanes + (uint32_t)(mt * 128 + h * 64 + jj * 32), v);
+                        tmem_ld32(tmem + lanes + (r ? colB : colA) + (uint32_t)(h * 64 + jj * 32), v);
                         if (n < N) {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                __stcg(reinterpret_cast<float4*>(dst + jj * 32) + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
-                        }
-                    }
-                } else {
-                    const int half = Dp / 2;
-                    float* dst = p.part_nce + (((size_t)mod * p.T_k + tile) * 128 + n) * Dp + h * half;
-#pragma unroll 1
-                    for (int jj = 0; jj < half / 32; ++jj) {
-                        float v[32];
-                        tmem_ld32(tmem + lanes + (uint32_t)(256 + h * half + jj * 32), v);
-                        if (n < N) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                __stcg(reinterpret_cast<float4*>(dst + jj * 32) + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+                            for (int k = 0; k < 4; ++k) st_v8(dst + (size_t)(r * 16 + h * 8 + jj * 4 + k) * 1024, v + 8 * k);
                         }
                     }
                 }
-                tc_fence_before();
-                __syncthreads();       // TMEM columns and (after the last round) the dz' image may be overwritten
+            } else {
+                const int half = Dp / 2;
+                float* dst = p.part_nce + ((size_t)(mod * p.T_k + tile) * (Dp / 8) * 128 + n) * 8;
+#pragma unroll 1
+                for (int jj = 0; jj < half / 32; ++jj) {
+                    float v[32];
+                    tmem_ld32(tmem + lanes + (uint32_t)(256 + h * half + jj * 32), v);
+                    if (n < N) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) st_v8(dst + (size_t)((h * half + jj * 32) / 8 + k) * 1024, v + 8 * k);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();                           // the drained TMEM columns may be overwritten
+            F_STAMP(11 + 2 * mt);
+            if (do_dw && mt == 0 && tid == 0) {
+                tc_fence_after();
+                const uint32_t e0 = smem_u32(sm.E), dz0 = smem_u32(sm.DZ);
+                const uint32_t id_w = idesc(128, 128, 1, 1);
+                for (int hh = 0; hh < NH; ++hh)
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_bf16(tmem + 256 + hh * 128, desc_mn(e0 + (2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES, p.variant),
+                                  desc_mn(dz0 + ks * 2048, BLOCK_BYTES, p.variant), id_w, (uint32_t)(ks > 0));
+                umma_commit(sm.bar_dw);
             }
         }
+        F_STAMP(6);
 
         if (do_dw) {
             // ---- dW tile = dWs - What * <dWs, What>_col   (dWs already carries the 1/||w|| factor)       losses.py:51
@@ -391,50 +521,60 @@ __device__ void tile_program(const FP& p, const Smem& sm, uint32_t tmem, int mod
                         tile4[d * 32 + ((j * 8 + k) ^ (d & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                 }
             }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) red[q * 128 + (h * 2 + jj) * 32 + lane] = csum[jj];
             __syncthreads();
+            F_STAMP(14);
             bool cv[4];
-            float sc[4], acc[4];
+            int cc[4];
+            float sc[4];
+            const int head = (p.variant & 8) ? 0 : sector_head(w, p.C, c0);  // full, aligned 128-byte segments: no partial-sector writes inside the tile
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { cv[j] = c0 + lane + 32 * j < p.C; sc[j] = sm.inv[lane + 32 * j]; acc[j] = 0.f; }
-            for (int d = w; d < p.D; d += 8) {
+            for (int j = 0; j < 4; ++j) {
+                const int c = (head + lane + 32 * j) & 127;
+                cc[j] = c;
+                cv[j] = c0 + c < p.C;
+                // What * <dWs, What> = W * (scale * dot); csum is in base-2 units: dot = csum * ln 2, scale = col.x * ln 2
+                sc[j] = (sm.col[c].x * F_LN2) * ((((red[c] + red[128 + c]) + red[256 + c]) + red[384 + c]) * F_LN2);
+            }
+            // What comes from the bf16 shared image of the tile (relative error 2^-9 on the subtracted projection only)
+            const uint8_t* wsrc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = cc[j];
+                wsrc[j] = sm.WB + (c >> 6) * F_WB_CHUNK + w * 128 + ((((c & 63) >> 3) ^ w) << 4) + (c & 7) * 2;
+            }
+#pragma unroll 4
+            for (int i = 0; i < p.D / 8; ++i) {
+                const int d = w + 8 * i;               // (d & 7) == w, (d >> 3) == i
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int c = lane + 32 * j;
-                    if (cv[j]) {
-                        const float wv = __ldg(p.W + (int64_t)d * p.C + c0 + c) * sc[j];
-                        acc[j] = fmaf(tile1[d * 128 + ((((c >> 2) ^ (d & 7))) << 2) + (c & 3)], wv, acc[j]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) red[w * 128 + lane + 32 * j] = acc[j];
-            __syncthreads();
-            if (tid < 128) {
-                float t = 0.f;
-#pragma unroll
-                for (int ww = 0; ww < 8; ++ww) t += red[ww * 128 + tid];
-                red[1024 + tid] = t;
-            }
-            __syncthreads();
-            float dot[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dot[j] = red[1024 + lane + 32 * j];
-            for (int d = w; d < p.D; d += 8) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = lane + 32 * j;
-                    if (cv[j]) {
-                        const float wv = __ldg(p.W + (int64_t)d * p.C + c0 + c) * sc[j];
-                        p.d_proj[(int64_t)d * p.C + c0 + c] = tile1[d * 128 + ((((c >> 2) ^ (d & 7))) << 2) + (c & 3)] - wv * dot[j];
-                    }
+                    const int c = cc[j];
+                    const float wv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(wsrc[j] + i * 1024));
+                    if (cv[j])
+                        p.d_proj[(int64_t)d * p.C + c0 + c] = fmaf(-wv, sc[j], tile1[d * 128 + ((((c >> 2) ^ w)) << 2) + (c & 3)]);
                 }
             }
         }
+        F_STAMP(7);
+    }
+}
+
+// 8 consecutive bf16 (one 16-byte chunk) of embedding row `row`, elements d0 .. d0+7, from a packed row block in shared memory
+__device__ __forceinline__ void smem_row_chunk(const uint8_t* blk0, int row, int d0, float (&out)[8]) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(blk0 + (d0 >> 6) * BLOCK_BYTES + (row >> 3) * 1024 + (row & 7) * 128 +
+                                                      ((((d0 & 63) >> 3) ^ (row & 7)) << 4));
+    const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        out[2 * k] = __uint_as_float(r[k] << 16);
+        out[2 * k + 1] = __uint_as_float(r[k] & 0xffff0000u);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// global align (losses.py:102-128): S = en_v en_t^T, pair losses, dS, dq_v = dS en_t, dq_t = dS^T en_v, normalise backward
+// global align (losses.py:102-128): S = en_v en_t^T, pair losses, dS, dq_v = dS en_t, dq_t = dS^T en_v, normalise backward.
+// One CTA; the bf16-rounded normalised embeddings in shared memory are used consistently (MMA operands and projection).
 // ------------------------------------------------------------------------------------------------------------------------
 __device__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, q = w & 3, h = w >> 2;
@@ -452,7 +592,7 @@ __device__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
     }
     // nothing here depends on the tiles' statistics: arrive at the first grid barrier right away, never wait on it
     if (tid == 0) atomicAdd(p.bar, 1u);
-    if (tid < 128) s_lab[tid] = tid < N ? p.labels[tid] : (int64_t)-1;
+    if (tid < 128) s_lab[tid] = tid < N ? p.labels[tid] : INT64_MIN;
     __syncthreads();
     const uint32_t e0 = smem_u32(sm.E), dz0 = smem_u32(sm.DZ);
     const uint32_t et0 = e0 + p.KC * BLOCK_BYTES;                       // text rows
@@ -468,10 +608,12 @@ __device__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
     mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
     mma_phase ^= 1;
     tc_fence_after();
+    F_STAMP(2);
 
     {
         const int64_t yi = s_lab[n];
         const float two_over_n = 2.0f / (float)N;
+        const float c_same = -p.sp * two_over_n, c_diff = p.sn * two_over_n;
         float acc = 0.f;
 #pragma unroll 1
         for (int jj = 0; jj < 2; ++jj) {
@@ -484,9 +626,10 @@ __device__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
                 const bool ok = n < N && col < N;
                 const bool same = s_lab[col] == yi;
                 const float x = same ? -p.sp * (v[i] - p.alpha) : p.sn * (v[i] - p.beta);
-                const float e = expf(x);
-                acc += ok ? logf(1.0f + e) : 0.f;                       // the reference's literal log(1+exp(x)), losses.py:123-124
-                v[i] = ok ? (same ? -p.sp : p.sn) * (e / (1.0f + e)) * two_over_n : 0.f;
+                const float e = __expf(x);
+                const float ope = 1.0f + e;
+                acc += ok ? __logf(ope) : 0.f;                           // the reference's literal log(1+exp(x)), losses.py:123-124
+                v[i] = ok ? (same ? c_same : c_diff) * __fdividef(e, ope) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -502,6 +645,7 @@ __device__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
     fence_async_smem();
     __syncthreads();
     if (h == 0 && n < N) p.rows_ga[n] = s_part[n] + s_part[128 + n];
+    F_STAMP(3);
 
     if (p.want_grad) {
         if (tid == 0) {
@@ -521,23 +665,24 @@ __device__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
         mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
         mma_phase ^= 1;
         tc_fence_after();
+        F_STAMP(5);
+        // normalise backward: d_ga[row] = (g - <g, en> en) / ||e||, thread = (row n, column half h)
         const int half = Dp / 2;
         for (int mod = 0; mod < 2; ++mod) {
             const uint32_t col0 = (mod == 0 ? 256u : 0u) + (uint32_t)(h * half);
-            const float* enr = p.en + ((int64_t)mod * N + (n < N ? n : 0)) * D;
+            const uint8_t* blk0 = sm.E + (size_t)mod * p.KC * BLOCK_BYTES;
             float dot = 0.f;
 #pragma unroll 1
             for (int jj = 0; jj < half / 32; ++jj) {
                 float v[32];
                 tmem_ld32(tmem + lanes + col0 + (uint32_t)(jj * 32), v);
                 const int d0 = h * half + jj * 32;
-                if (n < N && d0 < D) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float4 e4 = *reinterpret_cast<const float4*>(enr + d0 + 4 * k);
-                        dot = fmaf(v[4 * k], e4.x, dot); dot = fmaf(v[4 * k + 1], e4.y, dot);
-                        dot = fmaf(v[4 * k + 2], e4.z, dot); dot = fmaf(v[4 * k + 3], e4.w, dot);
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    float e8[8];
+                    smem_row_chunk(blk0, n, d0 + 8 * k, e8);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) dot = fmaf(v[8 * k + t], e8[t], dot);
                 }
             }
             __syncthreads();
@@ -551,50 +696,52 @@ __device__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
                 float v[32];
                 tmem_ld32(tmem + lanes + col0 + (uint32_t)(jj * 32), v);
                 const int d0 = h * half + jj * 32;
-                if (n < N && d0 < D) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float4 e4 = *reinterpret_cast<const float4*>(enr + d0 + 4 * k);
-                        float4 o;
-                        o.x = (v[4 * k] - dot * e4.x) * inv; o.y = (v[4 * k + 1] - dot * e4.y) * inv;
-                        o.z = (v[4 * k + 2] - dot * e4.z) * inv; o.w = (v[4 * k + 3] - dot * e4.w) * inv;
-                        *reinterpret_cast<float4*>(out + d0 + 4 * k) = o;
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    float e8[8], o[8];
+                    smem_row_chunk(blk0, n, d0 + 8 * k, e8);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) o[t] = (v[8 * k + t] - dot * e8[t]) * inv;
+                    if (n < N && d0 + 8 * k < D) st_v8(out + d0 + 8 * k, o);
                 }
             }
         }
+        F_STAMP(6);
     }
 }
 
-// after the second grid barrier: every CTA takes a share of the fixed-order partial reductions
+// after the second grid barrier: every CTA takes an equal share of the fixed-order partial reductions
 __device__ void finish_phase(const FP& p, const Smem& sm) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int N = p.N, D = p.D, Dp = p.KC * 64, G = gridDim.x;
     if (p.want_grad && p.n_inst) {
+        // d_inst[row, d] = sum_tiles partial[tile][row, d]: one float4 per thread, 22 independent loads in flight.  Work item
+        // idx = ((mod * D/4 + d4) * N + row): consecutive threads take consecutive rows of one column group (contiguous loads).
         const int per_row = D / 4, total4 = 2 * N * per_row;
-        const size_t tstride = (size_t)256 * Dp;
-        for (int idx = blockIdx.x * F_THREADS + tid; idx < total4; idx += G * F_THREADS) {
-            const int row = idx / per_row, d4 = idx % per_row;
-            const int mod = row / N, nn = row % N;
-            const float* src = p.part_inst + (size_t)(mod * 128 + nn) * Dp + d4 * 4;
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-            int t = 0;
-            for (; t + 1 < p.T_inst; t += 2) {
-                const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)t * tstride));
-                const float4 y = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(t + 1) * tstride));
-                a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
-                a1.x += y.x; a1.y += y.y; a1.z += y.z; a1.w += y.w;
+        const int per_cta = (total4 + G - 1) / G;
+        const size_t tstride = (size_t)2 * (Dp / 8) * 1024;
+        const int lo = blockIdx.x * per_cta, hi = min(total4, lo + per_cta);
+        for (int idx = lo + tid; idx < hi; idx += F_THREADS) {
+            const int nn = idx % N, t = idx / N;
+            const int d4 = t % per_row, mod = t / per_row;
+            const float* src = p.part_inst + ((size_t)(mod * (Dp / 8) + (d4 >> 1)) * 128 + nn) * 8 + (d4 & 1) * 4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t0 = 0; t0 < p.T_inst; t0 += 22) {
+                float4 x[22];
+#pragma unroll
+                for (int i = 0; i < 22; ++i)
+                    x[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)min(t0 + i, p.T_inst - 1) * tstride));
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 22; ++i)
+                    if (t0 + i < p.T_inst) { acc.x += x[i].x; acc.y += x[i].y; acc.z += x[i].z; acc.w += x[i].w; }
             }
-            if (t < p.T_inst) {
-                const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)t * tstride));
-                a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
-            }
-            *reinterpret_cast<float4*>(p.d_inst + (size_t)idx * 4) = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+            *reinterpret_cast<float4*>(p.d_inst + ((size_t)(mod * N + nn) * D + d4 * 4)) = acc;
         }
     }
     if (p.want_grad && p.n_nce) {
-        // d_nce[row] = normalise-backward( sum_tiles dq_part + dpos * key )   one warp per row
-        for (int row = blockIdx.x * 8 + w; row < 2 * N; row += G * 8) {
+        // d_nce[row] = normalise-backward( sum_tiles dq_part + dpos * key )   one warp per row, rows dealt round-robin to CTAs
+        for (int row = blockIdx.x + G * (7 - w); row < 2 * N; row += G * 8) {
             const int mod = row / N, nn = row % N;
             const float dp = __ldcg(p.dpos + row);
             const float* key = p.key_n[mod] + (int64_t)nn * D;
@@ -607,10 +754,16 @@ __device__ void finish_phase(const FP& p, const Smem& sm) {
                 g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (d4 * 4 < D) {
                     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float* src = p.part_nce + ((size_t)mod * p.T_k * 128 + nn) * Dp + d4 * 4;
-                    for (int t = 0; t < p.T_k; ++t) {
-                        const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)t * 128 * Dp));
-                        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+                    const float* src = p.part_nce + ((size_t)(mod * p.T_k) * (Dp / 8) * 128 + (size_t)(d4 >> 1) * 128 + nn) * 8 + (d4 & 1) * 4;
+                    for (int t0 = 0; t0 < p.T_k; t0 += 16) {
+                        float4 x[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            x[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)min(t0 + i, p.T_k - 1) * (Dp / 8) * 1024));
+                        asm volatile("" ::: "memory");
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (t0 + i < p.T_k) { a.x += x[i].x; a.y += x[i].y; a.z += x[i].z; a.w += x[i].w; }
                     }
                     const float4 k4 = *reinterpret_cast<const float4*>(key + d4 * 4);
                     const float4 q4 = *reinterpret_cast<const float4*>(qr + d4 * 4);
@@ -634,7 +787,7 @@ __device__ void finish_phase(const FP& p, const Smem& sm) {
             }
         }
     }
-    if (p.reduce_losses && blockIdx.x == 0) {
+    if (p.reduce_losses && blockIdx.x == G - 1) {
         float a = 0.f, b = 0.f, c = 0.f;
         for (int i = tid; i < 2 * N; i += F_THREADS) { a += __ldcg(p.rows_inst + i); b += __ldcg(p.rows_nce + i); }
         for (int i = tid; i < N; i += F_THREADS) c += __ldcg(p.rows_ga + i);
@@ -653,17 +806,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
     Smem sm;
     sm.E = smem + F_OFF_E; sm.DZ = smem + F_OFF_DZ; sm.WB = smem + F_OFF_WB;
     uint8_t* misc = smem + F_OFF_MISC;
-    sm.inv = reinterpret_cast<float*>(misc);
-    sm.valid = reinterpret_cast<uint32_t*>(misc + 512);
-    sm.bar_load = reinterpret_cast<uint64_t*>(misc + 528);
-    sm.bar_mma = reinterpret_cast<uint64_t*>(misc + 536);
-    sm.tmem_slot = reinterpret_cast<uint32_t*>(misc + 544);
-    sm.red32 = reinterpret_cast<float*>(misc + 576);
+    sm.col = reinterpret_cast<float2*>(misc);
+    sm.bar_load = reinterpret_cast<uint64_t*>(misc + 1024);
+    sm.bar_mma = reinterpret_cast<uint64_t*>(misc + 1032);
+    sm.bar_dw = reinterpret_cast<uint64_t*>(misc + 1040);
+    sm.tmem_slot = reinterpret_cast<uint32_t*>(misc + 1048);
+    sm.red32 = reinterpret_cast<float*>(misc + 1088);
     const int warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) {
         mbar_init(sm.bar_load, 1);
         mbar_init(sm.bar_mma, 1);
+        mbar_init(sm.bar_dw, 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(sm.tmem_slot, 512);
@@ -671,6 +825,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *sm.tmem_slot;
+    F_STAMP(0);
 
     const int b = blockIdx.x;
     if (b < p.n_inst) tile_program<true>(p, sm, tmem, 0, b);
@@ -678,7 +833,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
     else align_program(p, sm, tmem);
 
     grid_barrier(p.bar + 1, gridDim.x);
+    F_STAMP(8);
     finish_phase(p, sm);
+    F_STAMP(9);
 
     tc_fence_before();
     __syncthreads();
@@ -698,8 +855,54 @@ fused_prologue_kernel(const float* __restrict__ v_embed, const float* __restrict
                       int normalize_keys, float* __restrict__ v_key_n, float* __restrict__ t_key_n, float* __restrict__ E2,
                       float* __restrict__ en, float* __restrict__ inv_e, float* __restrict__ qn, float* __restrict__ inv_q,
                       float* __restrict__ pos, uint8_t* __restrict__ Ep, uint8_t* __restrict__ ENp, uint8_t* __restrict__ QNp,
-                      unsigned* __restrict__ bar, int N, int D, int KC) {
+                      unsigned* __restrict__ bar, int N, int D, int KC, const float* __restrict__ v_queue,
+                      const float* __restrict__ t_queue, uint8_t* __restrict__ QUp, int K, int T_k) {
     const int lane = threadIdx.x & 31;
+    if (blockIdx.x >= 32) {
+        // ---- queue re-pack: CTA = (modality, 8 consecutive d), warp = one full row of the fp32 [D, K] queue (contiguous, DRAM
+        //      friendly) -> bf16 into the per-tile shared-memory images [tile][2 column chunks][256 d][128 B] the InfoNCE CTAs
+        //      bulk-load.  Modality 0 (image queries) scores the TEXT queue (head.py:162,168).
+        const int b = blockIdx.x - 32, per_mod = KC * 8;          // Dp / 8 row groups
+        const int mod = b / per_mod, d = (b % per_mod) * 8 + (threadIdx.x >> 5);
+        const float* row = (mod ? v_queue : t_queue) + (int64_t)d * K;
+        uint8_t* img = QUp + (size_t)mod * T_k * F_WB_BYTES;
+        const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0 && d < D;
+        for (int t0 = 0; t0 < T_k; t0 += 16) {
+            float4 x[16];
+            if (vec) {                                 // all loads of the row in flight before the first use
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int k = min((t0 + i) * 128 + 4 * lane, K - 4);
+                    x[i] = __ldcs(reinterpret_cast<const float4*>(row + k));
+                }
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if ((t0 + i) * 128 + 4 * lane + 3 >= K) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int k = (t0 + i) * 128 + 4 * lane;
+                    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (d < D) {
+                        if (k < K) x[i].x = row[k];
+                        if (k + 1 < K) x[i].y = row[k + 1];
+                        if (k + 2 < K) x[i].z = row[k + 2];
+                        if (k + 3 < K) x[i].w = row[k + 3];
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (t0 + i < T_k) {
+                    uint2 o;
+                    o.x = pack2(x[i].x, x[i].y); o.y = pack2(x[i].z, x[i].w);
+                    *reinterpret_cast<uint2*>(img + (size_t)(t0 + i) * F_WB_BYTES + wb_offset(d, 4 * lane)) = o;
+                }
+            }
+        }
+        return;
+    }
     const int prow = blockIdx.x * 8 + (threadIdx.x >> 5);         // padded row: modality * 128 + n
     if (blockIdx.x == 0 && threadIdx.x < 2) bar[threadIdx.x] = 0u;
     if (prow >= 256) return;
@@ -757,8 +960,8 @@ fused_prologue_kernel(const float* __restrict__ v_embed, const float* __restrict
 }
 
 struct Scratch {
-    uint8_t *Ep, *ENp, *QNp;
-    float4 *st_inst, *st_nce;
+    uint8_t *Ep, *ENp, *QNp, *QUp;
+    float2 *ms_inst, *zz_inst, *ms_nce;
     float *part_inst, *part_nce;
     unsigned* bar;
     int64_t bytes;
@@ -773,8 +976,10 @@ Scratch carve_scratch(uint8_t* base, int N, int D, int K, int C) {
     auto take = [&](int64_t bytes) { uint8_t* r = p; p += (bytes + 1023) / 1024 * 1024; return r; };
     const int64_t img = (int64_t)2 * KC * BLOCK_BYTES;
     s.Ep = take(img); s.ENp = take(img); s.QNp = take(img);
-    s.st_inst = reinterpret_cast<float4*>(take((int64_t)256 * T_inst * 16));
-    s.st_nce = reinterpret_cast<float4*>(take((int64_t)256 * T_k * 16));
+    s.QUp = take((int64_t)2 * T_k * F_WB_BYTES);
+    s.ms_inst = reinterpret_cast<float2*>(take((int64_t)256 * T_inst * 8));
+    s.zz_inst = reinterpret_cast<float2*>(take((int64_t)256 * T_inst * 8));
+    s.ms_nce = reinterpret_cast<float2*>(take((int64_t)256 * T_k * 8));
     s.part_inst = reinterpret_cast<float*>(take((int64_t)T_inst * 256 * Dp * 4));
     s.part_nce = reinterpret_cast<float*>(take((int64_t)2 * T_k * 128 * Dp * 4));
     s.bar = reinterpret_cast<unsigned*>(take(256));
@@ -782,7 +987,15 @@ Scratch carve_scratch(uint8_t* base, int N, int D, int K, int C) {
     return s;
 }
 
+static unsigned long long* g_dbg = nullptr;
+
 }  // namespace
+
+// debug: copy the [160][16] phase timestamps (ns, %globaltimer) of the last fused launch to the host
+extern "C" int trb_debug_fused_stamps(unsigned long long* host_out) {
+    if (g_dbg == nullptr) return TRB_ERR_INVALID;
+    return (int)cudaMemcpy(host_out, g_dbg, 160 * 16 * 8, cudaMemcpyDeviceToHost);
+}
 
 bool fused_loss_supported(int N, int D, int K, int C, int sm_count) {
     if (N < 1 || N > 128 || D < 64 || D > 256 || (D % 64) != 0) return false;
@@ -796,9 +1009,12 @@ int fused_loss_prologue(const FusedLossArgs& a, cudaStream_t st) {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a.scratch) + 1023) & ~uintptr_t(1023));
     const Scratch s = carve_scratch(base, a.N, a.D, a.K, a.C);
     const int KC = (a.D + 127) / 128 * 2;
-    fused_prologue_kernel<<<32, 256, 0, st>>>(a.v_embed, a.t_embed, a.v_qraw, a.t_qraw, a.v_key, a.t_key, a.normalize_keys,
-                                              a.v_key_n, a.t_key_n, a.E2, a.en, a.inv_e, a.qn, a.inv_q, a.pos, s.Ep, s.ENp,
-                                              s.QNp, s.bar, a.N, a.D, KC);
+    const int T_k = (a.K + F_TILE - 1) / F_TILE;
+    const int pack_ctas = (a.roles & 2) ? 2 * KC * 8 : 0;     // queue re-pack for the InfoNCE tiles
+    fused_prologue_kernel<<<32 + pack_ctas, 256, 0, st>>>(a.v_embed, a.t_embed, a.v_qraw, a.t_qraw, a.v_key, a.t_key,
+                                                          a.normalize_keys, a.v_key_n, a.t_key_n, a.E2, a.en, a.inv_e, a.qn,
+                                                          a.inv_q, a.pos, s.Ep, s.ENp, s.QNp, s.bar, a.N, a.D, KC, a.v_queue,
+                                                          a.t_queue, s.QUp, a.K, T_k);
     TRB_LAUNCH_OK();
     return 0;
 }
@@ -824,9 +1040,15 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     p.queue[0] = a.t_queue; p.queue[1] = a.v_queue;
     p.key_n[0] = a.t_key_n; p.key_n[1] = a.v_key_n;
     p.labels = a.labels; p.id_queue = a.id_queue;
-    p.Ep = s.Ep; p.ENp = s.ENp; p.QNp = s.QNp;
+    p.Ep = s.Ep; p.ENp = s.ENp; p.QNp = s.QNp; p.QUp = s.QUp;
     p.en = a.en; p.qn = a.qn; p.inv_e = a.inv_e; p.inv_q = a.inv_q; p.pos = a.pos;
-    p.st_inst = s.st_inst; p.st_nce = s.st_nce; p.part_inst = s.part_inst; p.part_nce = s.part_nce;
+    p.ms_inst = s.ms_inst; p.zz_inst = s.zz_inst; p.ms_nce = s.ms_nce;
+    p.dbg = nullptr;
+    if (getenv("TRB_FUSED_DEBUG")) {          // debug only: phase timestamps of every CTA, read back with trb_debug_fused_stamps
+        if (g_dbg == nullptr && cudaMalloc(&g_dbg, 160 * 16 * 8) == cudaSuccess) cudaMemset(g_dbg, 0, 160 * 16 * 8);
+        p.dbg = g_dbg;
+    }
+    p.part_inst = s.part_inst; p.part_nce = s.part_nce;
     p.dpos = a.dpos; p.rows_inst = a.rows_inst; p.rows_nce = a.rows_nce; p.rows_ga = a.rows_ga;
     p.losses = a.losses; p.d_inst = a.d_inst; p.d_nce = a.d_nce; p.d_ga = a.d_ga; p.d_proj = a.d_proj;
     p.bar = s.bar;

@@ -136,7 +136,65 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= s;
 }
 
+// backward of the loss dict in one launch: per-loss gradients x upstream scalars (device pointers, NULL = 0) -> final gradients.
+// items [0, 2*nd): embedding gradients (modality = item / nd); items [2*nd, 2*nd + dc): projection gradient.
+__global__ void __launch_bounds__(256)
+grad_combine_kernel(const float* __restrict__ d_inst, const float* __restrict__ d_nce, const float* __restrict__ d_ga,
+                    const float* __restrict__ d_proj, const float* __restrict__ g_inst, const float* __restrict__ g_nce,
+                    const float* __restrict__ g_ga, int separate_q, int64_t nd, int64_t dc, float* __restrict__ out_v,
+                    float* __restrict__ out_t, float* __restrict__ out_vq, float* __restrict__ out_tq, float* __restrict__ out_proj,
+                    int vec4) {
+    const float gi = g_inst ? g_inst[0] : 0.f, gn = g_nce ? g_nce[0] : 0.f, gg = g_ga ? g_ga[0] : 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t e = tid; e < 2 * nd; e += stride) {
+        const int64_t i = e < nd ? e : e - nd;
+        float v = fmaf(gi, d_inst[e], 0.f);
+        if (separate_q) {
+            v = fmaf(gg, d_ga[e], v);
+            (e < nd ? out_vq : out_tq)[i] = fmaf(gn, d_nce[e], 0.f);
+        } else {
+            v = fmaf(gn, d_nce[e], v);
+            v = fmaf(gg, d_ga[e], v);
+        }
+        (e < nd ? out_v : out_t)[i] = v;
+    }
+    if (out_proj == nullptr) return;
+    if (vec4) {
+        const float4* src = reinterpret_cast<const float4*>(d_proj);
+        float4* dst = reinterpret_cast<float4*>(out_proj);
+        for (int64_t i = tid; i < dc / 4; i += stride) {
+            float4 x = src[i];
+            if (gi != 1.0f) { x.x *= gi; x.y *= gi; x.z *= gi; x.w *= gi; }
+            dst[i] = x;
+        }
+    } else {
+        for (int64_t i = tid; i < dc; i += stride) out_proj[i] = (gi != 1.0f) ? d_proj[i] * gi : d_proj[i];
+    }
+}
+
 }  // namespace
+
+extern "C" int trb_moco_grad_combine(const float* d_inst, const float* d_nce, const float* d_ga, const float* d_proj,
+                                     const float* g_inst, const float* g_nce, const float* g_ga, int separate_q, int64_t nd,
+                                     int64_t dc, float* out_v, float* out_t, float* out_vq, float* out_tq, float* out_proj,
+                                     trb_stream_t stream) {
+    TRB_REQUIRE(d_inst && d_nce && d_ga && out_v && out_t, "grad_combine: null pointer");
+    TRB_REQUIRE(!separate_q || (out_vq && out_tq), "grad_combine: separate_q needs out_vq / out_tq");
+    TRB_REQUIRE(out_proj == nullptr || d_proj != nullptr, "grad_combine: out_proj needs d_proj");
+    TRB_REQUIRE(nd >= 0 && dc >= 0, "grad_combine: negative size");
+    if (nd == 0 && (dc == 0 || out_proj == nullptr)) return 0;
+    const int vec4 = out_proj != nullptr && (dc % 4) == 0 && trb_aligned16(d_proj) && trb_aligned16(out_proj);
+    const int64_t items = 2 * nd > (vec4 ? dc / 4 : dc) ? 2 * nd : (vec4 ? dc / 4 : dc);
+    int64_t blocks = trb_ceil_div(items, 256 * 4);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    grad_combine_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_inst, d_nce, d_ga, d_proj, g_inst, g_nce, g_ga,
+                                                                             separate_q, nd, dc, out_v, out_t, out_vq, out_tq,
+                                                                             out_proj, vec4);
+    TRB_LAUNCH_OK();
+    return 0;
+}
 
 extern "C" int trb_ema_update_f32(float* p_k, const float* p_q, int64_t n, float m, float one_minus_m, trb_stream_t stream) {
     TRB_REQUIRE(p_k && p_q, "ema_update: null pointer");

@@ -36,6 +36,9 @@ def _workspace(shape: _lib.MocoShape, precision: int, device) -> torch.Tensor:
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous float32 view of ``t`` for pointer extraction (no copy, no dispatcher call, in the common case)."""
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t
     return t.detach().contiguous().float()
 
 
@@ -56,7 +59,8 @@ class _MoCoLossFunction(torch.autograd.Function):
         vq, tq = (_f32c(v_qraw), _f32c(t_qraw)) if separate_q else (ve, te)
         vk, tk = _f32c(v_key), _f32c(t_key)
         proj = _f32c(projection)
-        lab = labels.detach().reshape(-1).to(torch.int64).contiguous()
+        lab = labels if (labels.dtype is torch.int64 and labels.dim() == 1 and labels.is_contiguous()) \
+            else labels.detach().reshape(-1).to(torch.int64).contiguous()
         need_grad = any(ctx.needs_input_grad[:5])
         if enqueue:
             for q in (v_queue, t_queue):
@@ -86,6 +90,7 @@ class _MoCoLossFunction(torch.autograd.Function):
                 _lib.ptr(proj), C.byref(shape), C.byref(hp), precision, _lib.ptr(out["losses"]), _lib.ptr(out.get("d_inst")),
                 _lib.ptr(out.get("d_nce")), _lib.ptr(out.get("d_ga")), _lib.ptr(out.get("d_proj")), _lib.ptr(ws), ws.numel(),
                 _lib.stream_ptr(dev)), "trb_moco_loss")
+            _lib.add_launches(lib.trb_moco_loss_launches(C.byref(shape), precision))
             if do_enqueue:   # head.py:175 -- after the logits were taken from the old queue contents
                 _lib.check(lib.trb_enqueue(_lib.ptr(vqu), _lib.ptr(tqu), _lib.ptr(idq), _lib.ptr(queue_ptr), _lib.ptr(out["vkn"]),
                                            _lib.ptr(out["tkn"]), _lib.ptr(lab), N, D, K, _lib.stream_ptr(dev)), "trb_enqueue")
@@ -121,34 +126,26 @@ class _MoCoLossFunction(torch.autograd.Function):
         ctx.separate_q = separate_q
         ctx.grads = (out.get("d_inst"), out.get("d_nce"), out.get("d_ga"), out.get("d_proj"))
         ctx.mark_non_differentiable(out["vkn"], out["tkn"])
-        losses = out["losses"]
-        return losses[0], losses[1], losses[2], out["vkn"], out["tkn"]
+        li, ln, lg = out["losses"].unbind(0)
+        return li, ln, lg, out["vkn"], out["tkn"]
 
     @staticmethod
     def backward(ctx, g_inst, g_nce, g_ga, _gvk, _gtk):
+        """One launch (trb_moco_grad_combine): saved per-loss gradients x the three upstream scalars, read on the device."""
         lib = _lib.load()
         d_inst, d_nce, d_ga, d_proj = ctx.grads
         dev = d_inst.device
-        st = _lib.stream_ptr(dev)
-        zero = torch.zeros((), dtype=torch.float32, device=dev)
-        g = torch.stack([x.float() if x is not None else zero for x in (g_inst, g_nce, g_ga)]).contiguous()
-        n = d_inst[0].numel()
-
-        def comb(a, b, c):
-            out = torch.empty_like(d_inst[0])
-            _lib.check(lib.trb_combine3_f32(_lib.ptr(out), _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(g), n, st),
-                       "trb_combine3_f32")
-            return out
-
+        gs = [None if g is None else (g if g.dtype == torch.float32 and g.is_cuda else g.to(device=dev, dtype=torch.float32))
+              for g in (g_inst, g_nce, g_ga)]
+        gv, gt = torch.empty_like(d_inst[0]), torch.empty_like(d_inst[0])
         gvq = gtq = None
         if ctx.separate_q:
-            gv, gt = comb(d_inst[0], None, d_ga[0]), comb(d_inst[1], None, d_ga[1])
-            gvq, gtq = comb(None, d_nce[0], None), comb(None, d_nce[1], None)
-        else:
-            gv, gt = comb(d_inst[0], d_nce[0], d_ga[0]), comb(d_inst[1], d_nce[1], d_ga[1])
-        gp = d_proj.clone() if ctx.needs_input_grad[4] else None
-        if gp is not None:
-            _lib.check(lib.trb_scale_inplace_f32(_lib.ptr(gp), _lib.ptr(g), gp.numel(), st), "trb_scale_inplace_f32")
+            gvq, gtq = torch.empty_like(gv), torch.empty_like(gv)
+        gp = torch.empty_like(d_proj) if ctx.needs_input_grad[4] else None
+        _lib.check(lib.trb_moco_grad_combine(_lib.ptr(d_inst), _lib.ptr(d_nce), _lib.ptr(d_ga), _lib.ptr(d_proj), _lib.ptr(gs[0]),
+                                             _lib.ptr(gs[1]), _lib.ptr(gs[2]), int(ctx.separate_q), gv.numel(),
+                                             d_proj.numel(), _lib.ptr(gv), _lib.ptr(gt), _lib.ptr(gvq), _lib.ptr(gtq),
+                                             _lib.ptr(gp), _lib.stream_ptr(dev)), "trb_moco_grad_combine")
         return (gv, gt, gvq, gtq, gp) + (None,) * 13
 
 

@@ -37,6 +37,27 @@ def call(lib, _lib, inp, shape, hp, precision, grads=True):
     return out, ws
 
 
+
+def print_stamps(lib, roles, K, Cn, tag):
+    import numpy as np
+    buf = np.zeros(160 * 16, dtype=np.uint64)
+    lib.trb_debug_fused_stamps.argtypes = [C.c_void_p]
+    lib.trb_debug_fused_stamps(buf.ctypes.data_as(C.c_void_p))
+    st = buf.reshape(160, 16).astype(np.int64)
+    T_inst, T_k = (Cn + 127) // 128, (K + 127) // 128
+    n_inst = T_inst if roles & 1 else 0
+    n_nce = 2 * T_k if roles & 2 else 0
+    groups = [("inst", 0, n_inst), ("nce", n_inst, n_inst + n_nce), ("align", n_inst + n_nce, n_inst + n_nce + (1 if roles & 4 else 0))]
+    t0 = st[:n_inst + n_nce + 1, 0]
+    t0 = int(t0[t0 > 0].min())
+    for name, lo, hi in groups:
+        if hi <= lo:
+            continue
+        seg = st[lo:hi]
+        print("STAMPS[%s] %s: " % (tag, name) + "  ".join(
+            "%d:%.1f..%.1f" % (k, (seg[:, k][seg[:, k] > 0].min() - t0) / 1e3, (seg[:, k].max() - t0) / 1e3)
+            for k in range(16) if (seg[:, k] > 0).any()), flush=True)
+
 def child(roles, variant):
     os.environ["TRB_FUSED_ROLES"] = str(roles)
     os.environ["TRB_FUSED_VARIANT"] = str(variant)
@@ -111,7 +132,9 @@ def child(roles, variant):
                 torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b) * 1e3)
             ts.sort()
-            print("TIME roles=%d eager %s: median %.1f us  min %.1f us" % (roles, name, ts[len(ts) // 2], ts[0]), flush=True)
+            print("TIME roles=%d var=%d eager %s: median %.1f us  min %.1f us" % (roles, variant, name, ts[len(ts) // 2], ts[0]), flush=True)
+            if os.environ.get("TRB_FUSED_DEBUG") and roles:
+                print_stamps(lib, roles, K, Cn, name)
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
@@ -136,18 +159,22 @@ def child(roles, variant):
 
 def driver():
     results = {}
-    for roles in (1, 2, 4, 7, 0):
-        for variant in (0, 1):
-            if variant == 1 and (roles == 0 or results.get((roles, 0)) == 0):
-                continue
-            try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(roles), str(variant)], timeout=150,
-                                   capture_output=True, text=True)
-                rc, txt = r.returncode, r.stdout + r.stderr[-3000:]
-            except subprocess.TimeoutExpired as e:
-                rc, txt = 124, "TIMEOUT\n" + ((e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or ""))
-            results[(roles, variant)] = rc
-            print("=== roles=%d variant=%d rc=%d\n%s" % (roles, variant, rc, txt), flush=True)
+    full = "--full" in sys.argv
+    plan = [(r, v, False) for r in ((1, 2, 4, 7, 0) if full else (7,)) for v in (0,)] + [(7, 0, True)]
+    if "--variants" in sys.argv:
+        plan = [(7, v, True) for v in (0, 2, 8, 14)]
+    for roles, variant, debug in plan:
+        env = dict(os.environ)
+        if debug:
+            env["TRB_FUSED_DEBUG"] = "1"
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(roles), str(variant)], timeout=150,
+                               capture_output=True, text=True, env=env)
+            rc, txt = r.returncode, r.stdout + r.stderr[-3000:]
+        except subprocess.TimeoutExpired as e:
+            rc, txt = 124, "TIMEOUT\n" + ((e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or ""))
+        results[(roles, variant, debug)] = rc
+        print("=== roles=%d variant=%d debug=%d rc=%d\n%s" % (roles, variant, debug, rc, txt), flush=True)
     print("SUMMARY", results)
 
 
