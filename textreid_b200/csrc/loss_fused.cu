@@ -1009,6 +1009,11 @@ int fused_loss_prologue(const FusedLossArgs& a, cudaStream_t st) {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a.scratch) + 1023) & ~uintptr_t(1023));
     const Scratch s = carve_scratch(base, a.N, a.D, a.K, a.C);
     const int KC = (a.D + 127) / 128 * 2;
+    static bool attr = false;
+    if (!attr) {   // same shared-memory carve-out as the cooperative kernel that follows: no SM reconfiguration between the two
+        TRB_CUDA_OK(cudaFuncSetAttribute(fused_prologue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr = true;
+    }
     const int T_k = (a.K + F_TILE - 1) / F_TILE;
     const int pack_ctas = (a.roles & 2) ? 2 * KC * 8 : 0;     // queue re-pack for the InfoNCE tiles
     fused_prologue_kernel<<<32 + pack_ctas, 256, 0, st>>>(a.v_embed, a.t_embed, a.v_qraw, a.t_qraw, a.v_key, a.t_key,
