@@ -250,7 +250,8 @@ int trb_combine3_f32(float* out, const float* a, const float* b, const float* c,
  * gradients (DEVICE scalars; NULL = that loss did not take part in the backward pass, trainer.py:82,90 passes 1,1,1):
  *   out_v / out_t [N,D]   = g_inst * d_inst[m] + g_nce * d_nce[m] + g_ga * d_ga[m]          (m = 0 image, 1 text)
  *   separate_q (cfg.MODEL.MOCO.FC, head.py:118-124): the InfoNCE term goes to out_vq / out_tq instead
- *   out_proj [D,C]        = g_inst * d_proj   (NULL skips it; g_inst == 1 is a plain copy)
+ *   out_proj [D,C]        = g_inst * d_proj   (NULL skips it; may alias d_proj: then it is scaled in place, and left untouched
+ *                           without any memory traffic when g_inst == 1)
  * nd = N*D, dc = D*C. */
 int trb_moco_grad_combine(const float* d_inst, const float* d_nce, const float* d_ga, const float* d_proj,
                           const float* g_inst, const float* g_nce, const float* g_ga, int separate_q, int64_t nd,

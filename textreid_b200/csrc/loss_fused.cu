@@ -237,7 +237,7 @@ __device__ __forceinline__ float lane_transpose_sum(float (&u)[32], int lane) {
 // instance (INST) / InfoNCE tile
 // ------------------------------------------------------------------------------------------------------------------------
 template <bool INST>
-__device__ void tile_program(const FP& p, const Smem& sm, uint32_t tmem, int mod, int tile) {
+__device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32_t tmem, int mod, int tile) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, q = w & 3, h = w >> 2;
     const int n = q * 32 + lane;                       // row inside a 128-row block = TMEM lane
     const int N = p.N, Dp = p.KC * 64;
@@ -576,7 +576,7 @@ __device__ __forceinline__ void smem_row_chunk(const uint8_t* blk0, int row, int
 // global align (losses.py:102-128): S = en_v en_t^T, pair losses, dS, dq_v = dS en_t, dq_t = dS^T en_v, normalise backward.
 // One CTA; the bf16-rounded normalised embeddings in shared memory are used consistently (MMA operands and projection).
 // ------------------------------------------------------------------------------------------------------------------------
-__device__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
+__device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, q = w & 3, h = w >> 2;
     const int n = q * 32 + lane;
     const int N = p.N, D = p.D, Dp = p.KC * 64;
@@ -711,7 +711,7 @@ __device__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
 }
 
 // after the second grid barrier: every CTA takes an equal share of the fixed-order partial reductions
-__device__ void finish_phase(const FP& p, const Smem& sm) {
+__device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int N = p.N, D = p.D, Dp = p.KC * 64, G = gridDim.x;
     if (p.want_grad && p.n_inst) {
@@ -802,7 +802,8 @@ __device__ void finish_phase(const FP& p, const Smem& sm) {
 
 __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic (not through an integer) so that the compiler keeps the shared address space: LDS/STS, not LD/ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     Smem sm;
     sm.E = smem + F_OFF_E; sm.DZ = smem + F_OFF_DZ; sm.WB = smem + F_OFF_WB;
     uint8_t* misc = smem + F_OFF_MISC;

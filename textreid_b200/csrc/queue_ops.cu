@@ -140,9 +140,9 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ 
 // items [0, 2*nd): embedding gradients (modality = item / nd); items [2*nd, 2*nd + dc): projection gradient.
 __global__ void __launch_bounds__(256)
 grad_combine_kernel(const float* __restrict__ d_inst, const float* __restrict__ d_nce, const float* __restrict__ d_ga,
-                    const float* __restrict__ d_proj, const float* __restrict__ g_inst, const float* __restrict__ g_nce,
+                    const float* d_proj, const float* __restrict__ g_inst, const float* __restrict__ g_nce,
                     const float* __restrict__ g_ga, int separate_q, int64_t nd, int64_t dc, float* __restrict__ out_v,
-                    float* __restrict__ out_t, float* __restrict__ out_vq, float* __restrict__ out_tq, float* __restrict__ out_proj,
+                    float* __restrict__ out_t, float* __restrict__ out_vq, float* __restrict__ out_tq, float* out_proj,
                     int vec4) {
     const float gi = g_inst ? g_inst[0] : 0.f, gn = g_nce ? g_nce[0] : 0.f, gg = g_ga ? g_ga[0] : 0.f;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -160,6 +160,7 @@ grad_combine_kernel(const float* __restrict__ d_inst, const float* __restrict__ 
         (e < nd ? out_v : out_t)[i] = v;
     }
     if (out_proj == nullptr) return;
+    if (out_proj == d_proj && gi == 1.0f) return;      // in-place hand-over with upstream gradient 1 (trainer.py:82): no traffic
     if (vec4) {
         const float4* src = reinterpret_cast<const float4*>(d_proj);
         float4* dst = reinterpret_cast<float4*>(out_proj);

@@ -125,6 +125,8 @@ class _MoCoLossFunction(torch.autograd.Function):
             launch(out, _workspace(shape, precision, dev), enqueue)
         ctx.separate_q = separate_q
         ctx.grads = (out.get("d_inst"), out.get("d_nce"), out.get("d_ga"), out.get("d_proj"))
+        ctx.handover = not cuda_graph          # buffers belong to this call alone: backward may give d_proj away without a copy
+        ctx.set_materialize_grads(False)       # no zero-filled gradients for the (non-differentiable) key outputs
         ctx.mark_non_differentiable(out["vkn"], out["tkn"])
         li, ln, lg = out["losses"].unbind(0)
         return li, ln, lg, out["vkn"], out["tkn"]
@@ -133,6 +135,9 @@ class _MoCoLossFunction(torch.autograd.Function):
     def backward(ctx, g_inst, g_nce, g_ga, _gvk, _gtk):
         """One launch (trb_moco_grad_combine): saved per-loss gradients x the three upstream scalars, read on the device."""
         lib = _lib.load()
+        if ctx.grads is None:
+            raise RuntimeError("moco_loss_dict: the gradient buffers were handed over by the first backward pass; "
+                               "call moco_loss_dict again (or use cuda_graph=True) for a second one")
         d_inst, d_nce, d_ga, d_proj = ctx.grads
         dev = d_inst.device
         gs = [None if g is None else (g if g.dtype == torch.float32 and g.is_cuda else g.to(device=dev, dtype=torch.float32))
@@ -141,11 +146,18 @@ class _MoCoLossFunction(torch.autograd.Function):
         gvq = gtq = None
         if ctx.separate_q:
             gvq, gtq = torch.empty_like(gv), torch.empty_like(gv)
-        gp = torch.empty_like(d_proj) if ctx.needs_input_grad[4] else None
+        gp = None
+        if ctx.needs_input_grad[4]:
+            # eager / captured-by-the-caller steps own their buffers: d_proj itself becomes the gradient (scaled in place on the
+            # device, untouched when the upstream gradient is 1); a library-level graph replay overwrites its buffers, so copy
+            gp = d_proj if ctx.handover else torch.empty_like(d_proj)
         _lib.check(lib.trb_moco_grad_combine(_lib.ptr(d_inst), _lib.ptr(d_nce), _lib.ptr(d_ga), _lib.ptr(d_proj), _lib.ptr(gs[0]),
                                              _lib.ptr(gs[1]), _lib.ptr(gs[2]), int(ctx.separate_q), gv.numel(),
                                              d_proj.numel(), _lib.ptr(gv), _lib.ptr(gt), _lib.ptr(gvq), _lib.ptr(gtq),
                                              _lib.ptr(gp), _lib.stream_ptr(dev)), "trb_moco_grad_combine")
+        if ctx.handover:
+            ctx.grads = None
+            del d_proj
         return (gv, gt, gvq, gtq, gp) + (None,) * 13
 
 
