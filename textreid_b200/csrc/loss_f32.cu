@@ -407,6 +407,13 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     if (w.fused != nullptr) {
         roles = 7;
         if (const char* e = getenv("TRB_FUSED_ROLES")) roles = atoi(e) & 7;
+        // vector accesses of the fused kernels: 16-byte aligned inputs, 32-byte aligned embedding gradients
+        const void* in16[] = {v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, v_key_n, t_key_n};
+        for (const void* q : in16)
+            if (!trb_aligned16(q)) roles = 0;
+        const void* out32[] = {d_inst, d_nce, d_ga};
+        for (const void* q : out32)
+            if (reinterpret_cast<uintptr_t>(q) & 31u) roles = 0;
     }
     if (roles) {
         fa.N = N; fa.D = D; fa.K = K; fa.C = C;

@@ -45,7 +45,8 @@ struct FP {
     const float *en, *qn, *inv_e, *inv_q, *pos;
     float2 *ms_inst, *zz_inst, *ms_nce;     // per-tile softmax statistics [tile][256 rows]: (max, sum exp) and (sum z, z_y)
     unsigned long long* dbg;                // optional phase timestamps [cta][16] (TRB_FUSED_DEBUG)
-    float *part_inst, *part_nce, *dpos, *rows_inst, *rows_nce, *rows_ga, *losses, *d_inst, *d_nce, *d_ga, *d_proj;
+    uint4 *part_inst, *part_nce;            // partial dE tiles, bf16: [tile][row block][8-column chunk][128 rows] x 16 bytes
+    float *dpos, *rows_inst, *rows_nce, *rows_ga, *losses, *d_inst, *d_nce, *d_ga, *d_proj;
     unsigned* bar;
 };
 
@@ -460,9 +461,10 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             mma_phase ^= 1;
             tc_fence_after();
             // -- drain the partial dE of this tile to global (reduced over tiles after the second grid barrier)
-            // partial layout [tile][row block][8-column chunk][128 rows][8]: the 32 rows of a warp write 1 KiB contiguous
+            // partials are rounded to bf16 (their own error from the bf16 operands is 2^-8; they are summed in fp32) and laid out
+            // [tile][row block][8-column chunk][128 rows] x 16 bytes: the 32 rows of a warp write 512 contiguous bytes
             if (INST) {
-                float* dst = p.part_inst + ((size_t)(tile * 2 + mt) * (Dp / 8) * 128 + n) * 8;
+                uint4* dst = p.part_inst + (size_t)(tile * 2 + mt) * (Dp / 8) * 128 + n;
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     if (r == 1 && !two) break;
@@ -472,20 +474,26 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                         tmem_ld32(tmem + lanes + (r ? colB : colA) + (uint32_t)(h * 64 + jj * 32), v);
                         if (n < N) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) st_v8(dst + (size_t)(r * 16 + h * 8 + jj * 4 + k) * 1024, v + 8 * k);
+                            for (int k = 0; k < 4; ++k)
+                                __stcg(dst + (size_t)(r * 16 + h * 8 + jj * 4 + k) * 128,
+                                       make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
+                                                  pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
                         }
                     }
                 }
             } else {
                 const int half = Dp / 2;
-                float* dst = p.part_nce + ((size_t)(mod * p.T_k + tile) * (Dp / 8) * 128 + n) * 8;
+                uint4* dst = p.part_nce + (size_t)(mod * p.T_k + tile) * (Dp / 8) * 128 + n;
 #pragma unroll 1
                 for (int jj = 0; jj < half / 32; ++jj) {
                     float v[32];
                     tmem_ld32(tmem + lanes + (uint32_t)(256 + h * half + jj * 32), v);
                     if (n < N) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) st_v8(dst + (size_t)((h * half + jj * 32) / 8 + k) * 1024, v + 8 * k);
+                        for (int k = 0; k < 4; ++k)
+                            __stcg(dst + (size_t)((h * half + jj * 32) / 8 + k) * 128,
+                                   make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
+                                              pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
                     }
                 }
             }
@@ -544,15 +552,24 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                 const int c = cc[j];
                 wsrc[j] = sm.WB + (c >> 6) * F_WB_CHUNK + w * 128 + ((((c & 63) >> 3) ^ w) << 4) + (c & 7) * 2;
             }
-#pragma unroll 4
-            for (int i = 0; i < p.D / 8; ++i) {
-                const int d = w + 8 * i;               // (d & 7) == w, (d >> 3) == i
+            for (int i0 = 0; i0 < p.D / 8; i0 += 8) {   // 8 rows x 4 columns per batch: shared-memory reads first, then 32 stores
+                float o[8][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = cc[j];
-                    const float wv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(wsrc[j] + i * 1024));
-                    if (cv[j])
-                        p.d_proj[(int64_t)d * p.C + c0 + c] = fmaf(-wv, sc[j], tile1[d * 128 + ((((c >> 2) ^ w)) << 2) + (c & 3)]);
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u, d = w + 8 * i;   // (d & 7) == w, (d >> 3) == i
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = cc[j];
+                        const float wv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(wsrc[j] + i * 1024));
+                        o[u][j] = fmaf(-wv, sc[j], tile1[d * 128 + ((((c >> 2) ^ w)) << 2) + (c & 3)]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int d = w + 8 * (i0 + u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (cv[j]) p.d_proj[(int64_t)d * p.C + c0 + cc[j]] = o[u][j];
                 }
             }
         }
@@ -714,76 +731,117 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
 __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int N = p.N, D = p.D, Dp = p.KC * 64, G = gridDim.x;
-    if (p.want_grad && p.n_inst) {
-        // d_inst[row, d] = sum_tiles partial[tile][row, d]: one float4 per thread, 22 independent loads in flight.  Work item
-        // idx = ((mod * D/4 + d4) * N + row): consecutive threads take consecutive rows of one column group (contiguous loads).
-        const int per_row = D / 4, total4 = 2 * N * per_row;
-        const int per_cta = (total4 + G - 1) / G;
-        const size_t tstride = (size_t)2 * (Dp / 8) * 1024;
-        const int lo = blockIdx.x * per_cta, hi = min(total4, lo + per_cta);
-        for (int idx = lo + tid; idx < hi; idx += F_THREADS) {
-            const int nn = idx % N, t = idx / N;
-            const int d4 = t % per_row, mod = t / per_row;
-            const float* src = p.part_inst + ((size_t)(mod * (Dp / 8) + (d4 >> 1)) * 128 + nn) * 8 + (d4 & 1) * 4;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int t0 = 0; t0 < p.T_inst; t0 += 22) {
-                float4 x[22];
+    // the last CTA only forms the loss scalars; the partial reductions are shared by the others
+    const int GW = p.reduce_losses && G > 1 ? G - 1 : G;
+    const bool worker = blockIdx.x < GW;
+    if (p.want_grad && p.n_inst && worker) {
+        // d_inst[row, 8 columns] = sum_tiles partial: three threads per item (a third of the tiles each, all their 16-byte loads in
+        // flight at once), partial sums combined through shared memory in a fixed order.
+        // Item = ((mod * D/8 + c8) * N + row): consecutive threads take consecutive rows (contiguous loads).
+        constexpr int PARTS = 3, MAXT = 32;                      // up to 96 tiles in one batch; more tiles loop
+        const int per_mod = (D / 8) * N, items = 2 * per_mod;
+        const int per_cta = (items + GW - 1) / GW;
+        const size_t tstride = (size_t)2 * (Dp / 8) * 128;
+        const int lo = blockIdx.x * per_cta, hi = min(items, lo + per_cta);
+        float* comb = reinterpret_cast<float*>(sm.DZ);           // [<= 85 items][PARTS][8]
+        const int chunk = min(per_cta, F_THREADS / PARTS);       // items per pass
+        const int tper = (p.T_inst + PARTS - 1) / PARTS;         // tiles per part
+        for (int base = lo; base < hi; base += chunk) {
+            const int local = tid % chunk, part = tid / chunk;   // part-major: a warp reads consecutive rows of one tile
+            const int item = base + local;
+            const bool live = part < PARTS && item < hi;
+            if (live) {
+                const int nn = item % N, t = item / N;
+                const int c8 = t % (D / 8), mod = t / (D / 8);
+                const uint4* src = p.part_inst + (size_t)(mod * (Dp / 8) + c8) * 128 + nn;
+                const int tlo = part * tper, thi = min(p.T_inst, tlo + tper);
+                float acc[8];
 #pragma unroll
-                for (int i = 0; i < 22; ++i)
-                    x[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)min(t0 + i, p.T_inst - 1) * tstride));
-                asm volatile("" ::: "memory");
+                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+                for (int t0 = tlo; t0 < thi; t0 += MAXT) {
+                    uint4 x[MAXT];
 #pragma unroll
-                for (int i = 0; i < 22; ++i)
-                    if (t0 + i < p.T_inst) { acc.x += x[i].x; acc.y += x[i].y; acc.z += x[i].z; acc.w += x[i].w; }
+                    for (int i = 0; i < MAXT; ++i) x[i] = __ldcg(src + (size_t)min(t0 + i, thi - 1) * tstride);
+                    asm volatile("" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < MAXT; ++i) {
+                        if (t0 + i < thi) {
+                            const uint32_t r[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                acc[2 * k] += __uint_as_float(r[k] << 16);
+                                acc[2 * k + 1] += __uint_as_float(r[k] & 0xffff0000u);
+                            }
+                        }
+                    }
+                }
+                float4* o = reinterpret_cast<float4*>(comb + (size_t)(local * PARTS + part) * 8);
+                o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
             }
-            *reinterpret_cast<float4*>(p.d_inst + ((size_t)(mod * N + nn) * D + d4 * 4)) = acc;
+            __syncthreads();
+            if (tid < chunk && base + tid < hi) {
+                const int item2 = base + tid;
+                const int nn = item2 % N, t = item2 / N;
+                const int c8 = t % (D / 8), mod = t / (D / 8);
+                float out[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) out[e] = (comb[(tid * PARTS + 0) * 8 + e] + comb[(tid * PARTS + 1) * 8 + e]) + comb[(tid * PARTS + 2) * 8 + e];
+                st_v8(p.d_inst + ((size_t)(mod * N + nn) * D + c8 * 8), out);
+            }
+            __syncthreads();
         }
     }
-    if (p.want_grad && p.n_nce) {
-        // d_nce[row] = normalise-backward( sum_tiles dq_part + dpos * key )   one warp per row, rows dealt round-robin to CTAs
-        for (int row = blockIdx.x + G * (7 - w); row < 2 * N; row += G * 8) {
+    if (p.want_grad && p.n_nce) {      // (no block-level synchronisation below: idle CTAs / warps simply fall through)
+        // d_nce[row] = normalise-backward( sum_tiles dq_part + dpos * key )   one warp per row, rows dealt round-robin to CTAs;
+        // lane = 8-column chunk
+        for (int row = blockIdx.x + GW * (7 - w); worker && row < 2 * N; row += GW * 8) {
             const int mod = row / N, nn = row % N;
             const float dp = __ldcg(p.dpos + row);
             const float* key = p.key_n[mod] + (int64_t)nn * D;
             const float* qr = p.qn + (int64_t)row * D;
-            float4 g[2];
+            const bool on = lane * 8 < D;
+            float g[8], qv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = qv[e] = 0.f;
             float dot = 0.f;
+            if (on) {
+                const uint4* src = p.part_nce + (size_t)(mod * p.T_k) * (Dp / 8) * 128 + (size_t)lane * 128 + nn;
+                for (int t0 = 0; t0 < p.T_k; t0 += 16) {
+                    uint4 x[16];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int d4 = lane + 32 * u;
-                g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (d4 * 4 < D) {
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float* src = p.part_nce + ((size_t)(mod * p.T_k) * (Dp / 8) * 128 + (size_t)(d4 >> 1) * 128 + nn) * 8 + (d4 & 1) * 4;
-                    for (int t0 = 0; t0 < p.T_k; t0 += 16) {
-                        float4 x[16];
+                    for (int i = 0; i < 16; ++i) x[i] = __ldcg(src + (size_t)min(t0 + i, p.T_k - 1) * (Dp / 8) * 128);
+                    asm volatile("" ::: "memory");
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            x[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)min(t0 + i, p.T_k - 1) * (Dp / 8) * 1024));
-                        asm volatile("" ::: "memory");
+                    for (int i = 0; i < 16; ++i) {
+                        if (t0 + i < p.T_k) {
+                            const uint32_t r[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (t0 + i < p.T_k) { a.x += x[i].x; a.y += x[i].y; a.z += x[i].z; a.w += x[i].w; }
+                            for (int k = 0; k < 4; ++k) {
+                                g[2 * k] += __uint_as_float(r[k] << 16);
+                                g[2 * k + 1] += __uint_as_float(r[k] & 0xffff0000u);
+                            }
+                        }
                     }
-                    const float4 k4 = *reinterpret_cast<const float4*>(key + d4 * 4);
-                    const float4 q4 = *reinterpret_cast<const float4*>(qr + d4 * 4);
-                    a.x = fmaf(dp, k4.x, a.x); a.y = fmaf(dp, k4.y, a.y); a.z = fmaf(dp, k4.z, a.z); a.w = fmaf(dp, k4.w, a.w);
-                    dot = fmaf(a.x, q4.x, dot); dot = fmaf(a.y, q4.y, dot); dot = fmaf(a.z, q4.z, dot); dot = fmaf(a.w, q4.w, dot);
-                    g[u] = a;
+                }
+                const float4 k0 = *reinterpret_cast<const float4*>(key + lane * 8), k1 = *reinterpret_cast<const float4*>(key + lane * 8 + 4);
+                const float4 q0 = *reinterpret_cast<const float4*>(qr + lane * 8), q1 = *reinterpret_cast<const float4*>(qr + lane * 8 + 4);
+                const float kk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+                const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    qv[e] = qq[e];
+                    g[e] = fmaf(dp, kk[e], g[e]);
+                    dot = fmaf(g[e], qq[e], dot);
                 }
             }
             dot = warp_sum(dot);
             const float inv = p.inv_q[row];
+            if (on) {
+                float o[8];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int d4 = lane + 32 * u;
-                if (d4 * 4 < D) {
-                    const float4 q4 = *reinterpret_cast<const float4*>(qr + d4 * 4);
-                    float4 o;
-                    o.x = (g[u].x - dot * q4.x) * inv; o.y = (g[u].y - dot * q4.y) * inv;
-                    o.z = (g[u].z - dot * q4.z) * inv; o.w = (g[u].w - dot * q4.w) * inv;
-                    *reinterpret_cast<float4*>(p.d_nce + (int64_t)row * D + d4 * 4) = o;
-                }
+                for (int e = 0; e < 8; ++e) o[e] = (g[e] - dot * qv[e]) * inv;
+                st_v8(p.d_nce + (int64_t)row * D + lane * 8, o);
             }
         }
     }
@@ -915,12 +973,14 @@ fused_prologue_kernel(const float* __restrict__ v_embed, const float* __restrict
     for (int i = 0; i < 8; ++i) a[i] = b[i] = c[i] = 0.f;
     const bool live = n < N && k0 < D;
     const int row = mod * N + n;
-    if (live) {
-        const float* e = (mod ? t_embed : v_embed) + (int64_t)n * D + k0;
-        const float* r = (mod ? t_qraw : v_qraw) + (int64_t)n * D + k0;
-        const float* kin = (mod ? v_key : t_key) + (int64_t)n * D + k0;      // v queries pair with TEXT keys (head.py:160,166)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { a[i] = e[i]; b[i] = r[i]; c[i] = kin[i]; }
+    if (live) {                                                              // 16-byte aligned rows (checked by the caller)
+        const float4* e = reinterpret_cast<const float4*>((mod ? t_embed : v_embed) + (int64_t)n * D + k0);
+        const float4* r = reinterpret_cast<const float4*>((mod ? t_qraw : v_qraw) + (int64_t)n * D + k0);
+        const float4* kin = reinterpret_cast<const float4*>((mod ? v_key : t_key) + (int64_t)n * D + k0);   // v queries pair with TEXT keys (head.py:160,166)
+        const float4 e0 = e[0], e1 = e[1], r0 = r[0], r1 = r[1], c0 = kin[0], c1 = kin[1];
+        a[0] = e0.x; a[1] = e0.y; a[2] = e0.z; a[3] = e0.w; a[4] = e1.x; a[5] = e1.y; a[6] = e1.z; a[7] = e1.w;
+        b[0] = r0.x; b[1] = r0.y; b[2] = r0.z; b[3] = r0.w; b[4] = r1.x; b[5] = r1.y; b[6] = r1.z; b[7] = r1.w;
+        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
     }
     float se = 0.f, sr = 0.f, sk = 0.f;
 #pragma unroll
@@ -938,13 +998,16 @@ fused_prologue_kernel(const float* __restrict__ v_embed, const float* __restrict
     }
     dot = warp_sum(dot);
     if (live) {
-        float* kout = (mod ? v_key_n : t_key_n) + (int64_t)n * D + k0;
+        float4* kout = reinterpret_cast<float4*>((mod ? v_key_n : t_key_n) + (int64_t)n * D + k0);
+        float4* o_e = reinterpret_cast<float4*>(E2 + (int64_t)row * D + k0);
+        float4* o_en = reinterpret_cast<float4*>(en + (int64_t)row * D + k0);
+        float4* o_qn = reinterpret_cast<float4*>(qn + (int64_t)row * D + k0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            E2[(int64_t)row * D + k0 + i] = a[i];
-            en[(int64_t)row * D + k0 + i] = an[i];
-            qn[(int64_t)row * D + k0 + i] = qv[i];
-            kout[i] = kv[i];
+        for (int i = 0; i < 2; ++i) {
+            o_e[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+            o_en[i] = make_float4(an[4 * i], an[4 * i + 1], an[4 * i + 2], an[4 * i + 3]);
+            o_qn[i] = make_float4(qv[4 * i], qv[4 * i + 1], qv[4 * i + 2], qv[4 * i + 3]);
+            kout[i] = make_float4(kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
         }
     }
     if (n < N && lane == 0) { inv_e[row] = __fdiv_rn(1.0f, ne); inv_q[row] = __fdiv_rn(1.0f, nr); pos[row] = dot; }
@@ -963,7 +1026,7 @@ fused_prologue_kernel(const float* __restrict__ v_embed, const float* __restrict
 struct Scratch {
     uint8_t *Ep, *ENp, *QNp, *QUp;
     float2 *ms_inst, *zz_inst, *ms_nce;
-    float *part_inst, *part_nce;
+    uint4 *part_inst, *part_nce;
     unsigned* bar;
     int64_t bytes;
 };
@@ -981,8 +1044,8 @@ Scratch carve_scratch(uint8_t* base, int N, int D, int K, int C) {
     s.ms_inst = reinterpret_cast<float2*>(take((int64_t)256 * T_inst * 8));
     s.zz_inst = reinterpret_cast<float2*>(take((int64_t)256 * T_inst * 8));
     s.ms_nce = reinterpret_cast<float2*>(take((int64_t)256 * T_k * 8));
-    s.part_inst = reinterpret_cast<float*>(take((int64_t)T_inst * 256 * Dp * 4));
-    s.part_nce = reinterpret_cast<float*>(take((int64_t)2 * T_k * 128 * Dp * 4));
+    s.part_inst = reinterpret_cast<uint4*>(take((int64_t)T_inst * 256 * Dp * 2));
+    s.part_nce = reinterpret_cast<uint4*>(take((int64_t)2 * T_k * 128 * Dp * 2));
     s.bar = reinterpret_cast<unsigned*>(take(256));
     s.bytes = p - base;
     return s;
