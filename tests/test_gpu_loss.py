@@ -390,3 +390,26 @@ def test_grad_combine_single_launch_backward():
                 if separate:
                     torch.testing.assert_close(oq, -2.0 * d_nce[m], rtol=0, atol=0)
             torch.testing.assert_close(op, gi * d_proj, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("merged", [False, True])
+def test_fused_workspace_reuse_has_no_stale_operands(monkeypatch, merged):
+    """The operand images of the prologue live in the cached workspace; with TRB_FUSED_MERGED=1 they are produced and consumed
+    inside the SAME cooperative launch (one launch per step).  A second call with different data must not see the first call's
+    images, and the barrier words must be ready for the next call."""
+    from textreid_b200 import losses as L
+    if merged:
+        monkeypatch.setenv("TRB_FUSED_MERGED", "1")
+        assert _launches(64, 256, 1024, 3000, 1) == 1
+    L._workspaces.clear()
+    shape = (64, 256, 1024, 3000)
+    a = synth_loss_inputs(*shape, seed=21)
+    b = synth_loss_inputs(*shape, seed=22)
+    run_fused(a, 0.1, precision="bf16")
+    second = run_fused(b, 0.1, precision="bf16")              # reuses the workspace the first call left behind
+    L._workspaces.clear()
+    fresh = run_fused(b, 0.1, precision="bf16")               # brand-new zero-filled workspace
+    for k in KEYS:
+        assert torch.equal(second[0][k], fresh[0][k])
+    for x, y in zip(second[1:], fresh[1:]):
+        assert torch.equal(x, y)

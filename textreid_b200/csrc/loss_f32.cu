@@ -371,7 +371,10 @@ int64_t trb_moco_loss_workspace_bytes_tc(const trb_moco_shape* s) {
 // launches of one call (grads and d_projection requested); mirrors the sequence below
 int trb_moco_loss_launches_impl(const trb_moco_shape* s, int precision) {
     const bool use_tc = precision == 1;
-    if (use_tc && fused_loss_supported(s->N, s->D, s->K, s->C, sm_count()) && !getenv("TRB_FUSED_ROLES")) return 2;
+    if (use_tc && fused_loss_supported(s->N, s->D, s->K, s->C, sm_count())) {
+        const char* e = getenv("TRB_FUSED_ROLES");
+        if (e == nullptr || (atoi(e) & 7) == 7) return getenv("TRB_FUSED_MERGED") ? 1 : 2;
+    }
     const int per_gemm = use_tc ? 3 : 1;
     // prologue, mask, column norms, 3 row kernels, 2 normalise-backward, projection backward, loss reduce, 3 partial reductions
     return 13 + 10 * per_gemm;
@@ -426,7 +429,7 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
         fa.losses = losses; fa.d_inst = d_inst; fa.d_nce = d_nce; fa.d_ga = d_ga; fa.d_proj = d_projection;
         fa.scratch = w.fused; fa.roles = roles; fa.reduce_losses = roles == 7;
         if ((rc = fused_loss_prologue(fa, st))) return rc;
-        if (roles == 7) return fused_loss_launch(fa, st);       // the whole step: two launches, no helper streams
+        if (roles == 7) return fused_loss_launch(fa, st);       // the whole step: prologue + one cooperative launch, no helper streams
     } else {
         // ---- shared prologue on the caller's stream
         prologue_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, normalize_keys,

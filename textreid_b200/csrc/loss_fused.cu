@@ -33,6 +33,13 @@ constexpr int F_OFF_E = 0, F_OFF_DZ = F_E_BYTES, F_OFF_WB = F_OFF_DZ + F_DZ_BYTE
 constexpr int F_MISC_BYTES = 2048;
 constexpr int F_SMEM = F_OFF_MISC + F_MISC_BYTES + 1024;   // + alignment slack
 
+struct ProArgs {
+    const float *v_embed, *t_embed, *v_qraw, *t_qraw, *v_key, *t_key, *v_queue, *t_queue;
+    float *v_key_n, *t_key_n, *E2, *en, *inv_e, *qn, *inv_q, *pos;
+    uint8_t *Ep, *ENp, *QNp, *QUp;
+    int normalize_keys, N, D, KC, K, T_k;
+};
+
 struct FP {
     int N, D, K, C, KC, T_inst, T_k, n_inst, n_nce, n_ga, want_grad, reduce_losses, roles, variant;
     float T, eps, alpha, beta, sp, sn;
@@ -47,7 +54,9 @@ struct FP {
     unsigned long long* dbg;                // optional phase timestamps [cta][16] (TRB_FUSED_DEBUG)
     uint4 *part_inst, *part_nce;            // partial dE tiles, bf16: [tile][row block][8-column chunk][128 rows] x 16 bytes
     float *dpos, *rows_inst, *rows_nce, *rows_ga, *losses, *d_inst, *d_nce, *d_ga, *d_proj;
-    unsigned* bar;
+    unsigned* bar;                  // [0], [1] grid barriers, [2] prologue tasks done, [3] exit count; zero between launches
+    ProArgs pro;
+    int merged;                     // the prologue tasks run inside this kernel (InfoNCE / align CTAs)
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -234,6 +243,182 @@ __device__ __forceinline__ float lane_transpose_sum(float (&u)[32], int lane) {
     return u[0];
 }
 
+// thread 0: spin until *ctr >= target (acquire), bounded like the other waits
+__device__ __forceinline__ void wait_count(const unsigned* ctr, unsigned target) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) break;
+        __nanosleep(40);
+        if (clock64() - t0 > 4000000000LL) {
+            printf("trb: fused loss prologue wait timed out (block %d, %u of %u)\n", blockIdx.x, v, target);
+            __trap();
+        }
+    }
+    __threadfence();
+}
+
+// all threads: n16 16-byte words global (L2) -> shared, up to 32 loads in flight per thread
+__device__ __forceinline__ void copy_g2s(uint8_t* dst, const uint8_t* src, int n16) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int base = 0; base < n16; base += 32 * F_THREADS) {
+        uint4 x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __ldcg(s4 + min(base + i * F_THREADS + (int)threadIdx.x, n16 - 1));
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int idx = base + i * F_THREADS + (int)threadIdx.x;
+            if (idx < n16) d4[idx] = x[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// prologue tasks, one warp each.  Row task: fp32 artefacts of one padded embedding row as in loss_f32.cu's prologue (same
+// expressions) plus its slice of the three packed bf16 operand images (raw embeds, normalised embeds, normalised InfoNCE
+// queries), zero padded.  Pack task: one full row of a fp32 [D, K] queue (contiguous, DRAM friendly; a strided 128-column tile
+// read of the power-of-two-pitched queue crawls) -> bf16 into the per-tile shared-memory images
+// [tile][2 column chunks][256 d][128 B] that the InfoNCE CTAs copy in one piece.
+// They run either inside the cooperative kernel (all branches fused: the InfoNCE / align CTAs execute them while the instance
+// CTAs stream W) or as a separate launch (fused_prologue_kernel) when only some branches are fused.
+// ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pro_pack_task(const ProArgs& a, int mod, int d, int lane) {
+    const int K = a.K, T_k = a.T_k;
+    const float* row = (mod ? a.v_queue : a.t_queue) + (int64_t)d * K;       // image queries score the TEXT queue (head.py:162,168)
+    uint8_t* img = a.QUp + (size_t)mod * T_k * F_WB_BYTES;
+    const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0 && d < a.D;
+    for (int t0 = 0; t0 < T_k; t0 += 16) {
+        float4 x[16];
+        if (vec) {                                 // all loads of the row in flight before the first use
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = min((t0 + i) * 128 + 4 * lane, K - 4);
+                x[i] = __ldcs(reinterpret_cast<const float4*>(row + k));
+            }
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if ((t0 + i) * 128 + 4 * lane + 3 >= K) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = (t0 + i) * 128 + 4 * lane;
+                x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (d < a.D) {
+                    if (k < K) x[i].x = row[k];
+                    if (k + 1 < K) x[i].y = row[k + 1];
+                    if (k + 2 < K) x[i].z = row[k + 2];
+                    if (k + 3 < K) x[i].w = row[k + 3];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (t0 + i < T_k) {
+                uint2 o;
+                o.x = pack2(x[i].x, x[i].y); o.y = pack2(x[i].z, x[i].w);
+                *reinterpret_cast<uint2*>(img + (size_t)(t0 + i) * F_WB_BYTES + wb_offset(d, 4 * lane)) = o;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void pro_row_task(const ProArgs& p, int prow, int lane) {
+    const int N = p.N, D = p.D, KC = p.KC;
+    const int mod = prow >> 7, n = prow & 127;                     // padded row: modality * 128 + n
+    const int k0 = lane * 8;
+    const bool in_pad = k0 < KC * 64;
+    float a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = b[i] = c[i] = 0.f;
+    const bool live = n < N && k0 < D;
+    const int row = mod * N + n;
+    if (live) {                                                              // 16-byte aligned rows (checked by the caller)
+        const float4* e = reinterpret_cast<const float4*>((mod ? p.t_embed : p.v_embed) + (int64_t)n * D + k0);
+        const float4* r = reinterpret_cast<const float4*>((mod ? p.t_qraw : p.v_qraw) + (int64_t)n * D + k0);
+        const float4* kin = reinterpret_cast<const float4*>((mod ? p.v_key : p.t_key) + (int64_t)n * D + k0);   // v queries pair with TEXT keys (head.py:160,166)
+        const float4 e0 = e[0], e1 = e[1], r0 = r[0], r1 = r[1], c0 = kin[0], c1 = kin[1];
+        a[0] = e0.x; a[1] = e0.y; a[2] = e0.z; a[3] = e0.w; a[4] = e1.x; a[5] = e1.y; a[6] = e1.z; a[7] = e1.w;
+        b[0] = r0.x; b[1] = r0.y; b[2] = r0.z; b[3] = r0.w; b[4] = r1.x; b[5] = r1.y; b[6] = r1.z; b[7] = r1.w;
+        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+    }
+    float se = 0.f, sr = 0.f, sk = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { se = fmaf(a[i], a[i], se); sr = fmaf(b[i], b[i], sr); sk = fmaf(c[i], c[i], sk); }
+    se = warp_sum(se); sr = warp_sum(sr); sk = warp_sum(sk);
+    const float ne = fmaxf(sqrtf(se), 1e-12f), nr = fmaxf(sqrtf(sr), 1e-12f);
+    const float nk = p.normalize_keys ? fmaxf(sqrtf(sk), 1e-12f) : 1.0f;
+    float an[8], qv[8], kv[8], dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        an[i] = __fdiv_rn(a[i], ne);
+        qv[i] = __fdiv_rn(b[i], nr);
+        kv[i] = p.normalize_keys ? __fdiv_rn(c[i], nk) : c[i];
+        dot = fmaf(qv[i], kv[i], dot);
+    }
+    dot = warp_sum(dot);
+    if (live) {
+        float4* kout = reinterpret_cast<float4*>((mod ? p.v_key_n : p.t_key_n) + (int64_t)n * D + k0);
+        float4* o_e = reinterpret_cast<float4*>(p.E2 + (int64_t)row * D + k0);
+        float4* o_en = reinterpret_cast<float4*>(p.en + (int64_t)row * D + k0);
+        float4* o_qn = reinterpret_cast<float4*>(p.qn + (int64_t)row * D + k0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            o_e[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+            o_en[i] = make_float4(an[4 * i], an[4 * i + 1], an[4 * i + 2], an[4 * i + 3]);
+            o_qn[i] = make_float4(qv[4 * i], qv[4 * i + 1], qv[4 * i + 2], qv[4 * i + 3]);
+            kout[i] = make_float4(kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
+        }
+    }
+    if (n < N && lane == 0) { p.inv_e[row] = __fdiv_rn(1.0f, ne); p.inv_q[row] = __fdiv_rn(1.0f, nr); p.pos[row] = dot; }
+    if (in_pad) {
+        const int64_t off = packed_offset_bytes(prow, lane, KC);
+        uint4 o;
+        o.x = pack2(a[0], a[1]); o.y = pack2(a[2], a[3]); o.z = pack2(a[4], a[5]); o.w = pack2(a[6], a[7]);
+        *reinterpret_cast<uint4*>(p.Ep + off) = o;
+        o.x = pack2(an[0], an[1]); o.y = pack2(an[2], an[3]); o.z = pack2(an[4], an[5]); o.w = pack2(an[6], an[7]);
+        *reinterpret_cast<uint4*>(p.ENp + off) = o;
+        o.x = pack2(qv[0], qv[1]); o.y = pack2(qv[2], qv[3]); o.z = pack2(qv[4], qv[5]); o.w = pack2(qv[6], qv[7]);
+        *reinterpret_cast<uint4*>(p.QNp + off) = o;
+    }
+}
+
+// task t of the prologue: [0, 256) embedding rows, then the queue rows (2 * Dp) when `pack`
+__device__ __forceinline__ void pro_task(const ProArgs& a, int t, int lane) {
+    if (t < 256) pro_row_task(a, t, lane);
+    else { const int q = t - 256, Dp = a.KC * 64; pro_pack_task(a, q / Dp, q % Dp, lane); }
+}
+
+// stand-alone prologue (some branches unfused): one warp per task, also clears the grid-barrier words
+__global__ void __launch_bounds__(256) fused_prologue_kernel(const ProArgs a, unsigned* __restrict__ bar, int ntasks) {
+    if (blockIdx.x == 0 && threadIdx.x < 4) bar[threadIdx.x] = 0u;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t < ntasks) pro_task(a, t, threadIdx.x & 31);
+}
+
+// All branches fused: the prologue tasks run inside the cooperative kernel.  The instance CTAs take the (cheap) embedding-row
+// tasks before they stream W, the InfoNCE / align CTAs the queue re-pack tasks; bar[2] counts CTAs past the row phase (all of
+// them), bar[3] the CTAs done with the queue images.
+__device__ __forceinline__ void run_prologue_rows(const FP& p) {        // instance CTAs
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = blockIdx.x * 8 + w; t < 256; t += p.n_inst * 8) pro_row_task(p.pro, t, lane);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p.bar + 2, 1u);
+}
+__device__ __forceinline__ void run_prologue_pack(const FP& p) {        // InfoNCE / align CTAs
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw = (p.n_nce + p.n_ga) * 8, Dp = p.KC * 64;
+    if (threadIdx.x == 0) atomicAdd(p.bar + 2, 1u);                      // no row tasks here
+    for (int t = (blockIdx.x - p.n_inst) * 8 + w; t < 2 * Dp; t += nw) pro_pack_task(p.pro, t / Dp, t % Dp, lane);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p.bar + 3, 1u);
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
 // instance (INST) / InfoNCE tile
 // ------------------------------------------------------------------------------------------------------------------------
@@ -253,10 +438,12 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     int64_t* s_lab = reinterpret_cast<int64_t*>(sm.DZ + 8192);           // [128] batch ids (InfoNCE mask)
     float* s_lse2 = reinterpret_cast<float*>(sm.DZ + 16384);             // [256] base-2 row log-sum-exp
 
-    // ---- operand rows: packed bf16 image written by the prologue (instance: raw embeds, both modalities; InfoNCE: q rows).
-    //      InfoNCE also bulk-loads its queue tile: the prologue re-packed the fp32 [D, K] queues (whose power-of-two row pitch
-    //      makes a strided 128-column tile read crawl) into contiguous bf16 tile images.
-    if (tid == 0) {
+    if (p.merged) {
+        if (INST) run_prologue_rows(p);
+        else run_prologue_pack(p);
+    } else if (tid == 0) {
+        // operand rows (and, InfoNCE, the queue tile image) written by the prologue launch: bulk copies (TMA engine), in flight
+        // while the W tile streams in
         const uint8_t* src = INST ? p.Ep : p.QNp + (size_t)mod * p.KC * BLOCK_BYTES;
         const int blocks = MT * p.KC;
         mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES + (INST ? 0u : (uint32_t)F_WB_BYTES));
@@ -275,6 +462,20 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
 
     // ---- instance: W tile HBM -> bf16 shared image, column norms
     if (INST) load_tile_bf16(p.W, ncols, p.D, Dp, c0, ncols, (p.variant & 2) ? 0 : ((tile * 7) & 31), !(p.variant & 4), sm.WB, red);
+    // ---- merged mode: the operand images come from prologue tasks of other CTAs of this very grid: wait for them, then plain
+    //      L2 loads (no cross-proxy question)
+    if (p.merged) {
+        if (tid == 0) {
+            wait_count(p.bar + 2, gridDim.x);
+            if (!INST) wait_count(p.bar + 3, (unsigned)(p.n_nce + p.n_ga));
+        }
+        __syncthreads();
+        if (INST) copy_g2s(sm.E, p.Ep, MT * p.KC * (BLOCK_BYTES / 16));
+        else {
+            copy_g2s(sm.E, p.QNp + (size_t)mod * p.KC * BLOCK_BYTES, p.KC * (BLOCK_BYTES / 16));
+            copy_g2s(sm.WB, p.QUp + ((size_t)mod * p.T_k + tile) * F_WB_BYTES, F_WB_BYTES / 16);
+        }
+    }
     __syncthreads();
     if (tid < 128) {
         bool ok = c0 + tid < ncols;
@@ -301,7 +502,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
 
     // ---- forward logits: z[mt] = E[mt] . Wb   (M = 128 rows, N = 128 columns, K = Dp)
     if (tid == 0) {
-        mbar_wait(sm.bar_load, 0);
+        if (!p.merged) mbar_wait(sm.bar_load, 0);
         tc_fence_after();
         const uint32_t id_f = idesc(128, 128, 0, 1);
         const uint32_t e0 = smem_u32(sm.E), wb0 = smem_u32(sm.WB);
@@ -602,19 +803,25 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
     int64_t* s_lab = reinterpret_cast<int64_t*>(sm.WB);                 // [128]
     float* s_part = reinterpret_cast<float*>(sm.WB + 2048);             // [2][128]
 
-    if (tid == 0) {
+    // nothing here depends on the tiles' statistics: arrive at the first grid barrier right away, never wait on it
+    if (tid == 0) atomicAdd(p.bar, 1u);
+    if (p.merged) {
+        run_prologue_pack(p);
+        if (tid == 0) wait_count(p.bar + 2, gridDim.x);
+        __syncthreads();
+        copy_g2s(sm.E, p.ENp, 2 * p.KC * (BLOCK_BYTES / 16));
+    } else if (tid == 0) {
         const int blocks = 2 * p.KC;
         mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES);
         for (int b = 0; b < blocks; ++b) bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, p.ENp + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
     }
-    // nothing here depends on the tiles' statistics: arrive at the first grid barrier right away, never wait on it
-    if (tid == 0) atomicAdd(p.bar, 1u);
     if (tid < 128) s_lab[tid] = tid < N ? p.labels[tid] : INT64_MIN;
+    fence_async_smem();
     __syncthreads();
     const uint32_t e0 = smem_u32(sm.E), dz0 = smem_u32(sm.DZ);
     const uint32_t et0 = e0 + p.KC * BLOCK_BYTES;                       // text rows
     if (tid == 0) {
-        mbar_wait(sm.bar_load, 0);
+        if (!p.merged) mbar_wait(sm.bar_load, 0);
         tc_fence_after();
         const uint32_t id_s = idesc(128, 128, 0, 0);
         for (int ks = 0; ks < Dp / 16; ++ks)
@@ -902,124 +1109,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
-}
-
-// ------------------------------------------------------------------------------------------------------------------------
-// prologue: one warp per padded row (2 x 128).  fp32 artefacts as in loss_f32.cu's prologue (same expressions) plus the three
-// packed bf16 operand images (raw embeds, normalised embeds, normalised InfoNCE queries), zero padded, and the barrier reset.
-// ------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-fused_prologue_kernel(const float* __restrict__ v_embed, const float* __restrict__ t_embed, const float* __restrict__ v_qraw,
-                      const float* __restrict__ t_qraw, const float* __restrict__ v_key, const float* __restrict__ t_key,
-                      int normalize_keys, float* __restrict__ v_key_n, float* __restrict__ t_key_n, float* __restrict__ E2,
-                      float* __restrict__ en, float* __restrict__ inv_e, float* __restrict__ qn, float* __restrict__ inv_q,
-                      float* __restrict__ pos, uint8_t* __restrict__ Ep, uint8_t* __restrict__ ENp, uint8_t* __restrict__ QNp,
-                      unsigned* __restrict__ bar, int N, int D, int KC, const float* __restrict__ v_queue,
-                      const float* __restrict__ t_queue, uint8_t* __restrict__ QUp, int K, int T_k) {
-    const int lane = threadIdx.x & 31;
-    if (blockIdx.x >= 32) {
-        // ---- queue re-pack: CTA = (modality, 8 consecutive d), warp = one full row of the fp32 [D, K] queue (contiguous, DRAM
-        //      friendly) -> bf16 into the per-tile shared-memory images [tile][2 column chunks][256 d][128 B] the InfoNCE CTAs
-        //      bulk-load.  Modality 0 (image queries) scores the TEXT queue (head.py:162,168).
-        const int b = blockIdx.x - 32, per_mod = KC * 8;          // Dp / 8 row groups
-        const int mod = b / per_mod, d = (b % per_mod) * 8 + (threadIdx.x >> 5);
-        const float* row = (mod ? v_queue : t_queue) + (int64_t)d * K;
-        uint8_t* img = QUp + (size_t)mod * T_k * F_WB_BYTES;
-        const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0 && d < D;
-        for (int t0 = 0; t0 < T_k; t0 += 16) {
-            float4 x[16];
-            if (vec) {                                 // all loads of the row in flight before the first use
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int k = min((t0 + i) * 128 + 4 * lane, K - 4);
-                    x[i] = __ldcs(reinterpret_cast<const float4*>(row + k));
-                }
-                asm volatile("" ::: "memory");
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if ((t0 + i) * 128 + 4 * lane + 3 >= K) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int k = (t0 + i) * 128 + 4 * lane;
-                    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (d < D) {
-                        if (k < K) x[i].x = row[k];
-                        if (k + 1 < K) x[i].y = row[k + 1];
-                        if (k + 2 < K) x[i].z = row[k + 2];
-                        if (k + 3 < K) x[i].w = row[k + 3];
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (t0 + i < T_k) {
-                    uint2 o;
-                    o.x = pack2(x[i].x, x[i].y); o.y = pack2(x[i].z, x[i].w);
-                    *reinterpret_cast<uint2*>(img + (size_t)(t0 + i) * F_WB_BYTES + wb_offset(d, 4 * lane)) = o;
-                }
-            }
+    // no prologue launch clears the barrier words in merged mode: the last CTA to leave puts them back to zero
+    if (p.merged && threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(p.bar + 4, 1u) == gridDim.x - 1) {
+            p.bar[0] = 0u; p.bar[1] = 0u; p.bar[2] = 0u; p.bar[3] = 0u; p.bar[4] = 0u;
+            __threadfence();
         }
-        return;
-    }
-    const int prow = blockIdx.x * 8 + (threadIdx.x >> 5);         // padded row: modality * 128 + n
-    if (blockIdx.x == 0 && threadIdx.x < 2) bar[threadIdx.x] = 0u;
-    if (prow >= 256) return;
-    const int mod = prow >> 7, n = prow & 127;
-    const int k0 = lane * 8;
-    const bool in_pad = k0 < KC * 64;
-    float a[8], b[8], c[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = b[i] = c[i] = 0.f;
-    const bool live = n < N && k0 < D;
-    const int row = mod * N + n;
-    if (live) {                                                              // 16-byte aligned rows (checked by the caller)
-        const float4* e = reinterpret_cast<const float4*>((mod ? t_embed : v_embed) + (int64_t)n * D + k0);
-        const float4* r = reinterpret_cast<const float4*>((mod ? t_qraw : v_qraw) + (int64_t)n * D + k0);
-        const float4* kin = reinterpret_cast<const float4*>((mod ? v_key : t_key) + (int64_t)n * D + k0);   // v queries pair with TEXT keys (head.py:160,166)
-        const float4 e0 = e[0], e1 = e[1], r0 = r[0], r1 = r[1], c0 = kin[0], c1 = kin[1];
-        a[0] = e0.x; a[1] = e0.y; a[2] = e0.z; a[3] = e0.w; a[4] = e1.x; a[5] = e1.y; a[6] = e1.z; a[7] = e1.w;
-        b[0] = r0.x; b[1] = r0.y; b[2] = r0.z; b[3] = r0.w; b[4] = r1.x; b[5] = r1.y; b[6] = r1.z; b[7] = r1.w;
-        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
-    }
-    float se = 0.f, sr = 0.f, sk = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { se = fmaf(a[i], a[i], se); sr = fmaf(b[i], b[i], sr); sk = fmaf(c[i], c[i], sk); }
-    se = warp_sum(se); sr = warp_sum(sr); sk = warp_sum(sk);
-    const float ne = fmaxf(sqrtf(se), 1e-12f), nr = fmaxf(sqrtf(sr), 1e-12f);
-    const float nk = normalize_keys ? fmaxf(sqrtf(sk), 1e-12f) : 1.0f;
-    float an[8], qv[8], kv[8], dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        an[i] = __fdiv_rn(a[i], ne);
-        qv[i] = __fdiv_rn(b[i], nr);
-        kv[i] = normalize_keys ? __fdiv_rn(c[i], nk) : c[i];
-        dot = fmaf(qv[i], kv[i], dot);
-    }
-    dot = warp_sum(dot);
-    if (live) {
-        float4* kout = reinterpret_cast<float4*>((mod ? v_key_n : t_key_n) + (int64_t)n * D + k0);
-        float4* o_e = reinterpret_cast<float4*>(E2 + (int64_t)row * D + k0);
-        float4* o_en = reinterpret_cast<float4*>(en + (int64_t)row * D + k0);
-        float4* o_qn = reinterpret_cast<float4*>(qn + (int64_t)row * D + k0);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            o_e[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
-            o_en[i] = make_float4(an[4 * i], an[4 * i + 1], an[4 * i + 2], an[4 * i + 3]);
-            o_qn[i] = make_float4(qv[4 * i], qv[4 * i + 1], qv[4 * i + 2], qv[4 * i + 3]);
-            kout[i] = make_float4(kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
-        }
-    }
-    if (n < N && lane == 0) { inv_e[row] = __fdiv_rn(1.0f, ne); inv_q[row] = __fdiv_rn(1.0f, nr); pos[row] = dot; }
-    if (in_pad) {
-        const int64_t off = packed_offset_bytes(prow, lane, KC);
-        uint4 o;
-        o.x = pack2(a[0], a[1]); o.y = pack2(a[2], a[3]); o.z = pack2(a[4], a[5]); o.w = pack2(a[6], a[7]);
-        *reinterpret_cast<uint4*>(Ep + off) = o;
-        o.x = pack2(an[0], an[1]); o.y = pack2(an[2], an[3]); o.z = pack2(an[4], an[5]); o.w = pack2(an[6], an[7]);
-        *reinterpret_cast<uint4*>(ENp + off) = o;
-        o.x = pack2(qv[0], qv[1]); o.y = pack2(qv[2], qv[3]); o.z = pack2(qv[4], qv[5]); o.w = pack2(qv[6], qv[7]);
-        *reinterpret_cast<uint4*>(QNp + off) = o;
     }
 }
 
@@ -1069,21 +1165,35 @@ bool fused_loss_supported(int N, int D, int K, int C, int sm_count) {
 
 int64_t fused_loss_scratch_bytes(int N, int D, int K, int C) { return carve_scratch(nullptr, N, D, K, C).bytes + 1024; }
 
+static ProArgs make_pro_args(const FusedLossArgs& a, const Scratch& s) {
+    ProArgs q;
+    q.v_embed = a.v_embed; q.t_embed = a.t_embed; q.v_qraw = a.v_qraw; q.t_qraw = a.t_qraw; q.v_key = a.v_key; q.t_key = a.t_key;
+    q.v_queue = a.v_queue; q.t_queue = a.t_queue;
+    q.v_key_n = a.v_key_n; q.t_key_n = a.t_key_n; q.E2 = a.E2; q.en = a.en; q.inv_e = a.inv_e; q.qn = a.qn; q.inv_q = a.inv_q; q.pos = a.pos;
+    q.Ep = s.Ep; q.ENp = s.ENp; q.QNp = s.QNp; q.QUp = s.QUp;
+    q.normalize_keys = a.normalize_keys; q.N = a.N; q.D = a.D; q.KC = (a.D + 127) / 128 * 2; q.K = a.K;
+    q.T_k = (a.K + F_TILE - 1) / F_TILE;
+    return q;
+}
+
+// Measured on B200 (profiles/r01_loss_fused.md): running the prologue tasks inside the cooperative kernel costs more on its
+// critical path (row tasks + flag wait + operand copy through registers, 52 us) than the separate small launch whose outputs
+// arrive by bulk copy under the W stream (48 us), so the two-launch form is the default; TRB_FUSED_MERGED=1 selects the
+// one-launch form.
+static bool merged_prologue(const FusedLossArgs& a) { return a.roles == 7 && getenv("TRB_FUSED_MERGED") != nullptr; }
+
 int fused_loss_prologue(const FusedLossArgs& a, cudaStream_t st) {
+    if (merged_prologue(a)) return 0;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a.scratch) + 1023) & ~uintptr_t(1023));
     const Scratch s = carve_scratch(base, a.N, a.D, a.K, a.C);
-    const int KC = (a.D + 127) / 128 * 2;
     static bool attr = false;
     if (!attr) {   // same shared-memory carve-out as the cooperative kernel that follows: no SM reconfiguration between the two
         TRB_CUDA_OK(cudaFuncSetAttribute(fused_prologue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr = true;
     }
-    const int T_k = (a.K + F_TILE - 1) / F_TILE;
-    const int pack_ctas = (a.roles & 2) ? 2 * KC * 8 : 0;     // queue re-pack for the InfoNCE tiles
-    fused_prologue_kernel<<<32 + pack_ctas, 256, 0, st>>>(a.v_embed, a.t_embed, a.v_qraw, a.t_qraw, a.v_key, a.t_key,
-                                                          a.normalize_keys, a.v_key_n, a.t_key_n, a.E2, a.en, a.inv_e, a.qn,
-                                                          a.inv_q, a.pos, s.Ep, s.ENp, s.QNp, s.bar, a.N, a.D, KC, a.v_queue,
-                                                          a.t_queue, s.QUp, a.K, T_k);
+    const ProArgs q = make_pro_args(a, s);
+    const int ntasks = 256 + ((a.roles & 2) ? 2 * q.KC * 64 : 0);     // queue re-pack only for fused InfoNCE tiles
+    fused_prologue_kernel<<<(ntasks + 7) / 8, 256, 0, st>>>(q, s.bar, ntasks);
     TRB_LAUNCH_OK();
     return 0;
 }
@@ -1121,6 +1231,8 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     p.dpos = a.dpos; p.rows_inst = a.rows_inst; p.rows_nce = a.rows_nce; p.rows_ga = a.rows_ga;
     p.losses = a.losses; p.d_inst = a.d_inst; p.d_nce = a.d_nce; p.d_ga = a.d_ga; p.d_proj = a.d_proj;
     p.bar = s.bar;
+    p.pro = make_pro_args(a, s);
+    p.merged = merged_prologue(a) ? 1 : 0;
     const int grid = p.n_inst + p.n_nce + p.n_ga;
     if (grid == 0) return 0;
 

@@ -30,7 +30,7 @@ def _workspace(shape: _lib.MocoShape, precision: int, device) -> torch.Tensor:
         nbytes = _lib.load().trb_moco_loss_workspace_bytes(C.byref(shape), precision)
         if nbytes < 0:
             _lib.check(int(nbytes), "trb_moco_loss_workspace_bytes")
-        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)     # zero-filled: grid-barrier words of the fused kernel
         _workspaces[key] = ws
     return ws
 
@@ -111,7 +111,7 @@ class _MoCoLossFunction(torch.autograd.Function):
                 nbytes = lib.trb_moco_loss_workspace_bytes(C.byref(shape), precision)
                 if nbytes < 0:
                     _lib.check(int(nbytes), "trb_moco_loss_workspace_bytes")
-                ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+                ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=dev)
                 launch(out, ws, False)                   # eager warm-up (validates arguments, sets kernel attributes)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
