@@ -9,6 +9,7 @@ three losses AND their gradients come out of one stream-ordered library call in 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Iterable, Sequence, Tuple
 
 import numpy as np
@@ -23,6 +24,14 @@ LOSS_KEYS = ("instance_loss", "infonce_loss", "global_align_loss")
 _workspaces: Dict[Tuple, torch.Tensor] = {}
 
 
+def _alloc_workspace(nbytes: int, device) -> torch.Tensor:
+    """The one-launch form of the fused kernel (TRB_FUSED_MERGED=1) needs its grid-barrier words zero at the first call; the
+    default two-launch form clears them itself, so no fill kernel is spent (or captured into a caller's CUDA graph)."""
+    if os.environ.get("TRB_FUSED_MERGED"):
+        return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
 def _workspace(shape: _lib.MocoShape, precision: int, device) -> torch.Tensor:
     key = (shape.N, shape.D, shape.K, shape.C, precision, str(device), torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
@@ -30,7 +39,7 @@ def _workspace(shape: _lib.MocoShape, precision: int, device) -> torch.Tensor:
         nbytes = _lib.load().trb_moco_loss_workspace_bytes(C.byref(shape), precision)
         if nbytes < 0:
             _lib.check(int(nbytes), "trb_moco_loss_workspace_bytes")
-        ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)     # zero-filled: grid-barrier words of the fused kernel
+        ws = _alloc_workspace(int(nbytes), device)
         _workspaces[key] = ws
     return ws
 
@@ -111,7 +120,7 @@ class _MoCoLossFunction(torch.autograd.Function):
                 nbytes = lib.trb_moco_loss_workspace_bytes(C.byref(shape), precision)
                 if nbytes < 0:
                     _lib.check(int(nbytes), "trb_moco_loss_workspace_bytes")
-                ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=dev)
+                ws = _alloc_workspace(int(nbytes), dev)
                 launch(out, ws, False)                   # eager warm-up (validates arguments, sets kernel attributes)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
