@@ -122,3 +122,54 @@ def test_packed_layout_is_a_bijection_and_block_contiguous():
     assert offs[8, 0] - offs[0, 0] == 1024
     # Swizzle<3,4,3>: 16-byte chunk index XOR (row & 7)
     assert offs[3, 5] == 3 * 128 + ((5 ^ 3) << 4)
+
+
+def test_fused_loss_gate_and_argument_validation_without_gpu(lib):
+    """Pure host queries of the loss entry points: the shape gate of the fused kernel (148 SMs assumed when no device is
+    present), workspace sizes, and argument validation that happens before any CUDA call."""
+    import ctypes as C
+
+    def launches(N, D, K, Cn, precision):
+        shape = _lib.MocoShape(N, D, K, Cn)
+        return int(lib.trb_moco_loss_launches(C.byref(shape), precision))
+
+    assert launches(128, 256, 2048, 11003, 1) == 2         # prologue + one cooperative kernel
+    assert launches(128, 256, 2048, 11003, 0) > 2          # fp32 parity path: launch sequence
+    assert launches(256, 256, 4096, 11003, 1) > 2          # N > 128
+    assert launches(128, 320, 2048, 11003, 1) > 2          # D > 256
+    assert launches(128, 256, 2048, 20000, 1) > 2          # 157 + 32 + 1 tiles > 148 SMs
+    assert launches(0, 256, 2048, 11003, 1) == -1          # rejected shape
+    fits, big = _lib.MocoShape(128, 256, 2048, 11003), _lib.MocoShape(256, 256, 4096, 11003)
+    w_fused = lib.trb_moco_loss_workspace_bytes(C.byref(fits), 1)
+    w_f32 = lib.trb_moco_loss_workspace_bytes(C.byref(fits), 0)
+    assert w_fused > w_f32 > 0 and lib.trb_moco_loss_workspace_bytes(C.byref(big), 1) > 0
+    assert lib.trb_moco_loss_workspace_bytes(C.byref(fits), 7) == -1
+    rc = lib.trb_moco_grad_combine(None, None, None, None, None, None, None, 0, 16, 16, None, None, None, None, None, None)
+    assert rc == -1 and b"null" in lib.trb_last_error_string()
+
+
+def test_build_moco_head_precision_selection(monkeypatch):
+    """build_moco_head keeps the reference's factory signature; the arithmetic path comes from optional config keys or the
+    environment and defaults to the fp32 parity path."""
+    from types import SimpleNamespace
+    import torch.nn as nn
+
+    class Enc(nn.Module):
+        out_channels = 8
+
+        def __init__(self):
+            super().__init__()
+            self.lin = nn.Linear(4, 8)
+
+    def cfg(**moco):
+        return SimpleNamespace(MODEL=SimpleNamespace(EMBEDDING=SimpleNamespace(FEATURE_SIZE=16, EPSILON=0.1),
+                                                    MOCO=SimpleNamespace(K=32, M=0.999, FC=False, **moco), NUM_CLASSES=10))
+
+    monkeypatch.delenv("TRB_LOSS_PRECISION", raising=False)
+    monkeypatch.delenv("TRB_LOSS_GRAPH", raising=False)
+    head = textreid_b200.build_moco_head(cfg(), Enc(), Enc())
+    assert head.precision == "fp32" and head.cuda_graph is False
+    head = textreid_b200.build_moco_head(cfg(PRECISION="bf16", CUDA_GRAPH=True), Enc(), Enc())
+    assert head.precision == "bf16" and head.cuda_graph is True
+    monkeypatch.setenv("TRB_LOSS_PRECISION", "bf16")
+    assert textreid_b200.build_moco_head(cfg(), Enc(), Enc()).precision == "bf16"

@@ -413,3 +413,38 @@ def test_fused_workspace_reuse_has_no_stale_operands(monkeypatch, merged):
         assert torch.equal(second[0][k], fresh[0][k])
     for x, y in zip(second[1:], fresh[1:]):
         assert torch.equal(x, y)
+
+
+def test_fused_head_bf16_tracks_fp32_head():
+    """FusedMoCoHead(precision="bf16") -- the fused cooperative kernel behind the reference's module surface -- follows the fp32
+    head step by step (losses, parameter gradients, queue pointer, ids bit-exact; queue contents to fp32 rounding)."""
+    N, F, D, K, Cn = 32, 24, 64, 128, 500
+    cfg = SimpleNamespace(MODEL=SimpleNamespace(EMBEDDING=SimpleNamespace(FEATURE_SIZE=D, EPSILON=0.1),
+                                                MOCO=SimpleNamespace(K=K, M=0.999, FC=False), NUM_CLASSES=Cn))
+    torch.manual_seed(0)
+    ref = trb.FusedMoCoHead(cfg, StubEncoder(F, F), StubEncoder(F, F, take_captions=True), precision="fp32").to(DEV).train()
+    torch.manual_seed(0)
+    fused = trb.FusedMoCoHead(cfg, StubEncoder(F, F), StubEncoder(F, F, take_captions=True), precision="bf16").to(DEV).train()
+    fused.load_state_dict(ref.state_dict())
+    assert _launches(N, D, K, Cn, 1) == 2
+    g = torch.Generator().manual_seed(1)
+    for step in range(3):
+        images = torch.randn(N, F, generator=g).to(DEV)
+        cfeat = torch.randn(N, F, generator=g).to(DEV)
+        labels = torch.randint(0, Cn, (N // 4,), generator=g).repeat_interleave(4).to(DEV)
+        caps = [StubCaption(cfeat[i], labels[i]) for i in range(N)]
+        outs = []
+        for head in (ref, fused):
+            head.zero_grad()
+            losses = head(images, caps)
+            sum(losses.values()).backward()
+            outs.append(losses)
+        for k in KEYS:
+            torch.testing.assert_close(outs[1][k], outs[0][k], rtol=2e-3, atol=2e-4)
+        for (name, p), (_, q) in zip(ref.named_parameters(), fused.named_parameters()):
+            if p.grad is None:
+                continue
+            cos = torch.nn.functional.cosine_similarity(p.grad.flatten(), q.grad.flatten(), dim=0)
+            assert float(cos) > 0.999, (name, float(cos))
+        assert torch.equal(ref.queue_ptr, fused.queue_ptr) and torch.equal(ref.id_queue, fused.id_queue)
+        torch.testing.assert_close(fused.v_queue, ref.v_queue, rtol=1e-6, atol=1e-7)

@@ -41,7 +41,7 @@ struct ProArgs {
 };
 
 struct FP {
-    int N, D, K, C, KC, T_inst, T_k, n_inst, n_nce, n_ga, want_grad, reduce_losses, roles, variant;
+    int N, D, K, C, KC, T_inst, T_k, n_inst, n_nce, n_ga, want_grad, reduce_losses, roles;
     float T, eps, alpha, beta, sp, sn;
     const float* W;
     const float* queue[2];          // queue scored by modality m's queries: [0] = t_queue, [1] = v_queue  (head.py:162,168)
@@ -61,14 +61,13 @@ struct FP {
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// MN-major SWIZZLE_128B descriptor: 64-element groups along M/N are `lbo` bytes apart, 8-row groups along K 1024 B apart.
-__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo, int variant) {
-    uint32_t l = lbo >> 4, s = 1024 >> 4;
-    if (variant & 1) { const uint32_t t = l; l = s; s = t; }      // debug: swapped interpretation
+// MN-major SWIZZLE_128B descriptor (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): the 64-element groups
+// along M/N are `lbo` bytes apart, the 8-row groups along K 1024 bytes.
+__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)(l & 0x3FFF) << 16;
-    d |= (uint64_t)(s & 0x3FFF) << 32;
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
@@ -119,9 +118,9 @@ __device__ __forceinline__ int sector_head(int w, int64_t ld, int c0) { return (
 // constant.  All loads of the tile are issued before the first use; `rot` staggers the row order between CTAs so that CTAs
 // sweeping the same rows of a power-of-two-pitched matrix do not hit the same DRAM channels in lock step.
 __device__ __forceinline__ void load_tile_bf16(const float* __restrict__ src, int64_t ld, int nrows, int rows_pad, int c0,
-                                               int ncols, int rot, bool use_head, uint8_t* wb, float* red) {
+                                               int ncols, int rot, uint8_t* wb, float* red) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int head = use_head ? sector_head(w, ld, c0) : 0;
+    const int head = sector_head(w, ld, c0);
     const int groups = rows_pad >> 3;                      // 16 or 32 row groups
     float ss[4] = {0.f, 0.f, 0.f, 0.f};
     bool cv[4];
@@ -461,7 +460,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     }
 
     // ---- instance: W tile HBM -> bf16 shared image, column norms
-    if (INST) load_tile_bf16(p.W, ncols, p.D, Dp, c0, ncols, (p.variant & 2) ? 0 : ((tile * 7) & 31), !(p.variant & 4), sm.WB, red);
+    if (INST) load_tile_bf16(p.W, ncols, p.D, Dp, c0, ncols, (tile * 7) & 31, sm.WB, red);
     // ---- merged mode: the operand images come from prologue tasks of other CTAs of this very grid: wait for them, then plain
     //      L2 loads (no cross-proxy question)
     if (p.merged) {
@@ -509,7 +508,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
         for (int mt = 0; mt < MT; ++mt)
             for (int ks = 0; ks < Dp / 16; ++ks)
                 umma_bf16(tmem + mt * 128, umma_desc_sw128(e0 + (mt * p.KC + (ks >> 2)) * BLOCK_BYTES + (ks & 3) * 32),
-                          desc_mn(wb0 + ks * 2048, F_WB_CHUNK, p.variant), id_f, (uint32_t)(ks > 0));
+                          desc_mn(wb0 + ks * 2048, F_WB_CHUNK), id_f, (uint32_t)(ks > 0));
         umma_commit(sm.bar_mma);
     }
     mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
@@ -653,8 +652,8 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                     for (int hh = 0; hh < NH; ++hh)
                         for (int ks = 0; ks < 8; ++ks)
                             umma_bf16(tmem + 256 + hh * 128,
-                                      desc_mn(e0 + (p.KC + 2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES, p.variant),
-                                      desc_mn(dz0 + ks * 2048, BLOCK_BYTES, p.variant), id_w, 1u);
+                                      desc_mn(e0 + (p.KC + 2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES),
+                                      desc_mn(dz0 + ks * 2048, BLOCK_BYTES), id_w, 1u);
                 }
                 umma_commit(sm.bar_mma);
             }
@@ -707,8 +706,8 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                 const uint32_t id_w = idesc(128, 128, 1, 1);
                 for (int hh = 0; hh < NH; ++hh)
                     for (int ks = 0; ks < 8; ++ks)
-                        umma_bf16(tmem + 256 + hh * 128, desc_mn(e0 + (2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES, p.variant),
-                                  desc_mn(dz0 + ks * 2048, BLOCK_BYTES, p.variant), id_w, (uint32_t)(ks > 0));
+                        umma_bf16(tmem + 256 + hh * 128, desc_mn(e0 + (2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES),
+                                  desc_mn(dz0 + ks * 2048, BLOCK_BYTES), id_w, (uint32_t)(ks > 0));
                 umma_commit(sm.bar_dw);
             }
         }
@@ -737,7 +736,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             bool cv[4];
             int cc[4];
             float sc[4];
-            const int head = (p.variant & 8) ? 0 : sector_head(w, p.C, c0);  // full, aligned 128-byte segments: no partial-sector writes inside the tile
+            const int head = sector_head(w, p.C, c0);  // full, aligned 128-byte segments: no partial-sector writes inside the tile
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int c = (head + lane + 32 * j) & 127;
@@ -878,11 +877,11 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
             const uint32_t id_v = idesc(128, Dp, 0, 1);
             for (int ks = 0; ks < 8; ++ks)
                 umma_bf16(tmem + 256, umma_desc_sw128(dz0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
-                          desc_mn(et0 + ks * 2048, BLOCK_BYTES, p.variant), id_v, (uint32_t)(ks > 0));
+                          desc_mn(et0 + ks * 2048, BLOCK_BYTES), id_v, (uint32_t)(ks > 0));
             // dq_t[j, d] = sum_i dS[i, j] en_v[i, d]   -> columns [0, Dp)
             const uint32_t id_t = idesc(128, Dp, 1, 1);
             for (int ks = 0; ks < 8; ++ks)
-                umma_bf16(tmem, desc_mn(dz0 + ks * 2048, BLOCK_BYTES, p.variant), desc_mn(e0 + ks * 2048, BLOCK_BYTES, p.variant), id_t,
+                umma_bf16(tmem, desc_mn(dz0 + ks * 2048, BLOCK_BYTES), desc_mn(e0 + ks * 2048, BLOCK_BYTES), id_t,
                           (uint32_t)(ks > 0));
             umma_commit(sm.bar_mma);
         }
@@ -1212,8 +1211,6 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     p.n_ga = (a.roles & 4) ? 1 : 0;
     p.want_grad = a.d_inst != nullptr;
     p.reduce_losses = a.reduce_losses;
-    const char* var = getenv("TRB_FUSED_VARIANT");
-    p.variant = var ? atoi(var) : 0;
     p.T = a.T; p.eps = a.eps; p.alpha = a.alpha; p.beta = a.beta; p.sp = a.sp; p.sn = a.sn;
     p.W = a.projection;
     p.queue[0] = a.t_queue; p.queue[1] = a.v_queue;

@@ -12,6 +12,7 @@ gradients, the momentum update and the enqueue -- with no host synchronisation.
 from __future__ import annotations
 
 import copy
+import os
 
 import torch
 import torch.nn as nn
@@ -129,4 +130,13 @@ class FusedMoCoHead(nn.Module):
 
 
 def build_moco_head(cfg, visual_model, textual_model):
-    return FusedMoCoHead(cfg, visual_model, textual_model)
+    """Same factory signature as the reference (moco_head/head.py:185-187).  The arithmetic path is the fp32 parity path unless
+    the config carries ``MODEL.MOCO.PRECISION`` ("fp32" | "bf16") or ``MODEL.MOCO.CUDA_GRAPH`` (keys the reference's config does
+    not have), or the environment sets TRB_LOSS_PRECISION / TRB_LOSS_GRAPH: "bf16" runs the loss step as the fused tcgen05
+    kernel of csrc/loss_fused.cu."""
+    moco = cfg.MODEL.MOCO
+    precision = getattr(moco, "PRECISION", None) or os.environ.get("TRB_LOSS_PRECISION", "fp32")
+    graph = getattr(moco, "CUDA_GRAPH", None)
+    if graph is None:
+        graph = os.environ.get("TRB_LOSS_GRAPH", "0") not in ("0", "", "false", "False")
+    return FusedMoCoHead(cfg, visual_model, textual_model, precision=precision, cuda_graph=bool(graph))
