@@ -2,8 +2,8 @@
 output by output, and times the step.  Each configuration runs in its own subprocess under a timeout so that a trap or a
 hang in one of them cannot take the others down.
 
-    python tools/fused_probe.py                  # driver: all role sets, descriptor variant 1 only where variant 0 failed
-    python tools/fused_probe.py child R V        # one configuration
+    python tools/fused_probe.py [--full]         # driver: fused roles 7 (and, with --full, 1/2/4/0), then roles 7 with phase stamps
+    python tools/fused_probe.py child R 0        # one configuration (R = bit mask of fused branches: 1 instance, 2 InfoNCE, 4 align)
 """
 import ctypes as C
 import os
@@ -60,7 +60,6 @@ def print_stamps(lib, roles, K, Cn, tag):
 
 def child(roles, variant):
     os.environ["TRB_FUSED_ROLES"] = str(roles)
-    os.environ["TRB_FUSED_VARIANT"] = str(variant)
     import torch
     from textreid_b200 import _lib
     from textreid_b200.synthetic import loss_inputs
@@ -161,8 +160,6 @@ def driver():
     results = {}
     full = "--full" in sys.argv
     plan = [(r, v, False) for r in ((1, 2, 4, 7, 0) if full else (7,)) for v in (0,)] + [(7, 0, True)]
-    if "--variants" in sys.argv:
-        plan = [(7, v, True) for v in (0, 2, 8, 14)]
     for roles, variant, debug in plan:
         env = dict(os.environ)
         if debug:
