@@ -7,7 +7,8 @@
 //   align    S = q_v q_t^T, log(1+exp(.)) on same-id / other pairs           losses.py:102-128
 // Forward and backward are one stream-ordered launch sequence: logits are materialised in the
 // caller's workspace (a few MB), turned into their gradients in place, and contracted back.
-// The bf16 tcgen05 path (precision = 1) lives in loss_tc.cu and keeps them on chip instead.
+// The bf16 tcgen05 path (precision = 1) reuses this sequence with tensor-core GEMMs (tc_gemm.cu) or, when the shape fits, replaces
+// it by the fused cooperative kernel of loss_fused.cu, which keeps logits and their gradients on chip.
 #include "common.cuh"
 #include "sgemm.cuh"
 #include "tc_gemm.cuh"
