@@ -413,11 +413,12 @@ def main():
                 line["secondary"]["moco_loss_cpu_baseline"] = cpu_loss_sample()
                 best = line["secondary"].get("moco_loss_bf16_stepgraph")
                 if best:     # the other half of BASELINE's metric, lifted to the top level for readers of the one line
+                    base = line["secondary"].get("moco_loss_cpu_baseline") or {}
                     line["loss_step"] = {"metric": "MoCo loss steps/s at bs128 (fwd+bwd+enqueue, bf16 fused kernel, whole step in one CUDA graph)",
                                          "value": best["value"], "unit": "steps/s", "us_per_step": best["ms_per_step"] * 1e3,
-                                         "hbm_roofline_frac": best["roofline"]["frac"],
-                                         "library_launches": line["secondary"].get("moco_loss_kernel_launches", {}).get("bf16"),
-                                         "cpu_baseline_steps_per_s": line["secondary"]["moco_loss_cpu_baseline"].get("value")}
+                                         "hbm_roofline_frac": (best.get("roofline") or {}).get("frac"),
+                                         "library_launches": (line["secondary"].get("moco_loss_kernel_launches") or {}).get("bf16"),
+                                         "cpu_baseline_steps_per_s": base.get("value")}
             except Exception as e:   # pragma: no cover
                 line["secondary"] = {"error": str(e)[:300]}
         print(json.dumps(line))
