@@ -216,6 +216,28 @@ def test_retrieve_bf16_exact_arithmetic_fixture(Q, G, D, nsplit):
         assert torch.equal(thr[rel_ptr[q]:rel_ptr[q + 1]], sim[q, cols])
 
 
+def test_retrieve_bf16_zero_similarity_thresholds_take_the_exact_path():
+    """Thresholds with |similarity| < 2^-59 (here: exactly 0, from all-zero query vectors and from disjoint supports) cannot use
+    the FFMA.SAT indicator of the stream epilogue; they are counted by the exact slow path.  Every such row is one G-way tie,
+    so the ranks are decided by the gallery index alone."""
+    Q, G, D = 150, 700, 256
+    gen = torch.Generator().manual_seed(5)
+    image = (torch.randint(0, 2, (G, D), generator=gen).float() * 2 - 1) / 16.0
+    text = (torch.randint(0, 2, (Q, D), generator=gen).float() * 2 - 1) / 16.0
+    text[::5] = 0.0                                            # zero query: every similarity is +0
+    image[::3, 64:] = 0.0                                      # 64-sparse +-1/8 rows (unit norm, exact)
+    image[::3, :64] = image[::3, :64].sign() / 8.0
+    text[1::5, :64] = 0.0                                      # support disjoint from those rows: similarity exactly 0
+    text[1::5, 128:] = 0.0
+    text[1::5, 64:128] = text[1::5, 64:128].sign() / 8.0
+    ipid = torch.randint(0, G // 4, (G,), generator=gen)
+    tpid = ipid[torch.randint(0, G, (Q,), generator=gen)].clone()
+    res = trb.retrieve(T(text), T(image), T(tpid), T(ipid), (1, 5, 10), True, "bf16")
+    sim = O.similarity_matrix(text, image)
+    assert (sim == 0).any(dim=1).sum() >= Q // 5
+    check_against_matrix(res, sim, tpid, ipid)
+
+
 @pytest.mark.parametrize("Q,G", [(500, 2000), (130, 300)])
 def test_retrieve_bf16_gaussian_similarity_tolerance_and_self_consistency(Q, G):
     D = 256

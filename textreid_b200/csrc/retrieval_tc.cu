@@ -7,12 +7,12 @@
 // Replaces (with evaluation.py:117-120 fused in by trb_pack_rows_bf16) the reference's
 //   similarity = text @ image.T ; argsort ; matches ; cumsum        lib/data/metrics/evaluation.py:11-37,120
 //
-// Warp roles (640 threads, one persistent CTA per SM):
-//   warp 0 lane 0 : producer  - bulk copies: query tile (resident per work unit) + gallery k-chunk ring
+// Warp roles (2 control + 8 epilogue warps = 320 threads, one persistent CTA per SM):
+//   warp 0        : TMEM allocator / deallocator; lane 0 = producer - bulk copies: query tile (resident per work unit)
+//                   + gallery k-chunk ring
 //   warp 1 lane 0 : MMA issuer - tcgen05.mma into TMEM buffer t&1, tcgen05.commit -> barriers
-//   warp 2        : TMEM allocator / deallocator
-//   warps 4..19   : epilogue  - warp w reads TMEM lanes 32*(w%4).. (its 32 query rows) and the
-//                   64-column slice (w-4)/4 of the 256-column accumulator
+//   warps 2..9    : epilogue  - warp w reads TMEM lanes 32*(w%4).. (its 32 query rows) and the
+//                   128-column slice (w-2)/4 of the 256-column accumulator, 32 columns at a time
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -25,15 +25,41 @@ constexpr int TILE_N = 256;          // gallery rows per MMA tile (TMEM columns 
 constexpr int UMMA_K = 16;
 constexpr int STAGE_BYTES = 2 * BLOCK_BYTES;   // 256 gallery rows x 64 k  = 32 KiB
 #ifndef TRB_EPI_WARPS
-#define TRB_EPI_WARPS 16
+#define TRB_EPI_WARPS 8
 #endif
-constexpr int NUM_THREADS = 128 + 32 * TRB_EPI_WARPS;
-constexpr int EPI_WARP0 = 4;
+// two control warps (producer + TMEM allocator, MMA issuer) and the epilogue warps.  8 epilogue warps keep the whole row
+// state in registers (167, no spills); 16 warps at the 96-register cap spill inside the hot loop and measured slower
+// (71.7 vs 57.1 ms per 100k x 1M stream, gpurun_out/tc_ab.log of round 2)
+constexpr int EPI_WARP0 = 2;
+constexpr int NUM_THREADS = 32 * EPI_WARP0 + 32 * TRB_EPI_WARPS;
 constexpr int NUM_EPI_WARPS = TRB_EPI_WARPS;
 constexpr int COLS_PER_WARP = TILE_N / (NUM_EPI_WARPS / 4);   // 64 accumulator columns per epilogue warp
-constexpr int CHUNKS_PER_WARP = COLS_PER_WARP / 32;
+#ifndef TRB_TC_CHUNK
+#define TRB_TC_CHUNK 32
+#endif
+constexpr int CH = TRB_TC_CHUNK;                               // accumulator columns a thread holds in registers at a time (16 | 32)
+constexpr int CHUNKS_PER_WARP = COLS_PER_WARP / CH;
 constexpr int LISTS_PER_SPLIT = NUM_EPI_WARPS / 4;            // candidate lists a query gets per gallery split
 constexpr int MAX_STAGES = 8;
+// Build-time tuning knobs (A/B builds through textreid_b200.build.build_variant):
+//   TRB_TC_SKIP_R   : thresholds per row (sorted descending) that get a warp-uniform "no value of this chunk reaches it" test
+//   TRB_TC_HOT_SPIN : 1 = the producer / MMA threads poll their mbarriers in a hot loop (round-1 behaviour)
+//   TRB_TC_COUNT_FMA: 1 = rank counting on the FMA pipe (FFMA.SAT indicator + FADD), 0 = FADD + LEA.HI (FMA + ALU pipe)
+#ifndef TRB_TC_SKIP_R
+#define TRB_TC_SKIP_R 0
+#endif
+#ifndef TRB_TC_COUNT_FMA
+#define TRB_TC_COUNT_FMA 1
+#endif
+//   TRB_TC_PREFETCH : 1 = the epilogue keeps the TMEM load of the next chunk in flight while it consumes the current one
+//                     (measured slower on B200, 59.4 vs 56.3 ms: the second register buffer costs more than the latency it hides)
+#ifndef TRB_TC_PREFETCH
+#define TRB_TC_PREFETCH 0
+#endif
+
+#ifndef TRB_TC_HOT_SPIN
+#define TRB_TC_HOT_SPIN 0
+#endif
 constexpr int SMEM_MAX = 232448;      // 227 KiB opt-in limit per CTA on sm_100
 
 struct Params {
@@ -61,6 +87,29 @@ struct Params {
     uint32_t wait_hint_ns;   // suspend-time hint of the epilogue warps' accumulator waits
     int debug;               // builds with -DTRB_TC_PROBE only (TRB_TC_DEBUG env): 1 = epilogue skips the arithmetic, 2 = and the TMEM read
 };
+
+// Waits of the two single-thread roles.  Polling costs issue slots on the scheduler that also runs a quarter of the epilogue
+// warps: in the round-2 profile the try_wait loops of these two threads were 12 % of all issued instructions (try_wait with a
+// suspend hint compiles to TRYWAIT + NANOSLEEP.SYNCS, which wakes on every mbarrier event of the CTA, i.e. every ~16 ns here).
+// A plain nanosleep really parks the thread; the double-buffered accumulator and the multi-stage ring give both roles a full
+// tile / several stages of slack, so a wake-up granularity of `ns` costs nothing.
+__device__ __forceinline__ void role_wait(uint64_t* bar, uint32_t parity, uint32_t ns) {
+#if TRB_TC_HOT_SPIN
+    mbar_wait(bar, parity);
+#else
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (++n > (1u << 24)) {
+            printf("trb: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+#endif
+}
 
 struct UnitInfo {
     int64_t qt, split, t_lo, t_hi;
@@ -104,52 +153,191 @@ __device__ __forceinline__ UnitInfo unit_info(const Params& p, int64_t u) {
 // against thr itself, and only the one chunk that contains r needs a correction.  No per-value tie detection, no index
 // look-ups: 2 instructions per (value, threshold): d = t - v (FADD), count += bits(d) >> 31 (LEA.HI).
 // ---------------------------------------------------------------------------------------------
+// acc.lo += a, acc.hi += b in one instruction (packed fp32 add, SASS FADD2)
+__device__ __forceinline__ void add2(unsigned long long& acc, float a, float b) {
+    unsigned long long t;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(a), "f"(b));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(t));
+}
+constexpr float COUNT_SCALE = 1.2676506002282294e30f;     // 2^100
+constexpr float COUNT_MIN_ABS = 1.734723475976807e-18f;    // 2^-59
 __device__ __forceinline__ float next_below(float x) {        // largest float < x (x finite or +inf)
     const uint32_t b = __float_as_uint(x);
     const uint32_t r = (x > 0.0f) ? b - 1u : (((b << 1) == 0u) ? 0x80000001u : b + 1u);
     return __uint_as_float(r);
 }
 
-// v[j] for a run-time j without spilling v to local memory: 5-level select tree (31 FSEL)
-__device__ __forceinline__ float select32(const float (&v)[32], int j) {
-    float a[16], b[8], c[4];
+// v[j] for a run-time j without spilling v to local memory: select tree (CH - 1 FSEL)
+__device__ __forceinline__ float select_lane(const float (&v)[CH], int j) {
+    float a[CH / 2], b[CH / 4], c[CH / 8];
     const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8, b4 = j & 16;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] = b0 ? v[2 * i + 1] : v[2 * i];
+    for (int i = 0; i < CH / 2; ++i) a[i] = b0 ? v[2 * i + 1] : v[2 * i];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) b[i] = b1 ? a[2 * i + 1] : a[2 * i];
+    for (int i = 0; i < CH / 4; ++i) b[i] = b1 ? a[2 * i + 1] : a[2 * i];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] = b2 ? b[2 * i + 1] : b[2 * i];
-    const float d0 = b3 ? c[1] : c[0], d1 = b3 ? c[3] : c[2];
+    for (int i = 0; i < CH / 8; ++i) c[i] = b2 ? b[2 * i + 1] : b[2 * i];
+    const float d0 = b3 ? c[1] : c[0];
+    if (CH == 16) return d0;
+    const float d1 = b3 ? c[CH / 8 - 1] : c[CH / 8 - 2];
     return b4 ? d1 : d0;
+}
+
+// TMEM -> registers, split into issue and completion so that a load can be in flight under arithmetic.  The wait takes the
+// destination registers as read-write operands: every later use of them depends on it.
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+          "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+          "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]),
+                   "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]),
+                   "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
 }
 
 template <int RTN>
 struct RowState {
     float ts[TRB_TOPK];      // best-first similarities
     int tr[TRB_TOPK];        // their packed (= local) gallery rows
-    float thr[RTN];          // first RTN thresholds of the row (+inf = unused)
-    int rloc[RTN];           // local row of the relevant item: < 0 lives on a lower shard, >= G on a higher one
+    // Register-resident thresholds, sorted by similarity DESCENDING (unused slots = +inf sort first), so that slot r of
+    // every lane of a warp is "the r-th best relevant item of my row" and the warp-uniform skip test below fires together.
+    // te: the value the stream compares against -- nextbelow(thr) until the stream reaches the item (ties before it count),
+    // thr itself afterwards.  With TRB_TC_COUNT_FMA the register holds -te * 2^100 instead: sat(v * 2^100 - te * 2^100) is
+    // exactly 1 for v > te and 0 otherwise as long as |te| >= 2^-59 (the smallest positive difference, one ulp >= 2^-83, still
+    // scales to >= 1); thresholds closer to zero than that take the exact slow path (`slow`, CSR positions).
+    float te[RTN];
+    int sw[RTN];             // first chunk start g0 at which te switches to thr (= local row of the item - (CH - 1)); INT32_MAX = done
+#if TRB_TC_COUNT_FMA
+    unsigned long long cf[RTN];   // two fp32 counters per slot (even / odd values of a chunk), bumped by one FADD2 per value pair
+#else
     int cnt[RTN];
+#endif
+    int next_sw;             // min over sw[]
+    uint32_t perm;           // 4 bits per register slot: position of the item inside the row's CSR range
+    uint32_t slow;           // bit i: CSR position i (< RTN) is counted by the exact slow path, not in registers
     int64_t s_lo, s_hi;      // slot range of the row in the CSR
+
+    __device__ __forceinline__ int slot_of(int r) const { return (int)((perm >> (4 * r)) & 15u); }
+    __device__ __forceinline__ void clear(int r) {
+#if TRB_TC_COUNT_FMA
+        cf[r] = 0ull;
+#else
+        cnt[r] = 0;
+#endif
+    }
+    __device__ __forceinline__ int count_of(int r) const {
+#if TRB_TC_COUNT_FMA
+        return __float2int_rn(__uint_as_float((uint32_t)cf[r]) + __uint_as_float((uint32_t)(cf[r] >> 32)));
+#else
+        return cnt[r];
+#endif
+    }
+    // fp32 counters are exact up to 2^24: the epilogue drains them into the global counters every 256 tiles (<= 8192 per lane)
+    __device__ __forceinline__ void drain(const Params& p) {
+#pragma unroll
+        for (int r = 0; r < RTN; ++r) {
+            const int c = count_of(r);
+            if (s_lo + slot_of(r) < s_hi && c) atomicAdd(p.cnt + s_lo + slot_of(r), c);
+            clear(r);
+        }
+    }
+    static __device__ __forceinline__ float enc(float t) {       // register form of a compare value
+#if TRB_TC_COUNT_FMA
+        return -t * COUNT_SCALE;                                  // power-of-two scaling: exact (+inf -> -inf: never counts)
+#else
+        return t;
+#endif
+    }
 
     __device__ __forceinline__ void init(const Params& p, int64_t q) {
 #pragma unroll
         for (int k = 0; k < TRB_TOPK; ++k) { ts[k] = -CUDART_INF_F; tr[k] = -1; }
+        float th[RTN];
+        int slot[RTN];
 #pragma unroll
-        for (int r = 0; r < RTN; ++r) { thr[r] = CUDART_INF_F; rloc[r] = INT32_MAX; cnt[r] = 0; }
+        for (int r = 0; r < RTN; ++r) { th[r] = CUDART_INF_F; sw[r] = INT32_MAX; clear(r); slot[r] = r; }
         s_lo = s_hi = 0;
+        slow = 0;
         if (q >= 0 && p.rel_ptr != nullptr) {
             s_lo = p.rel_ptr[q];
             s_hi = p.rel_ptr[q + 1];
 #pragma unroll
             for (int r = 0; r < RTN; ++r)
                 if (s_lo + r < s_hi) {
-                    thr[r] = p.thr[s_lo + r];
+                    const float t = p.thr[s_lo + r];
+#if TRB_TC_COUNT_FMA
+                    if (!(fabsf(t) >= COUNT_MIN_ABS)) { slow |= 1u << r; continue; }      // also NaN
+#endif
+                    th[r] = t;
                     const int64_t l = p.thr_gidx[s_lo + r] - p.g_base;
-                    rloc[r] = l < 0 ? -1 : (l >= p.G ? INT32_MAX : (int)l);
+                    // item on a lower shard: the whole local stream lies after it (switch at once); on a higher shard: never
+                    sw[r] = l < 0 ? INT32_MIN : (l >= p.G ? INT32_MAX : (int)l - (CH - 1));
                 }
         }
+        // sort the register slots by threshold, descending (odd-even transposition network, static indices)
+#pragma unroll
+        for (int pass = 0; pass < RTN; ++pass) {
+#pragma unroll
+            for (int r = pass & 1; r + 1 < RTN; r += 2) {
+                if (th[r] < th[r + 1]) {
+                    const float tf = th[r]; th[r] = th[r + 1]; th[r + 1] = tf;
+                    const int ti = sw[r]; sw[r] = sw[r + 1]; sw[r + 1] = ti;
+                    const int tp = slot[r]; slot[r] = slot[r + 1]; slot[r + 1] = tp;
+                }
+            }
+        }
+        perm = 0;
+        next_sw = INT32_MAX;
+#pragma unroll
+        for (int r = 0; r < RTN; ++r) {
+            perm |= (uint32_t)slot[r] << (4 * r);
+            te[r] = th[r] == CUDART_INF_F ? enc(th[r]) : enc(next_below(th[r]));     // unused slot: never exceeded
+            next_sw = min(next_sw, sw[r]);
+        }
+    }
+
+    // The stream of this warp has reached chunk g0 >= next_sw: every item whose row is < g0 + 32 now compares strictly
+    // (te = thr).  Returns whether one of them lies INSIDE the chunk (the caller then corrects for ties that precede it).
+    __device__ __forceinline__ bool pass_items(const Params& p, int g0) {
+        bool own = false;
+        int nxt = INT32_MAX;
+#pragma unroll
+        for (int r = 0; r < RTN; ++r) {
+            if (g0 >= sw[r]) {
+                te[r] = enc(p.thr[s_lo + slot_of(r)]);
+                own |= sw[r] != INT32_MIN && g0 <= sw[r] + (CH - 1);
+                sw[r] = INT32_MAX;
+            }
+            nxt = min(nxt, sw[r]);
+        }
+        next_sw = nxt;
+        return own;
     }
 
     // the stream is in ascending index order, so a later value only displaces strictly smaller entries
@@ -171,9 +359,7 @@ struct RowState {
         int64_t* ci = p.cand_idx + (q * nlists + list) * TRB_TOPK;
 #pragma unroll
         for (int k = 0; k < TRB_TOPK; ++k) { cs[k] = ts[k]; ci[k] = tr[k] >= 0 ? p.g_base + tr[k] : INT64_MAX; }
-#pragma unroll
-        for (int r = 0; r < RTN; ++r)
-            if (s_lo + r < s_hi && cnt[r]) atomicAdd(p.cnt + s_lo + r, cnt[r]);
+        drain(p);
     }
 };
 
@@ -189,34 +375,41 @@ __device__ __forceinline__ void pad_list(const Params& p, int64_t q, int64_t nli
 //  fix_own_chunk : the chunk contains relevant items of this row; the fast path compared it against thr itself (">"),
 //                  values equal to thr that precede the item must be added.
 //  count_overflow: rows with more than RTN relevant items -- exact count of the extra slots for this chunk.
-__device__ __noinline__ void fix_own_chunk(const Params& p, const float* lv, int g0, int64_t s_lo, int64_t s_end) {
+__device__ __noinline__ void fix_own_chunk(const Params& p, const float* lv, int g0, int64_t s_lo, int64_t s_end, uint32_t slow) {
     for (int64_t slot = s_lo; slot < s_end; ++slot) {
+        if ((slow >> (int)(slot - s_lo)) & 1u) continue;           // counted exactly by count_exact
         const int64_t l = p.thr_gidx[slot] - p.g_base - g0;        // position of the item inside this chunk
-        if (l < 0 || l >= 32) continue;
+        if (l < 0 || l >= CH) continue;
         const float th = p.thr[slot];
         int c = 0;
         for (int j = 0; j < (int)l; ++j) c += (lv[j] == th) ? 1 : 0;
         if (c) atomicAdd(p.cnt + slot, c);
     }
 }
-__device__ __noinline__ void count_overflow(const Params& p, const float* lv, int g0, int64_t s_first, int64_t s_hi) {
-    for (int64_t slot = s_first; slot < s_hi; ++slot) {
+// exact count of this chunk for the CSR positions >= rtn (rows with more relevant items than register slots) and the
+// positions flagged in `slow`
+__device__ __noinline__ void count_exact(const Params& p, const float* lv, int g0, int64_t s_lo, int64_t s_hi, int rtn, uint32_t slow) {
+    for (int64_t slot = s_lo; slot < s_hi; ++slot) {
+        const int i = (int)(slot - s_lo);
+        if (i < rtn && !((slow >> i) & 1u)) continue;
         const float th = p.thr[slot];
         const int64_t ti = p.thr_gidx[slot] - p.g_base - g0;
         int c = 0;
-        for (int j = 0; j < 32; ++j) c += (lv[j] > th || (lv[j] == th && j < ti)) ? 1 : 0;
+        for (int j = 0; j < CH; ++j) c += (lv[j] > th || (lv[j] == th && j < ti)) ? 1 : 0;
         if (c) atomicAdd(p.cnt + slot, c);
     }
 }
 
 template <int RTN>
-__device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st, const float (&v)[32], int g0, bool row_valid,
+__device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st, const float (&v)[CH], int g0, bool row_valid,
                                              bool warp_has_thr) {
     // chunk maximum for the top-10 filter; ptxas folds this into 3-input FMNMX3
-    float m8[8];
+    constexpr int NG = CH / 4;
+    float m8[NG];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
-    const float cmax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+    for (int i = 0; i < NG; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
+    float cmax = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+    if (NG == 8) cmax = fmaxf(cmax, fmaxf(fmaxf(m8[NG - 4], m8[NG - 3]), fmaxf(m8[NG - 2], m8[NG - 1])));
 
     // ---- top-10: candidates are rare after the first tiles; only 4-value groups whose maximum beats the current
     //      10th best are scanned, and the hits go through a bit mask + select tree (keeps the hot loop compact) ----
@@ -224,7 +417,7 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
         const float kth = st.ts[TRB_TOPK - 1];
         uint32_t cand = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NG; ++i) {
             if (m8[i] > kth) {
                 uint32_t m = 0;
 #pragma unroll
@@ -236,37 +429,48 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
         while (cand) {
             const int j = __ffs(cand) - 1;
             cand &= cand - 1;
-            st.insert(select32(v, j), g0 + j);
+            st.insert(select_lane(v, j), g0 + j);
         }
     }
 
     // ---- exact rank counts ----
     if (!warp_has_thr) return;
     bool own = false;
+    if (g0 >= st.next_sw) own = st.pass_items(p, g0);      // rare: 1 + (relevant items of the row) times per stream
 #pragma unroll
     for (int r = 0; r < RTN; ++r) {
-        const int rl = st.rloc[r];
-        // whole chunk precedes the item -> ties count (>= thr as > nextbelow(thr)); otherwise strict
-        const float te = (g0 + 32 <= rl) ? next_below(st.thr[r]) : st.thr[r];
-        own |= (rl >= g0) & (rl < g0 + 32);
+        // no value of the chunk, in any row of the warp, reaches the r-th best threshold: nothing to count (thresholds of
+        // relevant items sit in the upper tail of the similarity distribution, so the first slots skip most chunks)
+#if TRB_TC_COUNT_FMA
+        const float c = st.te[r];                  // = -te * 2^100
+        if (r < TRB_TC_SKIP_R && !__any_sync(0xffffffffu, fmaf(cmax, COUNT_SCALE, c) > 0.f)) continue;
+        unsigned long long acc = st.cf[r];
+#pragma unroll
+        for (int j = 0; j < CH; j += 2)            // 2 x FFMA.SAT (immediate form) + 1 x FADD2: 1.5 instructions per value, FMA pipe
+            add2(acc, __saturatef(fmaf(v[j], COUNT_SCALE, c)), __saturatef(fmaf(v[j + 1], COUNT_SCALE, c)));
+        st.cf[r] = acc;
+#else
+        if (r < TRB_TC_SKIP_R && !__any_sync(0xffffffffu, cmax > st.te[r])) continue;
+        const float te = st.te[r];
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < CH; j += 4) {
             c0 += __float_as_uint(te - v[j]) >> 31;           // te - v < 0  <=>  v > te   (x - x = +0, never -0)
             c1 += __float_as_uint(te - v[j + 1]) >> 31;
             c2 += __float_as_uint(te - v[j + 2]) >> 31;
             c3 += __float_as_uint(te - v[j + 3]) >> 31;
         }
         st.cnt[r] += (int)((c0 + c1) + (c2 + c3));
+#endif
     }
-    const bool overflow = row_valid && (st.s_hi - st.s_lo > RTN);
+    const bool overflow = row_valid && ((st.s_hi - st.s_lo > RTN) || st.slow != 0u);
     own = own && row_valid;
     if (own || overflow) {
-        float lv[32];
+        float lv[CH];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) lv[j] = v[j];
-        if (own) fix_own_chunk(p, lv, g0, st.s_lo, min(st.s_lo + RTN, st.s_hi));
-        if (overflow) count_overflow(p, lv, g0, st.s_lo + RTN, st.s_hi);
+        for (int j = 0; j < CH; ++j) lv[j] = v[j];
+        if (own) fix_own_chunk(p, lv, g0, st.s_lo, min(st.s_lo + RTN, st.s_hi), st.slow);
+        if (overflow) count_exact(p, lv, g0, st.s_lo, st.s_hi, RTN, st.slow);
     }
 }
 
@@ -295,7 +499,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
         for (int i = 0; i < NS; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -309,14 +513,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
             for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
                 const UnitInfo ui = unit_info<MODE>(p, u);
                 if (ui.t_lo >= ui.t_hi) continue;
-                mbar_wait(a_empty, aphase ^ 1);
+                role_wait(a_empty, aphase ^ 1, 256);
                 mbar_expect_tx(a_full, (uint32_t)KC * BLOCK_BYTES);
                 for (int kc = 0; kc < KC; ++kc)
                     bulk_g2s(sA + (size_t)kc * BLOCK_BYTES, p.q_packed + ((size_t)ui.qt * KC + kc) * BLOCK_BYTES, BLOCK_BYTES, a_full);
                 aphase ^= 1;
                 for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
                     for (int kc = 0; kc < KC; ++kc) {
-                        mbar_wait(b_empty + stage, bphase ^ 1);
+                        role_wait(b_empty + stage, bphase ^ 1, 128);
+#ifdef TRB_TC_PROBE
+                        // probe: after the ring has been filled once, only signal (no L2 traffic; the MMAs re-use stale tiles)
+                        if ((p.debug & 4) && (t - ui.t_lo) * KC + kc >= NS) {
+                            mbar_arrive(b_full + stage);
+                            if (++stage == NS) { stage = 0; bphase ^= 1; }
+                            continue;
+                        }
+#endif
                         mbar_expect_tx(b_full + stage, STAGE_BYTES);
                         uint8_t* dst = sB + (size_t)stage * STAGE_BYTES;
                         bulk_g2s(dst, p.g_packed + ((size_t)(2 * t) * KC + kc) * BLOCK_BYTES, BLOCK_BYTES, b_full + stage);
@@ -336,15 +548,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
             for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
                 const UnitInfo ui = unit_info<MODE>(p, u);
                 if (ui.t_lo >= ui.t_hi) continue;
-                mbar_wait(a_full, aphase);
+                role_wait(a_full, aphase, 128);
                 aphase ^= 1;
                 tc_fence_after();
                 for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
-                    mbar_wait(t_empty + tbuf, tphase ^ 1);     // epilogue has drained this accumulator
+                    role_wait(t_empty + tbuf, tphase ^ 1, 256);     // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)tbuf * TILE_N;
                     for (int kc = 0; kc < KC; ++kc) {
-                        mbar_wait(b_full + stage, bphase);
+                        role_wait(b_full + stage, bphase, 64);
                         tc_fence_after();
                         const uint32_t a0 = a_addr + (uint32_t)kc * BLOCK_BYTES;
                         const uint32_t b0 = b_addr + (uint32_t)stage * STAGE_BYTES;
@@ -391,31 +603,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 mbar_wait_sleepy(t_full + tbuf, tphase, p.wait_hint_ns);
                 tc_fence_after();
                 const bool tail_tile = (t + 1) * TILE_N > p.G;         // only the last tile holds zero padding rows
-#pragma unroll 1
-                for (int chunk = 0; chunk < CHUNKS_PER_WARP; ++chunk) {
-                    float v[32];
-                    __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
+                const uint32_t taddr0 = lane_taddr + (uint32_t)(tbuf * TILE_N);
+                auto consume = [&](float (&v)[CH], int chunk) {
+                    const int g0 = (int)(t * TILE_N) + colgrp * COLS_PER_WARP + chunk * CH;   // packed gallery row of v[0]
 #ifdef TRB_TC_PROBE
-                    if (!(p.debug & 2)) tmem_ld32(lane_taddr + (uint32_t)(tbuf * TILE_N + chunk * 32), v);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                    }
-#else
-                    tmem_ld32(lane_taddr + (uint32_t)(tbuf * TILE_N + chunk * 32), v);
-#endif
-                    if (chunk == CHUNKS_PER_WARP - 1) {    // accumulator fully read by this warp: hand it back
-                        tc_fence_before();
-                        if (lane == 0) mbar_arrive(t_empty + tbuf);
-                    }
-                    const int g0 = (int)(t * TILE_N) + colgrp * COLS_PER_WARP + chunk * 32;   // packed gallery row of v[0]
-#ifdef TRB_TC_PROBE
-                    if (p.debug & 3) { if (v[5] == 12345.678f) p.cand_sim[0] = v[7]; continue; }
+                    if (p.debug & 3) { if (v[5] == 12345.678f) p.cand_sim[0] = v[7]; return; }
 #endif
                     if (MODE == 1) {
-                        if (q >= 0 && g0 < bhi && g0 + 32 > blo) {
+                        if (q >= 0 && g0 < bhi && g0 + CH > blo) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
+                            for (int j = 0; j < CH; ++j) {
                                 const int g = g0 + j;
                                 if (g >= blo && g < bhi) {
                                     p.thr[slot_base + (g - blo)] = v[j];
@@ -423,18 +620,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                                 }
                             }
                         }
-                        continue;
+                        return;
                     }
                     if (tail_tile) {                       // padded gallery rows (zero vectors) never rank
                         const int gvalid = (int)p.G;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
+                        for (int j = 0; j < CH; ++j)
                             if (g0 + j >= gvalid) v[j] = -CUDART_INF_F;
                     }
                     stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr);
+                };
+                auto release = [&]() {                     // accumulator fully read by this warp: hand it back
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(t_empty + tbuf);
+                };
+#if TRB_TC_PREFETCH
+                // two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is consumed
+                static_assert(CHUNKS_PER_WARP % 2 == 0, "the prefetching epilogue consumes chunks in pairs");
+                float va[CH], vb[CH];
+                __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
+                tmem_ld_issue(taddr0, va);
+                tmem_ld_wait(va);
+#pragma unroll 1
+                for (int chunk = 0; chunk < CHUNKS_PER_WARP; chunk += 2) {
+                    __syncwarp();
+                    tmem_ld_issue(taddr0 + (uint32_t)((chunk + 1) * CH), vb);
+                    consume(va, chunk);
+                    tmem_ld_wait(vb);
+                    const bool more = chunk + 2 < CHUNKS_PER_WARP;
+                    __syncwarp();
+                    if (more) tmem_ld_issue(taddr0 + (uint32_t)((chunk + 2) * CH), va);
+                    else release();
+                    consume(vb, chunk + 1);
+                    if (more) tmem_ld_wait(va);
                 }
+#else
+#pragma unroll 1
+                for (int chunk = 0; chunk < CHUNKS_PER_WARP; ++chunk) {
+                    float v[CH];
+                    __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
+                    tmem_ld_issue(taddr0 + (uint32_t)(chunk * CH), v);
+                    tmem_ld_wait(v);
+                    if (chunk == CHUNKS_PER_WARP - 1) release();
+                    consume(v, chunk);
+                }
+#endif
                 tbuf ^= 1;
                 if (tbuf == 0) tphase ^= 1;
+                if (MODE == 0 && TRB_TC_COUNT_FMA && ((t - ui.t_lo) & 255) == 255 && warp_has_thr) st.drain(p);
             }
 
             if (MODE == 0 && q >= 0) {
@@ -449,7 +682,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

@@ -24,6 +24,14 @@ def run(Q, G, D, get_map, n_ids, iters=3, nsplit=None):
 
 if __name__ == "__main__":
     Q, G = 100000, 1000000
+    if len(sys.argv) > 1 and sys.argv[1] == "one":
+        run(Q, G, 256, True, 250000, iters=1)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        run(Q, G, 256, True, 250000, iters=5)
+        run(Q, G, 256, False, 250000)
+        run(Q, G, 256, True, 125000)
+        sys.exit(0)
     run(Q, G, 256, True, 250000)
     run(Q, G, 256, False, 250000)
     run(Q, G, 128, True, 250000)

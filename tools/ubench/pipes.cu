@@ -1,0 +1,85 @@
+// Micro-benchmark of issue / pipe throughput for the instruction mixes the stream epilogue can count with (sm_100a).
+// Each kernel runs ITER iterations of a fully unrolled body on 32 independent values per thread; 4 warps per SMSP.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdint.h>
+#define ITER 2000
+__device__ __forceinline__ void add2(unsigned long long& acc, float a, float b) {
+    unsigned long long t;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(a), "f"(b));
+    asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(t));
+}
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, float* out, float c, long long* cycles) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = in[(threadIdx.x * 32 + i) & 1023];
+    unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    float f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+    unsigned long long a0 = 0, a1 = 0;
+    const float H = 1.2676506002282294e30f;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it) {
+        const float te = c + (float)it;          // changes per iteration: nothing hoists
+        const float cc = -te * H;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            if (MODE == 0) {        // FADD + LEA.HI
+                c0 += __float_as_uint(te - v[j]) >> 31; c1 += __float_as_uint(te - v[j + 1]) >> 31;
+                c2 += __float_as_uint(te - v[j + 2]) >> 31; c3 += __float_as_uint(te - v[j + 3]) >> 31;
+            } else if (MODE == 1) { // FFMA.SAT + FADD
+                f0 += __saturatef(fmaf(v[j], H, cc)); f1 += __saturatef(fmaf(v[j + 1], H, cc));
+                f2 += __saturatef(fmaf(v[j + 2], H, cc)); f3 += __saturatef(fmaf(v[j + 3], H, cc));
+            } else if (MODE == 2) { // 2 FFMA.SAT + FADD2
+                add2(a0, __saturatef(fmaf(v[j], H, cc)), __saturatef(fmaf(v[j + 1], H, cc)));
+                add2(a1, __saturatef(fmaf(v[j + 2], H, cc)), __saturatef(fmaf(v[j + 3], H, cc)));
+            } else if (MODE == 3) { // half/half mix of 0 and 1
+                c0 += __float_as_uint(te - v[j]) >> 31; c1 += __float_as_uint(te - v[j + 1]) >> 31;
+                f2 += __saturatef(fmaf(v[j + 2], H, cc)); f3 += __saturatef(fmaf(v[j + 3], H, cc));
+            } else if (MODE == 4) { // mix: 2 pairs FADD2-type, 2 pairs LEA-type
+                add2(a0, __saturatef(fmaf(v[j], H, cc)), __saturatef(fmaf(v[j + 1], H, cc)));
+                c2 += __float_as_uint(te - v[j + 2]) >> 31; c3 += __float_as_uint(te - v[j + 3]) >> 31;
+            } else if (MODE == 5) { // FADD only (FMA-pipe rate of a 2-register add)
+                f0 += v[j] + te; f1 += v[j + 1]; f2 += v[j + 2]; f3 += v[j + 3];
+            } else if (MODE == 6) { // FFMA.SAT only
+                f0 = __saturatef(fmaf(v[j], H, f0)); f1 = __saturatef(fmaf(v[j + 1], H, f1));
+                f2 = __saturatef(fmaf(v[j + 2], H, f2)); f3 = __saturatef(fmaf(v[j + 3], H, f3));
+            } else if (MODE == 7) { // FADD2 only
+                add2(a0, v[j], v[j + 1]); add2(a1, v[j + 2], v[j + 3]);
+            } else if (MODE == 8) { // FFMA.SAT + IADD-style accumulate of the indicator bits (ALU)  (acc += bits >> 29)
+                c0 += __float_as_uint(__saturatef(fmaf(v[j], H, cc))) >> 29; c1 += __float_as_uint(__saturatef(fmaf(v[j + 1], H, cc))) >> 29;
+                c2 += __float_as_uint(__saturatef(fmaf(v[j + 2], H, cc))) >> 29; c3 += __float_as_uint(__saturatef(fmaf(v[j + 3], H, cc))) >> 29;
+            }
+        }
+    }
+    long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(c0 + c1 + c2 + c3) + f0 + f1 + f2 + f3 + __uint_as_float((unsigned)a0) + __uint_as_float((unsigned)(a0 >> 32)) + __uint_as_float((unsigned)a1) + __uint_as_float((unsigned)(a1 >> 32));
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+template <int MODE> void run(const char* name, const float* in, float* out, long long* cyc) {
+    k<MODE><<<148, 512>>>(in, out, 0.5f, cyc);
+    cudaDeviceSynchronize();
+    k<MODE><<<148, 512>>>(in, out, 0.5f, cyc);
+    cudaDeviceSynchronize();
+    long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    // 16 warps / 4 SMSP = 4 warps per scheduler; pairs per warp = ITER*32
+    double per_pair = (double)h / (ITER * 32.0 * 4.0);
+    printf("%-44s %8lld cycles  %.3f SMSP-cycles per (value,threshold) warp-op\n", name, h, per_pair);
+}
+int main() {
+    float *in, *out; long long* cyc;
+    cudaMalloc(&in, 4096); cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 8);
+    float h[1024]; for (int i = 0; i < 1024; ++i) h[i] = (float)i / 1024.f;
+    cudaMemcpy(in, h, 4096, cudaMemcpyHostToDevice);
+    run<0>("FADD + LEA.HI", in, out, cyc);
+    run<1>("FFMA.SAT + FADD", in, out, cyc);
+    run<2>("2 FFMA.SAT + FADD2", in, out, cyc);
+    run<3>("mix 1:1 (FADD+LEA.HI | FFMA.SAT+FADD)", in, out, cyc);
+    run<4>("mix 1:1 (FFMA.SAT x2+FADD2 | FADD+LEA.HI x2)", in, out, cyc);
+    run<5>("FADD only (2 per slot... see code)", in, out, cyc);
+    run<6>("FFMA.SAT only", in, out, cyc);
+    run<7>("FADD2 only (1 per 2 values)", in, out, cyc);
+    run<8>("FFMA.SAT + LEA.HI(bits>>29)", in, out, cyc);
+    return 0;
+}
