@@ -234,7 +234,11 @@ int trb_moco_loss_launches(const trb_moco_shape* shape, int precision);
  * The three losses are independent between the shared prologue and the final reduction: the call forks two
  * internal helper streams off `stream` (created once per device, joined back before the call's last launch), so the
  * work is ordered after / before everything else on `stream` as usual and a CUDA-graph capture of the call yields a
- * 3-wide DAG.  One trb_moco_loss call may be in flight per device at a time. */
+ * 3-wide DAG (unfused launch sequences only; the fused bf16 path is two launches on `stream`).  The helper streams are the one
+ * piece of process-level state of the library: one trb_moco_loss / trb_moco_step call of an UNFUSED shape may be in flight per
+ * device at a time.
+ * A label outside [0, C) (the reference raises in scatter_, losses.py:33) yields a NaN instance loss instead of an
+ * out-of-bounds access. */
 int trb_moco_loss(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
                   const float* v_key, const float* t_key, int normalize_keys, float* v_key_n,
                   float* t_key_n, const int64_t* labels, const float* v_queue, const float* t_queue,
@@ -242,6 +246,33 @@ int trb_moco_loss(const float* v_embed, const float* t_embed, const float* v_qra
                   const trb_moco_hparams* hp, int precision, float* losses, float* d_inst, float* d_nce,
                   float* d_ga, float* d_projection, void* workspace, int64_t workspace_bytes,
                   trb_stream_t stream);
+
+/* trb_moco_loss followed by _dequeue_and_enqueue (head.py:175, :96-109) as ONE stream-ordered call -- what MoCoHead.forward's
+ * train branch does after the encoders.  Same arguments as trb_moco_loss; the queues, id_queue and queue_ptr [1] (int64, read
+ * and advanced on the device: no int(queue_ptr) sync) are written after the last read of the old queue contents.  Requires
+ * K % N == 0 like the reference's assert (head.py:101).  On the fused bf16 path the enqueue rides inside the cooperative
+ * kernel (the InfoNCE CTAs, idle at that point, write the key columns; the pointer moves after the last grid barrier), so the
+ * whole step stays at trb_moco_loss_launches() launches; otherwise two small launches follow the loss sequence.
+ * A queue_ptr outside [0, K-N] (a checkpoint written with another batch size) wraps modulo K instead of writing out of bounds. */
+int trb_moco_step(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
+                  const float* v_key, const float* t_key, int normalize_keys, float* v_key_n, float* t_key_n,
+                  const int64_t* labels, float* v_queue, float* t_queue, int64_t* id_queue, int64_t* queue_ptr,
+                  const float* projection, const trb_moco_shape* shape, const trb_moco_hparams* hp, int precision,
+                  float* losses, float* d_inst, float* d_nce, float* d_ga, float* d_projection, void* workspace,
+                  int64_t workspace_bytes, trb_stream_t stream);
+
+/* Kernel launches of one trb_moco_step call (2 on the fused bf16 path). */
+int trb_moco_step_launches(const trb_moco_shape* shape, int precision);
+
+/* Debug read-backs of the fused bf16 path (tests and tools only; both SYNCHRONISE and copy to HOST memory).  The data lives in
+ * the caller's workspace, the library owns no memory.
+ *   stamps: [160][16] uint64 %globaltimer phase stamps per CTA of the last launch made with the environment variable
+ *           TRB_FUSED_DEBUG set;
+ *   logits: [256][128] fp32 -- rows = (modality, batch row), columns = the 128 classes of instance tile t -- the logits
+ *           z = e . W/||W||_col exactly as the kernel's softmax saw them, for the last launch made with TRB_FUSED_DEBUG_LOGITS=t.
+ *           On the product path the logits never leave the SM. */
+int trb_moco_loss_debug_stamps(const void* workspace, const trb_moco_shape* shape, unsigned long long* host_out);
+int trb_moco_loss_debug_logits(const void* workspace, const trb_moco_shape* shape, float* host_out);
 
 /* out = g[0]*a + g[1]*b + g[2]*c with g a DEVICE array of 3 upstream gradients (any of a,b,c may
  * be NULL).  Backward of the loss dict without a host sync (trainer.py:82,90 uses g = 1,1,1). */
@@ -280,7 +311,8 @@ int trb_ema_update_chunks_f32(const trb_ema_chunk* chunks, int64_t nchunks, int6
 
 /* _dequeue_and_enqueue (head.py:96-109): queue[:, ptr:ptr+N] = keys^T for both queues and the ids,
  * then ptr = (ptr+N) % K, with ptr read and written on the device.  Requires K % N == 0 like the
- * reference's assert.  v_keys, t_keys [N,D] normalised; queues [D,K]; id_queue [K]; queue_ptr [1]. */
+ * reference's assert.  v_keys, t_keys [N,D] normalised; queues [D,K]; id_queue [K]; queue_ptr [1].
+ * A pointer outside [0, K-N] wraps modulo K (the reference's slice assignment raises there). */
 int trb_enqueue(float* v_queue, float* t_queue, int64_t* id_queue, int64_t* queue_ptr,
                 const float* v_keys, const float* t_keys, const int64_t* ids, int32_t N, int32_t D,
                 int32_t K, trb_stream_t stream);

@@ -150,7 +150,7 @@ def test_fused_loss_gate_and_argument_validation_without_gpu(lib):
 
 def test_build_moco_head_precision_selection(monkeypatch):
     """build_moco_head keeps the reference's factory signature; the arithmetic path comes from optional config keys or the
-    environment and defaults to the fp32 parity path."""
+    environment and defaults to the product path (bf16 operands; the fused tcgen05 step at the reference's shapes)."""
     from types import SimpleNamespace
     import torch.nn as nn
 
@@ -168,8 +168,14 @@ def test_build_moco_head_precision_selection(monkeypatch):
     monkeypatch.delenv("TRB_LOSS_PRECISION", raising=False)
     monkeypatch.delenv("TRB_LOSS_GRAPH", raising=False)
     head = textreid_b200.build_moco_head(cfg(), Enc(), Enc())
-    assert head.precision == "fp32" and head.cuda_graph is False
-    head = textreid_b200.build_moco_head(cfg(PRECISION="bf16", CUDA_GRAPH=True), Enc(), Enc())
-    assert head.precision == "bf16" and head.cuda_graph is True
-    monkeypatch.setenv("TRB_LOSS_PRECISION", "bf16")
-    assert textreid_b200.build_moco_head(cfg(), Enc(), Enc()).precision == "bf16"
+    assert head.precision == "bf16" and head.cuda_graph is False
+    head = textreid_b200.build_moco_head(cfg(PRECISION="fp32", CUDA_GRAPH=True), Enc(), Enc())
+    assert head.precision == "fp32" and head.cuda_graph is True
+    monkeypatch.setenv("TRB_LOSS_PRECISION", "fp32")
+    assert textreid_b200.build_moco_head(cfg(), Enc(), Enc()).precision == "fp32"
+    # a checkpoint whose queue pointer lies outside the queue is rejected at load time (the kernels never read it on the host)
+    sd = head.state_dict()
+    sd["queue_ptr"] = sd["queue_ptr"].clone().fill_(32)
+    import pytest as _pytest
+    with _pytest.raises(ValueError):
+        head.load_state_dict(sd)

@@ -25,7 +25,7 @@ def _single_thread():
     torch.set_num_threads(n)
 
 
-@pytest.mark.parametrize("name", ["loss_fn_small", "loss_fn_nomask", "loss_fn_allmask", "loss_fn_eps0"])
+@pytest.mark.parametrize("name", ["loss_fn_small", "loss_fn_nomask", "loss_fn_allmask", "loss_fn_eps0", "loss_fn_eps02"])
 def test_loss_functions_match_reference(golden_dir, name):
     g = load(golden_dir, name)
     eps = float(g["eps"])

@@ -58,6 +58,11 @@ SIGNATURES = {
     "trb_moco_loss": (_int, [_p, _p, _p, _p, _p, _p, _int, _p, _p, _p, _p, _p, _p, _p, C.POINTER(MocoShape),
                              C.POINTER(MocoHParams), _int, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "trb_moco_loss_launches": (_int, [C.POINTER(MocoShape), _int]),
+    "trb_moco_step": (_int, [_p, _p, _p, _p, _p, _p, _int, _p, _p, _p, _p, _p, _p, _p, _p, C.POINTER(MocoShape),
+                             C.POINTER(MocoHParams), _int, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "trb_moco_step_launches": (_int, [C.POINTER(MocoShape), _int]),
+    "trb_moco_loss_debug_stamps": (_int, [_p, C.POINTER(MocoShape), _p]),
+    "trb_moco_loss_debug_logits": (_int, [_p, C.POINTER(MocoShape), _p]),
     "trb_moco_grad_combine": (_int, [_p, _p, _p, _p, _p, _p, _p, _int, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "trb_combine3_f32": (_int, [_p, _p, _p, _p, _p, _i64, _p]),
     "trb_scale_inplace_f32": (_int, [_p, _p, _i64, _p]),
@@ -91,7 +96,7 @@ def load() -> C.CDLL:
 KERNELS_PER_CALL = {
     "trb_l2_normalize_rows_f32": 1, "trb_retrieval_thresholds_f32": 1, "trb_retrieval_stream_f32": 1,
     "trb_rank_similarity_f32": 1, "trb_rank_rerank_f64": 1, "trb_rank_scores_f64": 1, "trb_jaccard_f64": 1, "trb_similarity_f32": 1, "trb_retrieval_finish": 1, "trb_retrieval_metrics": 1,
-    "trb_pack_rows_bf16": 1, "trb_retrieval_stream_tc": 1, "trb_moco_loss": 0, "trb_moco_grad_combine": 1, "trb_combine3_f32": 1,
+    "trb_pack_rows_bf16": 1, "trb_retrieval_stream_tc": 1, "trb_moco_loss": 0, "trb_moco_step": 0, "trb_moco_grad_combine": 1, "trb_combine3_f32": 1,
     "trb_scale_inplace_f32": 1, "trb_ema_update_f32": 1, "trb_ema_update_chunks_f32": 1, "trb_enqueue": 2,
 }
 _launches = 0

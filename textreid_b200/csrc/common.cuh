@@ -35,6 +35,17 @@ void trb_set_error(const char* fmt, ...);
 
 #define TRB_LAUNCH_OK() TRB_CUDA_OK(cudaGetLastError())
 
+// cudaFuncSetAttribute is a PER-DEVICE setting: a call site remembers it per device ordinal (a zero-initialised static of this
+// type), not per process.  Setting an attribute twice from two host threads is harmless.
+struct TrbDeviceOnce { unsigned char done[64]; };
+static inline bool trb_first_on_device(TrbDeviceOnce& once) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (once.done[dev]) return false;
+    once.done[dev] = 1;
+    return true;
+}
+
 static inline bool trb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t trb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

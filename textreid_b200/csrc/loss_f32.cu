@@ -136,7 +136,11 @@ instance_rows_kernel(float* __restrict__ Z, const int64_t* __restrict__ labels, 
     __shared__ float red[32];
     const int row = blockIdx.x;
     float* z = Z + (int64_t)row * C;
-    const int y = (int)labels[row % N];
+    // a label outside [0, C) makes the reference raise (scatter_ in CrossEntropyLabelSmooth, losses.py:33); here the row's loss
+    // becomes NaN (and no class is treated as the target) instead of an out-of-bounds read
+    const int64_t lab = labels[row % N];
+    const bool bad_label = lab < 0 || lab >= (int64_t)C;
+    const int y = bad_label ? -1 : (int)lab;
     float m = -CUDART_INF_F, se = 0.f, sz = 0.f;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float v = z[c];
@@ -148,7 +152,7 @@ instance_rows_kernel(float* __restrict__ Z, const int64_t* __restrict__ labels, 
     se = block_sum(se * expf(m - mx), red);       // threads with no element carry m = -inf, se = 0 -> contribute 0
     sz = block_sum(sz, red);
     const float lse = mx + logf(se);
-    const float zy = z[y];
+    const float zy = bad_label ? CUDART_NAN_F : z[y];
     __syncthreads();
     if (threadIdx.x == 0) loss_row[row] = lse - (1.0f - eps) * zy - (eps / (float)C) * sz;
     if (!want_grad) return;
@@ -381,12 +385,13 @@ int trb_moco_loss_launches_impl(const trb_moco_shape* s, int precision) {
     return 13 + 10 * per_gemm;
 }
 
+// `queue_ptr` != NULL: the step ends with _dequeue_and_enqueue (head.py:175); the queues are then written (after every read)
 static int moco_loss_impl(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
                           const float* v_key, const float* t_key, int normalize_keys, float* v_key_n, float* t_key_n,
                           const int64_t* labels, const float* v_queue, const float* t_queue, const int64_t* id_queue,
                           const float* projection, const trb_moco_shape* shape, const trb_moco_hparams* hp, float* losses,
                           float* d_inst, float* d_nce, float* d_ga, float* d_projection, void* workspace,
-                          int64_t workspace_bytes, cudaStream_t st, bool use_tc) {
+                          int64_t workspace_bytes, cudaStream_t st, bool use_tc, int64_t* queue_ptr) {
     const int N = shape->N, D = shape->D, K = shape->K, C = shape->C;
     Workspace w = carve(workspace, N, D, K, C, use_tc);
     if (workspace_bytes < w.bytes) {
@@ -429,6 +434,12 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
         fa.pos = w.pos; fa.dpos = w.dpos; fa.rows_inst = w.rows_inst; fa.rows_nce = w.rows_nce; fa.rows_ga = w.rows_ga;
         fa.losses = losses; fa.d_inst = d_inst; fa.d_nce = d_nce; fa.d_ga = d_ga; fa.d_proj = d_projection;
         fa.scratch = w.fused; fa.roles = roles; fa.reduce_losses = roles == 7;
+        // the whole step fused: the enqueue rides in the cooperative kernel (its queue reads ended with the prologue's re-pack)
+        const bool enq_inside = roles == 7 && queue_ptr != nullptr;
+        fa.enq_v_queue = enq_inside ? const_cast<float*>(v_queue) : nullptr;
+        fa.enq_t_queue = enq_inside ? const_cast<float*>(t_queue) : nullptr;
+        fa.enq_ids = enq_inside ? const_cast<int64_t*>(id_queue) : nullptr;
+        fa.enq_ptr = enq_inside ? queue_ptr : nullptr;
         if ((rc = fused_loss_prologue(fa, st))) return rc;
         if (roles == 7) return fused_loss_launch(fa, st);       // the whole step: prologue + one cooperative launch, no helper streams
     } else {
@@ -522,6 +533,9 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     TRB_CUDA_OK(cudaStreamWaitEvent(st, fk->j2, 0));
     loss_reduce_kernel<<<1, 256, 0, st>>>(w.rows_inst, w.rows_nce, w.rows_ga, N, losses);
     TRB_LAUNCH_OK();
+    if (queue_ptr != nullptr)      // every branch has been joined back: the queues are no longer read
+        return trb_enqueue(const_cast<float*>(v_queue), const_cast<float*>(t_queue), const_cast<int64_t*>(id_queue), queue_ptr,
+                           v_key_n, t_key_n, labels, N, D, K, (trb_stream_t)st);
     return 0;
 }
 
@@ -530,10 +544,29 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
         const float *t_key, int normalize_keys, float *v_key_n, float *t_key_n, const int64_t *labels, const float *v_queue,   \
         const float *t_queue, const int64_t *id_queue, const float *projection, const trb_moco_shape *shape,                    \
         const trb_moco_hparams *hp, float *losses, float *d_inst, float *d_nce, float *d_ga, float *d_projection,              \
-        void *workspace, int64_t workspace_bytes, cudaStream_t st
+        void *workspace, int64_t workspace_bytes, cudaStream_t st, int64_t *queue_ptr
 #define TRB_LOSS_PASS                                                                                                          \
     v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, normalize_keys, v_key_n, t_key_n, labels, v_queue, t_queue, id_queue,      \
         projection, shape, hp, losses, d_inst, d_nce, d_ga, d_projection, workspace, workspace_bytes, st
 
-int trb_moco_loss_f32(TRB_LOSS_ARGS) { return moco_loss_impl(TRB_LOSS_PASS, false); }
-int trb_moco_loss_tc(TRB_LOSS_ARGS) { return moco_loss_impl(TRB_LOSS_PASS, true); }
+int trb_moco_loss_f32(TRB_LOSS_ARGS) { return moco_loss_impl(TRB_LOSS_PASS, false, queue_ptr); }
+int trb_moco_loss_tc(TRB_LOSS_ARGS) { return moco_loss_impl(TRB_LOSS_PASS, true, queue_ptr); }
+
+// launches of the enqueue that follows the loss sequence: 0 when it rides inside the fused cooperative kernel
+int trb_moco_step_extra_launches_impl(const trb_moco_shape* s, int precision) {
+    if (precision == 1 && fused_loss_supported(s->N, s->D, s->K, s->C, sm_count())) {
+        const char* e = getenv("TRB_FUSED_ROLES");
+        if (e == nullptr || (atoi(e) & 7) == 7) return 0;
+    }
+    return 2;
+}
+
+// debug read-back from the caller's workspace (fused bf16 path only)
+int trb_moco_loss_debug_impl(const void* workspace, const trb_moco_shape* s, int what, void* host_out) {
+    if (!fused_loss_supported(s->N, s->D, s->K, s->C, sm_count())) {
+        trb_set_error("moco_loss debug: the shape does not take the fused path");
+        return TRB_ERR_UNSUPPORTED;
+    }
+    const Workspace w = carve(const_cast<void*>(workspace), s->N, s->D, s->K, s->C, true);
+    return fused_loss_debug_copy(w.fused, s->N, s->D, s->K, s->C, what, host_out);
+}

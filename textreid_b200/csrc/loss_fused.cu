@@ -55,6 +55,12 @@ struct FP {
     uint4 *part_inst, *part_nce;            // partial dE tiles, bf16: [tile][row block][8-column chunk][128 rows] x 16 bytes
     float *dpos, *rows_inst, *rows_nce, *rows_ga, *losses, *d_inst, *d_nce, *d_ga, *d_proj;
     unsigned* bar;                  // [0], [1] grid barriers, [2] prologue tasks done, [3] exit count; zero between launches
+    // _dequeue_and_enqueue (head.py:96-109) folded into the kernel: the InfoNCE / align CTAs, which reach the second grid barrier
+    // long before the instance tiles, write the normalised keys and ids into the queues; the pointer moves after the barrier
+    float* enq_queue[2];            // [0] = v_queue <- v_key_n, [1] = t_queue <- t_key_n; NULL = no enqueue
+    int64_t *enq_ids, *enq_ptr;
+    float* dbg_logits;              // optional [256][128] fp32 logits of instance tile dbg_tile (trb_moco_loss_debug_logits)
+    int dbg_tile;
     ProArgs pro;
     int merged;                     // the prologue tasks run inside this kernel (InfoNCE / align CTAs)
 };
@@ -516,8 +522,21 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     tc_fence_after();
     F_STAMP(2);
 
+    // ---- debug: the logits of one instance tile leave the SM (never on the product path: dbg_logits is NULL)
+    if (INST && p.dbg_logits != nullptr && tile == p.dbg_tile && h < MT) {
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            float v[32];
+            tmem_ld32(tmem + lanes + (uint32_t)(h * 128 + j * 32), v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p.dbg_logits[(size_t)(h * 128 + n) * 128 + j * 32 + i] = v[i] * (sm.col[j * 32 + i].x * F_LN2);
+        }
+    }
     // ---- per-row partial softmax statistics of this tile, base 2 (thread = row n of block h): z2 = acc * scale * log2(e)
-    const int y = INST ? (int)p.labels[n < N ? n : 0] - c0 : -1;
+    // a label outside [0, C) makes the reference raise (scatter_ / CrossEntropyLoss); here the row's loss becomes NaN
+    const int64_t lab_n = INST ? p.labels[n < N ? n : 0] : 0;
+    const bool bad_label = INST && (lab_n < 0 || lab_n >= (int64_t)p.C);
+    const int y = INST ? (bad_label ? -(1 << 30) : (int)lab_n - c0) : -1;
     if (h < MT) {
         float m = F_NEG, s = 0.f, sz2 = 0.f, zy2 = 0.f;
 #pragma unroll 1
@@ -563,7 +582,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             s_lse2[row] = l2;
             if (tile == 0) {                                                    // losses.py:26-39 with label smoothing
                 const float2 zz = sum_of_row(p.zz_inst, row, tiles);
-                p.rows_inst[h * N + n] = l2 * F_LN2 - (1.0f - p.eps) * zz.y - (p.eps / (float)p.C) * zz.x;
+                p.rows_inst[h * N + n] = bad_label ? CUDART_NAN_F : l2 * F_LN2 - (1.0f - p.eps) * zz.y - (p.eps / (float)p.C) * zz.x;
             }
         } else {
             const float z02 = __fdiv_rn(p.pos[mod * N + n], p.T) * F_LOG2E;     // column 0 of the reference's logits (base 2)
@@ -1064,6 +1083,38 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
     }
 }
 
+// head.py:104-107 for CTA `part` of `parts`: queue[:, ptr:ptr+N] = keys^T (both modalities) and id_queue[ptr:ptr+N] = ids.
+// Element order [modality][d][n] with n fastest: the queue writes of a warp are contiguous.  The pointer is read, never written,
+// here (it moves after the grid barrier); a pointer outside [0, K-N] (a checkpoint taken with another batch size) wraps instead
+// of writing past the row / the allocation.
+__device__ __forceinline__ void enqueue_slice(const FP& p, int part, int parts) {
+    const int N = p.N, D = p.D, K = p.K;
+    const int64_t ptr = *p.enq_ptr;
+    const int total = 2 * D * N;
+    const int per = (total + parts - 1) / parts;
+    const int lo = part * per, hi = min(total, lo + per);
+    for (int e0 = lo + (int)threadIdx.x; e0 < hi; e0 += 8 * F_THREADS) {
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = min(e0 + i * F_THREADS, hi - 1);
+            const int mod = e / (D * N), r = e % (D * N), d = r / N, n = r % N;
+            x[i] = __ldcg((mod ? p.key_n[0] : p.key_n[1]) + (int64_t)n * D + d);     // key_n[0] = t_key_n, key_n[1] = v_key_n
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = e0 + i * F_THREADS;
+            if (e < hi) {
+                const int mod = e / (D * N), r = e % (D * N), d = r / N, n = r % N;
+                const int64_t col = (((ptr + n) % K) + K) % K;
+                p.enq_queue[mod][(int64_t)d * K + col] = x[i];
+            }
+        }
+    }
+    if (part == parts - 1)
+        for (int n = threadIdx.x; n < N; n += F_THREADS) p.enq_ids[(((ptr + n) % K) + K) % K] = p.labels[n];
+}
+
 __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
     extern __shared__ uint8_t smem_raw[];
     // align by pointer arithmetic (not through an integer) so that the compiler keeps the shared address space: LDS/STS, not LD/ST
@@ -1097,8 +1148,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
     else if (b < p.n_inst + p.n_nce) tile_program<false>(p, sm, tmem, (b - p.n_inst) / p.T_k, (b - p.n_inst) % p.T_k);
     else align_program(p, sm, tmem);
 
+    if (p.enq_ptr != nullptr && b >= p.n_inst) enqueue_slice(p, b - p.n_inst, p.n_nce + p.n_ga);
     grid_barrier(p.bar + 1, gridDim.x);
     F_STAMP(8);
+    // every enqueue slice has read the old pointer before the barrier: head.py:108-109
+    if (p.enq_ptr != nullptr && b == (int)gridDim.x - 1 && threadIdx.x == 0) *p.enq_ptr = (*p.enq_ptr + p.N) % p.K;
     finish_phase(p, sm);
     F_STAMP(9);
 
@@ -1123,6 +1177,8 @@ struct Scratch {
     float2 *ms_inst, *zz_inst, *ms_nce;
     uint4 *part_inst, *part_nce;
     unsigned* bar;
+    unsigned long long* dbg;       // [160][16] phase timestamps (TRB_FUSED_DEBUG)
+    float* dbg_logits;             // [256][128] logits of one instance tile (TRB_FUSED_DEBUG_LOGITS)
     int64_t bytes;
 };
 
@@ -1142,18 +1198,20 @@ Scratch carve_scratch(uint8_t* base, int N, int D, int K, int C) {
     s.part_inst = reinterpret_cast<uint4*>(take((int64_t)T_inst * 256 * Dp * 2));
     s.part_nce = reinterpret_cast<uint4*>(take((int64_t)2 * T_k * 128 * Dp * 2));
     s.bar = reinterpret_cast<unsigned*>(take(256));
+    s.dbg = reinterpret_cast<unsigned long long*>(take(160 * 16 * 8));
+    s.dbg_logits = reinterpret_cast<float*>(take(256 * 128 * 4));
     s.bytes = p - base;
     return s;
 }
 
-static unsigned long long* g_dbg = nullptr;
-
 }  // namespace
 
-// debug: copy the [160][16] phase timestamps (ns, %globaltimer) of the last fused launch to the host
-extern "C" int trb_debug_fused_stamps(unsigned long long* host_out) {
-    if (g_dbg == nullptr) return TRB_ERR_INVALID;
-    return (int)cudaMemcpy(host_out, g_dbg, 160 * 16 * 8, cudaMemcpyDeviceToHost);
+// debug read-backs (declared in include/textreid_b200.h): the buffers live in the CALLER's workspace, the library owns nothing
+int fused_loss_debug_copy(const uint8_t* scratch, int N, int D, int K, int C, int what, void* host_out) {
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~uintptr_t(1023));
+    const Scratch s = carve_scratch(base, N, D, K, C);
+    if (what == 0) return (int)cudaMemcpy(host_out, s.dbg, 160 * 16 * 8, cudaMemcpyDeviceToHost);
+    return (int)cudaMemcpy(host_out, s.dbg_logits, 256 * 128 * 4, cudaMemcpyDeviceToHost);
 }
 
 bool fused_loss_supported(int N, int D, int K, int C, int sm_count) {
@@ -1185,11 +1243,9 @@ int fused_loss_prologue(const FusedLossArgs& a, cudaStream_t st) {
     if (merged_prologue(a)) return 0;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a.scratch) + 1023) & ~uintptr_t(1023));
     const Scratch s = carve_scratch(base, a.N, a.D, a.K, a.C);
-    static bool attr = false;
-    if (!attr) {   // same shared-memory carve-out as the cooperative kernel that follows: no SM reconfiguration between the two
+    static TrbDeviceOnce attr;
+    if (trb_first_on_device(attr))   // same shared-memory carve-out as the cooperative kernel that follows: no SM reconfiguration between the two
         TRB_CUDA_OK(cudaFuncSetAttribute(fused_prologue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr = true;
-    }
     const ProArgs q = make_pro_args(a, s);
     const int ntasks = 256 + ((a.roles & 2) ? 2 * q.KC * 64 : 0);     // queue re-pack only for fused InfoNCE tiles
     fused_prologue_kernel<<<(ntasks + 7) / 8, 256, 0, st>>>(q, s.bar, ntasks);
@@ -1219,11 +1275,11 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     p.Ep = s.Ep; p.ENp = s.ENp; p.QNp = s.QNp; p.QUp = s.QUp;
     p.en = a.en; p.qn = a.qn; p.inv_e = a.inv_e; p.inv_q = a.inv_q; p.pos = a.pos;
     p.ms_inst = s.ms_inst; p.zz_inst = s.zz_inst; p.ms_nce = s.ms_nce;
-    p.dbg = nullptr;
-    if (getenv("TRB_FUSED_DEBUG")) {          // debug only: phase timestamps of every CTA, read back with trb_debug_fused_stamps
-        if (g_dbg == nullptr && cudaMalloc(&g_dbg, 160 * 16 * 8) == cudaSuccess) cudaMemset(g_dbg, 0, 160 * 16 * 8);
-        p.dbg = g_dbg;
-    }
+    // debug only (both live in the caller's workspace): phase timestamps of every CTA / the logits of one instance tile
+    p.dbg = getenv("TRB_FUSED_DEBUG") ? s.dbg : nullptr;
+    p.dbg_logits = nullptr;
+    if (const char* e = getenv("TRB_FUSED_DEBUG_LOGITS")) { p.dbg_logits = s.dbg_logits; p.dbg_tile = atoi(e); }
+    p.enq_queue[0] = a.enq_v_queue; p.enq_queue[1] = a.enq_t_queue; p.enq_ids = a.enq_ids; p.enq_ptr = a.enq_ptr;
     p.part_inst = s.part_inst; p.part_nce = s.part_nce;
     p.dpos = a.dpos; p.rows_inst = a.rows_inst; p.rows_nce = a.rows_nce; p.rows_ga = a.rows_ga;
     p.losses = a.losses; p.d_inst = a.d_inst; p.d_nce = a.d_nce; p.d_ga = a.d_ga; p.d_proj = a.d_proj;
@@ -1233,11 +1289,9 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     const int grid = p.n_inst + p.n_nce + p.n_ga;
     if (grid == 0) return 0;
 
-    static bool attr = false;
-    if (!attr) {
+    static TrbDeviceOnce attr;
+    if (trb_first_on_device(attr))
         TRB_CUDA_OK(cudaFuncSetAttribute(fused_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-        attr = true;
-    }
     // all CTAs meet at two grid barriers: the launch must be co-resident (cooperative), one CTA per SM
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -17,6 +17,9 @@ struct FusedLossArgs {
     float *losses, *d_inst, *d_nce, *d_ga, *d_proj;
     // fused scratch (fused_loss_scratch_bytes), 1024-byte aligned
     uint8_t* scratch;
+    // _dequeue_and_enqueue folded into the cooperative kernel (all roles fused only); NULL enq_ptr = no enqueue
+    float *enq_v_queue, *enq_t_queue;
+    int64_t *enq_ids, *enq_ptr;
     int roles;          // bit 0 instance, bit 1 InfoNCE, bit 2 global-align: which branches the fused kernel runs
     int reduce_losses;  // the fused kernel also forms the three loss scalars (all roles fused)
 };
@@ -28,3 +31,6 @@ int64_t fused_loss_scratch_bytes(int N, int D, int K, int C);
 int fused_loss_prologue(const FusedLossArgs& a, cudaStream_t st);
 // the cooperative kernel on `st` (after the prologue)
 int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st);
+// debug: copy the phase timestamps (what = 0, [160][16] u64) or the dumped logits tile (what = 1, [256][128] fp32) of the last
+// fused launch on this scratch to the host (synchronous)
+int fused_loss_debug_copy(const uint8_t* scratch, int N, int D, int K, int C, int what, void* host_out);

@@ -107,14 +107,16 @@ enqueue_kernel(float* __restrict__ v_queue, float* __restrict__ t_queue, int64_t
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
         const int d = d0 + r, n = n0 + tx;
-        if (n < N && d < D) queue[(int64_t)d * K + ptr + n] = tile[tx][r];
+        // a pointer outside [0, K-N] (a checkpoint written with another batch size: the reference's slice assignment raises
+        // there, head.py:104) wraps around instead of running over the end of the row / of the allocation
+        if (n < N && d < D) queue[(int64_t)d * K + (((ptr + n) % K) + K) % K] = tile[tx][r];
     }
-    if (blockIdx.z == 0 && blockIdx.y == 0 && ty == 0 && n0 + tx < N) id_queue[ptr + n0 + tx] = ids[n0 + tx];
+    if (blockIdx.z == 0 && blockIdx.y == 0 && ty == 0 && n0 + tx < N) id_queue[(((ptr + n0 + tx) % K) + K) % K] = ids[n0 + tx];
 
 }
 
 __global__ void advance_queue_ptr_kernel(int64_t* __restrict__ queue_ptr, int N, int K) {
-    *queue_ptr = (*queue_ptr + N) % K;
+    *queue_ptr = (((*queue_ptr + N) % K) + K) % K;
 }
 
 __global__ void __launch_bounds__(256)

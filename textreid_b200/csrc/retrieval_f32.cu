@@ -220,11 +220,9 @@ extern "C" int trb_retrieval_stream_f32(const float* qn, const float* gn, int64_
                 "stream_f32: rel_ptr, thr, thr_gidx and cnt must be given together");
     TRB_REQUIRE(trb_aligned16(qn) && trb_aligned16(gn), "stream_f32: operands must be 16-byte aligned");
     if (Q == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static TrbDeviceOnce attr_set;
+    if (trb_first_on_device(attr_set))
         TRB_CUDA_OK(cudaFuncSetAttribute(stream_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
-        attr_set = true;
-    }
     dim3 grid((unsigned)trb_ceil_div(Q, BM), (unsigned)nsplit);
     stream_f32_kernel<<<grid, 256, STREAM_SMEM, (cudaStream_t)stream>>>(qn, gn, Q, G, D, g_base, rel_ptr, thr, thr_gidx,
                                                                        nsplit, cand_sim, cand_idx, cnt);

@@ -223,11 +223,9 @@ int tc_gemm_launch(const void* A_packed, const void* B_packed, float* C, int64_t
     p.items = p.m_tiles * p.n_tiles * p.ksplit;
     if (p.items == 0) return 0;
     const int smem_bytes = G_STAGES * G_STAGE_BYTES + (2 * G_STAGES + 4) * 8 + 16 + 1024;
-    static bool attr = false;
-    if (!attr) {
+    static TrbDeviceOnce attr;
+    if (trb_first_on_device(attr))
         TRB_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr = true;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

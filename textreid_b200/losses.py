@@ -18,8 +18,18 @@ import torch
 from . import _lib
 
 PRECISIONS = {"fp32": 0, "bf16": 1}
-_GRAPHS: Dict[Tuple, tuple] = {}       # pointer-keyed CUDA graphs of the loss step (see moco_loss_dict(cuda_graph=True))
+_GRAPHS: Dict[Tuple, tuple] = {}       # CUDA graphs of the loss step, keyed by shapes / flags / persistent state (see moco_loss_dict)
 _GRAPH_CAP = 8
+REFERENCE_SMOOTHING = 0.1              # CrossEntropyLabelSmooth's default epsilon (losses.py:18)
+
+
+def effective_smoothing(epsilon: float, smoothing=None) -> float:
+    """Label-smoothing weight the reference actually applies for a configured EPSILON: ``instance_loss`` only tests
+    ``epsilon > 0`` and then builds ``CrossEntropyLabelSmooth(num_classes=...)`` without forwarding the value (losses.py:56-57),
+    so every positive EPSILON smooths with the class default 0.1 (losses.py:18).  ``smoothing`` overrides it explicitly."""
+    if smoothing is not None:
+        return float(smoothing)
+    return REFERENCE_SMOOTHING if epsilon > 0 else 0.0
 LOSS_KEYS = ("instance_loss", "infonce_loss", "global_align_loss")
 _workspaces: Dict[Tuple, torch.Tensor] = {}
 
@@ -92,27 +102,32 @@ class _MoCoLossFunction(torch.autograd.Function):
                 out["d_proj"] = torch.empty(D, Cn, dtype=torch.float32, device=dev)
             return out
 
-        def launch(out, ws, do_enqueue):
-            _lib.check(lib.trb_moco_loss(
-                _lib.ptr(ve), _lib.ptr(te), _lib.ptr(vq), _lib.ptr(tq), _lib.ptr(vk), _lib.ptr(tk), int(normalize_keys),
-                _lib.ptr(out["vkn"]), _lib.ptr(out["tkn"]), _lib.ptr(lab), _lib.ptr(vqu), _lib.ptr(tqu), _lib.ptr(idq),
-                _lib.ptr(proj), C.byref(shape), C.byref(hp), precision, _lib.ptr(out["losses"]), _lib.ptr(out.get("d_inst")),
-                _lib.ptr(out.get("d_nce")), _lib.ptr(out.get("d_ga")), _lib.ptr(out.get("d_proj")), _lib.ptr(ws), ws.numel(),
-                _lib.stream_ptr(dev)), "trb_moco_loss")
-            _lib.add_launches(lib.trb_moco_loss_launches(C.byref(shape), precision))
-            if do_enqueue:   # head.py:175 -- after the logits were taken from the old queue contents
-                _lib.check(lib.trb_enqueue(_lib.ptr(vqu), _lib.ptr(tqu), _lib.ptr(idq), _lib.ptr(queue_ptr), _lib.ptr(out["vkn"]),
-                                           _lib.ptr(out["tkn"]), _lib.ptr(lab), N, D, K, _lib.stream_ptr(dev)), "trb_enqueue")
+        def launch(out, ws, do_enqueue, src=None):
+            a_ve, a_te, a_vq, a_tq, a_vk, a_tk, a_lab = src if src is not None else (ve, te, vq, tq, vk, tk, lab)
+            common_in = (_lib.ptr(a_ve), _lib.ptr(a_te), _lib.ptr(a_vq), _lib.ptr(a_tq), _lib.ptr(a_vk), _lib.ptr(a_tk),
+                         int(normalize_keys), _lib.ptr(out["vkn"]), _lib.ptr(out["tkn"]), _lib.ptr(a_lab), _lib.ptr(vqu),
+                         _lib.ptr(tqu), _lib.ptr(idq))
+            common_out = (_lib.ptr(proj), C.byref(shape), C.byref(hp), precision, _lib.ptr(out["losses"]),
+                          _lib.ptr(out.get("d_inst")), _lib.ptr(out.get("d_nce")), _lib.ptr(out.get("d_ga")),
+                          _lib.ptr(out.get("d_proj")), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+            if do_enqueue:   # head.py:175 -- the queues are written after the logits were taken from their old contents
+                _lib.check(lib.trb_moco_step(*common_in, _lib.ptr(queue_ptr), *common_out), "trb_moco_step")
+                _lib.add_launches(lib.trb_moco_step_launches(C.byref(shape), precision))
+            else:
+                _lib.check(lib.trb_moco_loss(*common_in, *common_out), "trb_moco_loss")
+                _lib.add_launches(lib.trb_moco_loss_launches(C.byref(shape), precision))
 
         if cuda_graph:
-            # The whole step is a fixed launch sequence on fixed addresses: replay it as one CUDA graph.  Graphs are keyed
-            # by the input pointers (steady-state training loops hand back the same addresses from the caching allocator);
-            # the outputs of a replay are valid until the next replay of the same graph.
-            key = (ve.data_ptr(), te.data_ptr(), vq.data_ptr(), tq.data_ptr(), vk.data_ptr(), tk.data_ptr(), lab.data_ptr(),
-                   vqu.data_ptr(), tqu.data_ptr(), idq.data_ptr(), proj.data_ptr(), queue_ptr.data_ptr() if enqueue else 0,
-                   N, D, K, Cn, precision, bool(normalize_keys), need_grad, bool(enqueue),
+            # The whole step is a fixed launch sequence: replay it as one CUDA graph.  The per-step inputs (embeddings, keys,
+            # labels) are fresh allocations in a real training loop, so the graph reads them from STATIC buffers it owns and
+            # one multi-tensor copy refreshes those before each replay; the cache key holds shapes, flags and the addresses
+            # of the persistent state only (queues, pointer, projection: module buffers / parameters).  The outputs of a
+            # replay live in graph-owned buffers that the next replay overwrites.
+            key = (vqu.data_ptr(), tqu.data_ptr(), idq.data_ptr(), proj.data_ptr(), queue_ptr.data_ptr() if enqueue else 0,
+                   N, D, K, Cn, precision, bool(normalize_keys), bool(separate_q), need_grad, bool(enqueue), str(dev),
                    hp.T, hp.epsilon, hp.alpha, hp.beta, hp.scale_pos, hp.scale_neg)
             entry = _GRAPHS.get(key)
+            live = (ve, te, vq, tq, vk, tk) if separate_q else (ve, te, vk, tk)
             if entry is None:
                 if len(_GRAPHS) >= _GRAPH_CAP:
                     _GRAPHS.pop(next(iter(_GRAPHS)))
@@ -121,12 +136,23 @@ class _MoCoLossFunction(torch.autograd.Function):
                 if nbytes < 0:
                     _lib.check(int(nbytes), "trb_moco_loss_workspace_bytes")
                 ws = _alloc_workspace(int(nbytes), dev)
-                launch(out, ws, False)                   # eager warm-up (validates arguments, sets kernel attributes)
+                static = [torch.empty_like(t) for t in live]
+                s_lab = torch.empty_like(lab)
+                torch._foreach_copy_(static, list(live))
+                s_lab.copy_(lab)
+                if separate_q:
+                    src = (static[0], static[1], static[2], static[3], static[4], static[5], s_lab)
+                else:
+                    src = (static[0], static[1], static[0], static[1], static[2], static[3], s_lab)
+                launch(out, ws, False, src)              # eager warm-up (validates arguments, sets kernel attributes)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    launch(out, ws, enqueue)
-                entry = (graph, out, ws, (ve, te, vq, tq, vk, tk, lab, vqu, tqu, idq, proj))   # keep the addresses alive
+                    launch(out, ws, enqueue, src)
+                entry = (graph, out, ws, static, s_lab)
                 _GRAPHS[key] = entry
+            else:
+                torch._foreach_copy_(entry[3], list(live))
+                entry[4].copy_(lab)
             entry[0].replay()
             out = entry[1]
         else:
@@ -173,7 +199,8 @@ class _MoCoLossFunction(torch.autograd.Function):
 def moco_loss_dict(v_embed, t_embed, v_key, t_key, labels, v_queue, t_queue, id_queue, queue_ptr, projection, *,
                    T: float = 0.07, epsilon: float = 0.0, alpha: float = 0.6, beta: float = 0.4, scale_pos: float = 10,
                    scale_neg: float = 40, enqueue: bool = True, v_embed_q=None, t_embed_q=None,
-                   normalize_keys: bool = False, precision: str = "fp32", cuda_graph: bool = False) -> Dict[str, torch.Tensor]:
+                   normalize_keys: bool = False, precision: str = "fp32", cuda_graph: bool = False,
+                   smoothing=None) -> Dict[str, torch.Tensor]:
     """Functional core of MoCoHead.forward's train branch (head.py:126-175) + LossComputation.forward
     (moco_head/loss.py:21-39).
 
@@ -181,21 +208,39 @@ def moco_loss_dict(v_embed, t_embed, v_key, t_key, labels, v_queue, t_queue, id_
     v_key, t_key     [N, D]  key embeddings; L2-normalised already unless ``normalize_keys``
     v_embed_q/t_embed_q      InfoNCE query inputs of the FC=True variant (head.py:118-124); default = embeds
     queues [D, K] fp32, id_queue [1, K] int64, queue_ptr [1] int64 are mutated in place when ``enqueue``.
-    ``cuda_graph=True`` replays the whole step (loss, gradients, enqueue) as one CUDA graph keyed by the input addresses;
-    the returned losses / saved gradients then live in graph-owned buffers that the next replay overwrites (fine for the
-    reference's loop: ``backward()`` runs before the next ``forward()``, trainer.py:81-91).
+    ``epsilon`` follows the reference: it is cfg.MODEL.EMBEDDING.EPSILON, and any positive value switches label smoothing on
+    with the weight 0.1 (see ``effective_smoothing``); ``smoothing`` sets the weight explicitly instead.
+    ``cuda_graph=True`` replays the whole step (loss, gradients, enqueue) as one CUDA graph: the per-step inputs are copied
+    into graph-owned static buffers (one multi-tensor copy), so freshly allocated inputs hit the same graph every step; the
+    returned losses / saved gradients live in graph-owned buffers that the next replay overwrites (fine for the reference's
+    loop: ``backward()`` runs before the next ``forward()``, trainer.py:81-91).  Worth it for the unfused launch sequences
+    (fp32: 23 launches, bf16 outside the fused gate: 43); the fused bf16 step is two launches and gains nothing.
     """
     if precision not in PRECISIONS:
         raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
     separate_q = v_embed_q is not None or t_embed_q is not None
     if separate_q and (v_embed_q is None or t_embed_q is None):
         raise ValueError("v_embed_q and t_embed_q must be given together")
-    hp = _lib.MocoHParams(T, epsilon, alpha, beta, scale_pos, scale_neg)
+    hp = _lib.MocoHParams(T, effective_smoothing(epsilon, smoothing), alpha, beta, scale_pos, scale_neg)
     li, ln, lg, vkn, tkn = _MoCoLossFunction.apply(
         v_embed, t_embed, v_embed_q if separate_q else v_embed, t_embed_q if separate_q else t_embed, projection,
         v_key, t_key, labels, v_queue, t_queue, id_queue, hp, PRECISIONS[precision], normalize_keys, separate_q,
         queue_ptr, bool(enqueue), bool(cuda_graph))
     return {"instance_loss": li, "infonce_loss": ln, "global_align_loss": lg}
+
+
+def fused_debug_logits(shape_ndkc, precision: str = "bf16", device=None):
+    """Debug: the [256, 128] logits tile dumped by the last fused launch made with TRB_FUSED_DEBUG_LOGITS=<instance tile> (and no
+    ``cuda_graph``) for this shape on the current stream.  Rows = modality * 128 + batch row; columns = the tile's classes."""
+    N, D, K, Cn = [int(x) for x in shape_ndkc]
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    shape = _lib.MocoShape(N, D, K, Cn)
+    ws = _workspace(shape, PRECISIONS[precision], dev)
+    out = np.empty((256, 128), dtype=np.float32)
+    torch.cuda.synchronize(dev)
+    _lib.check(_lib.load().trb_moco_loss_debug_logits(_lib.ptr(ws), C.byref(shape), out.ctypes.data_as(C.c_void_p)),
+               "trb_moco_loss_debug_logits")
+    return torch.from_numpy(out)
 
 
 @torch.no_grad()

@@ -40,7 +40,7 @@ def make_loss_evaluator(cfg):
 
 
 class FusedMoCoHead(nn.Module):
-    def __init__(self, cfg, visual_model, textual_model, precision: str = "fp32", cuda_graph: bool = False):
+    def __init__(self, cfg, visual_model, textual_model, precision: str = "bf16", cuda_graph: bool = False):
         super().__init__()
         self.embed_size = cfg.MODEL.EMBEDDING.FEATURE_SIZE
         self.K = cfg.MODEL.MOCO.K
@@ -78,6 +78,16 @@ class FusedMoCoHead(nn.Module):
         self.loss_evaluator = make_loss_evaluator(cfg)
         self._momentum = MomentumUpdater(self.m)
         self._init_weight()
+        self.register_load_state_dict_post_hook(FusedMoCoHead._check_queue_ptr)
+
+    @staticmethod
+    def _check_queue_ptr(module, incompatible_keys):
+        """A checkpoint's ``queue_ptr`` is consumed on the device without a host read (head.py:100 does ``int(self.queue_ptr)``
+        every step).  Validate it once, at load time: the reference's slice assignment (head.py:104) raises when the pointer
+        does not leave room for a whole batch; the kernels wrap modulo K instead, so say so here."""
+        ptr = int(module.queue_ptr.reshape(-1)[0])
+        if not 0 <= ptr < module.K:
+            raise ValueError("checkpoint queue_ptr=%d lies outside the queue [0, %d)" % (ptr, module.K))
 
     def _init_weight(self):
         for mod in self.modules():
@@ -130,12 +140,15 @@ class FusedMoCoHead(nn.Module):
 
 
 def build_moco_head(cfg, visual_model, textual_model):
-    """Same factory signature as the reference (moco_head/head.py:185-187).  The arithmetic path is the fp32 parity path unless
-    the config carries ``MODEL.MOCO.PRECISION`` ("fp32" | "bf16") or ``MODEL.MOCO.CUDA_GRAPH`` (keys the reference's config does
-    not have), or the environment sets TRB_LOSS_PRECISION / TRB_LOSS_GRAPH: "bf16" runs the loss step as the fused tcgen05
-    kernel of csrc/loss_fused.cu."""
+    """Same factory signature as the reference (moco_head/head.py:185-187), so the import swap of INTEGRATION.md section 2 is
+    all a maintainer does.  Default arithmetic = the product path: bf16 operands / fp32 accumulation, which at the reference's
+    shapes (batch <= 128, FEATURE_SIZE <= 256) is the fused tcgen05 step of csrc/loss_fused.cu -- two launches, enqueue
+    included.  ``MODEL.MOCO.PRECISION = "fp32"`` (a key the reference's config does not have) or TRB_LOSS_PRECISION=fp32 selects
+    the 1e-5 FFMA parity path.  ``MODEL.MOCO.CUDA_GRAPH`` / TRB_LOSS_GRAPH=1 replays the loss step from a library-level CUDA
+    graph; it is off by default because the fused step is already two launches (a graph would add an input copy and save
+    nothing) -- it pays for the unfused sequences (fp32, or bf16 outside the fused gate such as batch 256)."""
     moco = cfg.MODEL.MOCO
-    precision = getattr(moco, "PRECISION", None) or os.environ.get("TRB_LOSS_PRECISION", "fp32")
+    precision = getattr(moco, "PRECISION", None) or os.environ.get("TRB_LOSS_PRECISION", "bf16")
     graph = getattr(moco, "CUDA_GRAPH", None)
     if graph is None:
         graph = os.environ.get("TRB_LOSS_GRAPH", "0") not in ("0", "", "false", "False")

@@ -38,11 +38,10 @@ def call(lib, _lib, inp, shape, hp, precision, grads=True):
 
 
 
-def print_stamps(lib, roles, K, Cn, tag):
+def print_stamps(lib, roles, K, Cn, tag, ws=None, sh=None):
     import numpy as np
     buf = np.zeros(160 * 16, dtype=np.uint64)
-    lib.trb_debug_fused_stamps.argtypes = [C.c_void_p]
-    lib.trb_debug_fused_stamps(buf.ctypes.data_as(C.c_void_p))
+    _lib.check(lib.trb_moco_loss_debug_stamps(_lib.ptr(ws), C.byref(sh), buf.ctypes.data_as(C.c_void_p)), "trb_moco_loss_debug_stamps")
     st = buf.reshape(160, 16).astype(np.int64)
     T_inst, T_k = (Cn + 127) // 128, (K + 127) // 128
     n_inst = T_inst if roles & 1 else 0
@@ -108,7 +107,16 @@ def child(roles, variant):
     p = _lib.ptr
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+    qptr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    with_enqueue = os.environ.get("TRB_PROBE_ENQUEUE", "1") != "0"      # the product call: loss + gradients + enqueue
+
     def step():
+        if with_enqueue:
+            _lib.check(lib.trb_moco_step(p(inp["v_embed"]), p(inp["t_embed"]), p(inp["v_embed"]), p(inp["t_embed"]), p(inp["v_key"]), p(inp["t_key"]), 0,
+                                         p(out["vkn"]), p(out["tkn"]), p(inp["labels"]), p(inp["v_queue"]), p(inp["t_queue"]), p(inp["id_queue"]), p(qptr),
+                                         p(inp["projection"]), C.byref(sh), C.byref(hp), 1, p(out["losses"]), p(out["d_inst"]), p(out["d_nce"]),
+                                         p(out["d_ga"]), p(out["d_proj"]), p(ws), ws.numel(), _lib.stream_ptr("cuda")), "trb_moco_step")
+            return
         _lib.check(lib.trb_moco_loss(p(inp["v_embed"]), p(inp["t_embed"]), p(inp["v_embed"]), p(inp["t_embed"]), p(inp["v_key"]), p(inp["t_key"]), 0,
                                      p(out["vkn"]), p(out["tkn"]), p(inp["labels"]), p(inp["v_queue"]), p(inp["t_queue"]), p(inp["id_queue"]),
                                      p(inp["projection"]), C.byref(sh), C.byref(hp), 1, p(out["losses"]), p(out["d_inst"]), p(out["d_nce"]),
@@ -133,7 +141,7 @@ def child(roles, variant):
             ts.sort()
             print("TIME roles=%d var=%d eager %s: median %.1f us  min %.1f us" % (roles, variant, name, ts[len(ts) // 2], ts[0]), flush=True)
             if os.environ.get("TRB_FUSED_DEBUG") and roles:
-                print_stamps(lib, roles, K, Cn, name)
+                print_stamps(lib, roles, K, Cn, name, ws, sh)
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):

@@ -328,6 +328,8 @@ def main():
     golden_loss_functions(out, "loss_fn_nomask", N=8, D=32, K=32, C=37, eps=0.1, seed=2, mask_mode="none")
     golden_loss_functions(out, "loss_fn_allmask", N=8, D=32, K=32, C=37, eps=0.1, seed=3, mask_mode="all")
     golden_loss_functions(out, "loss_fn_eps0", N=8, D=64, K=32, C=50, eps=0.0, seed=4)
+    # EPSILON other than 0.1: the reference only tests `epsilon > 0` and smooths with the class default 0.1 (losses.py:56-57,18)
+    golden_loss_functions(out, "loss_fn_eps02", N=8, D=32, K=32, C=41, eps=0.2, seed=7)
     golden_moco_head(out, "moco_head_small", N=16, F=24, D=32, K=64, C=101, eps=0.1, fc=False,
                      steps=3, seed=5, id_pool=40)
     golden_moco_head(out, "moco_head_fc", N=8, F=16, D=32, K=32, C=53, eps=0.1, fc=True,
