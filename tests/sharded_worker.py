@@ -148,6 +148,45 @@ def shard_slices(G, world, uneven=True):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+class _GoldenSplit:
+    """Dataset / loader / model stand-ins that replay the embeddings of tests/golden/evaluation_small.npz (recorded from the
+    unmodified reference); rank r encodes the items idx % world == r, and item 0 twice (a sampler that pads)."""
+
+    def __init__(self, rank, world):
+        import numpy as np
+        g = np.load(os.path.join(ROOT, "tests", "golden", "evaluation_small.npz"))
+        self.v, self.t = torch.from_numpy(g["v"]), torch.from_numpy(g["t"])
+        self.image_ids, self.pids = [int(x) for x in g["image_ids"]], [int(x) for x in g["pids"]]
+        self.mine = [i for i in range(self.v.shape[0]) if i % world == rank] + ([0] if rank == world - 1 else [])
+        self.r1 = torch.from_numpy(g["plain.r1"])
+        outer = self
+
+        class DS:
+            def __len__(self): return len(outer.image_ids)
+            def get_id_info(self, idx): return outer.image_ids[idx], outer.pids[idx]
+
+        class Cap:
+            def to(self, device): return self
+
+        class Loader:
+            dataset = DS()
+
+            def __iter__(self):
+                for b0 in range(0, len(outer.mine), 16):
+                    idx = outer.mine[b0:b0 + 16]
+                    yield torch.tensor(idx, dtype=torch.float32).unsqueeze(1), [Cap() for _ in idx], tuple(idx)
+
+        class Model(torch.nn.Module):
+            pad = 0         # zero columns appended to the embeddings (cosine similarities unchanged; bf16 path needs D % 64 == 0)
+
+            def forward(self, images, captions):
+                idx = images[:, 0].long().cpu()
+                f = torch.nn.functional.pad
+                return [f(outer.v[idx], (0, self.pad)).to(images.device), f(outer.t[idx], (0, self.pad)).to(images.device)]
+
+        self.loader, self.model = Loader(), Model()
+
+
 def worker(rank, world, backend_name, port, out_dir, precision="fp32", Q=151, G=700, D=64, exact=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -160,21 +199,49 @@ def worker(rank, world, backend_name, port, out_dir, precision="fp32", Q=151, G=
         dist.init_process_group("gloo", rank=rank, world_size=world)
         dev = torch.device("cpu")
         backend = OracleBackend()
+    from textreid_b200 import sharded
     from textreid_b200.sharded import retrieve_sharded
     text, image, tpid, ipid = make_case(Q, G, D, max(G // 5, 1), seed=5, exact=exact)
     lo, hi = shard_slices(G, world)[rank]
-    res = retrieve_sharded(text.to(dev), image[lo:hi].to(dev), tpid.to(dev), ipid[lo:hi].to(dev), (1, 5, 10), True,
+    tpid_d, ipid_d = tpid.to(dev), ipid[lo:hi].to(dev).contiguous()
+    res = retrieve_sharded(text.to(dev), image[lo:hi].to(dev), tpid_d, ipid_d, (1, 5, 10), True,
                            precision, backend=backend, return_hit_ranks=True)
-    res_topk = retrieve_sharded(text.to(dev), image[lo:hi].to(dev), tpid.to(dev), ipid[lo:hi].to(dev), (1, 5, 10), False,
+    res_topk = retrieve_sharded(text.to(dev), image[lo:hi].to(dev), tpid_d, ipid_d, (1, 5, 10), False,
                                 precision, backend=backend)
-    torch.save({"cmc": res.cmc.cpu(), "mAP": res.mAP.cpu(), "top_idx": res.top_idx.cpu(), "top_sim": res.top_sim.cpu(),
-                "hit_ranks": res.hit_ranks.cpu(), "rel_ptr": res.rel_ptr.cpu(), "ap": res.ap.cpu(),
-                "cmc_topk": res_topk.cmc.cpu(), "top_idx_topk": res_topk.top_idx.cpu()},
-               os.path.join(out_dir, "rank%d.pt" % rank))
+    # second evaluation of the same split (same pid tensors, new embeddings objects): served from the cached plan, same result
+    before = dict(sharded.plan_cache_stats)
+    res2 = retrieve_sharded(text.to(dev).clone(), image[lo:hi].to(dev).clone(), tpid_d, ipid_d, (1, 5, 10), True,
+                            precision, backend=backend, return_hit_ranks=True)
+    assert sharded.plan_cache_stats["hits"] == before["hits"] + 1 and sharded.plan_cache_stats["misses"] == before["misses"]
+    assert torch.equal(res2.top_idx, res.top_idx) and torch.equal(res2.cmc, res.cmc) and torch.equal(res2.hit_ranks, res.hit_ranks)
+    out = {"cmc": res.cmc.cpu(), "mAP": res.mAP.cpu(), "top_idx": res.top_idx.cpu(), "top_sim": res.top_sim.cpu(),
+           "hit_ranks": res.hit_ranks.cpu(), "rel_ptr": res.rel_ptr.cpu(), "ap": res.ap.cpu(),
+           "cmc_topk": res_topk.cmc.cpu(), "top_idx_topk": res_topk.top_idx.cpu()}
+    # the embedding hand-off of inference(): every rank encodes a part of the split, device all-gather, rows by dataset index
+    from textreid_b200.evaluation import compute_on_dataset_tensors, gather_embeddings
+    split = _GoldenSplit(rank, world)
+    idx, v_loc, t_loc = compute_on_dataset_tensors(split.model, split.loader, dev)
+    idx_all, v_all, t_all = gather_embeddings(idx, v_loc, t_loc)
+    n = split.v.shape[0]
+    assert idx_all.tolist() == list(range(n)) and torch.equal(v_all.cpu(), split.v) and torch.equal(t_all.cpu(), split.t)
+    if backend_name == "cuda":
+        # the reference entry under a process group: sharded evaluation, value on the main process only (inference.py:86-87)
+        from textreid_b200.evaluation import inference
+        for prec in ("fp32", "bf16"):
+            split.model.pad = 32 if prec == "bf16" else 0
+            r1 = inference(split.model, split.loader, device=str(dev), output_folder=out_dir, save_data=False, rerank=False,
+                           precision=prec)
+            assert (r1 is None) == (rank != 0)
+            if rank == 0:
+                out["inference_r1_" + prec] = r1.cpu()
+        out["inference_r1_golden"] = split.r1
+    torch.save(out, os.path.join(out_dir, "rank%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
 
 
-if __name__ == "__main__":      # torchrun entry: python tests/sharded_worker.py <backend> <out_dir> <precision>
+if __name__ == "__main__":      # torchrun entry: python tests/sharded_worker.py <backend> <out_dir> <precision> <exact 0|1>
+    exact = len(sys.argv) > 4 and sys.argv[4] == "1"
     worker(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), sys.argv[1], int(os.environ.get("MASTER_PORT", "29511")),
-           sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "fp32", Q=300, G=3000, D=64, exact=False)
+           sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "fp32", Q=300 if not exact else 151, G=3000 if not exact else 700, D=64,
+           exact=exact)

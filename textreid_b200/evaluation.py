@@ -245,32 +245,16 @@ def retrieve(text_embed: torch.Tensor, image_embed: torch.Tensor, text_pid: torc
     _lib.require_cuda(text_embed, image_embed, text_pid, image_pid)
     if text_embed.dim() != 2 or image_embed.dim() != 2 or text_embed.shape[1] != image_embed.shape[1]:
         raise ValueError("embeddings must be [Q, D] and [G, D]")
-    dev = text_embed.device
-    q_pids = text_pid.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
-    g_pids = image_pid.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
-    if precision == "bf16":
-        from .retrieval_tc import retrieve_tc
-        return retrieve_tc(text_embed, image_embed, q_pids, g_pids, topk, get_mAP, normalized, nsplit)
-    if precision != "fp32":
+    if precision not in ("fp32", "bf16"):
         raise ValueError("precision must be 'fp32' or 'bf16'")
-    lib = _lib.load()
-    Q, D = text_embed.shape
-    G = image_embed.shape[0]
-    qn = text_embed.contiguous().float() if normalized else l2_normalize_rows(text_embed)
-    gn = image_embed.contiguous().float() if normalized else l2_normalize_rows(image_embed)
-    rel = build_relevance(q_pids, g_pids) if get_mAP else None
-    thr = cnt = None
-    if get_mAP:
-        thr = torch.zeros(max(rel.total, 1), dtype=torch.float32, device=dev)
-        cnt = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=dev)
-        _lib.check(lib.trb_retrieval_thresholds_f32(_lib.ptr(qn), _lib.ptr(gn), _lib.ptr(rel.rel_ptr),
-                                                    rel.col_ptr(), _lib.ptr(thr), Q, D,
-                                                    _lib.stream_ptr(dev)), "trb_retrieval_thresholds_f32")
-    if nsplit is None:
-        nsplit = _choose_nsplit(Q, G, 128, 128, _sm_count(dev))
-    cand_sim, cand_idx = _stream_fp32(qn, gn, 0, rel.rel_ptr if get_mAP else None, thr,
-                                      rel.store if get_mAP else None, cnt, nsplit)
-    return _finish_and_metrics(cand_sim, cand_idx, nsplit, q_pids, g_pids, rel, cnt, topk)
+    dev = text_embed.device
+    from .sharded import _as_pid, retrieve_sharded_local
+    q_pids = _as_pid(text_pid if text_pid.device == dev else text_pid.to(dev))
+    g_pids = _as_pid(image_pid if image_pid.device == dev else image_pid.to(dev))
+    # one shard, no collectives; the pid bookkeeping (sort orders, relevance CSR, band arrays) is cached in a ShardPlan keyed
+    # by the pid tensors, so evaluating the same split again (trainer.py:124: every EVALUATE_PERIOD epochs) only packs,
+    # captures thresholds, streams and merges
+    return retrieve_sharded_local(text_embed, [image_embed], q_pids, [g_pids], topk, get_mAP, precision, None, nsplit, normalized)
 
 
 # --------------------------------------------------------------------------------------------
@@ -294,89 +278,174 @@ def _table(rows, headers):
         return "\n".join(str(r) for r in [headers] + list(rows))
 
 
-def evaluation(dataset, predictions, output_folder, topk, save_data=True, rerank=True, precision="fp32"):
+def eval_precision(precision=None) -> str:
+    """Arithmetic path of the evaluation entries: explicit argument, else the environment variable TRB_EVAL_PRECISION, else
+    "fp32" -- the path on which indices, R@k and mAP are bit-exact with the stable-sort reference.  "bf16" selects the tcgen05
+    stream (the path the 1/2/4/8-GPU throughput numbers are quoted on)."""
+    p = precision or os.environ.get("TRB_EVAL_PRECISION", "fp32")
+    if p not in ("fp32", "bf16"):
+        raise ValueError("evaluation precision must be 'fp32' or 'bf16' (got %r)" % (p,))
+    return p
+
+
+# pid / image-id bookkeeping of a dataset split: pure metadata, identical at every evaluation of the split.  Cached per
+# (dataset object, index list) so that (a) the per-item Python loop of evaluation.py:101-106 runs once and (b) the SAME pid
+# tensors are handed to retrieve() every time, which is what lets the ShardPlan cache recognise the split.
+_ID_CACHE: dict = {}
+
+
+class SplitInfo:
+    def __init__(self, dataset, idx: np.ndarray, dev):
+        image_ids, pids = [], []
+        for i in idx.tolist():
+            image_id, pid = dataset.get_id_info(i)
+            image_ids.append(image_id)
+            pids.append(pid)
+        self.text_pid = torch.as_tensor(np.asarray(pids), device=dev).to(torch.int64).contiguous()
+        self.keep = first_occurrence_index(image_ids, dev)
+        self.image_pid = self.text_pid[self.keep].contiguous()
+        self.shards: dict = {}
+
+    def shard(self, which: str, lo: int, hi: int) -> torch.Tensor:
+        key = (which, lo, hi)
+        if key not in self.shards:
+            src = self.image_pid if which == "image" else self.text_pid
+            self.shards[key] = src[lo:hi].contiguous()
+        return self.shards[key]
+
+
+def split_info(dataset, idx, dev) -> SplitInfo:
+    idx = np.asarray(idx, dtype=np.int64)
+    key = (id(dataset), str(dev), idx.shape[0], hash(idx.tobytes()))
+    hit = _ID_CACHE.get(key)
+    if hit is None or hit[0] is not dataset:
+        if len(_ID_CACHE) >= 4:
+            _ID_CACHE.pop(next(iter(_ID_CACHE)))
+        hit = (dataset, SplitInfo(dataset, idx, dev))
+        _ID_CACHE[key] = hit
+    return hit[1]
+
+
+def _even_bounds(n: int, world: int, rank: int):
+    per = -(-n // world)
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def evaluate_embeddings(dataset, idx, image_all, text_all, output_folder, topk, save_data=True, rerank=True, precision=None,
+                        group=None):
+    """Core of ``evaluation`` on contiguous tensors: ``idx`` [n] dataset indices (host), ``image_all`` / ``text_all`` [n, D]
+    device tensors in the same order (row i = the model's outputs for dataset item idx[i]).  With an initialised process
+    group and the trainer's flags (save_data=False, rerank=False) every rank must call it with the SAME full tensors; each
+    rank then scores its contiguous slice of the gallery (textreid_b200.sharded) and all ranks return the same value."""
+    logger = logging.getLogger("PersonSearch.inference")
+    precision = eval_precision(precision)
+    dev = text_all.device
+    topk_list = [int(k) for k in (topk.tolist() if torch.is_tensor(topk) else topk)]
+    info = split_info(dataset, idx, dev)
+    image_n = l2_normalize_rows(image_all[info.keep])
+    text_n = l2_normalize_rows(text_all)
+    results = {}
+    from .rerank import jaccard_rerank_matrix, neighbor_lists, rerank_rank, similarity_matrix
+    single = isinstance(group, str)         # "single": evaluate in this process even though a process group exists
+    world = 1
+    if not single and torch.distributed.is_available() and torch.distributed.is_initialized():
+        world = torch.distributed.get_world_size(group)
+    if not save_data and not rerank:
+        # fast path (trainer.py:124): nothing needs the [Q, G] matrix
+        if world > 1:
+            from .sharded import retrieve_sharded
+            rank_ = torch.distributed.get_rank(group)
+            G, Qn = image_n.shape[0], text_n.shape[0]
+            g_sizes = [_even_bounds(G, world, r)[1] - _even_bounds(G, world, r)[0] for r in range(world)]
+            t_sizes = [_even_bounds(Qn, world, r)[1] - _even_bounds(Qn, world, r)[0] for r in range(world)]
+            g_lo, g_hi = _even_bounds(G, world, rank_)
+            t_lo, t_hi = _even_bounds(Qn, world, rank_)
+            t2i = retrieve_sharded(text_n, image_n[g_lo:g_hi], info.text_pid, info.shard("image", g_lo, g_hi), topk_list, False,
+                                   precision, group=group, shard_sizes=g_sizes, normalized=True)
+            i2t = retrieve_sharded(image_n, text_n[t_lo:t_hi], info.image_pid, info.shard("text", t_lo, t_hi), topk_list, False,
+                                   precision, group=group, shard_sizes=t_sizes, normalized=True)
+        else:
+            t2i = retrieve(text_n, image_n, info.text_pid, info.image_pid, topk_list, get_mAP=False, precision=precision, normalized=True)
+            i2t = retrieve(image_n, text_n, info.image_pid, info.text_pid, topk_list, get_mAP=False, precision=precision, normalized=True)
+        results["t2i"], results["i2t"] = t2i.cmc, i2t.cmc
+        rows = [[k, float(results["t2i"][j]), float(results["i2t"][j])] for j, k in enumerate(topk_list)]
+        logger.info("\n" + _table(rows, ["topk", "t2i", "i2t"]))
+        evaluation.last_results = results
+        return results["t2i"][0]
+    return _evaluate_materialised(logger, output_folder, topk_list, save_data, rerank, info.image_pid, info.text_pid, None,
+                                  image_n, text_n, None, None)
+
+
+def evaluation(dataset, predictions, output_folder, topk, save_data=True, rerank=True, precision=None):
     """Drop-in for lib/data/metrics/evaluation.py:76-173.  Returns t2i R@1 (0-d fp32 tensor, percent).
 
     ``predictions``: {dataset_index: [image_embed(D), text_embed(D)]} or None to read
     ``inference_data.npz`` from ``output_folder`` like the reference.  Re-ranking (k-reciprocal,
-    evaluation.py:40-65) is applied when ``rerank`` is True.
+    evaluation.py:40-65) is applied when ``rerank`` is True.  ``precision``: see ``eval_precision``.
     """
     logger = logging.getLogger("PersonSearch.inference")
     data_dir = os.path.join(output_folder, "inference_data.npz")
     dev = torch.device("cuda", torch.cuda.current_device())
     topk_list = [int(k) for k in (topk.tolist() if torch.is_tensor(topk) else topk)]
-
-    if predictions is None:
-        data = np.load(data_dir)
-        logger.info("Load inference data from {}".format(data_dir))
-        image_pid = torch.as_tensor(data["image_pid"], device=dev)
-        text_pid = torch.as_tensor(data["text_pid"], device=dev)
-        similarity = torch.as_tensor(data["similarity"], device=dev)
-        image_n = text_n = None
-        rvn_mat = torch.as_tensor(data["rvn_mat"], device=dev) if rerank else None
-        rtn_mat = torch.as_tensor(data["rtn_mat"], device=dev) if rerank else None
-    else:
+    if predictions is not None:
         keys = list(predictions.keys())
-        image_ids, pids = [], []
-        for idx in keys:
-            image_id, pid = dataset.get_id_info(idx)
-            image_ids.append(image_id)
-            pids.append(pid)
-        pid_t = torch.as_tensor(np.asarray(pids), device=dev)
         image_all = torch.stack([predictions[i][0] for i in keys], dim=0).to(dev)
         text_all = torch.stack([predictions[i][1] for i in keys], dim=0).to(dev)
-        keep = first_occurrence_index(image_ids, dev)
-        image_pid, text_pid = pid_t[keep], pid_t
-        image_n = l2_normalize_rows(image_all[keep])
-        text_n = l2_normalize_rows(text_all)
-        similarity = rvn_mat = rtn_mat = None
+        return evaluate_embeddings(dataset, keys, image_all, text_all, output_folder, topk_list, save_data, rerank, precision)
+    data = np.load(data_dir)
+    logger.info("Load inference data from {}".format(data_dir))
+    image_pid = torch.as_tensor(data["image_pid"], device=dev)
+    text_pid = torch.as_tensor(data["text_pid"], device=dev)
+    similarity = torch.as_tensor(data["similarity"], device=dev)
+    rvn_mat = torch.as_tensor(data["rvn_mat"], device=dev) if rerank else None
+    rtn_mat = torch.as_tensor(data["rtn_mat"], device=dev) if rerank else None
+    return _evaluate_materialised(logger, output_folder, topk_list, save_data, rerank, image_pid, text_pid, similarity, None, None,
+                                  rvn_mat, rtn_mat)
 
-    results = {}
+
+def _evaluate_materialised(logger, output_folder, topk_list, save_data, rerank, image_pid, text_pid, similarity, image_n, text_n,
+                           rvn_mat, rtn_mat):
+    """The compatibility paths of evaluation.py:120-173 that need the [Q, G] matrix: npz cache, k-reciprocal re-ranking, and the
+    cached-npz replay.  fp32 FFMA arithmetic throughout."""
     from .rerank import jaccard_rerank_matrix, neighbor_lists, rerank_rank, similarity_matrix
-    if similarity is None and not save_data and not rerank:
-        # fast path (trainer.py:124): nothing needs the matrix
-        t2i = retrieve(text_n, image_n, text_pid, image_pid, topk_list, get_mAP=False, precision=precision, normalized=True)
-        i2t = retrieve(image_n, text_n, image_pid, text_pid, topk_list, get_mAP=False, precision=precision, normalized=True)
-        results["t2i"], results["i2t"] = t2i.cmc, i2t.cmc
-    else:
-        nn_t2i = nn_i2t = None
-        if similarity is None:
-            similarity = similarity_matrix(text_n, image_n)
-            if rerank:
-                nn_t2i = neighbor_lists(text_n, image_n)      # (text -> image, image -> image)
-                nn_i2t = neighbor_lists(image_n, text_n)      # (image -> text, text -> text)
-            if save_data:
-                payload = dict(image_pid=image_pid.cpu().numpy(), text_pid=text_pid.cpu().numpy(),
-                               similarity=similarity.cpu().numpy())
-                if rerank:
-                    payload.update(rvn_mat=jaccard_rerank_matrix(text_n, image_n).cpu().numpy(),
-                                   rtn_mat=jaccard_rerank_matrix(image_n, text_n).cpu().numpy())
-                np.savez(data_dir, **payload)
+    data_dir = os.path.join(output_folder, "inference_data.npz")
+    results = {}
+    nn_t2i = nn_i2t = None
+    if similarity is None:
+        similarity = similarity_matrix(text_n, image_n)
         if rerank:
-            sim_t = similarity.t()
-            c, m, _ = rank(sim_t, image_pid, text_pid, topk_list, get_mAP=True)
-            results["i2t"], results["i2t_mAP"] = c, m
-            c, m, _ = rank(similarity, text_pid, image_pid, topk_list, get_mAP=True)
-            results["t2i"], results["t2i_mAP"] = c, m
-            if nn_t2i is not None:
-                r = rerank_rank(sim_t, nn_i2t[0], nn_i2t[1], image_pid, text_pid, topk_list)
-                results["re_i2t"], results["re_i2t_mAP"] = r.cmc, r.mAP
-                r = rerank_rank(similarity, nn_t2i[0], nn_t2i[1], text_pid, image_pid, topk_list)
-                results["re_t2i"], results["re_t2i_mAP"] = r.cmc, r.mAP
-            else:   # cached npz: the float64 matrices were loaded; their sum with the similarity is ranked as float64 scores
-                for key, mat, s_, qp, gp in (("re_i2t", rtn_mat, sim_t, image_pid, text_pid), ("re_t2i", rvn_mat, similarity, text_pid, image_pid)):
-                    c, m = _rank_float64_matrix(mat + s_, qp, gp, topk_list)
-                    results[key], results[key + "_mAP"] = c, m
-        else:
-            results["t2i"], _ = rank(similarity, text_pid, image_pid, topk_list, get_mAP=False)
-            results["i2t"], _ = rank(similarity.t(), image_pid, text_pid, topk_list, get_mAP=False)
-
+            nn_t2i = neighbor_lists(text_n, image_n)      # (text -> image, image -> image)
+            nn_i2t = neighbor_lists(image_n, text_n)      # (image -> text, text -> text)
+        if save_data:
+            payload = dict(image_pid=image_pid.cpu().numpy(), text_pid=text_pid.cpu().numpy(),
+                           similarity=similarity.cpu().numpy())
+            if rerank:
+                payload.update(rvn_mat=jaccard_rerank_matrix(text_n, image_n, nn=nn_t2i).cpu().numpy(),
+                               rtn_mat=jaccard_rerank_matrix(image_n, text_n, nn=nn_i2t).cpu().numpy())
+            np.savez(data_dir, **payload)
     if rerank:
+        sim_t = similarity.t()
+        c, m, _ = rank(sim_t, image_pid, text_pid, topk_list, get_mAP=True)
+        results["i2t"], results["i2t_mAP"] = c, m
+        c, m, _ = rank(similarity, text_pid, image_pid, topk_list, get_mAP=True)
+        results["t2i"], results["t2i_mAP"] = c, m
+        if nn_t2i is not None:
+            r = rerank_rank(sim_t, nn_i2t[0], nn_i2t[1], image_pid, text_pid, topk_list)
+            results["re_i2t"], results["re_i2t_mAP"] = r.cmc, r.mAP
+            r = rerank_rank(similarity, nn_t2i[0], nn_t2i[1], text_pid, image_pid, topk_list)
+            results["re_t2i"], results["re_t2i_mAP"] = r.cmc, r.mAP
+        else:   # cached npz: the float64 matrices were loaded; their sum with the similarity is ranked as float64 scores
+            for key, mat, s_, qp, gp in (("re_i2t", rtn_mat, sim_t, image_pid, text_pid), ("re_t2i", rvn_mat, similarity, text_pid, image_pid)):
+                c, m = _rank_float64_matrix(mat + s_, qp, gp, topk_list)
+                results[key], results[key + "_mAP"] = c, m
         cols = ["t2i", "re_t2i", "i2t", "re_i2t"]
         rows = [[k] + [float(results[c][j]) for c in cols] for j, k in enumerate(topk_list)]
         rows.append(["mAP"] + [float(results[c + "_mAP"]) for c in cols])
         logger.info("\n" + _table(rows, ["topk", "t2i", "re-t2i", "i2t", "re-i2t"]))
     else:
+        results["t2i"], _ = rank(similarity, text_pid, image_pid, topk_list, get_mAP=False)
+        results["i2t"], _ = rank(similarity.t(), image_pid, text_pid, topk_list, get_mAP=False)
         rows = [[k, float(results["t2i"][j]), float(results["i2t"][j])] for j, k in enumerate(topk_list)]
         logger.info("\n" + _table(rows, ["topk", "t2i", "i2t"]))
     evaluation.last_results = results
@@ -401,7 +470,8 @@ def _rank_float64_matrix(scores: torch.Tensor, q_pids, g_pids, topk):
 
 
 def compute_on_dataset(model, data_loader, device):
-    """lib/engine/inference.py:14-26, with the per-item dict kept for signature compatibility."""
+    """lib/engine/inference.py:14-26, with the per-item dict kept for signature compatibility (callers that want the
+    reference's ``{idx: [v, t]}``); ``inference`` itself uses ``compute_on_dataset_tensors``."""
     model.eval()
     results: Dict[int, list] = {}
     for batch in data_loader:
@@ -416,24 +486,76 @@ def compute_on_dataset(model, data_loader, device):
     return results
 
 
+def compute_on_dataset_tensors(model, data_loader, device):
+    """The embedding hand-off without the dict: dataset indices [n] (host int64 array) and the model's two outputs as
+    contiguous [n, D] device tensors, rows in loader order.  An index the sampler yields twice keeps its first outputs, like
+    ``prediction[0], prediction[1]`` of the reference's per-index list (evaluation.py:105-106)."""
+    model.eval()
+    idx, vs, ts = [], [], []
+    for images, captions, image_ids in data_loader:
+        images = images.to(device)
+        captions = [c.to(device) for c in captions]
+        with torch.no_grad():
+            v, t = model(images, captions)
+        idx.extend(int(i) for i in image_ids)
+        vs.append(v)
+        ts.append(t)
+    idx = np.asarray(idx, dtype=np.int64)
+    v_all, t_all = torch.cat(vs, dim=0), torch.cat(ts, dim=0)
+    _, first = np.unique(idx, return_index=True)
+    if first.shape[0] != idx.shape[0]:
+        first = np.sort(first)
+        sel = torch.as_tensor(first, device=v_all.device)
+        idx, v_all, t_all = idx[first], v_all[sel], t_all[sel]
+    return idx, v_all.contiguous(), t_all.contiguous()
+
+
+def gather_embeddings(idx, v_local, t_local, group=None):
+    """Replacement of _accumulate_predictions_from_multiple_gpus (inference.py:29-45, comm.py:47-87: pickle + CPU tensors):
+    all-gather of the index vectors and of the [n_r, D] embedding blocks on the device (NCCL), rows then ordered by dataset
+    index on EVERY rank (the sharded evaluation needs the full query set everywhere)."""
+    from .sharded import _all_gather_varlen
+    dev = v_local.device
+    idx_t = torch.as_tensor(idx, device=dev)
+    idx_all = torch.cat(_all_gather_varlen(idx_t, group))
+    v_all = torch.cat(_all_gather_varlen(v_local.contiguous(), group))
+    t_all = torch.cat(_all_gather_varlen(t_local.contiguous(), group))
+    idx_host = idx_all.cpu().numpy()
+    uniq, first = np.unique(idx_host, return_index=True)          # sorted by dataset index; first occurrence wins
+    sel = torch.as_tensor(first, device=dev)
+    if uniq.shape[0] and uniq.shape[0] != int(uniq[-1]) + 1:
+        logging.getLogger("PersonSearch.inference").warning(
+            "Number of images that were gathered from multiple processes is not a contiguous set. "
+            "Some images might be missing from the evaluation")
+    return uniq, v_all[sel].contiguous(), t_all[sel].contiguous()
+
+
 def inference(model, data_loader, dataset_name="cuhkpedes-test", device="cuda", output_folder="", save_data=True,
-              rerank=True):
-    """Drop-in for lib/engine/inference.py:48-96 (single process; the sharded multi-GPU evaluation lives in
-    textreid_b200.sharded)."""
+              rerank=True, precision=None):
+    """Drop-in for lib/engine/inference.py:48-96.  Embeddings stay on the device as contiguous [n, D] tensors from the
+    encoder loop to the kernels (no per-item dict, no pickle).  Under an initialised process group every rank encodes its
+    part of the split; the blocks are all-gathered over NCCL and -- with the trainer's flags save_data=False, rerank=False
+    (trainer.py:124) -- every rank scores its slice of the gallery (``textreid_b200.sharded``).  Like the reference, only the
+    main process returns the value (others return None); the compatibility modes that need the [Q, G] matrix (npz cache,
+    re-ranking) run on the main process alone."""
     logger = logging.getLogger("PersonSearch.inference")
     dataset = data_loader.dataset
     logger.info("Start evaluation on {} dataset({} images).".format(dataset_name, len(dataset)))
-    predictions = None
-    if not os.path.exists(os.path.join(output_folder, "inference_data.npz")):
-        predictions = compute_on_dataset(model, data_loader, torch.device(device))
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.barrier()
-            gathered = [None] * torch.distributed.get_world_size()
-            torch.distributed.all_gather_object(gathered, {k: [t.cpu() for t in v] for k, v in predictions.items()})
-            if torch.distributed.get_rank() != 0:
+    dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+    main = (not dist_on) or torch.distributed.get_rank() == 0
+    if os.path.exists(os.path.join(output_folder, "inference_data.npz")):
+        if not main:
+            return None
+        return evaluation(dataset=dataset, predictions=None, output_folder=output_folder, save_data=save_data, rerank=rerank,
+                          topk=[1, 5, 10], precision=precision)
+    idx, v_all, t_all = compute_on_dataset_tensors(model, data_loader, torch.device(device))
+    if dist_on:
+        idx, v_all, t_all = gather_embeddings(idx, v_all, t_all)
+        if save_data or rerank:
+            if not main:
                 return None
-            predictions = {}
-            for part in gathered:
-                predictions.update(part)
-    return evaluation(dataset=dataset, predictions=predictions, output_folder=output_folder, save_data=save_data,
-                      rerank=rerank, topk=[1, 5, 10])
+            r = evaluate_embeddings(dataset, idx, v_all, t_all, output_folder, [1, 5, 10], save_data, rerank, precision,
+                                    group="single")
+            return r
+    r = evaluate_embeddings(dataset, idx, v_all, t_all, output_folder, [1, 5, 10], save_data, rerank, precision)
+    return r if main else None

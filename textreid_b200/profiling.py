@@ -4,16 +4,14 @@ from __future__ import annotations
 
 import torch
 
-from .sharded import CudaBackend, ShardWorker
+from .sharded import CudaBackend, ShardWorker, _as_pid, _local_plans
 
 
 def time_stream_kernel(text, image, q_pid, g_pid, precision, iters=5, flush=None):
     """Median duration (ms) of the gallery stream kernel alone (single shard), thresholds already captured."""
-    q_pids = q_pid.reshape(-1).to(torch.int64).contiguous()
-    g_pids = g_pid.reshape(-1).to(torch.int64).contiguous()
-    w = ShardWorker(text, image, q_pids, g_pids, 0, True, precision, CudaBackend())
-    w.set_layout(w.local_counts().unsqueeze(0), 0)
-    w.set_thresholds(*w.local_thresholds())
+    plan = _local_plans(_as_pid(q_pid), [_as_pid(g_pid)], [0], True, precision)[0]
+    w = ShardWorker(text, image, plan, CudaBackend())
+    w.set_thresholds(w.local_thresholds())
     w.stream()                          # warm-up
     w.record_events = True
     times = []

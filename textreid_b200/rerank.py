@@ -37,9 +37,10 @@ def neighbor_lists(q_feats: torch.Tensor, g_feats: torch.Tensor, neighbor_num: i
     return qg.contiguous(), gg.contiguous()
 
 
-def jaccard_rerank_matrix(q_feats: torch.Tensor, g_feats: torch.Tensor, neighbor_num: int = 5, alpha: float = 0.05):
-    """Drop-in for k_reciprocal (evaluation.py:40-65): alpha * Jaccard as a float64 [Q, G] matrix."""
-    qg, gg = neighbor_lists(q_feats, g_feats, neighbor_num)
+def jaccard_rerank_matrix(q_feats: torch.Tensor, g_feats: torch.Tensor, neighbor_num: int = 5, alpha: float = 0.05, nn=None):
+    """Drop-in for k_reciprocal (evaluation.py:40-65): alpha * Jaccard as a float64 [Q, G] matrix.  ``nn`` = the neighbour
+    lists ``neighbor_lists(q_feats, g_feats, neighbor_num)`` when the caller already has them."""
+    qg, gg = nn if nn is not None else neighbor_lists(q_feats, g_feats, neighbor_num)
     Q, G = q_feats.shape[0], g_feats.shape[0]
     out = torch.empty(Q, G, dtype=torch.float64, device=q_feats.device)
     _lib.check(_lib.load().trb_jaccard_f64(_lib.ptr(qg), _lib.ptr(gg), neighbor_num, float(alpha), _lib.ptr(out), Q, G,

@@ -3,7 +3,8 @@
 Only the gallery shards: every rank holds all Q queries and a contiguous slice of
 the gallery.  Exchange steps, all tiny next to the per-rank GEMM stream:
 
-  0. all-gather the gallery pids                         -> every rank builds the same relevance CSR
+  0. once per (dataset, sharding), cached in a ShardPlan: all-gather of the per-query COUNTS of relevant items and
+     all-reduce of the slot -> global gallery index table  -> every rank builds the same relevance CSR
   1. per rank: similarities of ITS relevant items        -> all-reduce(sum) of the threshold vector
      (each slot is written by exactly one rank, so the sum with zeros is exact)
   2. per rank: one stream over its slice                 -> all-gather of per-query top-10 candidate
@@ -115,59 +116,33 @@ class CudaBackend:
         return top_sim, top_idx
 
 
-class ShardWorker:
-    """State of one gallery shard between the exchange steps.
+class ShardPlan:
+    """Everything about one gallery shard that depends on the PIDS only (not on the embeddings): sort orders, the relevance
+    CSR, this rank's slot offsets, the global gallery index of every slot, the band arrays of the tensor-core threshold
+    capture.  The reference evaluates the same test split every EVALUATE_PERIOD epochs (trainer.py:124) with a new model each
+    time, so a plan is built once per (dataset, sharding) and reused: the per-evaluation work is then pack + thresholds +
+    stream + merge, with no sort, no host read and one collective less.
 
     Slot layout of the relevance CSR (one slot per (query, relevant gallery item)): the slots of query q are ordered by
     global gallery index, i.e. by (owning rank, position in the rank's pid-sorted shard).  A rank therefore only needs
     every rank's per-query COUNT of relevant items to place its own slots: no global pid gather, no global sort."""
 
-    def __init__(self, text_embed, image_shard, q_pids, g_pids_local, g_base, get_mAP, precision, backend, normalized=False):
-        self.backend = backend
-        self.precision = precision
-        self.get_mAP = get_mAP
-        self.g_base = int(g_base)
-        self.q_pids = q_pids
-        self.g_pids_local = g_pids_local
-        self.Gs = image_shard.shape[0]
-        self.Q = q_pids.numel()
-        self.dev = text_embed.device
-        self.record_events = False       # bench.py: CUDA events around the stream kernel alone
-        self.stream_events = None
-        self.rel: Optional[RelevanceIndex] = None
-        self.max_rel = 0
-        dev = self.dev
+    def __init__(self, q_pids, g_pids_local, g_base, get_mAP, precision):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
-        need_sorted_queries = precision == "bf16" or get_mAP
-        if need_sorted_queries:
+        self.precision, self.get_mAP, self.g_base = precision, bool(get_mAP), int(g_base)
+        self.q_pids, self.g_pids_local = q_pids, g_pids_local
+        self.Q, self.Gs, self.dev = q_pids.numel(), g_pids_local.numel(), q_pids.device
+        self.rel: Optional[RelevanceIndex] = None
+        self.max_rel = self.total = self.total_local = 0
+        self.g_pids_all = None            # top-k-only mode: pids of every shard (first hit inside the top-10)
+        self.shard_sizes = None
+        if precision == "bf16" or get_mAP:
             self.q_sorted, self.q_order = torch.sort(q_pids, stable=True)
         if get_mAP:
             self.g_sorted, self.g_order = torch.sort(g_pids_local, stable=True)   # stable: ascending index inside a pid
             self.lo_s = torch.searchsorted(self.g_sorted, self.q_sorted, right=False)   # per pid-sorted query row
             self.hi_s = torch.searchsorted(self.g_sorted, self.q_sorted, right=True)
-        if precision == "fp32":
-            self.qn = text_embed.contiguous().float() if normalized else backend.normalize(text_embed)
-            self.gn = image_shard.contiguous().float() if normalized else backend.normalize(image_shard)
-        else:
-            from .retrieval_tc import pack_rows
-            lib = _lib.load()
-            self.Qp, self.Gp = int(lib.trb_packed_rows(self.Q)), int(lib.trb_packed_rows(self.Gs))
-            self.D = text_embed.shape[1]
-            # queries once, in pid order; gallery in INDEX order for the stream (ties resolved by position) and, when
-            # ranks are wanted, again in pid order for the threshold capture (relevant items form a contiguous band)
-            self.q_packed = pack_rows(text_embed, self.q_order, normalize=not normalized)
-            self.q_row_id = torch.full((self.Qp,), -1, dtype=torch.int64, device=dev)
-            self.q_row_id[:self.Q] = self.q_order
-            self.g_packed = pack_rows(image_shard, None, normalize=not normalized)
-            if get_mAP:
-                self.g_packed_pid = pack_rows(image_shard, self.g_order, normalize=not normalized)
-                self.g_row_id = torch.full((self.Gp,), -1, dtype=torch.int64, device=dev)
-                self.g_row_id[:self.Gs] = self.g_order + self.g_base
-                self.band_lo = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
-                self.band_hi = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
-                self.band_lo[:self.Q] = self.lo_s.to(torch.int32)
-                self.band_hi[:self.Q] = self.hi_s.to(torch.int32)
 
     # ---- step 0: how many relevant items of every query live on this shard ----
     def local_counts(self) -> torch.Tensor:
@@ -176,7 +151,8 @@ class ShardWorker:
         return counts
 
     def set_layout(self, counts_all: torch.Tensor, rank: int) -> None:
-        """counts_all [P, Q] int32 (rank-major).  Fixes the CSR and this rank's offsets; ONE host read."""
+        """counts_all [P, Q] int32 (rank-major).  Fixes the CSR, this rank's offsets and the local slot arithmetic; ONE host
+        read, once per plan."""
         dev = self.dev
         c64 = counts_all.to(torch.int64)
         per_q = c64.sum(0)
@@ -186,51 +162,95 @@ class ShardWorker:
         local = c64[rank]
         host = torch.stack([rel_ptr[-1], per_q.max() if self.Q else rel_ptr[-1], local.sum()]).cpu()
         total, self.max_rel, self.total_local = int(host[0]), int(host[1]), int(host[2])
+        self.total = total
         self.gidx_store = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)
         self.rel = RelevanceIndex(rel_ptr, self.gidx_store[:total], total, self.gidx_store)
         self.off_q = off                                   # [Q] slots of lower ranks, original query order
-        if self.precision == "bf16":
+        # local slots: query (pid-sorted row i) owns sorted-gallery rows [lo_s[i], hi_s[i])
+        cnt_s = self.hi_s - self.lo_s
+        row_i = torch.repeat_interleave(torch.arange(self.Q, device=dev), cnt_s, output_size=self.total_local)
+        start = torch.cumsum(cnt_s, 0) - cnt_s
+        within = torch.arange(self.total_local, device=dev) - start[row_i]
+        q = self.q_order[row_i]
+        self.slot = rel_ptr[q] + off[q] + within                         # [total_local] global slot of every local slot
+        self.slot_row = self.g_order[self.lo_s[row_i] + within]          # its LOCAL gallery row
+        # global gallery index of this shard's slots (zeros elsewhere); summed over the ranks by set_gidx
+        self.gidx_store[self.slot] = self.slot_row + self.g_base
+        if self.precision == "fp32":
+            self.rel_row = torch.full((max(total, 1),), -1, dtype=torch.int64, device=dev)
+            self.rel_row[self.slot] = self.slot_row
+        else:
+            lib = _lib.load()
+            self.Qp, self.Gp = int(lib.trb_packed_rows(self.Q)), int(lib.trb_packed_rows(self.Gs))
             self.rel_off = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
             self.rel_off[:self.Q] = off[self.q_order].to(torch.int32)
+            self.g_row_id = torch.full((self.Gp,), -1, dtype=torch.int64, device=dev)
+            self.g_row_id[:self.Gs] = self.g_order + self.g_base
+            self.band_lo = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
+            self.band_hi = torch.zeros(self.Qp, dtype=torch.int32, device=dev)
+            self.band_lo[:self.Q] = self.lo_s.to(torch.int32)
+            self.band_hi[:self.Q] = self.hi_s.to(torch.int32)
+            self.gidx_scratch = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)   # the capture kernel's own copy
 
-    # ---- step 1: similarities (and global indices) of this shard's relevant items; zeros elsewhere ----
-    def local_thresholds(self):
-        rel = self.rel
-        dev = self.dev
-        thr = torch.zeros(max(rel.total, 1), dtype=torch.float32, device=dev)
-        gidx = torch.zeros(max(rel.total, 1), dtype=torch.int64, device=dev)
+    def finish_common(self):
+        if self.precision == "bf16":
+            lib = _lib.load()
+            if not hasattr(self, "Qp"):
+                self.Qp, self.Gp = int(lib.trb_packed_rows(self.Q)), int(lib.trb_packed_rows(self.Gs))
+            self.q_row_id = torch.full((self.Qp,), -1, dtype=torch.int64, device=self.dev)
+            self.q_row_id[:self.Q] = self.q_order
+
+
+class ShardWorker:
+    """Per-evaluation state of one gallery shard between the exchange steps: the normalised / packed embeddings and the
+    thresholds.  Everything pid-derived comes from the ShardPlan."""
+
+    def __init__(self, text_embed, image_shard, plan: ShardPlan, backend, normalized=False):
+        self.backend, self.plan = backend, plan
+        self.precision, self.get_mAP, self.g_base = plan.precision, plan.get_mAP, plan.g_base
+        self.Q, self.Gs, self.dev = plan.Q, plan.Gs, text_embed.device
+        if text_embed.shape[0] != plan.Q or image_shard.shape[0] != plan.Gs:
+            raise ValueError("embeddings do not match the plan (%d x %d expected)" % (plan.Q, plan.Gs))
+        self.record_events = False       # bench.py: CUDA events around the stream kernel alone
+        self.stream_events = None
+        self.rel, self.max_rel = plan.rel, plan.max_rel
         if self.precision == "fp32":
-            # local slots: query (pid-sorted row i) owns sorted-gallery rows [lo_s[i], hi_s[i])
-            cnt_s = self.hi_s - self.lo_s
-            row_i = torch.repeat_interleave(torch.arange(self.Q, device=dev), cnt_s, output_size=self.total_local)
-            start = torch.cumsum(cnt_s, 0) - cnt_s
-            within = torch.arange(self.total_local, device=dev) - start[row_i]
-            q = self.q_order[row_i]
-            slot = rel.rel_ptr[q] + self.off_q[q] + within
-            rows = self.g_order[self.lo_s[row_i] + within]
-            rel_row = torch.full((max(rel.total, 1),), -1, dtype=torch.int64, device=dev)
-            rel_row[slot] = rows
-            gidx[slot] = rows + self.g_base
-            self.backend.thresholds_fp32(self.qn, self.gn, rel.rel_ptr, rel_row, thr)
+            self.qn = text_embed.contiguous().float() if normalized else backend.normalize(text_embed)
+            self.gn = image_shard.contiguous().float() if normalized else backend.normalize(image_shard)
+        else:
+            from .retrieval_tc import pack_rows
+            self.D = text_embed.shape[1]
+            # queries once, in pid order; gallery in INDEX order for the stream (ties resolved by position) and, when
+            # ranks are wanted, again in pid order for the threshold capture (relevant items form a contiguous band)
+            self.q_packed = pack_rows(text_embed, plan.q_order, normalize=not normalized)
+            self.g_packed = pack_rows(image_shard, None, normalize=not normalized)
+            if self.get_mAP:
+                self.g_packed_pid = pack_rows(image_shard, plan.g_order, normalize=not normalized)
+
+    # ---- step 1: similarities of this shard's relevant items; zeros elsewhere ----
+    def local_thresholds(self):
+        plan, rel, dev = self.plan, self.plan.rel, self.dev
+        thr = torch.zeros(max(rel.total, 1), dtype=torch.float32, device=dev)
+        if self.precision == "fp32":
+            self.backend.thresholds_fp32(self.qn, self.gn, rel.rel_ptr, plan.rel_row, thr)
         else:
             _lib.check(_lib.load().trb_retrieval_stream_tc(
-                _lib.ptr(self.q_packed), _lib.ptr(self.g_packed_pid), self.Q, self.Gs, self.D, _lib.ptr(self.q_row_id),
-                _lib.ptr(self.g_row_id), self.g_base, _lib.ptr(rel.rel_ptr), _lib.ptr(thr), _lib.ptr(gidx), _lib.ptr(self.band_lo),
-                _lib.ptr(self.band_hi), _lib.ptr(self.rel_off), 1, 1, self.max_rel, None, None, None, _lib.stream_ptr(dev)),
-                "trb_retrieval_stream_tc(mode=1)")
-        return thr, gidx
+                _lib.ptr(self.q_packed), _lib.ptr(self.g_packed_pid), self.Q, self.Gs, self.D, _lib.ptr(plan.q_row_id),
+                _lib.ptr(plan.g_row_id), self.g_base, _lib.ptr(rel.rel_ptr), _lib.ptr(thr), _lib.ptr(plan.gidx_scratch),
+                _lib.ptr(plan.band_lo), _lib.ptr(plan.band_hi), _lib.ptr(plan.rel_off), 1, 1, self.max_rel, None, None, None,
+                _lib.stream_ptr(dev)), "trb_retrieval_stream_tc(mode=1)")
+        return thr
 
-    def set_thresholds(self, thr: torch.Tensor, gidx: torch.Tensor) -> None:
-        """Thresholds / item indices of ALL shards (after the exchange)."""
+    def set_thresholds(self, thr: torch.Tensor) -> None:
+        """Thresholds of ALL shards (after the exchange)."""
         self.thr = thr
-        self.gidx_store.copy_(gidx)
 
     # ---- step 2 ----
     def stream(self, nsplit: Optional[int] = None):
-        rel = self.rel
+        plan, rel = self.plan, self.plan.rel
         cnt = torch.zeros(max(rel.total, 1), dtype=torch.int32, device=self.dev) if self.get_mAP else None
         thr = self.thr if self.get_mAP else None
-        gidx = self.gidx_store if self.get_mAP else None
+        gidx = plan.gidx_store if self.get_mAP else None
         Q = self.Q
         if self.precision == "fp32":
             ns = nsplit or self.backend.nsplit(Q, self.Gs, self.dev)
@@ -249,7 +269,7 @@ class ShardWorker:
         cand_idx = torch.empty(Q, lists, TOPK_DEPTH, dtype=torch.int64, device=self.dev)
         ev = self._events()
         _lib.check(lib.trb_retrieval_stream_tc(
-            _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, self.D, _lib.ptr(self.q_row_id), None, self.g_base,
+            _lib.ptr(self.q_packed), _lib.ptr(self.g_packed), Q, self.Gs, self.D, _lib.ptr(plan.q_row_id), None, self.g_base,
             _lib.ptr(rel.rel_ptr) if self.get_mAP else None, _lib.ptr(thr), _lib.ptr(gidx), None, None, None, 0, ns,
             self.max_rel, _lib.ptr(cand_sim), _lib.ptr(cand_idx), _lib.ptr(cnt), _lib.stream_ptr(self.dev)), "trb_retrieval_stream_tc(mode=0)")
         self._events(ev)
@@ -266,6 +286,43 @@ class ShardWorker:
         return None
 
 
+# ---- plan cache: keyed by the identity (address, version, size) of the pid tensors, which the entries keep alive ----
+_PLAN_CACHE: dict = {}
+_PLAN_CACHE_CAP = 8
+plan_cache_stats = {"hits": 0, "misses": 0}
+
+
+def _plan_key(q_pids, g_pids_list, get_mAP, precision, tag):
+    k = [q_pids.data_ptr(), q_pids._version, q_pids.numel(), str(q_pids.device), bool(get_mAP), precision, tag]
+    for g in g_pids_list:
+        k += [g.data_ptr(), g._version, g.numel()]
+    return tuple(k)
+
+
+def _cache_get(key):
+    e = _PLAN_CACHE.get(key)
+    plan_cache_stats["hits" if e is not None else "misses"] += 1
+    return e
+
+
+def _cache_put(key, value):
+    if len(_PLAN_CACHE) >= _PLAN_CACHE_CAP:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    _PLAN_CACHE[key] = value
+
+
+def clear_plan_cache():
+    _PLAN_CACHE.clear()
+
+
+def _as_pid(t: torch.Tensor) -> torch.Tensor:
+    """int64 contiguous 1-D view; returns the SAME tensor object when it already is one, so that the plan cache can recognise
+    the pid vectors of the previous evaluation."""
+    if t.dtype is torch.int64 and t.dim() == 1 and t.is_contiguous():
+        return t
+    return t.reshape(-1).to(torch.int64).contiguous()
+
+
 def _finish(backend, cand_sims, cand_idxs, q_pids, g_pids_all, rel, cnt, topk):
     cand_sim = torch.cat(cand_sims, dim=1).contiguous() if len(cand_sims) > 1 else cand_sims[0].contiguous()
     cand_idx = torch.cat(cand_idxs, dim=1).contiguous() if len(cand_idxs) > 1 else cand_idxs[0].contiguous()
@@ -274,36 +331,56 @@ def _finish(backend, cand_sims, cand_idxs, q_pids, g_pids_all, rel, cnt, topk):
     return backend.finish(cand_sim, cand_idx, cand_sim.shape[1], q_pids, g_pids_all, rel, cnt, topk)
 
 
+def _local_plans(q_pids, pids, bases, get_mAP, precision):
+    """Plans of all shards of a single-process (multi-shard) evaluation, cached on the identity of the pid tensors."""
+    key = _plan_key(q_pids, pids, get_mAP, precision, ("local",) + tuple(bases))
+    hit = _cache_get(key)
+    if hit is not None:
+        return hit[0]
+    plans = [ShardPlan(q_pids, p, base, get_mAP, precision) for p, base in zip(pids, bases)]
+    if get_mAP:
+        counts_all = torch.stack([pl.local_counts() for pl in plans])
+        for r, pl in enumerate(plans):
+            pl.set_layout(counts_all, r)
+        gidx = torch.stack([pl.gidx_store for pl in plans]).sum(0)          # one contributor per slot
+        for pl in plans:
+            pl.gidx_store.copy_(gidx)
+    else:
+        g_all = torch.cat(pids).contiguous()
+        for pl in plans:
+            pl.g_pids_all = g_all
+    for pl in plans:
+        pl.finish_common()
+    _cache_put(key, (plans, q_pids, pids))      # the entry keeps the pid tensors (and so their addresses) alive
+    return plans
+
+
 def retrieve_sharded_local(text_embed, image_shards: Sequence[torch.Tensor], text_pid, image_pid_shards, topk=(1, 5, 10),
                            get_mAP=True, precision="fp32", backend=None, nsplit=None, normalized=False) -> RetrievalResult:
     """All shards processed by ONE process, with the collectives replaced by local sums / concatenation.
     Same code path per shard as the distributed driver; used to validate the exchange protocol (and, with a single
     shard, as the single-GPU tensor-core entry)."""
     backend = backend or CudaBackend()
-    q_pids = text_pid.reshape(-1).to(torch.int64).contiguous()
-    pids = [p.reshape(-1).to(torch.int64).contiguous() for p in image_pid_shards]
+    q_pids = _as_pid(text_pid)
+    pids = [_as_pid(p) for p in image_pid_shards]
     bases, b = [], 0
     for s in image_shards:
         bases.append(b)
         b += s.shape[0]
-    workers = [ShardWorker(text_embed, s, q_pids, p, base, get_mAP, precision, backend, normalized)
-               for s, p, base in zip(image_shards, pids, bases)]
-    g_pids_all = None
+    plans = _local_plans(q_pids, pids, bases, get_mAP, precision)
+    workers = [ShardWorker(text_embed, s, pl, backend, normalized) for s, pl in zip(image_shards, plans)]
+    thr = None
     if get_mAP:
-        counts_all = torch.stack([w.local_counts() for w in workers])
-        for r, w in enumerate(workers):
-            w.set_layout(counts_all, r)
         parts = [w.local_thresholds() for w in workers]
-        thr = torch.stack([p[0] for p in parts]).sum(0)
-        gidx = torch.stack([p[1] for p in parts]).sum(0)
+        thr = torch.stack(parts).sum(0) if len(parts) > 1 else parts[0]
         for w in workers:
-            w.set_thresholds(thr, gidx)
-    else:
-        g_pids_all = torch.cat(pids).contiguous()
+            w.set_thresholds(thr)
     outs = [w.stream(nsplit) for w in workers]
-    cnt = torch.stack([o[2] for o in outs]).sum(0).to(torch.int32) if get_mAP else None
-    res = _finish(backend, [o[0] for o in outs], [o[1] for o in outs], q_pids, g_pids_all, workers[0].rel, cnt, topk)
-    res.thresholds = thr[:workers[0].rel.total] if get_mAP else None
+    cnt = None
+    if get_mAP:
+        cnt = torch.stack([o[2] for o in outs]).sum(0).to(torch.int32) if len(outs) > 1 else outs[0][2]
+    res = _finish(backend, [o[0] for o in outs], [o[1] for o in outs], q_pids, plans[0].g_pids_all, plans[0].rel, cnt, topk)
+    res.thresholds = thr[:plans[0].rel.total] if get_mAP else None
     return res
 
 
@@ -317,26 +394,25 @@ def _unpack_f32_i32(p: torch.Tensor):
     return f, p >> 32
 
 
-def _finish_scattered(backend, cand_sim, cand_idx, rel, cnt, topk, group, want_hit_ranks):
+def _finish_scattered(backend, cand_sim, cand_idx, plan, cnt, topk, group, want_hit_ranks):
     """Finish with the queries partitioned over the ranks: an all-to-all hands every rank the candidate list of ITS
     Q/P queries from every rank (8 B per candidate), each rank derives top-10 / first hit / AP for them, and the small
     per-query results are gathered back, so every rank ends with identical results.  Indices travel as 31-bit values
     packed next to the fp32 similarity (the caller checks the gallery size)."""
     dev = cand_sim.device
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    rel = plan.rel
+    world = dist.get_world_size(group)
     Q, K = cand_sim.shape[0], cand_sim.shape[2]
-    Qc = -(-Q // world)
+    Qc = plan.Qc
     Qp = Qc * world
-    tx = torch.full((Qp, K), -1 << 32, dtype=torch.int64, device=dev)
-    tx[:, :] = _pack_f32_i32(torch.full((1,), float("-inf"), device=dev), torch.full((1,), -1, dtype=torch.int64, device=dev))
+    tx = torch.empty((Qp, K), dtype=torch.int64, device=dev)
     tx[:Q] = _pack_f32_i32(cand_sim[:, 0], cand_idx[:, 0].clamp(min=-1))
+    if Qp > Q:
+        tx[Q:] = _pack_f32_i32(torch.full((1,), float("-inf"), device=dev), torch.full((1,), -1, dtype=torch.int64, device=dev))
     rx = torch.empty_like(tx)                                              # [P, Qc, K]: lists of my queries
     dist.all_to_all_single(rx.reshape(-1), tx.reshape(-1), group=group)
     sim_my, idx_my = _unpack_f32_i32(rx.reshape(world, Qc, K).permute(1, 0, 2).contiguous())   # [Qc, P, K]
-    rel_ptr_pad = torch.full((Qp + 1,), rel.total, dtype=torch.int64, device=dev)
-    rel_ptr_pad[:Q + 1] = rel.rel_ptr
-    my_ptr = rel_ptr_pad[rank * Qc: (rank + 1) * Qc + 1].contiguous()
-    top_sim, top_idx, first_hit, ap, hit_ranks = backend.finish_partial(sim_my.contiguous(), idx_my.contiguous(), my_ptr, cnt,
+    top_sim, top_idx, first_hit, ap, hit_ranks = backend.finish_partial(sim_my.contiguous(), idx_my.contiguous(), plan.my_ptr, cnt,
                                                                          rel.total)
     # per-query results -> one int64 block: 10 x (sim, idx) pairs + (ap, first_hit)
     block = torch.cat([_pack_f32_i32(top_sim, top_idx), _pack_f32_i32(ap, first_hit.to(torch.int64)).unsqueeze(1)], dim=1)
@@ -377,59 +453,78 @@ def _all_gather_varlen(t: torch.Tensor, group=None) -> List[torch.Tensor]:
     return [b[:s] for b, s in zip(bufs, sizes)]
 
 
+def _distributed_plan(q_pids, g_pids_local, get_mAP, precision, group, shard_sizes) -> ShardPlan:
+    """This rank's plan; built with two small collectives (per-query counts, slot indices) and one host read, then cached.
+    Every rank sees the same hit / miss sequence as long as every rank re-uses (or re-creates) its pid tensors alike."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    key = _plan_key(q_pids, [g_pids_local], get_mAP, precision, ("dist", rank, world, id(group)))
+    hit = _cache_get(key)
+    if hit is not None:
+        return hit[0]
+    dev = q_pids.device
+    if shard_sizes is None:
+        n = torch.tensor([g_pids_local.numel()], dtype=torch.int64, device=dev)
+        shard_sizes = _all_gather_stack(n, group).reshape(-1).tolist()      # one host read
+    shard_sizes = [int(x) for x in shard_sizes]
+    plan = ShardPlan(q_pids, g_pids_local, int(sum(shard_sizes[:rank])), get_mAP, precision)
+    plan.shard_sizes = shard_sizes
+    if get_mAP:
+        plan.set_layout(_all_gather_stack(plan.local_counts(), group), rank)
+        dist.all_reduce(plan.gidx_store, op=dist.ReduceOp.SUM, group=group)    # one contributor per slot: the sum is exact
+        # scattered finish: the queries are dealt to the ranks in contiguous blocks of Qc
+        Qc = -(-plan.Q // world)
+        rel_ptr_pad = torch.full((Qc * world + 1,), plan.total, dtype=torch.int64, device=dev)
+        rel_ptr_pad[:plan.Q + 1] = plan.rel.rel_ptr
+        plan.Qc = Qc
+        plan.my_ptr = rel_ptr_pad[rank * Qc: (rank + 1) * Qc + 1].contiguous()
+    else:
+        plan.g_pids_all = torch.cat(_all_gather_varlen(g_pids_local, group)).contiguous()   # pids of the top-10 candidates
+    plan.finish_common()
+    _cache_put(key, (plan, q_pids, g_pids_local))
+    return plan
+
+
 def retrieve_sharded(text_embed, image_shard, text_pid, image_pid_shard, topk=(1, 5, 10), get_mAP=True, precision="fp32",
                      group=None, backend=None, nsplit=None, shard_sizes: Optional[Sequence[int]] = None,
-                     return_hit_ranks: bool = False) -> RetrievalResult:
+                     return_hit_ranks: bool = False, normalized: bool = False) -> RetrievalResult:
     """Distributed driver: call on every rank with the full query set and this rank's gallery slice
     (slices are contiguous and ordered by rank).  Returns the same RetrievalResult on every rank.
     ``shard_sizes`` (rows per rank) saves the size exchange when the caller knows the split; ``return_hit_ranks``
-    additionally gathers the per-slot hit ranks (a diagnostic; R@k / AP / mAP do not need it)."""
+    additionally gathers the per-slot hit ranks (a diagnostic; R@k / AP / mAP do not need it).
+
+    Collectives per evaluation once the plan of this (dataset, sharding) is cached: all-reduce of the thresholds (4 B per
+    relevant pair), all-reduce of the rank counts (4 B per pair), all-to-all of the per-query top-10 candidates (8 B each) and
+    all-gather of the per-query results.  No collective touches similarity data."""
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("retrieve_sharded needs an initialised torch.distributed process group")
     backend = backend or CudaBackend()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    dev = text_embed.device
     PhaseTimer.mark("start")
-    q_pids = text_pid.reshape(-1).to(torch.int64).contiguous()
-    g_pids_local = image_pid_shard.reshape(-1).to(torch.int64).contiguous()
-    if shard_sizes is None:
-        n = torch.tensor([g_pids_local.numel()], dtype=torch.int64, device=dev)
-        shard_sizes = _all_gather_stack(n, group).reshape(-1).tolist()      # one host read
-    g_base = int(sum(shard_sizes[:rank]))
-    w = ShardWorker(text_embed, image_shard, q_pids, g_pids_local, g_base, get_mAP, precision, backend)
-    PhaseTimer.mark("prepare(sort,pack)")
-    g_pids_all = None
+    q_pids = _as_pid(text_pid)
+    g_pids_local = _as_pid(image_pid_shard)
+    plan = _distributed_plan(q_pids, g_pids_local, get_mAP, precision, group, shard_sizes)
+    PhaseTimer.mark("plan")
+    w = ShardWorker(text_embed, image_shard, plan, backend, normalized)
+    PhaseTimer.mark("prepare(pack)")
     if get_mAP:
-        counts = w.local_counts()
-        w.set_layout(_all_gather_stack(counts, group), rank)
-        PhaseTimer.mark("layout(allgather counts)")
-        thr, gidx = w.local_thresholds()
+        thr = w.local_thresholds()
         PhaseTimer.mark("thresholds")
-        if int(sum(shard_sizes)) < (1 << 31) - 1:
-            packed = _pack_f32_i32(thr, gidx)             # one contributor per slot, zeros elsewhere: the sum is exact
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-            thr, gidx = _unpack_f32_i32(packed)
-            thr, gidx = thr.contiguous(), gidx.contiguous()
-        else:
-            dist.all_reduce(thr, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(gidx, op=dist.ReduceOp.SUM, group=group)
-        w.set_thresholds(thr, gidx)
+        dist.all_reduce(thr, op=dist.ReduceOp.SUM, group=group)      # one contributor per slot, zeros elsewhere: exact
+        w.set_thresholds(thr)
         PhaseTimer.mark("allreduce_thr")
-    else:
-        g_pids_all = torch.cat(_all_gather_varlen(g_pids_local, group)).contiguous()   # pids of the top-10 candidates
     cand_sim, cand_idx, cnt = w.stream(nsplit)
     PhaseTimer.mark("stream")
     if get_mAP:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     PhaseTimer.mark("allreduce_cnt")
-    # candidate lists: merge this rank's L lists to one per query, then all-gather [Q, 10] x (fp32, int64)
-    g_total = int(sum(shard_sizes))
+    # candidate lists: merge this rank's L lists to one per query, then hand every rank the lists of ITS queries
+    g_total = int(sum(plan.shard_sizes))
     if get_mAP and hasattr(backend, "finish_partial") and world > 1 and g_total < (1 << 31) - 1:
         cand_sim, cand_idx = backend.merge_lists(cand_sim, cand_idx)
         PhaseTimer.mark("local_merge")
-        res = _finish_scattered(backend, cand_sim, cand_idx, w.rel, cnt, topk, group, return_hit_ranks)
+        res = _finish_scattered(backend, cand_sim, cand_idx, plan, cnt, topk, group, return_hit_ranks)
         PhaseTimer.mark("scattered_finish+metrics")
-        res.thresholds = w.thr[:w.rel.total]
+        res.thresholds = w.thr[:plan.rel.total]
         return res
     if hasattr(backend, "merge_lists"):
         cand_sim, cand_idx = backend.merge_lists(cand_sim, cand_idx)
@@ -440,7 +535,7 @@ def retrieve_sharded(text_embed, image_shard, text_pid, image_pid_shard, topk=(1
         sim_parts = [x.permute(1, 0, 2) for x in _all_gather_varlen(cand_sim.permute(1, 0, 2).contiguous(), group)]
         idx_parts = [x.permute(1, 0, 2) for x in _all_gather_varlen(cand_idx.permute(1, 0, 2).contiguous(), group)]
     PhaseTimer.mark("merge+allgather_cand")
-    res = _finish(backend, sim_parts, idx_parts, q_pids, g_pids_all, w.rel, cnt, topk)
+    res = _finish(backend, sim_parts, idx_parts, q_pids, plan.g_pids_all, plan.rel, cnt, topk)
     PhaseTimer.mark("finish+metrics")
-    res.thresholds = w.thr[:w.rel.total] if get_mAP else None
+    res.thresholds = w.thr[:plan.rel.total] if get_mAP else None
     return res

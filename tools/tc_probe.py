@@ -3,14 +3,14 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from textreid_b200.synthetic import eval_data
-from textreid_b200.sharded import ShardWorker, CudaBackend
+from textreid_b200.sharded import ShardWorker, CudaBackend, _local_plans, _as_pid
 
 def run(Q, G, D, get_map, n_ids, iters=3, nsplit=None):
     text, q_pid, image, g_pid = eval_data(Q, G, D, n_ids, 0, G, "cuda", torch.bfloat16)
-    w = ShardWorker(text, image, q_pid.long(), g_pid.long(), 0, get_map, "bf16", CudaBackend())
+    plan = _local_plans(_as_pid(q_pid.long()), [_as_pid(g_pid.long())], [0], get_map, "bf16")[0]
+    w = ShardWorker(text, image, plan, CudaBackend())
     if get_map:
-        w.set_layout(w.local_counts().unsqueeze(0), 0)
-        w.set_thresholds(*w.local_thresholds())
+        w.set_thresholds(w.local_thresholds())
     w.stream(nsplit)
     w.record_events = True
     ts = []
@@ -20,7 +20,7 @@ def run(Q, G, D, get_map, n_ids, iters=3, nsplit=None):
         a, b = w.stream_events
         ts.append(a.elapsed_time(b))
     ms = sorted(ts)[len(ts) // 2]
-    print("Q=%d G=%d D=%d mAP=%s max_rel=%d nsplit=%s: %.2f ms  %.1f TFLOP/s" % (Q, G, D, get_map, w.max_rel, nsplit, ms, 2.0 * Q * G * D / ms / 1e9), flush=True)
+    print("Q=%d G=%d D=%d mAP=%s max_rel=%d nsplit=%s: %.2f ms  %.1f TFLOP/s" % (Q, G, D, get_map, plan.max_rel, nsplit, ms, 2.0 * Q * G * D / ms / 1e9), flush=True)
 
 if __name__ == "__main__":
     Q, G = 100000, 1000000
