@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the TextReID hot path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--workload ...]
 
 Headline (BASELINE.json metric): retrieval queries/s -- similarity + top-10 + R@k + mAP -- on the scaled
 gallery configuration (configs[3]: 100k text queries x 1M gallery images, D=256, bf16 storage), the
@@ -14,7 +14,10 @@ One "step" = one full evaluation of the workload: pid bookkeeping, normalise+pac
 gallery stream (the GEMM), merge, metrics.  `value` has inputs resident in HBM; `e2e` goes through the
 public Python API from pinned HOST buffers with the H2D copies and the D2H read of R@k/mAP timed.
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, kind "port": the
-reference is pure Python/PyTorch and cannot travel to the GPU box) on a bounded sample of the workload.
+reference is pure Python/PyTorch and cannot travel to the GPU box) on a bounded sample of the workload: a few hundred
+queries against the FULL gallery, so the G log G sort and the memory footprint are measured, not extrapolated; only the
+(embarrassingly parallel) query count is scaled.  `--impl reference-gpu` runs the same restated ATen call sequence
+(normalise, matmul, argsort, per-column AP loop) on the B200 under torch 2.11 for context.
 """
 from __future__ import annotations
 
@@ -112,25 +115,49 @@ def shard_bounds(G, world, rank):
 # ---------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port on a bounded sample of the workload
 # ---------------------------------------------------------------------------------------------------
-def cpu_retrieval_sample(cfg, steps, warmup, Qs=1024, Gs=32768):
+def reference_retrieval_sample(cfg, steps, warmup, device="cpu", Qs=None, Gs=None, budget_s=25.0):
+    """The reference's algorithm (oracle.retrieve: normalise + fp32 matmul + full stable argsort + the per-column AP loop of
+    evaluation.py:33) on Qs queries x the workload's WHOLE gallery.  Queries are independent, so queries/s = Qs / time is a
+    measurement at the stated gallery size, not an extrapolation over G.  The first run sizes the sample: if one step takes
+    longer than `budget_s` the number of timed steps is cut so that the whole arm stays within a few minutes."""
     from oracle import textreid_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Qs, Gs = min(Qs, cfg["Q"]), min(Gs, cfg["G"])
-    text, q_pid, image, g_pid = make_eval_data(Qs, Gs, cfg["D"], max(Gs // 4, 1), 0, Gs, "cpu", torch.float32, seed=1)
+    G = cfg["G"] if Gs is None else min(Gs, cfg["G"])
+    if Qs is None:
+        Qs = 128 if G > 200_000 else min(cfg["Q"], 2048)
+    Qs = min(Qs, cfg["Q"])
+    text, q_pid, image, g_pid = make_eval_data(Qs, G, cfg["D"], cfg["n_ids"] if G == cfg["G"] else max(G // 4, 1), 0, G, device,
+                                               torch.float32, seed=1)
+    sync = (lambda: torch.cuda.synchronize()) if str(device).startswith("cuda") else (lambda: None)
     times = []
-    for i in range(warmup + steps):
+    planned = warmup + steps
+    i = 0
+    while i < planned:
+        sync()
         t0 = time.perf_counter()
         O.retrieve(text, image, q_pid, g_pid, (1, 5, 10), get_mAP=True, per_column_loop=True)
+        sync()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        elif dt > budget_s:              # a slow box: the warm-up run becomes the measurement
+            times.append(dt)
+            break
+        if len(times) >= 1 and sum(times) > 4 * budget_s:
+            break
+        i += 1
     mean = sum(times) / len(times)
-    pair_rate = Qs * Gs / mean
-    return dict(value=pair_rate / cfg["G"], unit="queries/s", cores=cores, kind="port",
-                sample="oracle.retrieve (normalise + fp32 matmul + full argsort + reference per-column AP loop) on %d queries x %d "
-                       "gallery, %d timed runs, %.2f s each; pair rate scaled to the workload's G=%d" % (Qs, Gs, len(times), mean, cfg["G"]),
-                sample_seconds=mean, ms_per_step=mean * 1e3)
+    where = "CPU, %d threads" % cores if device == "cpu" else "B200, torch %s ATen kernels" % torch.__version__
+    return dict(value=Qs / mean, unit="queries/s", cores=cores, kind="port",
+                sample="oracle.retrieve (normalise + fp32 matmul + full stable argsort + reference per-column AP loop) on %d queries x "
+                       "the full %d-row gallery (%s), %d timed run(s), %.2f s each; queries are independent, so queries/s = %d / time "
+                       "at the stated gallery size" % (Qs, G, where, len(times), mean, Qs),
+                sample_seconds=mean, ms_per_step=mean * 1e3, steps_timed=len(times))
+
+
+def cpu_retrieval_sample(cfg, steps, warmup):
+    return reference_retrieval_sample(cfg, steps, warmup, "cpu")
 
 
 def cpu_loss_sample(steps=5, warmup=2, N=128, D=256, K=2048, C=11003):
@@ -169,72 +196,162 @@ def time_cuda(fn, iters, warmup, flush=None):
     return ts[len(ts) // 2], ts[0]
 
 
+LOSS_SHAPES = {
+    # algorithmic bytes (each operand once) and FLOPs of the loss dict fwd+bwd
+    "n128_k2048": dict(N=128, D=256, K=2048, C=11003, bytes=27.8e6, flops=4.89e9, desc="configs[1]: bs128, queue 2048"),
+    "n256_k4096": dict(N=256, D=256, K=4096, C=11003, bytes=33.0e6, flops=10.9e9, desc="configs[2]: bs256, queue 4096"),
+}
+
+
+def loss_step_line(trb, pk, device, flush, shape_key, prec, mode, iters=40):
+    """One trainer-style loss step (trainer.py:81-90 on the head's output): loss dict -> sum -> backward (+ enqueue), timed with
+    CUDA events, L2 flushed between steps.  The labels of the NEXT step are drawn during the (untimed) flush, like a data
+    loader would: new ids every step keep the queue from degenerating into "every slot masked"."""
+    from textreid_b200.synthetic import loss_inputs as synth_loss_inputs
+    sh = LOSS_SHAPES[shape_key]
+    N, D, K, C = sh["N"], sh["D"], sh["K"], sh["C"]
+    inp = {k: v.to(device) for k, v in synth_loss_inputs(N, D, K, C, seed=0).items()}
+    ve, te, pr = inp["v_embed"].requires_grad_(True), inp["t_embed"].requires_grad_(True), inp["projection"].requires_grad_(True)
+    ptr = torch.zeros(1, dtype=torch.int64, device=device)
+    labels = inp["labels"]
+
+    def loss_step(inner_graph):
+        d = trb.moco_loss_dict(ve, te, inp["v_key"], inp["t_key"], labels, inp["v_queue"], inp["t_queue"], inp["id_queue"],
+                               ptr, pr, epsilon=0.1, enqueue=True, precision=prec, cuda_graph=inner_graph)
+        (d["instance_loss"] + d["infonce_loss"] + d["global_align_loss"]).backward()
+
+    def flush_and_relabel():
+        labels.add_(97).remainder_(C)
+        flush()
+
+    if mode == "stepgraph":
+        # the whole step captured once with torch.cuda.graph and replayed: the way a production loop removes the host from
+        # the path; gradients land in static .grad tensors
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                ve.grad = te.grad = pr.grad = None
+                loss_step(False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ve.grad = te.grad = pr.grad = None
+        whole = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(whole):
+            loss_step(False)
+        fn = whole.replay
+    else:
+        def fn(inner=(mode == "graph")):
+            ve.grad = te.grad = pr.grad = None
+            loss_step(inner)
+    med, best = time_cuda(fn, iters, 8, flush_and_relabel)
+    t_s = med * 1e-3
+    hbm_frac = sh["bytes"] / t_s / 1e9 / pk["hbm"]
+    tensor_frac = sh["flops"] / t_s / 1e12 / pk["tf_burst"]
+    roof_s = max(sh["bytes"] / (pk["hbm"] * 1e9), sh["flops"] / (pk["tf_burst"] * 1e12))
+    shape = trb._lib.MocoShape(N, D, K, C)
+    launches = int(trb._lib.load().trb_moco_step_launches(__import__("ctypes").byref(shape), 1 if prec == "bf16" else 0))
+    return {
+        "metric": "MoCo loss steps/s (loss dict fwd+bwd + enqueue, %s, D=%d, C=%d)" % (sh["desc"], D, C), "value": 1e3 / med,
+        "unit": "steps/s", "ms_per_step": med, "ms_best": best, "dtype": "bf16" if prec == "bf16" else "f32",
+        "mode": {"stepgraph": "whole step captured in one CUDA graph (torch.cuda.graph around loss dict + backward)",
+                 "graph": "library call replayed from its own CUDA graph, autograd glue eager",
+                 "eager": "every launch issued from Python"}[mode],
+        "l2_flushed": True, "library_launches": launches,
+        "roofline": {"bound": "hbm" if sh["bytes"] / (pk["hbm"] * 1e9) >= sh["flops"] / (pk["tf_burst"] * 1e12) else "tensor",
+                     "achieved": sh["bytes"] / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": hbm_frac,
+                     "tensor_frac": tensor_frac, "roofline_time_us": roof_s * 1e6, "frac_of_roofline_time": roof_s / t_s,
+                     "traffic": None,
+                     "note": "whole step (loss dict + gradients + enqueue in the library call, loss sum, backward combine); algorithmic "
+                             "%.1f MB / %.2f GFLOP (BASELINE.md section 3); tensor peak = measured burst (a kernel timed alone)"
+                             % (sh["bytes"] / 1e6, sh["flops"] / 1e9)}}
+
+
+def loss_e2e_line(trb, device, shape_key="n128_k2048", prec="bf16", iters=30):
+    """The loss step end to end from HOST buffers: pinned embeddings / keys / labels -> device, loss dict + backward + enqueue,
+    losses and the three gradients back to pinned host memory; every copy inside the timed region."""
+    from textreid_b200.synthetic import loss_inputs as synth_loss_inputs
+    sh = LOSS_SHAPES[shape_key]
+    N, D, K, C = sh["N"], sh["D"], sh["K"], sh["C"]
+    inp = synth_loss_inputs(N, D, K, C, seed=0)
+    host = {k: inp[k].pin_memory() for k in ("v_embed", "t_embed", "v_key", "t_key", "labels")}
+    dev = {k: inp[k].to(device) for k in ("v_queue", "t_queue", "id_queue")}
+    pr = inp["projection"].to(device).requires_grad_(True)
+    ptr = torch.zeros(1, dtype=torch.int64, device=device)
+    out_host = {"losses": torch.empty(3).pin_memory(), "gv": torch.empty(N, D).pin_memory(), "gt": torch.empty(N, D).pin_memory(),
+                "gp": torch.empty(D, C).pin_memory()}
+
+    def step():
+        ve = host["v_embed"].to(device, non_blocking=True).requires_grad_(True)
+        te = host["t_embed"].to(device, non_blocking=True).requires_grad_(True)
+        vk, tk = host["v_key"].to(device, non_blocking=True), host["t_key"].to(device, non_blocking=True)
+        lab = host["labels"].to(device, non_blocking=True)
+        pr.grad = None
+        d = trb.moco_loss_dict(ve, te, vk, tk, lab, dev["v_queue"], dev["t_queue"], dev["id_queue"], ptr, pr, epsilon=0.1,
+                               enqueue=True, precision=prec)
+        (d["instance_loss"] + d["infonce_loss"] + d["global_align_loss"]).backward()
+        out_host["losses"].copy_(torch.stack([d[k].detach() for k in ("instance_loss", "infonce_loss", "global_align_loss")]), non_blocking=True)
+        out_host["gv"].copy_(ve.grad, non_blocking=True)
+        out_host["gt"].copy_(te.grad, non_blocking=True)
+        out_host["gp"].copy_(pr.grad, non_blocking=True)
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+    return {"metric": "MoCo loss steps/s end to end from pinned host buffers (%s)" % sh["desc"], "value": 1e3 / ms, "unit": "steps/s",
+            "ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "dtype": prec,
+            "note": "back-to-back eager steps (2 library launches + autograd glue); the 11.3 MB projection gradient dominates the D2H"}
+
+
+def reference_gpu_loss_line(device, shape_key="n128_k2048", iters=20):
+    """The reference's ATen call sequence for the loss dict (oracle restatement: queue mask with nonzero/unique syncs, gathers,
+    CPU one-hot replaced by a device scatter) forward + autograd backward on the B200, for context beside the fused step."""
+    from oracle import textreid_oracle as O
+    from textreid_b200.synthetic import loss_inputs as synth_loss_inputs
+    sh = LOSS_SHAPES[shape_key]
+    inp = {k: v.to(device) for k, v in synth_loss_inputs(sh["N"], sh["D"], sh["K"], sh["C"], seed=0).items()}
+    args = [inp[k] for k in ("v_embed", "t_embed", "v_key", "t_key", "labels", "v_queue", "t_queue", "id_queue", "projection")]
+    for _ in range(3):
+        O.moco_loss_dict_with_grads(*args, epsilon=0.1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        O.moco_loss_dict_with_grads(*args, epsilon=0.1)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / iters * 1e3
+    return {"metric": "reference ATen loss dict fwd + autograd bwd on the B200 (oracle restatement, torch %s, eager, wall clock)" % torch.__version__,
+            "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms}
+
+
 def secondary_measurements(pk, device):
     import textreid_b200 as trb
-    from textreid_b200.synthetic import loss_inputs as synth_loss_inputs
     out = {}
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > 126 MB L2
 
     def flush():
         flush_buf.fill_(1)
 
-    # ---- MoCo loss dict fwd+bwd (+ enqueue), configs[1]: N=128, K=2048, D=256, C=11003 ----
-    # one step = what trainer.py:81-90 does with the head's output: loss dict -> sum -> backward.  Labels change every step
-    # (device-side) so that the queue never degenerates into "every slot masked".
-    N, D, K, C = 128, 256, 2048, 11003
-    bytes_alg = 27.8e6            # queues + projection read + dProjection write + embeddings
-    launches = {}
+    # ---- MoCo loss step, configs[1] (N=128, K=2048) in three host modes and both precisions; configs[2] (N=256, K=4096) ----
     for prec in ("bf16", "fp32"):
         for mode in ("stepgraph", "graph", "eager"):
-            inp = {k: v.to(device) for k, v in synth_loss_inputs(N, D, K, C, seed=0).items()}
-            ve, te, pr = inp["v_embed"].requires_grad_(True), inp["t_embed"].requires_grad_(True), inp["projection"].requires_grad_(True)
-            ptr = torch.zeros(1, dtype=torch.int64, device=device)
-            labels = inp["labels"]
-
-            def loss_step(inner_graph):
-                labels.add_(97).remainder_(C)
-                d = trb.moco_loss_dict(ve, te, inp["v_key"], inp["t_key"], labels, inp["v_queue"], inp["t_queue"], inp["id_queue"],
-                                       ptr, pr, epsilon=0.1, enqueue=True, precision=prec, cuda_graph=inner_graph)
-                (d["instance_loss"] + d["infonce_loss"] + d["global_align_loss"]).backward()
-
-            if mode == "stepgraph":
-                # the whole trainer-style step (loss dict -> sum -> backward -> enqueue) captured once with torch.cuda.graph and
-                # replayed: the way a production loop removes the host from the path; gradients land in static .grad tensors
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    for _ in range(3):
-                        ve.grad = te.grad = pr.grad = None
-                        loss_step(False)
-                torch.cuda.current_stream().wait_stream(side)
-                torch.cuda.synchronize()
-                ve.grad = te.grad = pr.grad = None
-                whole = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(whole):
-                    loss_step(False)
-                fn = whole.replay
-            else:
-                def fn(inner=(mode == "graph")):
-                    ve.grad = te.grad = pr.grad = None
-                    loss_step(inner)
-
-            med, best = time_cuda(fn, 40, 8, flush)
-            key = "moco_loss_%s_%s" % (prec, mode)
-            out[key] = {
-                "metric": "MoCo loss steps/s (loss dict fwd+bwd + enqueue, bs128, queue 2048, D=256, C=11003)", "value": 1e3 / med,
-                "unit": "steps/s", "ms_per_step": med, "ms_best": best, "dtype": "bf16" if prec == "bf16" else "f32",
-                "mode": {"stepgraph": "whole step captured in one CUDA graph (torch.cuda.graph around loss dict + backward)",
-                         "graph": "library call replayed from its own CUDA graph, autograd glue eager",
-                         "eager": "every launch issued from Python"}[mode],
-                "l2_flushed": True,
-                "roofline": {"bound": "hbm", "achieved": bytes_alg / (med * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                             "frac": bytes_alg / (med * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
-                             "note": "whole step (two label kernels, loss dict + gradients, loss sum, backward combine, enqueue); "
-                                     "algorithmic 27.8 MB"}}
-            del fn
-        shape = trb._lib.MocoShape(N, D, K, C)
-        launches[prec] = int(trb._lib.load().trb_moco_loss_launches(__import__("ctypes").byref(shape), 1 if prec == "bf16" else 0))
-    out["moco_loss_kernel_launches"] = launches
+            out["moco_loss_%s_%s" % (prec, mode)] = loss_step_line(trb, pk, device, flush, "n128_k2048", prec, mode)
+    for prec in ("bf16", "fp32"):
+        out["moco_loss_%s_stepgraph_n256_k4096" % prec] = loss_step_line(trb, pk, device, flush, "n256_k4096", prec, "stepgraph", iters=20)
+    out["moco_loss_kernel_launches"] = {p_: out["moco_loss_%s_eager" % p_]["library_launches"] for p_ in ("bf16", "fp32")}
+    out["moco_loss_bf16_e2e"] = loss_e2e_line(trb, device)
+    try:
+        out["moco_loss_reference_gpu"] = reference_gpu_loss_line(device)
+    except Exception as e:      # pragma: no cover
+        out["moco_loss_reference_gpu"] = {"error": str(e)[:200]}
     # ---- EMA over an RN50+GRU-sized arena: 41,755,488 fp32 parameters ----
     P = 41_755_488
     pk_, pq_ = torch.randn(P, device=device), torch.randn(P, device=device)
@@ -243,14 +360,80 @@ def secondary_measurements(pk, device):
                            "roofline": {"bound": "hbm", "achieved": 12.0 * P / (med * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                         "frac": 12.0 * P / (med * 1e-3) / 1e9 / pk["hbm"], "traffic": None}}
     del pk_, pq_
-    # ---- CUHK-PEDES-sized evaluation, configs[0] ----
+    # ---- CUHK-PEDES-sized evaluation, configs[0]: repeated evaluations of one split (plan cached, like trainer.py:124) ----
     cfg = WORKLOADS["retrieval_cuhk"]
     text, q_pid, image, g_pid = make_eval_data(cfg["Q"], cfg["G"], cfg["D"], cfg["n_ids"], 0, cfg["G"], device, torch.float32, seed=2)
     for prec in ("fp32", "bf16"):
         med, best = time_cuda(lambda: trb.retrieve(text, image, q_pid, g_pid, (1, 5, 10), True, prec), 10, 3, flush)
-        out["retrieval_cuhk_" + prec] = {"metric": "retrieval queries/s, 6156 x 3074, D=256 (full step incl. pid bookkeeping)",
+        out["retrieval_cuhk_" + prec] = {"metric": "retrieval queries/s, 6156 x 3074, D=256 (R@k + mAP; pid plan cached across evaluations)",
                                          "value": cfg["Q"] / (med * 1e-3), "unit": "queries/s", "ms_per_step": med, "dtype": prec}
+        trb.clear_plan_cache()
+        t0 = time.perf_counter()
+        trb.retrieve(text, image, q_pid, g_pid, (1, 5, 10), True, prec)
+        torch.cuda.synchronize()
+        out["retrieval_cuhk_" + prec]["first_evaluation_ms"] = (time.perf_counter() - t0) * 1e3
+    # the reference's entry points on the same split: evaluation() fast path (trainer.py:124) and with re-ranking (test_net.py:107)
+    n = cfg["Q"]
+
+    class _Split:
+        def __init__(self, image_ids, pids): self.image_ids, self.pids = image_ids, pids
+        def __len__(self): return len(self.pids)
+        def get_id_info(self, idx): return self.image_ids[idx], self.pids[idx]
+
+    gen = torch.Generator().manual_seed(3)
+    img_of_caption = torch.randint(0, cfg["G"], (n,), generator=gen)
+    img_of_caption[:cfg["G"]] = torch.arange(cfg["G"])                        # every image has at least one caption
+    ds = _Split(img_of_caption.tolist(), g_pid.cpu()[img_of_caption].tolist())
+    image_all = image[img_of_caption.to(device)].contiguous()
+    idx = list(range(n))
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, kw in (("evaluation_entry_cuhk_fast", dict(save_data=False, rerank=False)),
+                         ("evaluation_entry_cuhk_rerank", dict(save_data=False, rerank=True))):
+            fn = lambda: trb.evaluate_embeddings(ds, idx, image_all, text, tmp, [1, 5, 10], **kw)
+            med, best = time_cuda(fn, 5, 2, flush)
+            out[name] = {"metric": "evaluation() core on [n, D] device tensors, 6156 captions x 3074 images, %s" % (
+                             "t2i + i2t top-k (trainer.py:124)" if "fast" in name else "4 rankings incl. k-reciprocal re-rank (test_net.py:107)"),
+                         "ms_per_call": med, "value": 1e3 / med, "unit": "evaluations/s"}
+    del text, image
+    # ---- configs[3] on the fp32 FFMA parity path and at D = 512 on the tensor-core path (one step each) ----
+    big = WORKLOADS["retrieval_1m"]
+    for name, D, prec, Qn in (("retrieval_1m_fp32", 256, "fp32", 20_000), ("retrieval_1m_d512_bf16", 512, "bf16", 50_000)):
+        try:
+            dt = torch.float32 if prec == "fp32" else torch.bfloat16
+            text, q_pid, image, g_pid = make_eval_data(Qn, big["G"], D, big["n_ids"], 0, big["G"], device, dt)
+            trb.retrieve(text, image, q_pid, g_pid, (1, 5, 10), True, prec)
+            med, best = time_cuda(lambda: trb.retrieve(text, image, q_pid, g_pid, (1, 5, 10), True, prec), 2, 0)
+            fl = 2.0 * Qn * big["G"] * D
+            out[name] = {"metric": "retrieval queries/s, %d x %d, D=%d, %s" % (Qn, big["G"], D, prec), "value": Qn / (med * 1e-3),
+                         "unit": "queries/s", "ms_per_step": med, "tflops": fl / (med * 1e-3) / 1e12,
+                         "frac_of_bf16_sustained": (fl / (med * 1e-3) / 1e12 / pk["tf_sustained"]) if prec == "bf16" else None}
+            del text, image
+            torch.cuda.empty_cache()
+        except Exception as e:      # pragma: no cover
+            out[name] = {"error": str(e)[:200]}
     return out
+
+
+def stored_traffic(workload, precision, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the stream kernel, extracted from the committed ncu capture by
+    tools/ncu_traffic.py into profiles/stream_traffic.json (never a literal here)."""
+    path = os.path.join(ROOT, "profiles", "stream_traffic.json")
+    if world != 1 or not os.path.exists(path):
+        return None
+    try:
+        t = json.load(open(path))
+        e = t.get("%s/%s" % (workload, precision))
+        return None if e is None else {"bytes": e["dram_bytes"], "source": e["source"]}
+    except Exception:      # pragma: no cover
+        return None
+
+
+# R@1 / R@5 / R@10 / mAP of the seeded synthetic workloads (single-GPU bf16 run of round 1, BENCH_r01.json): exact integer
+# artefacts, so every later run -- any number of GPUs, any kernel revision -- must reproduce them bit for bit.
+STORED_RESULTS = {
+    "retrieval_1m/bf16": {"R@1": 39.49300003051758, "R@5": 60.90899658203125, "R@10": 69.00799560546875, "mAP": 21.91847038269043},
+}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -259,7 +442,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="retrieval_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-secondary", action="store_true")
@@ -275,12 +458,17 @@ def main():
               "cache": "inputs larger than L2 (gallery %.0f MB per rank)" % (cfg["G"] / world * cfg["D"] * 2 / 1e6)
               if cfg["G"] * cfg["D"] * 2 / world > 130e6 else "L2 flushed between timed iterations"}
 
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-gpu"):
         if rank != 0:
             return 0
-        r = cpu_retrieval_sample(cfg, max(1, args.steps), max(0, min(args.warmup, 1)))
-        line = {"impl": "reference", "metric": "retrieval queries/s (sim+top-k+R@k/mAP)", "value": r["value"], "unit": "queries/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        on_gpu = args.impl == "reference-gpu"
+        if on_gpu and not torch.cuda.is_available():
+            print(json.dumps({"impl": "reference-gpu", "unavailable": "no CUDA device"}))
+            return 0
+        r = reference_retrieval_sample(cfg, max(1, args.steps), max(0, min(args.warmup, 1)), "cuda" if on_gpu else "cpu",
+                                       Qs=1024 if on_gpu else None)
+        line = {"impl": args.impl, "metric": "retrieval queries/s (sim+top-k+R@k/mAP)", "value": r["value"], "unit": "queries/s",
+                "n_gpus": args.gpus, "steps": r["steps_timed"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -305,11 +493,10 @@ def main():
     g_lo, g_hi = shard_bounds(G, world, rank)
     text, q_pid, image, g_pid = make_eval_data(Q, G, D, cfg["n_ids"], g_lo, g_hi, device, dtype)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device) if "flushed" in config["cache"] else None
-    stream_ms = []
+    sizes = [shard_bounds(G, world, r)[1] - shard_bounds(G, world, r)[0] for r in range(world)]
 
     def step(text_d, image_d, q_pid_d, g_pid_d):
         if world > 1:
-            sizes = [shard_bounds(G, world, r)[1] - shard_bounds(G, world, r)[0] for r in range(world)]
             return retrieve_sharded(text_d, image_d, q_pid_d, g_pid_d, (1, 5, 10), True, args.precision, shard_sizes=sizes)
         return trb.retrieve(text_d, image_d, q_pid_d, g_pid_d, (1, 5, 10), True, args.precision)
 
@@ -318,7 +505,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing ----
+    # ---- device-resident timing: repeated evaluations of one (dataset, sharding), like the trainer's periodic evaluation
+    #      (trainer.py:124): the pid bookkeeping of the split is planned once, during the warm-up ----
     for _ in range(args.warmup):
         res = step(text, image, q_pid, g_pid)
     barrier()
@@ -355,12 +543,29 @@ def main():
     except Exception as e:          # pragma: no cover
         config["kernel_timing_error"] = str(e)[:200]
 
+    # ---- sampled parity check of the result at this very size (N = 1: the whole gallery is on this device) ----
+    parity = None
+    if world == 1 and args.precision == "bf16":
+        try:
+            from textreid_b200 import verify
+            rep = verify.sampled_check(text, image, q_pid, g_pid, res, n_sample=64, seed=0, margin=1e-6)
+            parity = {"status": rep["status"], "queries": rep["n_queries"], "top10_match": "%d/%d" % (rep["top10_match"], rep["top10_decided"]),
+                      "hit_ranks_exact": "%d/%d decided, %d outside the margin interval" % (rep["slots_decided_exact"], rep["slots_decided"],
+                                                                                          rep["slots_outside_interval"]),
+                      "max_similarity_error": rep["max_sim_err"],
+                      "how": "float64 re-evaluation of 64 random queries x the full gallery from the kernel's own bf16 operands "
+                             "(textreid_b200/verify.py; cross-check against the CPU restatement in tests/test_gpu_retrieval.py)"}
+        except Exception as e:      # pragma: no cover
+            parity = {"status": "error", "error": str(e)[:200]}
+
     # ---- end to end through the public API from pinned host buffers ----
     h_text, h_image = text.cpu().pin_memory(), image.cpu().pin_memory()
     h_qpid, h_gpid = q_pid.cpu().pin_memory(), g_pid.cpu().pin_memory()
     h2d = sum(x.numel() * x.element_size() for x in (h_text, h_image, h_qpid, h_gpid))
 
     def e2e_step():
+        # everything is uploaded every step, pid vectors included: new device tensors each time, which the plan cache
+        # recognises by content (one device-side comparison) instead of re-planning the split
         r = step(h_text.to(device, non_blocking=True), h_image.to(device, non_blocking=True),
                  h_qpid.to(device, non_blocking=True), h_gpid.to(device, non_blocking=True))
         return torch.cat([r.cmc, r.mAP.reshape(1)]).cpu()
@@ -385,25 +590,30 @@ def main():
         roof = None
         if kern_ms:
             ach = flops / (kern_ms * 1e-3) / 1e12
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-            # (profiles/r01_ncu_retrieval_tc_final.md: 100k x 1M x 256 on one GPU); algorithmic bytes are 563 MB
-            traffic = 4.24e9 if (world == 1 and args.workload == "retrieval_1m" and args.precision == "bf16") else None
+            tr = stored_traffic(args.workload, args.precision, world)
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": traffic, "kernel": "retrieval_tc_kernel<0>" if args.precision == "bf16" else "stream_f32_kernel",
+                    "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                    "kernel": "retrieval_tc_kernel<0>" if args.precision == "bf16" else "stream_f32_kernel",
                     "kernel_ms": kern_ms, "peak_source": pk["source"] + " bf16 sustained (kernel timed back to back inside a long step)",
-                    "algorithmic_flops_per_launch": flops}
+                    "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": (Q + (g_hi - g_lo)) * D * 2.0}
             if args.precision == "fp32":
                 roof["note"] = "fp32 FFMA parity path; the tensor-core denominator does not apply"
+        result = {"R@1": float(res.cmc[0]), "R@5": float(res.cmc[1]), "R@10": float(res.cmc[2]), "mAP": float(res.mAP)}
+        stored = STORED_RESULTS.get("%s/%s" % (args.workload, args.precision))
+        if stored is not None:
+            result["matches_stored_single_gpu_result"] = all(result[k] == stored[k] for k in stored)
+        if parity is not None:
+            result["parity_sample"] = parity["status"]
+            result["parity_sample_detail"] = parity
         line = {"metric": "retrieval queries/s (sim+top-k+R@k/mAP)", "value": Q / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
                 "clocks": clocks.summary(), "gpu_launches": launches,
                 "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": e2e_ms},
-                "roofline": roof,
-                "result": {"R@1": float(res.cmc[0]), "R@5": float(res.cmc[1]), "R@10": float(res.cmc[2]), "mAP": float(res.mAP)}}
+                "roofline": roof, "result": result}
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_retrieval_sample(cfg, 2, 1)
+            r = cpu_retrieval_sample(cfg, 1, 0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if world == 1 and not args.no_secondary:
             del text, image, h_text, h_image
@@ -414,10 +624,13 @@ def main():
                 best = line["secondary"].get("moco_loss_bf16_stepgraph")
                 if best:     # the other half of BASELINE's metric, lifted to the top level for readers of the one line
                     base = line["secondary"].get("moco_loss_cpu_baseline") or {}
+                    e2e_l = line["secondary"].get("moco_loss_bf16_e2e") or {}
                     line["loss_step"] = {"metric": "MoCo loss steps/s at bs128 (fwd+bwd+enqueue, bf16 fused kernel, whole step in one CUDA graph)",
                                          "value": best["value"], "unit": "steps/s", "us_per_step": best["ms_per_step"] * 1e3,
                                          "hbm_roofline_frac": (best.get("roofline") or {}).get("frac"),
-                                         "library_launches": (line["secondary"].get("moco_loss_kernel_launches") or {}).get("bf16"),
+                                         "library_launches": best.get("library_launches"),
+                                         "e2e": {"value": e2e_l.get("value"), "unit": "steps/s", "h2d_bytes_per_step": e2e_l.get("h2d_bytes_per_step"),
+                                                 "d2h_bytes_per_step": e2e_l.get("d2h_bytes_per_step")},
                                          "cpu_baseline_steps_per_s": base.get("value")}
             except Exception as e:   # pragma: no cover
                 line["secondary"] = {"error": str(e)[:300]}

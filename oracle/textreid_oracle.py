@@ -103,7 +103,7 @@ def _smoothed_ce(logits: torch.Tensor, labels: torch.Tensor, epsilon: float) -> 
     n, c = logits.shape
     logp = torch.log_softmax(logits, dim=1)
     target = torch.zeros_like(logp)
-    target[torch.arange(n), labels.reshape(-1).long()] = 1.0
+    target[torch.arange(n, device=logits.device), labels.reshape(-1).long()] = 1.0
     target = (1 - epsilon) * target + epsilon / c
     return (-target * logp).mean(0).sum()
 
@@ -124,7 +124,7 @@ def instance_loss(projection, v_embed, t_embed, labels, epsilon: float = 0.0,
     if epsilon > 0:
         return _smoothed_ce(zv, labels, REFERENCE_SMOOTHING) + _smoothed_ce(zt, labels, REFERENCE_SMOOTHING)
     lab = labels.reshape(-1).long()
-    idx = torch.arange(zv.shape[0])
+    idx = torch.arange(zv.shape[0], device=zv.device)
     ce = lambda z: (torch.logsumexp(z, dim=1) - z[idx, lab]).mean()
     return ce(zv) + ce(zt)
 
@@ -217,7 +217,7 @@ def rank(similarity: torch.Tensor, q_pids: torch.Tensor, g_pids: torch.Tensor,
     identical (same fp32 division per element) and exists for large cases.
     Returns (cmc, mAP, indices) or (cmc, indices) like the reference.
     """
-    topk_t = torch.as_tensor(list(topk) if not torch.is_tensor(topk) else topk)
+    topk_t = torch.as_tensor(list(topk) if not torch.is_tensor(topk) else topk).to(similarity.device)
     depth = int(topk_t.max())
     if get_mAP:
         order = torch.argsort(similarity, dim=1, descending=True, stable=stable)
@@ -241,7 +241,7 @@ def rank(similarity: torch.Tensor, q_pids: torch.Tensor, g_pids: torch.Tensor,
         cols = [running[:, i] / (i + 1.0) for i in range(running.shape[1])]
         prec = torch.stack(cols, 1) * hit
     else:
-        denom = torch.arange(1, running.shape[1] + 1, dtype=torch.float32)
+        denom = torch.arange(1, running.shape[1] + 1, dtype=torch.float32, device=similarity.device)
         prec = (running.to(torch.float32) / denom) * hit
     ap = prec.sum(1) / n_rel
     return cmc, ap.mean() * 100, order
@@ -269,6 +269,33 @@ def hit_ranks(similarity: torch.Tensor, q_pids: torch.Tensor, g_pids: torch.Tens
     order = torch.argsort(similarity, dim=1, descending=True, stable=True)
     hit = g_pids[order] == q_pids.reshape(-1, 1)
     return [row.nonzero(as_tuple=False).reshape(-1) for row in hit]
+
+
+def hit_rank_bounds(similarity: torch.Tensor, q_pids: torch.Tensor, g_pids: torch.Tensor, margin: float = 0.0):
+    """The same integer artefacts as ``hit_ranks`` by COUNTING instead of sorting (usable on [few queries, 10^6] matrices):
+    for every (query, relevant item r) the 0-based rank  #{g : s_g > s_r} + #{g : s_g == s_r and g < r}  under the pinned
+    order (similarity descending, index ascending) -- equivalent to the position of r in the stable descending argsort of
+    evaluation.py:14.  With ``margin`` > 0 it returns the interval [lo, hi] the rank can lie in when similarities closer
+    than ``margin`` to s_r are treated as undecided (accumulation noise of a lower-precision implementation); margin = 0
+    gives lo == hi == the exact rank.  Returns (rel_ptr [Q+1], rel_col [total], lo [total], hi [total]), slots per query in
+    ascending gallery index."""
+    Q, G = similarity.shape
+    idx = torch.arange(G)
+    ptr, cols, los, his = [0], [], [], []
+    for q in range(Q):
+        rel = (g_pids == q_pids[q]).nonzero().reshape(-1)
+        s = similarity[q]
+        for r in rel.tolist():
+            t = s[r]
+            if margin > 0:
+                lo = int((s > t + margin).sum())
+                hi = int((s >= t - margin).sum()) - 1                      # everything that may precede r, minus r itself
+            else:
+                lo = hi = int((s > t).sum()) + int(((s == t) & (idx < r)).sum())
+            cols.append(r); los.append(lo); his.append(hi)
+        ptr.append(len(cols))
+    return (torch.tensor(ptr, dtype=torch.int64), torch.tensor(cols, dtype=torch.int64), torch.tensor(los, dtype=torch.int64),
+            torch.tensor(his, dtype=torch.int64))
 
 
 def retrieve(text_embed, image_embed, text_pid, image_pid, topk=(1, 5, 10), get_mAP=True,

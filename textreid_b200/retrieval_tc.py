@@ -34,6 +34,18 @@ def pack_rows(x: torch.Tensor, perm: Optional[torch.Tensor] = None, normalize: b
     return packed
 
 
+def unpack_rows(packed: torch.Tensor, rows: torch.Tensor, dim: int) -> torch.Tensor:
+    """Read rows back out of a packed image (the TRB-P layout of csrc/tc_common.cuh): [len(rows), dim] bf16, exactly the
+    operand values the tensor cores consume.  Index arithmetic in torch; for tests, parity checks and debugging."""
+    kchunks = dim // 64
+    r = rows.to(torch.int64).reshape(-1, 1)                       # packed row numbers
+    c16 = torch.arange(dim // 8, device=packed.device).reshape(1, -1)
+    rb, rr, kc, c = r >> 7, r & 127, c16 >> 3, c16 & 7
+    byte = (rb * kchunks + kc) * 16384 + (rr >> 3) * 1024 + (rr & 7) * 128 + ((c ^ (rr & 7)) << 4)
+    elem = (byte >> 1).unsqueeze(-1) + torch.arange(8, device=packed.device)
+    return packed.view(torch.bfloat16)[elem.reshape(r.shape[0], -1)]
+
+
 def choose_nsplit_tc(num_qtiles: int, num_gtiles: int, sms: int) -> int:
     """Gallery split factor for the query tiles of the LAST (partial) wave of the persistent grid.
 

@@ -299,8 +299,29 @@ def _plan_key(q_pids, g_pids_list, get_mAP, precision, tag):
     return tuple(k)
 
 
-def _cache_get(key):
+def _cache_get(key, q_pids=None, g_pids_list=None, group=None, distributed=False):
+    """Look a plan up by the identity of its pid tensors; on a miss, fall back to CONTENT equality with the cached entries of
+    the same shapes (an evaluation loop that re-uploads the split's pid vectors every time creates new tensors with the same
+    values).  The content check is one device-side comparison and a host read -- far cheaper than re-planning (two sorts, the
+    slot arithmetic, two collectives); under a process group the verdict is min-reduced so that every rank takes the same
+    branch."""
     e = _PLAN_CACHE.get(key)
+    if e is None and q_pids is not None:
+        for k2, cand in list(_PLAN_CACHE.items()):
+            cq, cg = cand[1], cand[2]
+            cg = cg if isinstance(cg, (list, tuple)) else [cg]
+            if k2[3:7] != key[3:7] or cq.numel() != q_pids.numel() or len(cg) != len(g_pids_list):
+                continue
+            if any(a.numel() != b.numel() for a, b in zip(cg, g_pids_list)):
+                continue
+            same = torch.equal(cq, q_pids) and all(torch.equal(a, b) for a, b in zip(cg, g_pids_list))
+            if distributed:
+                flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=q_pids.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                same = bool(int(flag.item()))
+            if same:
+                e = cand
+            break
     plan_cache_stats["hits" if e is not None else "misses"] += 1
     return e
 
@@ -334,7 +355,7 @@ def _finish(backend, cand_sims, cand_idxs, q_pids, g_pids_all, rel, cnt, topk):
 def _local_plans(q_pids, pids, bases, get_mAP, precision):
     """Plans of all shards of a single-process (multi-shard) evaluation, cached on the identity of the pid tensors."""
     key = _plan_key(q_pids, pids, get_mAP, precision, ("local",) + tuple(bases))
-    hit = _cache_get(key)
+    hit = _cache_get(key, q_pids, pids)
     if hit is not None:
         return hit[0]
     plans = [ShardPlan(q_pids, p, base, get_mAP, precision) for p, base in zip(pids, bases)]
@@ -458,7 +479,7 @@ def _distributed_plan(q_pids, g_pids_local, get_mAP, precision, group, shard_siz
     Every rank sees the same hit / miss sequence as long as every rank re-uses (or re-creates) its pid tensors alike."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     key = _plan_key(q_pids, [g_pids_local], get_mAP, precision, ("dist", rank, world, id(group)))
-    hit = _cache_get(key)
+    hit = _cache_get(key, q_pids, [g_pids_local], group, distributed=True)
     if hit is not None:
         return hit[0]
     dev = q_pids.device

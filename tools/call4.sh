@@ -1,5 +1,5 @@
 set -u
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --timeout 300 -x > gpurun_out/pytest_all.log 2>&1
+timeout 1500 python -m pytest tests/test_gpu_retrieval.py -m gpu -q --timeout 900 -x -s -k "config4" > gpurun_out/pytest_cfg.log 2>&1
 echo "pytest exit $?"
-tail -n 30 gpurun_out/pytest_all.log
+tail -n 30 gpurun_out/pytest_cfg.log
