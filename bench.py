@@ -332,6 +332,73 @@ def reference_gpu_loss_line(device, shape_key="n128_k2048", iters=20):
             "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms}
 
 
+def train_step_lines(trb, device, N=128, iters=6, warmup=3):
+    """BASELINE configs[4]: one whole train step -- CLIP RN50 image encoder + bi-GRU text encoder (PyTorch / cuDNN, out of the
+    accelerated scope) + MoCo head, batch 128, 384 x 128 images, captions of up to 100 tokens, queue 2048, 11003 classes,
+    Adam -- once with the reference's head as an ATen call sequence (oracle/reference_head.py) and once with FusedMoCoHead
+    (bf16 fused loss step, one-launch momentum update).  Same encoders, same data, same optimizer in both arms."""
+    from types import SimpleNamespace
+    from oracle.reference_head import ReferenceStyleHead
+    from textreid_b200.encoders import BiGRUTextEncoder, ClipResNetEncoder, synthetic_vocab_table
+    from textreid_b200.synthetic import train_batch
+    cfg = SimpleNamespace(MODEL=SimpleNamespace(EMBEDDING=SimpleNamespace(FEATURE_SIZE=256, EPSILON=0.1),
+                                                MOCO=SimpleNamespace(K=2048, M=0.999, FC=False), NUM_CLASSES=11003))
+    table = synthetic_vocab_table()
+    batches = [train_batch(N, 11003, table.shape[0], seed=s, device=device) for s in range(2)]
+    out = {}
+    for arm in ("reference_head", "fused_head"):
+        torch.manual_seed(0)
+        vis, txt = ClipResNetEncoder(), BiGRUTextEncoder(table)
+        head = (ReferenceStyleHead(cfg, vis, txt) if arm == "reference_head" else trb.FusedMoCoHead(cfg, vis, txt, precision="bf16"))
+        head = head.to(device).train()
+        opt = torch.optim.Adam([p for p in head.parameters() if p.requires_grad], lr=1e-4)
+
+        def step(i):
+            images, caps, _ = batches[i % 2]
+            opt.zero_grad(set_to_none=True)
+            losses = head(images, caps)
+            sum(losses.values()).backward()
+            opt.step()
+            return losses
+
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        syncs0 = getattr(head, "host_syncs", 0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for i in range(iters):
+            losses = step(i)
+        b.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / iters * 1e3
+        line = {"ms_per_step": a.elapsed_time(b) / iters, "wall_ms_per_step": wall, "steps_per_s": 1e3 / (a.elapsed_time(b) / iters),
+                "losses": {k: float(v) for k, v in losses.items()}}
+        if arm == "reference_head":
+            line["host_syncs_per_step_in_head"] = (head.host_syncs - syncs0) // iters
+        try:        # kernel launches of ONE step (encoders included), counted by the profiler
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step(0)
+                torch.cuda.synchronize()
+            line["cuda_kernel_launches_per_step"] = sum(e.count for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA)
+        except Exception as e:      # pragma: no cover
+            line["cuda_kernel_launches_per_step"] = None
+        out[arm] = line
+        del head, opt, vis, txt
+        torch.cuda.empty_cache()
+    r, f = out["reference_head"], out["fused_head"]
+    out["metric"] = "end-to-end train step, RN50 + bi-GRU + MoCo head, bs%d, 384x128, <=100 tokens, K=2048, C=11003, Adam (BASELINE configs[4])" % N
+    out["speedup"] = r["ms_per_step"] / f["ms_per_step"]
+    if r.get("cuda_kernel_launches_per_step") and f.get("cuda_kernel_launches_per_step"):
+        out["launches_removed_per_step"] = r["cuda_kernel_launches_per_step"] - f["cuda_kernel_launches_per_step"]
+    out["note"] = ("encoders run in fp32 (cuDNN TF32 convolutions, torch defaults) in both arms and dominate the step; the arms differ in "
+                   "the head only: per-parameter momentum loop + host-synchronising loss sequence vs one-launch momentum update + "
+                   "two-launch fused loss step")
+    return out
+
+
 def secondary_measurements(pk, device):
     import textreid_b200 as trb
     out = {}
@@ -396,6 +463,13 @@ def secondary_measurements(pk, device):
                              "t2i + i2t top-k (trainer.py:124)" if "fast" in name else "4 rankings incl. k-reciprocal re-rank (test_net.py:107)"),
                          "ms_per_call": med, "value": 1e3 / med, "unit": "evaluations/s"}
     del text, image
+    torch.cuda.empty_cache()
+    # ---- configs[4]: the whole train step, reference-style head vs fused head around the same encoders ----
+    try:
+        out["train_step_config5"] = train_step_lines(trb, device)
+    except Exception as e:      # pragma: no cover
+        out["train_step_config5"] = {"error": str(e)[:300]}
+    torch.cuda.empty_cache()
     # ---- configs[3] on the fp32 FFMA parity path and at D = 512 on the tensor-core path (one step each) ----
     big = WORKLOADS["retrieval_1m"]
     for name, D, prec, Qn in (("retrieval_1m_fp32", 256, "fp32", 20_000), ("retrieval_1m_d512_bf16", 512, "bf16", 50_000)):

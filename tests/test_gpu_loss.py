@@ -568,3 +568,62 @@ def test_fused_step_enqueues_inside_the_kernel_like_the_separate_call():
         for k in state[0]:
             assert torch.equal(state[0][k], state[1][k]), (step, k)
         assert int(ptrs[0]) == int(ptrs[1]) == ((step + 1) * N) % K
+
+
+# ---------------------------------------------------------------------------------------------------
+# one whole train step with REAL encoders (no stubs) -- FusedMoCoHead vs the reference's step
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol_loss,tol_grad", [("fp32", 2e-5, 2e-3), ("bf16", 2e-3, 5e-2)])
+def test_train_step_with_real_encoders_matches_the_reference_step(precision, tol_loss, tol_grad):
+    """CLIP-style ResNet + bi-GRU (textreid_b200/encoders.py, pinned to the reference's encoder modules by tests/test_encoders.py)
+    under FusedMoCoHead, against oracle/reference_head.py (the reference's MoCoHead step, pinned to reference-recorded goldens):
+    same initial state, two steps; losses, parameter gradients, momentum encoders, queues, pointer."""
+    from oracle.reference_head import ReferenceStyleHead
+    from textreid_b200.encoders import BiGRUTextEncoder, ClipResNetEncoder, synthetic_vocab_table
+    from textreid_b200.synthetic import train_batch
+    torch.manual_seed(0)
+    D, K, C, N = 64, 64, 97, 16
+    cfg = SimpleNamespace(MODEL=SimpleNamespace(EMBEDDING=SimpleNamespace(FEATURE_SIZE=D, EPSILON=0.1),
+                                                MOCO=SimpleNamespace(K=K, M=0.999, FC=False), NUM_CLASSES=C))
+    table = synthetic_vocab_table(300, 32, seed=1)
+
+    def encoders():
+        return (ClipResNetEncoder(layers=[1, 1, 1, 1], output_dim=48, heads=4, input_resolution=(64, 32), width=8),
+                BiGRUTextEncoder(table, hidden_dim=24, embed_size=32))
+
+    fused = trb.FusedMoCoHead(cfg, *encoders(), precision=precision)
+    ref = ReferenceStyleHead(cfg, *encoders())
+    ref.load_state_dict(fused.state_dict(), strict=True)
+    fused.to(DEV).train()
+    ref.to(DEV).train()
+    for step in range(2):
+        images, caps, ids = train_batch(N, C, 300, max_len=12, min_tokens=3, max_tokens=12, height=64, width=32, seed=step, device=DEV)
+        fused.zero_grad()
+        ref.zero_grad()
+        lf, lr = fused(images, caps), ref(images, caps)
+        sum(lf.values()).backward()
+        sum(lr.values()).backward()
+        for k in KEYS:
+            assert abs(float(lf[k]) - float(lr[k])) <= tol_loss * max(1.0, abs(float(lr[k]))), (step, k, float(lf[k]), float(lr[k]))
+        pr = dict(ref.named_parameters())
+        for k, p in fused.named_parameters():
+            if p.grad is None:
+                assert pr[k].grad is None or float(pr[k].grad.abs().max()) == 0.0, k
+                continue
+            scale = float(pr[k].grad.abs().max())
+            if scale < 1e-4 and k.endswith("k_proj.bias"):   # analytically zero (softmax is shift-invariant): rounding noise only
+                assert float(p.grad.abs().max()) < 1e-3, (step, k)
+                continue
+            assert float((p.grad - pr[k].grad).abs().max()) / scale <= tol_grad, (step, k, scale)
+        sf, sr = fused.state_dict(), ref.state_dict()
+        for k in sf:
+            if "encoder_k" in k or k in ("id_queue", "queue_ptr"):
+                assert torch.equal(sf[k], sr[k]), (step, k)                       # momentum update / ids / pointer: bit-exact
+            elif k in ("v_queue", "t_queue"):
+                torch.testing.assert_close(sf[k], sr[k], rtol=1e-5, atol=1e-6)
+        # keep the two models on the same trajectory for the second step
+        with torch.no_grad():
+            for k, p in fused.named_parameters():
+                if p.grad is not None:
+                    p -= 0.01 * p.grad
+                    pr[k] -= 0.01 * p.grad

@@ -195,3 +195,58 @@ def test_hit_ranks_consistent_with_rank(golden_dir):
     ap = torch.tensor([sum((j + 1) / (int(r) + 1) for j, r in enumerate(rs)) / len(rs) for rs in ranks])
     _, mAP, _ = O.rank(sim, tp, ip, (1, 5, 10), get_mAP=True)
     assert abs(float(ap.mean() * 100) - float(mAP)) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# oracle/reference_head.py: the reference's step as an ATen call sequence (bench baseline arm) -- pinned to the same fixtures
+# ---------------------------------------------------------------------------------------------------
+class _StubEncoder(torch.nn.Module):
+    def __init__(self, in_dim, out_channels, take_captions=False):
+        super().__init__()
+        self.lin = torch.nn.Linear(in_dim, out_channels)
+        self.out_channels = out_channels
+        self.take_captions = take_captions
+
+    def forward(self, x):
+        if self.take_captions:
+            x = torch.stack([c.feat for c in x])
+        return self.lin(x)
+
+
+class _StubCaption:
+    def __init__(self, feat, pid):
+        self.feat, self._id = feat, pid
+
+    def get_field(self, name):
+        return self._id
+
+
+@pytest.mark.parametrize("name", ["moco_head_small", "moco_head_fc"])
+def test_reference_style_head_replays_reference_steps(golden_dir, name):
+    from types import SimpleNamespace
+    from oracle.reference_head import ReferenceStyleHead
+    g = load(golden_dir, name)
+    N, F, D, K, C, steps, fc = [int(x) for x in g["meta"]]
+    cfg = SimpleNamespace(MODEL=SimpleNamespace(EMBEDDING=SimpleNamespace(FEATURE_SIZE=D, EPSILON=float(g["eps"])),
+                                                MOCO=SimpleNamespace(K=K, M=0.999, FC=bool(fc)), NUM_CLASSES=C))
+    head = ReferenceStyleHead(cfg, _StubEncoder(F, F), _StubEncoder(F, F, take_captions=True))
+    head.load_state_dict({k[len("state0."):]: T(v) for k, v in g.items() if k.startswith("state0.")}, strict=True)
+    head.train()
+    for s in range(steps):
+        images, cfeat, labels = T(g[f"s{s}.images"]), T(g[f"s{s}.cfeat"]), T(g[f"s{s}.labels"])
+        head.zero_grad()
+        losses = head(images, [_StubCaption(cfeat[i], labels[i]) for i in range(N)])
+        sum(losses.values()).backward()
+        for k in losses:
+            torch.testing.assert_close(losses[k].detach(), T(g[f"s{s}.loss.{k}"]), rtol=2e-6, atol=1e-6)
+        for k, p in head.named_parameters():
+            if f"s{s}.grad.{k}" in g:
+                torch.testing.assert_close(p.grad, T(g[f"s{s}.grad.{k}"]), rtol=1e-4, atol=2e-6)
+        sd = head.state_dict()
+        for k in sd:
+            if f"s{s}.state.{k}" in g:
+                ref = T(g[f"s{s}.state.{k}"])
+                if ref.dtype.is_floating_point and "encoder_k" not in k and "fc_k" not in k:
+                    torch.testing.assert_close(sd[k], ref, rtol=1e-5, atol=1e-6)
+                else:
+                    assert torch.equal(sd[k], ref), k

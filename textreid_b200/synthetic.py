@@ -49,3 +49,34 @@ def eval_data(Q, G, D, n_ids, g_lo, g_hi, device, dtype, seed=0, signal=0.55):
     if not imgs:
         return text, q_pid, torch.zeros(0, D, device=dev, dtype=dtype), torch.zeros(0, dtype=torch.int64, device=dev)
     return text, q_pid, torch.cat(imgs), torch.cat(pids)
+
+
+class SyntheticCaption:
+    """Duck-typed stand-in for lib/utils/caption.py's Caption as the encoders and the head use it: ``text`` [1, L] int64 token
+    ids (zero padded), ``length`` [1] int64, ``get_field("id")`` the person id, ``to(device)``."""
+
+    def __init__(self, text, length, pid):
+        self.text, self.length, self._id = text, length, pid
+
+    def to(self, device):
+        return SyntheticCaption(self.text.to(device), self.length.to(device), self._id.to(device))
+
+    def get_field(self, name):
+        if name != "id":
+            raise KeyError(name)
+        return self._id
+
+
+def train_batch(N, n_classes, vocab, max_len=105, min_tokens=20, max_tokens=100, height=384, width=128, seed=0, device="cpu"):
+    """One synthetic training batch of BASELINE configs[4]: ``N`` 384 x 128 images, captions of up to 100 tokens padded to 105
+    (lib/data/build.py:26), TripletSampler-shaped ids (N/4 identities x 4)."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(N, 3, height, width, generator=g)
+    ids = torch.randint(0, n_classes, (max(N // 4, 1),), generator=g).repeat_interleave(4)[:N]
+    caps = []
+    for i in range(N):
+        n_tok = int(torch.randint(min_tokens, max_tokens + 1, (1,), generator=g))
+        text = torch.zeros(1, max_len, dtype=torch.int64)
+        text[0, :n_tok] = torch.randint(1, vocab, (n_tok,), generator=g)
+        caps.append(SyntheticCaption(text.to(device), torch.tensor([n_tok], dtype=torch.int64, device=device), ids[i].to(device)))
+    return images.to(device), caps, ids.to(device)

@@ -304,6 +304,48 @@ def golden_evaluation(out, name, *, n_caps, n_imgs, D, n_ids, seed):
     print("wrote", name, float(rec["plain.r1"]), float(rec["rerank.r1"]))
 
 
+def golden_encoders(out, name, seed):
+    """The reference's own encoders (m_resnet.py ModifiedResNet, gru.py GRU), small instances, one forward each: the fixture
+    that pins textreid_b200/encoders.py (same state dict -> same outputs).  The vocabulary table is written to a scratch
+    <root>/datasets/cuhkpedes/clip_vocab_vit.npy because GRU.__init__ loads it from disk (directory.py:20-23)."""
+    from lib.models.backbones.gru import GRU
+    from lib.models.backbones.m_resnet import ModifiedResNet
+    from lib.utils.caption import Caption
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    vis = ModifiedResNet(layers=[1, 2, 1, 1], output_dim=32, heads=4, last_stride=1, input_resolution=(64, 32), width=8).eval()
+    with torch.no_grad():           # non-trivial running statistics so that the BatchNorm layers matter
+        for m in vis.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1, generator=g)
+                m.running_var.uniform_(0.5, 1.5, generator=g)
+    images = torch.randn(3, 3, 64, 32, generator=g)
+    with torch.no_grad():
+        v_out = vis(images)
+    root = tempfile.mkdtemp(prefix="trb_vocab_")
+    os.makedirs(os.path.join(root, "datasets", "cuhkpedes"))
+    V, E, H, L = 50, 24, 16, 9
+    table = torch.randn(V, E, generator=g)
+    np.save(os.path.join(root, "datasets", "cuhkpedes", "clip_vocab_vit.npy"), table.numpy())
+    rec = {}
+    for tag, embed in (("same", E), ("proj", 12)):        # vocab_size == embed_size (no Linear) and the projected variant
+        txt = GRU(H, E, embed, 1, 0.0, True, "clip_vit", root).eval()
+        lengths = [9, 4, 7, 1, 9]
+        caps = []
+        for n_tok in lengths:
+            toks = torch.randint(1, V, (n_tok,), generator=g)
+            caps.append(Caption([toks], max_length=L, padded=False))
+        with torch.no_grad():
+            t_out = txt(caps)
+        rec.update({"%s.tokens" % tag: tnp(torch.stack([c.text for c in caps], 1).view(-1, L)),
+                    "%s.lengths" % tag: np.asarray(lengths, dtype=np.int64), "%s.out" % tag: tnp(t_out)})
+        rec.update({"%s.state.%s" % (tag, k): tnp(v) for k, v in txt.state_dict().items()})
+    rec.update({"vis.images": tnp(images), "vis.out": tnp(v_out), "table": tnp(table)})
+    rec.update({"vis.state." + k: tnp(v) for k, v in vis.state_dict().items()})
+    np.savez_compressed(os.path.join(out, name + ".npz"), **rec)
+    print("wrote", name, v_out.shape, t_out.shape)
+
+
 def golden_ema(out, name, seed):
     """Reference momentum update arithmetic (head.py:78-85) on one tensor."""
     g = torch.Generator().manual_seed(seed)
@@ -338,6 +380,7 @@ def main():
     golden_rank(out, "rank_exact", Q=80, G=70, D=256, n_ids=25, seed=8, exact=True)
     golden_rank(out, "rank_exact_le2", Q=64, G=60, D=256, n_ids=30, seed=9, exact=True, max_per_id=2)
     golden_evaluation(out, "evaluation_small", n_caps=60, n_imgs=31, D=32, n_ids=12, seed=10)
+    golden_encoders(out, "encoders_small", seed=13)
     golden_ema(out, "ema", seed=11)
 
 
