@@ -235,6 +235,28 @@ def worker(rank, world, backend_name, port, out_dir, precision="fp32", Q=151, G=
             if rank == 0:
                 out["inference_r1_" + prec] = r1.cpu()
         out["inference_r1_golden"] = split.r1
+        # cross-rank MoCo queue: every rank steps on its own batch, the keys of all ranks enter every queue
+        import textreid_b200 as trb
+        from textreid_b200.synthetic import loss_inputs
+        N, D, K, C = 8, 64, 64, 101
+        base = loss_inputs(N, D, K, C, seed=77)
+        vq, tq, idq = base["v_queue"].to(dev), base["t_queue"].to(dev), base["id_queue"].to(dev)
+        ptr = torch.zeros(1, dtype=torch.int64, device=dev)
+        exp_v, exp_t, exp_id, exp_ptr = base["v_queue"].clone(), base["t_queue"].clone(), base["id_queue"].clone(), torch.zeros(1, dtype=torch.int64)
+        pr = base["projection"].to(dev)
+        for step in range(3):
+            per_rank = [loss_inputs(N, D, K, C, seed=1000 * step + r) for r in range(world)]
+            mine = {k: v.to(dev) for k, v in per_rank[rank].items()}
+            d = trb.moco_loss_dict(mine["v_embed"], mine["t_embed"], mine["v_key"], mine["t_key"], mine["labels"], vq, tq, idq, ptr, pr,
+                                   epsilon=0.1, precision="fp32", gather_group=True)
+            ref_l, _, _, _ = O.moco_loss_dict_with_grads(*[per_rank[rank][k] for k in ("v_embed", "t_embed", "v_key", "t_key", "labels")],
+                                                         exp_v, exp_t, exp_id, base["projection"], epsilon=0.1)
+            for k in ref_l:       # logits from the queue as it was BEFORE this step's global enqueue
+                assert abs(float(d[k]) - float(ref_l[k])) <= 2e-5 * max(1.0, abs(float(ref_l[k]))), (step, k)
+            O.enqueue(exp_v, exp_t, exp_id, exp_ptr, torch.cat([p["v_key"] for p in per_rank]), torch.cat([p["t_key"] for p in per_rank]),
+                      torch.cat([p["labels"] for p in per_rank]))
+            assert torch.equal(vq.cpu(), exp_v) and torch.equal(tq.cpu(), exp_t) and torch.equal(idq.cpu(), exp_id) and int(ptr) == int(exp_ptr)
+        out["cross_rank_queue_ok"] = torch.tensor(1)
     torch.save(out, os.path.join(out_dir, "rank%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()

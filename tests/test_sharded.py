@@ -86,3 +86,4 @@ def test_sharded_nccl(tmp_path, precision, exact):
     o = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
     assert torch.equal(o["inference_r1_fp32"], o["inference_r1_golden"])          # reference-recorded R@1, bit for bit
     assert abs(float(o["inference_r1_bf16"]) - float(o["inference_r1_golden"])) <= 100.0 * 2 / 60
+    assert int(o["cross_rank_queue_ok"]) == 1          # global queue under data parallelism (asserted inside the worker)

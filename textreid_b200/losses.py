@@ -200,7 +200,7 @@ def moco_loss_dict(v_embed, t_embed, v_key, t_key, labels, v_queue, t_queue, id_
                    T: float = 0.07, epsilon: float = 0.0, alpha: float = 0.6, beta: float = 0.4, scale_pos: float = 10,
                    scale_neg: float = 40, enqueue: bool = True, v_embed_q=None, t_embed_q=None,
                    normalize_keys: bool = False, precision: str = "fp32", cuda_graph: bool = False,
-                   smoothing=None) -> Dict[str, torch.Tensor]:
+                   smoothing=None, gather_group=None) -> Dict[str, torch.Tensor]:
     """Functional core of MoCoHead.forward's train branch (head.py:126-175) + LossComputation.forward
     (moco_head/loss.py:21-39).
 
@@ -210,6 +210,11 @@ def moco_loss_dict(v_embed, t_embed, v_key, t_key, labels, v_queue, t_queue, id_
     queues [D, K] fp32, id_queue [1, K] int64, queue_ptr [1] int64 are mutated in place when ``enqueue``.
     ``epsilon`` follows the reference: it is cfg.MODEL.EMBEDDING.EPSILON, and any positive value switches label smoothing on
     with the weight 0.1 (see ``effective_smoothing``); ``smoothing`` sets the weight explicitly instead.
+    ``gather_group`` (a torch.distributed process group, or True for the default group): cross-rank queue -- the normalised
+    keys and ids of EVERY rank are all-gathered (NCCL, rank order) and enqueued on every rank, so data-parallel training keeps
+    one global queue like single-GPU training with the global batch.  The reference keeps per-rank
+    queues (DDP with broadcast_buffers=False, train_net.py:50-56); this is opt-in and changes behaviour, not speed.  The
+    logits of the step are taken from the queue as it was before, exactly like the local enqueue.  Needs K % (N * world) == 0.
     ``cuda_graph=True`` replays the whole step (loss, gradients, enqueue) as one CUDA graph: the per-step inputs are copied
     into graph-owned static buffers (one multi-tensor copy), so freshly allocated inputs hit the same graph every step; the
     returned losses / saved gradients live in graph-owned buffers that the next replay overwrites (fine for the reference's
@@ -222,11 +227,32 @@ def moco_loss_dict(v_embed, t_embed, v_key, t_key, labels, v_queue, t_queue, id_
     if separate_q and (v_embed_q is None or t_embed_q is None):
         raise ValueError("v_embed_q and t_embed_q must be given together")
     hp = _lib.MocoHParams(T, effective_smoothing(epsilon, smoothing), alpha, beta, scale_pos, scale_neg)
+    cross_rank = bool(enqueue) and gather_group is not None and gather_group is not False
     li, ln, lg, vkn, tkn = _MoCoLossFunction.apply(
         v_embed, t_embed, v_embed_q if separate_q else v_embed, t_embed_q if separate_q else t_embed, projection,
         v_key, t_key, labels, v_queue, t_queue, id_queue, hp, PRECISIONS[precision], normalize_keys, separate_q,
-        queue_ptr, bool(enqueue), bool(cuda_graph))
+        queue_ptr, bool(enqueue) and not cross_rank, bool(cuda_graph))
+    if cross_rank:
+        enqueue_all_ranks(v_queue, t_queue, id_queue, queue_ptr, vkn, tkn, labels, None if gather_group is True else gather_group)
     return {"instance_loss": li, "infonce_loss": ln, "global_align_loss": lg}
+
+
+@torch.no_grad()
+def enqueue_all_ranks(v_queue, t_queue, id_queue, queue_ptr, v_keys, t_keys, ids, group=None) -> None:
+    """_dequeue_and_enqueue (head.py:96-109) with the keys of every rank: one all-gather of [v_keys | t_keys] (fp32) and one of
+    the ids over NCCL, then the ordinary enqueue of world * N columns in rank order -- every rank ends with the same queues."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("cross-rank queue needs an initialised torch.distributed process group")
+    world = dist.get_world_size(group)
+    N, D = v_keys.shape
+    both = torch.cat([_f32c(v_keys), _f32c(t_keys)], dim=1).contiguous()                 # [N, 2D]
+    gathered = torch.empty(world * N, 2 * D, dtype=torch.float32, device=both.device)
+    dist.all_gather_into_tensor(gathered, both, group=group)
+    ids = ids.detach().reshape(-1).to(torch.int64).contiguous()
+    all_ids = torch.empty(world * N, dtype=torch.int64, device=ids.device)
+    dist.all_gather_into_tensor(all_ids, ids, group=group)
+    dequeue_and_enqueue(v_queue, t_queue, id_queue, queue_ptr, gathered[:, :D].contiguous(), gathered[:, D:].contiguous(), all_ids)
 
 
 def fused_debug_logits(shape_ndkc, precision: str = "bf16", device=None):

@@ -40,7 +40,8 @@ def make_loss_evaluator(cfg):
 
 
 class FusedMoCoHead(nn.Module):
-    def __init__(self, cfg, visual_model, textual_model, precision: str = "bf16", cuda_graph: bool = False):
+    def __init__(self, cfg, visual_model, textual_model, precision: str = "bf16", cuda_graph: bool = False,
+                 cross_rank_queue: bool = False):
         super().__init__()
         self.embed_size = cfg.MODEL.EMBEDDING.FEATURE_SIZE
         self.K = cfg.MODEL.MOCO.K
@@ -48,6 +49,9 @@ class FusedMoCoHead(nn.Module):
         self.fc = cfg.MODEL.MOCO.FC
         self.precision = precision
         self.cuda_graph = cuda_graph
+        # opt-in: one global queue under data parallelism (keys of all ranks all-gathered before the enqueue) instead of the
+        # reference's per-rank queues (train_net.py:50-56 wraps the model in DDP with broadcast_buffers=False)
+        self.cross_rank_queue = cross_rank_queue
 
         self.v_encoder_q = visual_model
         self.t_encoder_q = textual_model
@@ -136,7 +140,9 @@ class FusedMoCoHead(nn.Module):
         return moco_loss_dict(v_embed, t_embed, v_k, t_k, id_q, self.v_queue, self.t_queue, self.id_queue,
                               self.queue_ptr, ev.projection, T=ev.T, epsilon=ev.epsilon, enqueue=True,
                               v_embed_q=v_q, t_embed_q=t_q, normalize_keys=True, precision=self.precision,
-                              cuda_graph=self.cuda_graph)
+                              cuda_graph=self.cuda_graph,
+                              gather_group=True if (self.cross_rank_queue and torch.distributed.is_available()
+                                                    and torch.distributed.is_initialized()) else None)
 
 
 def build_moco_head(cfg, visual_model, textual_model):
@@ -152,4 +158,7 @@ def build_moco_head(cfg, visual_model, textual_model):
     graph = getattr(moco, "CUDA_GRAPH", None)
     if graph is None:
         graph = os.environ.get("TRB_LOSS_GRAPH", "0") not in ("0", "", "false", "False")
-    return FusedMoCoHead(cfg, visual_model, textual_model, precision=precision, cuda_graph=bool(graph))
+    cross = getattr(moco, "CROSS_RANK_QUEUE", None)
+    if cross is None:
+        cross = os.environ.get("TRB_CROSS_RANK_QUEUE", "0") not in ("0", "", "false", "False")
+    return FusedMoCoHead(cfg, visual_model, textual_model, precision=precision, cuda_graph=bool(graph), cross_rank_queue=bool(cross))
