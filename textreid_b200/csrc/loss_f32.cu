@@ -358,7 +358,7 @@ Workspace carve(void* base, int N, int D, int K, int C, bool use_tc) {
     }
     w.part_nce = take((int64_t)SPLIT_NCE * N * D);
     w.fused = nullptr;
-    if (use_tc && fused_loss_supported(N, D, K, C, sm_count()))
+    if (use_tc && (fused_loss_supported(N, D, K, C, sm_count()) || fused_windows_supported(N, D, K, C, sm_count())))
         w.fused = reinterpret_cast<uint8_t*>(take(fused_loss_scratch_bytes(N, D, K, C) / 4 + 64));
     w.bytes = p - static_cast<char*>(base);
     return w;
@@ -381,6 +381,15 @@ int trb_moco_loss_launches_impl(const trb_moco_shape* s, int precision) {
         if (e == nullptr || (atoi(e) & 7) == 7) return getenv("TRB_FUSED_MERGED") ? 1 : 2;
     }
     const int per_gemm = use_tc ? 3 : 1;
+    if (use_tc && fused_windows_supported(s->N, s->D, s->K, s->C, sm_count())) {
+        const char* e = getenv("TRB_FUSED_ROLES");
+        if (e == nullptr || (atoi(e) & 3) == 3) {
+            // shared prologue + the unfused global-align branch (3 contractions, pair losses, normalise backward) + per 128-row
+            // window a fused prologue and one cooperative launch per role + loss reduce
+            const int windows = (s->N + 127) / 128;
+            return 1 + (3 * per_gemm + 2) + 3 * windows + 1;
+        }
+    }
     // prologue, mask, column norms, 3 row kernels, 2 normalise-backward, projection backward, loss reduce, 3 partial reductions
     return 13 + 10 * per_gemm;
 }
@@ -413,9 +422,13 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     //      branches named in `roles` (bit 0 instance, 1 InfoNCE, 2 align; TRB_FUSED_ROLES narrows it for debugging)
     int roles = 0;
     FusedLossArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    // batches of more than 128 rows run the fused kernel once per 128-row window and role (instance tiles, InfoNCE tiles); the
+    // global-align branch, whose N x N similarity couples the windows, stays on the unfused tensor-core sequence (helper stream)
+    const bool windows = w.fused != nullptr && N > 128;
     if (w.fused != nullptr) {
-        roles = 7;
-        if (const char* e = getenv("TRB_FUSED_ROLES")) roles = atoi(e) & 7;
+        roles = windows ? 3 : 7;
+        if (const char* e = getenv("TRB_FUSED_ROLES")) roles = windows ? (((atoi(e) & 3) == 3) ? 3 : 0) : (atoi(e) & 7);
         // vector accesses of the fused kernels: 16-byte aligned inputs, 32-byte aligned embedding gradients
         const void* in16[] = {v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, v_key_n, t_key_n};
         for (const void* q : in16)
@@ -423,6 +436,7 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
         const void* out32[] = {d_inst, d_nce, d_ga};
         for (const void* q : out32)
             if (reinterpret_cast<uintptr_t>(q) & 31u) roles = 0;
+        if (windows && (D % 8) != 0) roles = 0;
     }
     if (roles) {
         fa.N = N; fa.D = D; fa.K = K; fa.C = C;
@@ -434,6 +448,8 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
         fa.pos = w.pos; fa.dpos = w.dpos; fa.rows_inst = w.rows_inst; fa.rows_nce = w.rows_nce; fa.rows_ga = w.rows_ga;
         fa.losses = losses; fa.d_inst = d_inst; fa.d_nce = d_nce; fa.d_ga = d_ga; fa.d_proj = d_projection;
         fa.scratch = w.fused; fa.roles = roles; fa.reduce_losses = roles == 7;
+    }
+    if (roles && !windows) {
         // the whole step fused: the enqueue rides in the cooperative kernel (its queue reads ended with the prologue's re-pack)
         const bool enq_inside = roles == 7 && queue_ptr != nullptr;
         fa.enq_v_queue = enq_inside ? const_cast<float*>(v_queue) : nullptr;
@@ -451,7 +467,31 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     TRB_CUDA_OK(cudaEventRecord(fk->fork, st));
     TRB_CUDA_OK(cudaStreamWaitEvent(s_nce, fk->fork, 0));
     TRB_CUDA_OK(cudaStreamWaitEvent(s_ga, fk->fork, 0));
-    if (roles && (rc = fused_loss_launch(fa, st))) return rc;
+    if (roles && !windows && (rc = fused_loss_launch(fa, st))) return rc;
+    if (roles && windows) {
+        // ---- row windows on the caller's stream: per window a prologue (operand images of the window; the queue images only once)
+        //      and one cooperative launch per role -- 86 instance + 2 x 32 InfoNCE tiles do not fit the SMs together at K = 4096
+        for (int r0 = 0; r0 < N; r0 += 128) {
+            FusedLossArgs fw = fa;
+            const int64_t o = (int64_t)r0 * D;
+            fw.N = N - r0 < 128 ? N - r0 : 128;
+            fw.NS = N; fw.mask_labels = labels; fw.n_mask = N; fw.accum_dw = r0 > 0; fw.skip_pack = r0 > 0;
+            fw.v_embed = v_embed + o; fw.t_embed = t_embed + o; fw.v_qraw = v_qraw + o; fw.t_qraw = t_qraw + o;
+            fw.v_key = v_key + o; fw.t_key = t_key + o; fw.v_key_n = v_key_n + o; fw.t_key_n = t_key_n + o;
+            fw.labels = labels + r0;
+            fw.E2 = w.E2 + o; fw.en = w.en + o; fw.qn = w.qn + o; fw.inv_e = w.inv_e + r0; fw.inv_q = w.inv_q + r0;
+            fw.pos = w.pos + r0; fw.dpos = w.dpos + r0; fw.rows_inst = w.rows_inst + r0; fw.rows_nce = w.rows_nce + r0;
+            fw.d_inst = d_inst ? d_inst + o : nullptr; fw.d_nce = d_nce ? d_nce + o : nullptr;
+            fw.reduce_losses = 0;
+            fw.roles = 3;
+            if ((rc = fused_loss_prologue(fw, st))) return rc;
+            fw.roles = 1;
+            if ((rc = fused_loss_launch(fw, st))) return rc;
+            if ((rc = fused_loss_reset_barriers(fw, st))) return rc;
+            fw.roles = 2;
+            if ((rc = fused_loss_launch(fw, st))) return rc;
+        }
+    }
 
     // ---- InfoNCE branch (helper stream 1): mask, logits of v queries x text queue and t queries x image queue
     //      (head.py:148-170), row-wise CE (losses.py:206-217), dq = dS @ queue^T + dpos * key, normalise backward

@@ -38,10 +38,19 @@ struct ProArgs {
     float *v_key_n, *t_key_n, *E2, *en, *inv_e, *qn, *inv_q, *pos;
     uint8_t *Ep, *ENp, *QNp, *QUp;
     int normalize_keys, N, D, KC, K, T_k;
+    int NS;            // stride between the two modalities in the row-indexed fp32 arrays (= the FULL batch size; see FP::NS)
+    int skip_pack;     // the queue images of this step are already in QUp (a later row window of the same step)
 };
 
 struct FP {
     int N, D, K, C, KC, T_inst, T_k, n_inst, n_nce, n_ga, want_grad, reduce_losses, roles;
+    // Row windows: a batch of more than 128 rows runs as several launches of <= 128 rows each (N = rows of this window).  The
+    // row-indexed arrays keep their full-batch layout [modality][Nn rows]: every pointer below is pre-offset to the window's
+    // first row by the host, `NS` (= Nn) is the stride between the modalities, and every mean is taken over the full batch Nn.
+    int NS, Nn;
+    const int64_t* mask_labels;     // ids of the WHOLE batch (queue mask, head.py:148-157), n_mask of them
+    int n_mask;
+    int accum_dw;                   // the projection gradient of this window is added to what the previous windows left
     float T, eps, alpha, beta, sp, sn;
     const float* W;
     const float* queue[2];          // queue scored by modality m's queries: [0] = t_queue, [1] = v_queue  (head.py:162,168)
@@ -340,7 +349,7 @@ __device__ __forceinline__ void pro_row_task(const ProArgs& p, int prow, int lan
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = b[i] = c[i] = 0.f;
     const bool live = n < N && k0 < D;
-    const int row = mod * N + n;
+    const int row = mod * p.NS + n;
     if (live) {                                                              // 16-byte aligned rows (checked by the caller)
         const float4* e = reinterpret_cast<const float4*>((mod ? p.t_embed : p.v_embed) + (int64_t)n * D + k0);
         const float4* r = reinterpret_cast<const float4*>((mod ? p.t_qraw : p.v_qraw) + (int64_t)n * D + k0);
@@ -460,9 +469,9 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
         }
     }
     int64_t slot_id = -1;
-    if (!INST && tid < 128) {
-        s_lab[tid] = tid < N ? p.labels[tid] : INT64_MIN;
-        if (c0 + tid < ncols) slot_id = p.id_queue[c0 + tid];
+    if (!INST) {
+        s_lab[tid] = tid < p.n_mask ? p.mask_labels[tid] : INT64_MIN;       // 256 threads: up to 256 batch ids
+        if (tid < 128 && c0 + tid < ncols) slot_id = p.id_queue[c0 + tid];
     }
 
     // ---- instance: W tile HBM -> bf16 shared image, column norms
@@ -493,8 +502,9 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
         } else {
             if (ok) {                                                           // head.py:148-157: drop slots holding a batch id
                 bool hit = false;
+                const int nm = (p.n_mask + 7) & ~7;
 #pragma unroll 8
-                for (int i = 0; i < 128; ++i) hit |= (s_lab[i] == slot_id);
+                for (int i = 0; i < nm; ++i) hit |= (s_lab[i] == slot_id);
                 ok = !hit;
             }
             if (ok) scale = __fdiv_rn(1.0f, p.T);
@@ -582,15 +592,15 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             s_lse2[row] = l2;
             if (tile == 0) {                                                    // losses.py:26-39 with label smoothing
                 const float2 zz = sum_of_row(p.zz_inst, row, tiles);
-                p.rows_inst[h * N + n] = bad_label ? CUDART_NAN_F : l2 * F_LN2 - (1.0f - p.eps) * zz.y - (p.eps / (float)p.C) * zz.x;
+                p.rows_inst[h * p.NS + n] = bad_label ? CUDART_NAN_F : l2 * F_LN2 - (1.0f - p.eps) * zz.y - (p.eps / (float)p.C) * zz.x;
             }
         } else {
-            const float z02 = __fdiv_rn(p.pos[mod * N + n], p.T) * F_LOG2E;     // column 0 of the reference's logits (base 2)
+            const float z02 = __fdiv_rn(p.pos[mod * p.NS + n], p.T) * F_LOG2E;     // column 0 of the reference's logits (base 2)
             const float l2 = lse2_of_row(p.ms_nce, mod * 128 + n, tiles, z02, 1.0f);
             s_lse2[n] = l2;
             if (tile == 0) {                                                    // losses.py:206-217, target 0
-                p.rows_nce[mod * N + n] = (l2 - z02) * F_LN2;                   // exactly 0 when only the positive is left
-                p.dpos[mod * N + n] = (exp2f(z02 - l2) - 1.0f) / ((float)N * p.T);
+                p.rows_nce[mod * p.NS + n] = (l2 - z02) * F_LN2;                // exactly 0 when only the positive is left
+                p.dpos[mod * p.NS + n] = (exp2f(z02 - l2) - 1.0f) / ((float)p.Nn * p.T);
             }
         }
     }
@@ -602,7 +612,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     F_STAMP(5);
 
     if (p.want_grad) {
-        const float rs = n < N ? F_LN2 / (float)N : 0.f;          // dz' = (softmax - target) / N * scale, scale = col.x * ln 2
+        const float rs = n < N ? F_LN2 / (float)p.Nn : 0.f;          // dz' = (softmax - target) / N * scale, scale = col.x * ln 2
         const float uni = INST ? p.eps / (float)p.C : 0.f;
         const float uni_hot = uni + (INST ? 1.0f - p.eps : 0.f);
         const bool do_dw = INST && p.d_proj != nullptr;
@@ -782,6 +792,20 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                         const float wv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(wsrc[j] + i * 1024));
                         o[u][j] = fmaf(-wv, sc[j], tile1[d * 128 + ((((c >> 2) ^ w)) << 2) + (c & 3)]);
                     }
+                }
+                if (p.accum_dw) {                      // a later row window: add to the gradient the earlier windows wrote
+                    float old[8][4];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int d = w + 8 * (i0 + u);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) old[u][j] = __ldcg(p.d_proj + (int64_t)d * p.C + min(c0 + cc[j], p.C - 1));
+                    }
+                    asm volatile("" ::: "memory");
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o[u][j] += old[u][j];
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -1012,7 +1036,7 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
                 float out[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) out[e] = (comb[(tid * PARTS + 0) * 8 + e] + comb[(tid * PARTS + 1) * 8 + e]) + comb[(tid * PARTS + 2) * 8 + e];
-                st_v8(p.d_inst + ((size_t)(mod * N + nn) * D + c8 * 8), out);
+                st_v8(p.d_inst + ((size_t)(mod * p.NS + nn) * D + c8 * 8), out);
             }
             __syncthreads();
         }
@@ -1022,9 +1046,10 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
         // lane = 8-column chunk
         for (int row = blockIdx.x + GW * (7 - w); worker && row < 2 * N; row += GW * 8) {
             const int mod = row / N, nn = row % N;
-            const float dp = __ldcg(p.dpos + row);
+            const int grow = mod * p.NS + nn;                     // position in the full-batch arrays
+            const float dp = __ldcg(p.dpos + grow);
             const float* key = p.key_n[mod] + (int64_t)nn * D;
-            const float* qr = p.qn + (int64_t)row * D;
+            const float* qr = p.qn + (int64_t)grow * D;
             const bool on = lane * 8 < D;
             float g[8], qv[8];
 #pragma unroll
@@ -1061,12 +1086,12 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
                 }
             }
             dot = warp_sum(dot);
-            const float inv = p.inv_q[row];
+            const float inv = p.inv_q[grow];
             if (on) {
                 float o[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = (g[e] - dot * qv[e]) * inv;
-                st_v8(p.d_nce + (int64_t)row * D + lane * 8, o);
+                st_v8(p.d_nce + (int64_t)grow * D + lane * 8, o);
             }
         }
     }
@@ -1220,6 +1245,18 @@ bool fused_loss_supported(int N, int D, int K, int C, int sm_count) {
     return ctas <= sm_count;
 }
 
+bool fused_windows_supported(int N, int D, int K, int C, int sm_count) {
+    if (N <= 128 || N > 1024 || D < 64 || D > 256 || (D % 64) != 0) return false;
+    return (C + F_TILE - 1) / F_TILE <= sm_count && 2 * ((K + F_TILE - 1) / F_TILE) <= sm_count;
+}
+
+int fused_loss_reset_barriers(const FusedLossArgs& a, cudaStream_t st) {
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a.scratch) + 1023) & ~uintptr_t(1023));
+    const Scratch s = carve_scratch(base, a.N, a.D, a.K, a.C);
+    TRB_CUDA_OK(cudaMemsetAsync(s.bar, 0, 32, st));
+    return 0;
+}
+
 int64_t fused_loss_scratch_bytes(int N, int D, int K, int C) { return carve_scratch(nullptr, N, D, K, C).bytes + 1024; }
 
 static ProArgs make_pro_args(const FusedLossArgs& a, const Scratch& s) {
@@ -1230,6 +1267,8 @@ static ProArgs make_pro_args(const FusedLossArgs& a, const Scratch& s) {
     q.Ep = s.Ep; q.ENp = s.ENp; q.QNp = s.QNp; q.QUp = s.QUp;
     q.normalize_keys = a.normalize_keys; q.N = a.N; q.D = a.D; q.KC = (a.D + 127) / 128 * 2; q.K = a.K;
     q.T_k = (a.K + F_TILE - 1) / F_TILE;
+    q.NS = a.NS > 0 ? a.NS : a.N;
+    q.skip_pack = a.skip_pack;
     return q;
 }
 
@@ -1247,7 +1286,7 @@ int fused_loss_prologue(const FusedLossArgs& a, cudaStream_t st) {
     if (trb_first_on_device(attr))   // same shared-memory carve-out as the cooperative kernel that follows: no SM reconfiguration between the two
         TRB_CUDA_OK(cudaFuncSetAttribute(fused_prologue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     const ProArgs q = make_pro_args(a, s);
-    const int ntasks = 256 + ((a.roles & 2) ? 2 * q.KC * 64 : 0);     // queue re-pack only for fused InfoNCE tiles
+    const int ntasks = 256 + (((a.roles & 2) && !q.skip_pack) ? 2 * q.KC * 64 : 0);     // queue re-pack only for fused InfoNCE tiles
     fused_prologue_kernel<<<(ntasks + 7) / 8, 256, 0, st>>>(q, s.bar, ntasks);
     TRB_LAUNCH_OK();
     return 0;
@@ -1260,6 +1299,11 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     memset(&p, 0, sizeof(p));
     p.N = a.N; p.D = a.D; p.K = a.K; p.C = a.C;
     p.KC = (a.D + 127) / 128 * 2;
+    p.NS = a.NS > 0 ? a.NS : a.N;
+    p.Nn = a.NS > 0 ? a.NS : a.N;
+    p.mask_labels = a.mask_labels ? a.mask_labels : a.labels;
+    p.n_mask = a.mask_labels ? a.n_mask : a.N;
+    p.accum_dw = a.accum_dw;
     p.T_inst = (a.C + F_TILE - 1) / F_TILE; p.T_k = (a.K + F_TILE - 1) / F_TILE;
     p.roles = a.roles;
     p.n_inst = (a.roles & 1) ? p.T_inst : 0;
