@@ -635,12 +635,31 @@ def main():
     # ---- end to end through the public API from pinned host buffers ----
     h_text, h_image = text.cpu().pin_memory(), image.cpu().pin_memory()
     h_qpid, h_gpid = q_pid.cpu().pin_memory(), g_pid.cpu().pin_memory()
-    h2d = sum(x.numel() * x.element_size() for x in (h_text, h_image, h_qpid, h_gpid))
+
+    # N > 1: every rank needs ALL queries on its device, but nothing says each must pull them over its own PCIe link: rank r
+    # uploads rows [r*Qc, (r+1)*Qc) and the ranks all-gather the block over NVLink (the way inference() hands the embeddings
+    # over: textreid_b200.evaluation.gather_embeddings).  The gallery shard and the pid vectors are uploaded whole.
+    Qc = -(-Q // world)
+    h_text_part = h_text[rank * Qc: min(Q, (rank + 1) * Qc)]
+    h2d_rank = sum(x.numel() * x.element_size() for x in ((h_text_part if world > 1 else h_text), h_image, h_qpid, h_gpid))
+    t = torch.tensor([h2d_rank], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    h2d = int(t.item())                      # whole job, all ranks
+
+    def upload_queries():
+        if world == 1:
+            return h_text.to(device, non_blocking=True)
+        part = torch.zeros(Qc, D, dtype=h_text.dtype, device=device)
+        part[:h_text_part.shape[0]].copy_(h_text_part, non_blocking=True)
+        full = torch.empty(Qc * world, D, dtype=h_text.dtype, device=device)
+        dist.all_gather_into_tensor(full, part)
+        return full[:Q]
 
     def e2e_step():
         # everything is uploaded every step, pid vectors included: new device tensors each time, which the plan cache
         # recognises by content (one device-side comparison) instead of re-planning the split
-        r = step(h_text.to(device, non_blocking=True), h_image.to(device, non_blocking=True),
+        r = step(upload_queries(), h_image.to(device, non_blocking=True),
                  h_qpid.to(device, non_blocking=True), h_gpid.to(device, non_blocking=True))
         return torch.cat([r.cmc, r.mAP.reshape(1)]).cpu()
 
@@ -684,7 +703,9 @@ def main():
                 "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
                 "clocks": clocks.summary(), "gpu_launches": launches,
                 "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": e2e_ms},
+                        "d2h_bytes_per_step": int(out_host.numel() * 4) * world, "ms_per_step": e2e_ms,
+                        "note": "bytes are whole-job totals over all ranks; for N > 1 each rank uploads 1/N of the query block (all-gathered "
+                                "over NVLink), its gallery shard and the pid vectors"},
                 "roofline": roof, "result": result}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_retrieval_sample(cfg, 1, 0)

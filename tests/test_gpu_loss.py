@@ -216,7 +216,8 @@ def test_loss_dict_bf16_tensor_core_path(N, D, K, C, masked):
     for got, ref in ((gv, rv), (gt, rt), (gp, rp)):
         got = got.cpu().double()
         err = (got - ref).abs().max() / ref.abs().max()
-        assert float(err) < (2e-2 if N >= 32 else 4e-2), float(err)
+        # measured on B200: 7.5e-3 (embedding gradients, fused kernel: bf16 operands + bf16 partial tiles), 4e-3 (projection)
+        assert float(err) < (1.2e-2 if N >= 32 else 2.5e-2), float(err)
         cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0)
         assert float(cos) > 0.9995, float(cos)
     # and the two precisions agree with each other far inside the bf16 budget

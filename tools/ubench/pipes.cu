@@ -57,6 +57,58 @@ __global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, float*
     out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(c0 + c1 + c2 + c3) + f0 + f1 + f2 + f3 + __uint_as_float((unsigned)a0) + __uint_as_float((unsigned)(a0 >> 32)) + __uint_as_float((unsigned)a1) + __uint_as_float((unsigned)(a1 >> 32));
     if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
+// Four thresholds per value like the stream epilogue: NF of them counted on the FMA pipe (2 x FFMA.SAT + FADD2 per value pair),
+// the rest with a packed difference (FADD2 te2 - v2) and two LEA.HI sign-bit accumulates on the ALU pipe.
+__device__ __forceinline__ void sub2(float& d0, float& d1, float te, float v0, float v1) {
+    unsigned long long a, b;
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(te));
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(-v0), "f"(-v1));
+    asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+    asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(a));
+}
+template <int NF>
+__global__ void __launch_bounds__(512, 1) k4(const float* __restrict__ in, float* out, float c, long long* cycles) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = in[(threadIdx.x * 32 + i) & 1023];
+    unsigned cnt[4] = {0, 0, 0, 0};
+    unsigned long long acc[4] = {0, 0, 0, 0};
+    const float H = 1.2676506002282294e30f;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float te = c + (float)(it + r);
+            const float cc = -te * H;
+            if (r < NF) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) add2(acc[r], __saturatef(fmaf(v[j], H, cc)), __saturatef(fmaf(v[j + 1], H, cc)));
+            } else {
+                unsigned c0 = 0, c1 = 0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float d0, d1;
+                    sub2(d0, d1, te, v[j], v[j + 1]);
+                    c0 += __float_as_uint(d0) >> 31; c1 += __float_as_uint(d1) >> 31;
+                }
+                cnt[r] += c0 + c1;
+            }
+        }
+    }
+    long long t1 = clock64();
+    float s = 0.f;
+    for (int r = 0; r < 4; ++r) s += (float)cnt[r] + __uint_as_float((unsigned)acc[r]) + __uint_as_float((unsigned)(acc[r] >> 32));
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+template <int NF> void run4(const float* in, float* out, long long* cyc, int threads) {
+    for (int rep = 0; rep < 2; ++rep) { k4<NF><<<148, threads>>>(in, out, 0.5f, cyc); cudaDeviceSynchronize(); }
+    long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    const double warps_per_smsp = threads / 32.0 / 4.0;
+    printf("4 thresholds, %d on the FMA pipe / %d on the ALU pipe, %2.0f warps per SMSP: %8lld cycles  %.3f SMSP-cycles per (value,threshold) warp-op\n",
+           NF, 4 - NF, warps_per_smsp, h, (double)h / (ITER * 32.0 * 4.0 * warps_per_smsp));
+}
 template <int MODE> void run(const char* name, const float* in, float* out, long long* cyc) {
     k<MODE><<<148, 512>>>(in, out, 0.5f, cyc);
     cudaDeviceSynchronize();
@@ -81,5 +133,9 @@ int main() {
     run<6>("FFMA.SAT only", in, out, cyc);
     run<7>("FADD2 only (1 per 2 values)", in, out, cyc);
     run<8>("FFMA.SAT + LEA.HI(bits>>29)", in, out, cyc);
+    for (int threads : {256, 512}) {
+        run4<4>(in, out, cyc, threads); run4<3>(in, out, cyc, threads); run4<2>(in, out, cyc, threads);
+        run4<1>(in, out, cyc, threads); run4<0>(in, out, cyc, threads);
+    }
     return 0;
 }
