@@ -238,7 +238,8 @@ def worker(rank, world, backend_name, port, out_dir, precision="fp32", Q=151, G=
         # cross-rank MoCo queue: every rank steps on its own batch, the keys of all ranks enter every queue
         import textreid_b200 as trb
         from textreid_b200.synthetic import loss_inputs
-        N, D, K, C = 8, 64, 64, 101
+        N, D, C = 8, 64, 101
+        K = 4 * N * world      # the global batch N * world must divide the queue (head.py:101), also at world 3
         base = loss_inputs(N, D, K, C, seed=77)
         vq, tq, idq = base["v_queue"].to(dev), base["t_queue"].to(dev), base["id_queue"].to(dev)
         ptr = torch.zeros(1, dtype=torch.int64, device=dev)

@@ -40,6 +40,7 @@ def call(lib, _lib, inp, shape, hp, precision, grads=True):
 
 def print_stamps(lib, roles, K, Cn, tag, ws=None, sh=None):
     import numpy as np
+    from textreid_b200 import _lib
     buf = np.zeros(160 * 16, dtype=np.uint64)
     _lib.check(lib.trb_moco_loss_debug_stamps(_lib.ptr(ws), C.byref(sh), buf.ctypes.data_as(C.c_void_p)), "trb_moco_loss_debug_stamps")
     st = buf.reshape(160, 16).astype(np.int64)
