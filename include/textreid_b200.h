@@ -209,9 +209,7 @@ int64_t trb_moco_loss_workspace_bytes(const trb_moco_shape* shape, int precision
 
 /* Kernel launches one trb_moco_loss call issues for this shape on the current device: 2 when precision = 1 takes the fused
  * path (a small prologue + ONE cooperative tcgen05 kernel for the three losses and all gradients; needs N <= 128, D a multiple
- * of 64 up to 256 and ceil(C/128) + 2*ceil(K/128) + 1 <= #SMs), otherwise the length of the unfused launch sequence.
- * The environment variable TRB_FUSED_MERGED=1 selects a one-launch form (prologue tasks inside the cooperative kernel; returns
- * 1 here); it needs the workspace zero-filled at the first call (its grid-barrier words clean themselves afterwards). */
+ * of 64 up to 256 and ceil(C/128) + 2*ceil(K/128) + 1 <= #SMs), otherwise the length of the unfused launch sequence. */
 int trb_moco_loss_launches(const trb_moco_shape* shape, int precision);
 
 /* Loss dict and its gradients in one stream-ordered call (fwd and bwd fused: the softmax

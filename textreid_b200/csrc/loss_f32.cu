@@ -378,7 +378,7 @@ int trb_moco_loss_launches_impl(const trb_moco_shape* s, int precision) {
     const bool use_tc = precision == 1;
     if (use_tc && fused_loss_supported(s->N, s->D, s->K, s->C, sm_count())) {
         const char* e = getenv("TRB_FUSED_ROLES");
-        if (e == nullptr || (atoi(e) & 7) == 7) return getenv("TRB_FUSED_MERGED") ? 1 : 2;
+        if (e == nullptr || (atoi(e) & 7) == 7) return 2;
     }
     const int per_gemm = use_tc ? 3 : 1;
     if (use_tc && fused_windows_supported(s->N, s->D, s->K, s->C, sm_count())) {
@@ -457,7 +457,10 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
         fa.enq_ids = enq_inside ? const_cast<int64_t*>(id_queue) : nullptr;
         fa.enq_ptr = enq_inside ? queue_ptr : nullptr;
         if ((rc = fused_loss_prologue(fa, st))) return rc;
-        if (roles == 7) return fused_loss_launch(fa, st);       // the whole step: prologue + one cooperative launch, no helper streams
+        if (roles == 7) {                                        // the whole step: prologue + one cooperative launch, no helper streams
+            fa.after_prologue = 1;
+            return fused_loss_launch(fa, st);
+        }
     } else {
         // ---- shared prologue on the caller's stream
         prologue_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(v_embed, t_embed, v_qraw, t_qraw, v_key, t_key, normalize_keys,
@@ -486,7 +489,9 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
             fw.roles = 3;
             if ((rc = fused_loss_prologue(fw, st))) return rc;
             fw.roles = 1;
+            fw.after_prologue = 1;
             if ((rc = fused_loss_launch(fw, st))) return rc;
+            fw.after_prologue = 0;
             if ((rc = fused_loss_reset_barriers(fw, st))) return rc;
             fw.roles = 2;
             if ((rc = fused_loss_launch(fw, st))) return rc;

@@ -24,6 +24,14 @@ namespace {
 using namespace tc;
 
 constexpr int F_THREADS = 256;
+#ifndef FIN_PARTS_N
+#define FIN_PARTS_N 4
+#endif
+#ifndef FIN_UNROLL
+#define FIN_UNROLL 4
+#endif
+constexpr int FIN_UNROLL_C = FIN_UNROLL;
+constexpr int FIN_PARTS = FIN_PARTS_N;              // final reduction: work units per 16-byte slot
 constexpr int F_TILE = 128;                         // classes / queue slots per CTA
 constexpr int F_E_BYTES = 8 * BLOCK_BYTES;          // 128 KiB  embedding rows: [2 row-blocks][<=4 k-chunks][16 KiB]
 constexpr int F_DZ_BYTES = 2 * BLOCK_BYTES;         // 32 KiB   logit gradient of one 128-row block: [2 column chunks][16 KiB]
@@ -51,6 +59,8 @@ struct FP {
     const int64_t* mask_labels;     // ids of the WHOLE batch (queue mask, head.py:148-157), n_mask of them
     int n_mask;
     int accum_dw;                   // the projection gradient of this window is added to what the previous windows left
+    int row_helpers;                // this many spare CTAs form the instance row losses (0: tile 0 does)
+    int fin_early;                  // the partial reductions belong to the CTAs behind the instance tiles (see fused_loss_kernel)
     float T, eps, alpha, beta, sp, sn;
     const float* W;
     const float* queue[2];          // queue scored by modality m's queries: [0] = t_queue, [1] = v_queue  (head.py:162,168)
@@ -59,20 +69,26 @@ struct FP {
     const uint8_t *Ep, *ENp, *QNp;
     const uint8_t* QUp;             // bf16 tile images of the two queues [modality][tile][64 KiB], written by the prologue
     const float *en, *qn, *inv_e, *inv_q, *pos;
-    float2 *ms_inst, *zz_inst, *ms_nce;     // per-tile softmax statistics [tile][256 rows]: (max, sum exp) and (sum z, z_y)
+    float *ls_inst, *ls_nce;                // per-tile softmax statistics [tile][256 rows]: log2 sum_c 2^(z2_c) over the tile's columns
+    float2* zz_inst;                        // ... and (sum z, z_y) of the instance tiles (label smoothing / target logit)
     unsigned long long* dbg;                // optional phase timestamps [cta][16] (TRB_FUSED_DEBUG)
     uint4 *part_inst, *part_nce;            // partial dE tiles, bf16: [tile][row block][8-column chunk][128 rows] x 16 bytes
     float *dpos, *rows_inst, *rows_nce, *rows_ga, *losses, *d_inst, *d_nce, *d_ga, *d_proj;
-    unsigned* bar;                  // [0], [1] grid barriers, [2] prologue tasks done, [3] exit count; zero between launches
+    unsigned* bar;                  // [0] instance statistics, [1] partial tiles written, [2], [3] InfoNCE statistics per modality;
+                                    // zeroed by the prologue launch
     // _dequeue_and_enqueue (head.py:96-109) folded into the kernel: the InfoNCE / align CTAs, which reach the second grid barrier
     // long before the instance tiles, write the normalised keys and ids into the queues; the pointer moves after the barrier
     float* enq_queue[2];            // [0] = v_queue <- v_key_n, [1] = t_queue <- t_key_n; NULL = no enqueue
     int64_t *enq_ids, *enq_ptr;
     float* dbg_logits;              // optional [256][128] fp32 logits of instance tile dbg_tile (trb_moco_loss_debug_logits)
     int dbg_tile;
-    ProArgs pro;
-    int merged;                     // the prologue tasks run inside this kernel (InfoNCE / align CTAs)
 };
+
+// Programmatic dependent launch: the cooperative kernel is launched while the prologue still runs (its CTAs start as SMs free
+// up) and streams its W tiles; everything the prologue writes is touched only after griddep_wait().  Both are no-ops for a
+// launch without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -91,21 +107,25 @@ __device__ __forceinline__ uint32_t idesc(int M, int N, int a_mn, int b_mn) {
     return umma_idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned total) {
+// Grid-wide counters in two halves.  arrive: everything this CTA wrote so far is published (bar.sync, then one thread fences and
+// bumps the counter); wait: one thread spins until `total` CTAs have arrived.  CTAs that only produce (the instance tiles at
+// the second counter) arrive and move on; CTAs that only consume (the spare CTAs) wait without arriving.
+__device__ __forceinline__ void grid_arrive(unsigned* ctr) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(ctr, 1u);
+    }
+}
+__device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned total) {
+    if (threadIdx.x == 0) {
         const long long t0 = clock64();
         for (;;) {
             unsigned v;
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
             if (v >= total) break;
-            __nanosleep(40);
-            if (clock64() - t0 > 4000000000LL) {
-                printf("trb: fused loss grid barrier timed out (block %d, %u of %u)\n", blockIdx.x, v, total);
-                __trap();
-            }
+            __nanosleep(20);
+            if (clock64() - t0 > 4000000000LL) wait_timed_out(1);
         }
         __threadfence();
     }
@@ -132,8 +152,9 @@ __device__ __forceinline__ int sector_head(int w, int64_t ld, int c0) { return (
 // Warp w takes rows d = w + 8 i, so (d & 7) == w and (d >> 3) == i: the swizzled column part of the address is a per-thread
 // constant.  All loads of the tile are issued before the first use; `rot` staggers the row order between CTAs so that CTAs
 // sweeping the same rows of a power-of-two-pitched matrix do not hit the same DRAM channels in lock step.
+template <typename Mid>
 __device__ __forceinline__ void load_tile_bf16(const float* __restrict__ src, int64_t ld, int nrows, int rows_pad, int c0,
-                                               int ncols, int rot, uint8_t* wb, float* red) {
+                                               int ncols, int rot, uint8_t* wb, float* red, Mid&& mid) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = sector_head(w, ld, c0);
     const int groups = rows_pad >> 3;                      // 16 or 32 row groups
@@ -159,6 +180,7 @@ __device__ __forceinline__ void load_tile_bf16(const float* __restrict__ src, in
         for (int j = 0; j < 4; ++j) v[u][j] = (rv && cv[j]) ? __ldcg(r + cc[j]) : 0.f;   // L2 only: with a power-of-two pitch
                                                                                           // every row of the tile maps to the same L1 sets
     }
+    mid();                                                  // with the whole tile in flight
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
         const int i = (u + rot) & (groups - 1);
@@ -207,24 +229,26 @@ __device__ __forceinline__ void st_v8(float* p, const float* v) {
                  : "memory");
 }      // finite stand-in for -inf in the running maxima (exp underflows to exactly 0)
 
-// base-2 log-sum-exp of one row from the per-tile statistics ms[tile][256] = (max2, sum 2^(z2 - max2)); (M, S) = running start.
-// 32 independent loads in flight per batch: the loop is latency-, not bandwidth-bound.
-__device__ __forceinline__ float lse2_of_row(const float2* __restrict__ ms, int row, int tiles, float M, float S) {
-    for (int t0 = 0; t0 < tiles; t0 += 48) {
-        float2 a[48];
+// base-2 log-sum-exp of one row from the per-tile values ls[tile][256] = log2 sum_c 2^(z2_c) of that tile (4 bytes per row and
+// tile: this combine is bound by the bytes each SM pulls from L2, ~40 GB/s per SM); l0 = a first term (InfoNCE: the positive
+// logit; F_NEG for none).  All loads of a batch are in flight together.
+__device__ __forceinline__ float lse2_of_row(const float* __restrict__ ls, int row, int tiles, float l0) {
+    constexpr int B = 96;
+    float M = l0, S = 1.0f;                       // running max and sum of 2^(l - M); l0 = F_NEG contributes 2^(F_NEG - M) = 0 later
+    for (int t0 = 0; t0 < tiles; t0 += B) {
+        float a[B];
 #pragma unroll
-        for (int i = 0; i < 48; ++i) a[i] = __ldcg(ms + (size_t)min(t0 + i, tiles - 1) * 256 + row);
+        for (int i = 0; i < B; ++i) a[i] = __ldcg(ls + (size_t)min(t0 + i, tiles - 1) * 256 + row);
         asm volatile("" ::: "memory");
         float mb = M;
 #pragma unroll
-        for (int i = 0; i < 48; ++i) {
-            if (t0 + i >= tiles) a[i] = make_float2(F_NEG, 0.f);
-            a[i].x = fmaxf(a[i].x, F_NEG);
-            mb = fmaxf(mb, a[i].x);
+        for (int i = 0; i < B; ++i) {
+            a[i] = (t0 + i < tiles) ? fmaxf(a[i], F_NEG) : F_NEG;
+            mb = fmaxf(mb, a[i]);
         }
         float acc = S * ex2(M - mb);
 #pragma unroll
-        for (int i = 0; i < 48; ++i) acc += a[i].y * ex2(a[i].x - mb);
+        for (int i = 0; i < B; ++i) acc += ex2(a[i] - mb);
         M = mb; S = acc;
     }
     return M + log2f(S);
@@ -257,47 +281,14 @@ __device__ __forceinline__ float lane_transpose_sum(float (&u)[32], int lane) {
     return u[0];
 }
 
-// thread 0: spin until *ctr >= target (acquire), bounded like the other waits
-__device__ __forceinline__ void wait_count(const unsigned* ctr, unsigned target) {
-    const long long t0 = clock64();
-    for (;;) {
-        unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        if (v >= target) break;
-        __nanosleep(40);
-        if (clock64() - t0 > 4000000000LL) {
-            printf("trb: fused loss prologue wait timed out (block %d, %u of %u)\n", blockIdx.x, v, target);
-            __trap();
-        }
-    }
-    __threadfence();
-}
-
-// all threads: n16 16-byte words global (L2) -> shared, up to 32 loads in flight per thread
-__device__ __forceinline__ void copy_g2s(uint8_t* dst, const uint8_t* src, int n16) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(src);
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    for (int base = 0; base < n16; base += 32 * F_THREADS) {
-        uint4 x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = __ldcg(s4 + min(base + i * F_THREADS + (int)threadIdx.x, n16 - 1));
-        asm volatile("" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int idx = base + i * F_THREADS + (int)threadIdx.x;
-            if (idx < n16) d4[idx] = x[i];
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------------------
 // prologue tasks, one warp each.  Row task: fp32 artefacts of one padded embedding row as in loss_f32.cu's prologue (same
 // expressions) plus its slice of the three packed bf16 operand images (raw embeds, normalised embeds, normalised InfoNCE
 // queries), zero padded.  Pack task: one full row of a fp32 [D, K] queue (contiguous, DRAM friendly; a strided 128-column tile
 // read of the power-of-two-pitched queue crawls) -> bf16 into the per-tile shared-memory images
 // [tile][2 column chunks][256 d][128 B] that the InfoNCE CTAs copy in one piece.
-// They run either inside the cooperative kernel (all branches fused: the InfoNCE / align CTAs execute them while the instance
-// CTAs stream W) or as a separate launch (fused_prologue_kernel) when only some branches are fused.
+// They run as a separate small launch (fused_prologue_kernel) whose outputs reach the cooperative kernel by bulk copy while the
+// W tiles stream in.  (A one-launch form -- these tasks inside the cooperative kernel -- was measured slower and removed.)
 // ------------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pro_pack_task(const ProArgs& a, int mod, int d, int lane) {
     const int K = a.K, T_k = a.T_k;
@@ -408,29 +399,10 @@ __device__ __forceinline__ void pro_task(const ProArgs& a, int t, int lane) {
 
 // stand-alone prologue (some branches unfused): one warp per task, also clears the grid-barrier words
 __global__ void __launch_bounds__(256) fused_prologue_kernel(const ProArgs a, unsigned* __restrict__ bar, int ntasks) {
+    griddep_launch_dependents();         // the cooperative kernel may start streaming W now; it waits for this grid before it reads
     if (blockIdx.x == 0 && threadIdx.x < 4) bar[threadIdx.x] = 0u;
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (t < ntasks) pro_task(a, t, threadIdx.x & 31);
-}
-
-// All branches fused: the prologue tasks run inside the cooperative kernel.  The instance CTAs take the (cheap) embedding-row
-// tasks before they stream W, the InfoNCE / align CTAs the queue re-pack tasks; bar[2] counts CTAs past the row phase (all of
-// them), bar[3] the CTAs done with the queue images.
-__device__ __forceinline__ void run_prologue_rows(const FP& p) {        // instance CTAs
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int t = blockIdx.x * 8 + w; t < 256; t += p.n_inst * 8) pro_row_task(p.pro, t, lane);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(p.bar + 2, 1u);
-}
-__device__ __forceinline__ void run_prologue_pack(const FP& p) {        // InfoNCE / align CTAs
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nw = (p.n_nce + p.n_ga) * 8, Dp = p.KC * 64;
-    if (threadIdx.x == 0) atomicAdd(p.bar + 2, 1u);                      // no row tasks here
-    for (int t = (blockIdx.x - p.n_inst) * 8 + w; t < 2 * Dp; t += nw) pro_pack_task(p.pro, t / Dp, t % Dp, lane);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(p.bar + 3, 1u);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -452,44 +424,34 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     int64_t* s_lab = reinterpret_cast<int64_t*>(sm.DZ + 8192);           // [128] batch ids (InfoNCE mask)
     float* s_lse2 = reinterpret_cast<float*>(sm.DZ + 16384);             // [256] base-2 row log-sum-exp
 
-    if (p.merged) {
-        if (INST) run_prologue_rows(p);
-        else run_prologue_pack(p);
-    } else if (tid == 0) {
-        // operand rows (and, InfoNCE, the queue tile image) written by the prologue launch: bulk copies (TMA engine), in flight
-        // while the W tile streams in
-        const uint8_t* src = INST ? p.Ep : p.QNp + (size_t)mod * p.KC * BLOCK_BYTES;
-        const int blocks = MT * p.KC;
-        mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES + (INST ? 0u : (uint32_t)F_WB_BYTES));
-        for (int b = 0; b < blocks; ++b) bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, src + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
-        if (!INST) {
-            const uint8_t* qsrc = p.QUp + ((size_t)mod * p.T_k + tile) * F_WB_BYTES;
-            for (int b = 0; b < F_WB_BYTES / BLOCK_BYTES; ++b)
-                bulk_g2s(sm.WB + (size_t)b * BLOCK_BYTES, qsrc + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
+    // operand rows (and, InfoNCE, the queue tile image) are written by the prologue launch, which may still be running
+    // (programmatic dependent launch): wait for it, then thread 0 starts the bulk copies (TMA engine).  The instance tiles
+    // do this with their whole W tile already in flight.
+    auto after_prologue = [&]() {
+        griddep_wait();
+        if (tid == 0) {
+            const uint8_t* src = INST ? p.Ep : p.QNp + (size_t)mod * p.KC * BLOCK_BYTES;
+            const int blocks = MT * p.KC;
+            mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES + (INST ? 0u : (uint32_t)F_WB_BYTES));
+#pragma unroll 1
+            for (int b = 0; b < blocks; ++b) bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, src + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
+            if (!INST) {
+                const uint8_t* qsrc = p.QUp + ((size_t)mod * p.T_k + tile) * F_WB_BYTES;
+#pragma unroll 1
+                for (int b = 0; b < F_WB_BYTES / BLOCK_BYTES; ++b)
+                    bulk_g2s(sm.WB + (size_t)b * BLOCK_BYTES, qsrc + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
+            }
         }
-    }
+    };
     int64_t slot_id = -1;
     if (!INST) {
         s_lab[tid] = tid < p.n_mask ? p.mask_labels[tid] : INT64_MIN;       // 256 threads: up to 256 batch ids
         if (tid < 128 && c0 + tid < ncols) slot_id = p.id_queue[c0 + tid];
+        after_prologue();
     }
 
     // ---- instance: W tile HBM -> bf16 shared image, column norms
-    if (INST) load_tile_bf16(p.W, ncols, p.D, Dp, c0, ncols, (tile * 7) & 31, sm.WB, red);
-    // ---- merged mode: the operand images come from prologue tasks of other CTAs of this very grid: wait for them, then plain
-    //      L2 loads (no cross-proxy question)
-    if (p.merged) {
-        if (tid == 0) {
-            wait_count(p.bar + 2, gridDim.x);
-            if (!INST) wait_count(p.bar + 3, (unsigned)(p.n_nce + p.n_ga));
-        }
-        __syncthreads();
-        if (INST) copy_g2s(sm.E, p.Ep, MT * p.KC * (BLOCK_BYTES / 16));
-        else {
-            copy_g2s(sm.E, p.QNp + (size_t)mod * p.KC * BLOCK_BYTES, p.KC * (BLOCK_BYTES / 16));
-            copy_g2s(sm.WB, p.QUp + ((size_t)mod * p.T_k + tile) * F_WB_BYTES, F_WB_BYTES / 16);
-        }
-    }
+    if (INST) load_tile_bf16(p.W, ncols, p.D, Dp, c0, ncols, (tile * 7) & 31, sm.WB, red, after_prologue);
     __syncthreads();
     if (tid < 128) {
         bool ok = c0 + tid < ncols;
@@ -517,11 +479,12 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
 
     // ---- forward logits: z[mt] = E[mt] . Wb   (M = 128 rows, N = 128 columns, K = Dp)
     if (tid == 0) {
-        if (!p.merged) mbar_wait(sm.bar_load, 0);
+        mbar_wait(sm.bar_load, 0);
         tc_fence_after();
         const uint32_t id_f = idesc(128, 128, 0, 1);
         const uint32_t e0 = smem_u32(sm.E), wb0 = smem_u32(sm.WB);
         for (int mt = 0; mt < MT; ++mt)
+#pragma unroll 1
             for (int ks = 0; ks < Dp / 16; ++ks)
                 umma_bf16(tmem + mt * 128, umma_desc_sw128(e0 + (mt * p.KC + (ks >> 2)) * BLOCK_BYTES + (ks & 3) * 32),
                           desc_mn(wb0 + ks * 2048, F_WB_CHUNK), id_f, (uint32_t)(ks > 0));
@@ -575,28 +538,34 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
         }
         if (n < N) {
             const size_t at = (size_t)tile * 256 + (INST ? h : mod) * 128 + n;
-            (INST ? p.ms_inst : p.ms_nce)[at] = make_float2(m, s);
+            (INST ? p.ls_inst : p.ls_nce)[at] = m + log2f(s);      // s >= 1 (the maximum contributes 2^0)
             if (INST) p.zz_inst[at] = make_float2(sz2 * F_LN2, zy2 * F_LN2);
         }
     }
     F_STAMP(3);
 
-    grid_barrier(p.bar, gridDim.x);
+    // the row statistics of a loss only involve its own tiles: one counter per group (instance; InfoNCE per modality), so the
+    // InfoNCE tiles never wait for the (later) instance tiles
+    {
+        unsigned* ctr = INST ? p.bar : p.bar + 2 + mod;
+        grid_arrive(ctr);
+        grid_wait(ctr, (unsigned)tiles);
+    }
     F_STAMP(4);
 
     // ---- row log-sum-exp over all tiles (one thread per row, shared through shared memory); the first tile writes the row losses
     if (h < MT && n < N) {
         if (INST) {
             const int row = h * 128 + n;
-            const float l2 = lse2_of_row(p.ms_inst, row, tiles, F_NEG, 0.f);
+            const float l2 = lse2_of_row(p.ls_inst, row, tiles, F_NEG);
             s_lse2[row] = l2;
-            if (tile == 0) {                                                    // losses.py:26-39 with label smoothing
+            if (tile == 0 && p.row_helpers == 0) {                              // losses.py:26-39 with label smoothing (else: spare CTAs)
                 const float2 zz = sum_of_row(p.zz_inst, row, tiles);
                 p.rows_inst[h * p.NS + n] = bad_label ? CUDART_NAN_F : l2 * F_LN2 - (1.0f - p.eps) * zz.y - (p.eps / (float)p.C) * zz.x;
             }
         } else {
             const float z02 = __fdiv_rn(p.pos[mod * p.NS + n], p.T) * F_LOG2E;     // column 0 of the reference's logits (base 2)
-            const float l2 = lse2_of_row(p.ms_nce, mod * 128 + n, tiles, z02, 1.0f);
+            const float l2 = lse2_of_row(p.ls_nce, mod * 128 + n, tiles, z02);
             s_lse2[n] = l2;
             if (tile == 0) {                                                    // losses.py:206-217, target 0
                 p.rows_nce[mod * p.NS + n] = (l2 - z02) * F_LN2;                // exactly 0 when only the positive is left
@@ -617,16 +586,18 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
         const float uni_hot = uni + (INST ? 1.0f - p.eps : 0.f);
         const bool do_dw = INST && p.d_proj != nullptr;
         const int NH = Dp / 128;
-        float csum[2] = {0.f, 0.f};                    // <dz', z2>_rows of this thread's two 32-column chunks (column = lane)
+        float csum0 = 0.f, csum1 = 0.f;                // <dz', z2>_rows of this thread's two 32-column chunks (column = lane)
         // TMEM columns: Z0 = [0,128) and Z1 = [128,256) hold the logits of row blocks 0 / 1, W0|W1 = [256,512) the dWs accumulator.
         // Row block 0: dE halves go to Z0 (its logits are consumed) and W0 (dWs has not started); once they are drained, dWs(0)
         // is issued and runs under the gradient math of row block 1.  Row block 1: dE halves go to Z1 and Z0, dWs(1)
         // accumulates on top; one wait, one drain.
-#pragma unroll
+        // Real loops (no unrolling over row blocks / chunks): the kernel is instruction-fetch bound when this is straight-line
+        // code (ncu: `no instruction` was the top stall reason), so every body below is fetched once and re-used.
+#pragma unroll 1
         for (int mt = 0; mt < MT; ++mt) {
-            // -- logit gradient of row block mt -> bf16 (thread = row n, 64 columns of chunk h), staged in registers
-            uint4 o[2][4];
-#pragma unroll
+            const float lse_mt = mt == 0 ? lse2[0] : lse2[MT - 1];
+            // -- logit gradient of row block mt -> bf16 (thread = row n, 64 columns of chunk h)
+#pragma unroll 1
             for (int jj = 0; jj < 2; ++jj) {
                 const int j = h * 2 + jj;
                 const int yy = y - j * 32;
@@ -636,27 +607,29 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                 for (int i = 0; i < 32; ++i) {
                     const float sc2 = sm.col[j * 32 + i].x;
                     const float z2 = v[i] * sc2;
-                    const float g = ex2(z2 - lse2[mt]) - ((i == yy) ? uni_hot : uni);
+                    const float g = ex2(z2 - lse_mt) - ((i == yy) ? uni_hot : uni);
                     v[i] = g * (sc2 * rs);                         // exactly 0 for excluded columns and padding rows
                     u[i] = v[i] * z2;
                 }
+                uint4 o[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    o[jj][k].x = pack2(v[8 * k + 0], v[8 * k + 1]); o[jj][k].y = pack2(v[8 * k + 2], v[8 * k + 3]);
-                    o[jj][k].z = pack2(v[8 * k + 4], v[8 * k + 5]); o[jj][k].w = pack2(v[8 * k + 6], v[8 * k + 7]);
+                    o[k].x = pack2(v[8 * k + 0], v[8 * k + 1]); o[k].y = pack2(v[8 * k + 2], v[8 * k + 3]);
+                    o[k].z = pack2(v[8 * k + 4], v[8 * k + 5]); o[k].w = pack2(v[8 * k + 6], v[8 * k + 7]);
                 }
                 // <dWs, What>_col = sum_rows dz'[row, c] * z[row, c]  (dWs = E^T dz', z = E What): the column-normalisation
                 // Jacobian needs no second pass over W
-                if (do_dw) csum[jj] += lane_transpose_sum(u, lane);
-            }
-            if (mt == 1 && do_dw) {                    // dWs(0) still reads the previous image
-                mbar_wait_sleepy(sm.bar_dw, 0, 32);
-                tc_fence_after();
-            }
+                if (do_dw) {
+                    const float t = lane_transpose_sum(u, lane);
+                    if (jj) csum1 += t; else csum0 += t;
+                }
+                if (mt == 1 && jj == 0 && do_dw) {     // dWs(0) still reads the previous image
+                    mbar_wait_sleepy(sm.bar_dw, 0, 32);
+                    tc_fence_after();
+                }
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sm.DZ + dz_offset(h, n, jj * 4 + k)) = o[jj][k];
+                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sm.DZ + dz_offset(h, n, jj * 4 + k)) = o[k];
+            }
             tc_fence_before();
             fence_async_smem();
             __syncthreads();
@@ -671,6 +644,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                 // dE[row, d] = sum_c dz'[row, c] * Wb[d, c]           (M = 128 rows, N = d, K = 128 columns)
                 const uint32_t id_e = idesc(128, INST ? 128 : Dp, 0, 0);
                 for (int r = 0; r < (two ? 2 : 1); ++r)
+#pragma unroll 1
                     for (int ks = 0; ks < 8; ++ks)
                         umma_bf16(tmem + (r ? colB : colA), umma_desc_sw128(dz0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
                                   umma_desc_sw128(wb0 + (ks >> 2) * F_WB_CHUNK + r * (128 * 128) + (ks & 3) * 32), id_e,
@@ -679,6 +653,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                     // dWs[d, c] += sum_rows E[row, d] * dz'[row, c]   (M = 128 d per half, N = 128 columns, K = 128 rows)
                     const uint32_t id_w = idesc(128, 128, 1, 1);
                     for (int hh = 0; hh < NH; ++hh)
+#pragma unroll 1
                         for (int ks = 0; ks < 8; ++ks)
                             umma_bf16(tmem + 256 + hh * 128,
                                       desc_mn(e0 + (p.KC + 2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES),
@@ -694,20 +669,17 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             // [tile][row block][8-column chunk][128 rows] x 16 bytes: the 32 rows of a warp write 512 contiguous bytes
             if (INST) {
                 uint4* dst = p.part_inst + (size_t)(tile * 2 + mt) * (Dp / 8) * 128 + n;
+#pragma unroll 1
+                for (int rj = 0; rj < (two ? 4 : 2); ++rj) {
+                    const int r = rj >> 1, jj = rj & 1;
+                    float v[32];
+                    tmem_ld32(tmem + lanes + (r ? colB : colA) + (uint32_t)(h * 64 + jj * 32), v);
+                    if (n < N) {
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    if (r == 1 && !two) break;
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        float v[32];
-                        tmem_ld32(tmem + lanes + (r ? colB : colA) + (uint32_t)(h * 64 + jj * 32), v);
-                        if (n < N) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                __stcg(dst + (size_t)(r * 16 + h * 8 + jj * 4 + k) * 128,
-                                       make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
-                                                  pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
-                        }
+                        for (int k = 0; k < 4; ++k)
+                            __stcg(dst + (size_t)(r * 16 + h * 8 + jj * 4 + k) * 128,
+                                   make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
+                                              pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
                     }
                 }
             } else {
@@ -734,6 +706,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                 const uint32_t e0 = smem_u32(sm.E), dz0 = smem_u32(sm.DZ);
                 const uint32_t id_w = idesc(128, 128, 1, 1);
                 for (int hh = 0; hh < NH; ++hh)
+#pragma unroll 1
                     for (int ks = 0; ks < 8; ++ks)
                         umma_bf16(tmem + 256 + hh * 128, desc_mn(e0 + (2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES),
                                   desc_mn(dz0 + ks * 2048, BLOCK_BYTES), id_w, (uint32_t)(ks > 0));
@@ -741,6 +714,9 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             }
         }
         F_STAMP(6);
+        // the partial dE tiles are out: the CTAs that reduce them (InfoNCE / align / spare CTAs, see fused_loss_kernel) can start
+        // while this CTA still writes its dW tile
+        if (INST && p.fin_early) grid_arrive(p.bar + 1);
 
         if (do_dw) {
             // ---- dW tile = dWs - What * <dWs, What>_col   (dWs already carries the 1/||w|| factor)       losses.py:51
@@ -759,7 +735,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                 }
             }
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) red[q * 128 + (h * 2 + jj) * 32 + lane] = csum[jj];
+            for (int jj = 0; jj < 2; ++jj) red[q * 128 + (h * 2 + jj) * 32 + lane] = jj ? csum1 : csum0;
             __syncthreads();
             F_STAMP(14);
             bool cv[4];
@@ -817,6 +793,8 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             }
         }
         F_STAMP(7);
+    } else if (INST && p.fin_early) {
+        grid_arrive(p.bar + 1);
     }
 }
 
@@ -845,16 +823,11 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
     int64_t* s_lab = reinterpret_cast<int64_t*>(sm.WB);                 // [128]
     float* s_part = reinterpret_cast<float*>(sm.WB + 2048);             // [2][128]
 
-    // nothing here depends on the tiles' statistics: arrive at the first grid barrier right away, never wait on it
-    if (tid == 0) atomicAdd(p.bar, 1u);
-    if (p.merged) {
-        run_prologue_pack(p);
-        if (tid == 0) wait_count(p.bar + 2, gridDim.x);
-        __syncthreads();
-        copy_g2s(sm.E, p.ENp, 2 * p.KC * (BLOCK_BYTES / 16));
-    } else if (tid == 0) {
+    griddep_wait();
+    if (tid == 0) {
         const int blocks = 2 * p.KC;
         mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES);
+#pragma unroll 1
         for (int b = 0; b < blocks; ++b) bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, p.ENp + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
     }
     if (tid < 128) s_lab[tid] = tid < N ? p.labels[tid] : INT64_MIN;
@@ -863,9 +836,10 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
     const uint32_t e0 = smem_u32(sm.E), dz0 = smem_u32(sm.DZ);
     const uint32_t et0 = e0 + p.KC * BLOCK_BYTES;                       // text rows
     if (tid == 0) {
-        if (!p.merged) mbar_wait(sm.bar_load, 0);
+        mbar_wait(sm.bar_load, 0);
         tc_fence_after();
         const uint32_t id_s = idesc(128, 128, 0, 0);
+#pragma unroll 1
         for (int ks = 0; ks < Dp / 16; ++ks)
             umma_bf16(tmem, umma_desc_sw128(e0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
                       umma_desc_sw128(et0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32), id_s, (uint32_t)(ks > 0));
@@ -912,17 +886,21 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
     __syncthreads();
     if (h == 0 && n < N) p.rows_ga[n] = s_part[n] + s_part[128 + n];
     F_STAMP(3);
+    // nothing the reducing CTAs need comes after the row losses: arrive now, the gradient below runs beside the reductions
+    if (p.fin_early) grid_arrive(p.bar + 1);
 
     if (p.want_grad) {
         if (tid == 0) {
             tc_fence_after();
             // dq_v[i, d] = sum_j dS[i, j] en_t[j, d]   -> columns [256, 256 + Dp)
             const uint32_t id_v = idesc(128, Dp, 0, 1);
+#pragma unroll 1
             for (int ks = 0; ks < 8; ++ks)
                 umma_bf16(tmem + 256, umma_desc_sw128(dz0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
                           desc_mn(et0 + ks * 2048, BLOCK_BYTES), id_v, (uint32_t)(ks > 0));
             // dq_t[j, d] = sum_i dS[i, j] en_v[i, d]   -> columns [0, Dp)
             const uint32_t id_t = idesc(128, Dp, 1, 1);
+#pragma unroll 1
             for (int ks = 0; ks < 8; ++ks)
                 umma_bf16(tmem, desc_mn(dz0 + ks * 2048, BLOCK_BYTES), desc_mn(e0 + ks * 2048, BLOCK_BYTES), id_t,
                           (uint32_t)(ks > 0));
@@ -976,81 +954,93 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
     }
 }
 
-// after the second grid barrier: every CTA takes an equal share of the fixed-order partial reductions
-__device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const int N = p.N, D = p.D, Dp = p.KC * 64, G = gridDim.x;
-    // the last CTA only forms the loss scalars; the partial reductions are shared by the others
-    const int GW = p.reduce_losses && G > 1 ? G - 1 : G;
-    const bool worker = blockIdx.x < GW;
-    if (p.want_grad && p.n_inst && worker) {
-        // d_inst[row, 8 columns] = sum_tiles partial: three threads per item (a third of the tiles each, all their 16-byte loads in
-        // flight at once), partial sums combined through shared memory in a fixed order.
-        // Item = ((mod * D/8 + c8) * N + row): consecutive threads take consecutive rows (contiguous loads).
-        constexpr int PARTS = 3, MAXT = 32;                      // up to 96 tiles in one batch; more tiles loop
-        const int per_mod = (D / 8) * N, items = 2 * per_mod;
-        const int per_cta = (items + GW - 1) / GW;
-        const size_t tstride = (size_t)2 * (Dp / 8) * 128;
-        const int lo = blockIdx.x * per_cta, hi = min(items, lo + per_cta);
-        float* comb = reinterpret_cast<float*>(sm.DZ);           // [<= 85 items][PARTS][8]
-        const int chunk = min(per_cta, F_THREADS / PARTS);       // items per pass
-        const int tper = (p.T_inst + PARTS - 1) / PARTS;         // tiles per part
-        for (int base = lo; base < hi; base += chunk) {
-            const int local = tid % chunk, part = tid / chunk;   // part-major: a warp reads consecutive rows of one tile
-            const int item = base + local;
-            const bool live = part < PARTS && item < hi;
-            if (live) {
-                const int nn = item % N, t = item / N;
-                const int c8 = t % (D / 8), mod = t / (D / 8);
-                const uint4* src = p.part_inst + (size_t)(mod * (Dp / 8) + c8) * 128 + nn;
-                const int tlo = part * tper, thi = min(p.T_inst, tlo + tper);
-                float acc[8];
+// Instance row losses (losses.py:26-39 with label smoothing) on spare CTA `hs` of `H`: the sums of z and z_y over all tiles are
+// 176 KB that only the loss value needs -- on tile 0 they made that CTA the straggler of the whole grid.  One warp per row,
+// lanes over the tiles (at most 160), fixed shuffle order.
+__device__ __forceinline__ void spare_rows_program(const FP& p, int hs, int H) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.T_inst;
+#pragma unroll 1
+    for (int r = hs * 8 + w; r < 2 * p.N; r += H * 8) {
+        const int mod = r / p.N, n = r - mod * p.N, srow = mod * 128 + n;
+        float l[5];
+        float2 z[5];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-                for (int t0 = tlo; t0 < thi; t0 += MAXT) {
-                    uint4 x[MAXT];
+        for (int i = 0; i < 5; ++i) {
+            const int t = lane + 32 * i;
+            l[i] = t < tiles ? fmaxf(__ldcg(p.ls_inst + (size_t)t * 256 + srow), F_NEG) : F_NEG;
+            z[i] = t < tiles ? __ldcg(p.zz_inst + (size_t)t * 256 + srow) : make_float2(0.f, 0.f);
+        }
+        float M = fmaxf(fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3])), l[4]);
+        M = warp_max(M);
+        float S = 0.f, sx = 0.f, sy = 0.f;
 #pragma unroll
-                    for (int i = 0; i < MAXT; ++i) x[i] = __ldcg(src + (size_t)min(t0 + i, thi - 1) * tstride);
-                    asm volatile("" ::: "memory");
-#pragma unroll
-                    for (int i = 0; i < MAXT; ++i) {
-                        if (t0 + i < thi) {
-                            const uint32_t r[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                acc[2 * k] += __uint_as_float(r[k] << 16);
-                                acc[2 * k + 1] += __uint_as_float(r[k] & 0xffff0000u);
-                            }
-                        }
-                    }
-                }
-                float4* o = reinterpret_cast<float4*>(comb + (size_t)(local * PARTS + part) * 8);
-                o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            }
-            __syncthreads();
-            if (tid < chunk && base + tid < hi) {
-                const int item2 = base + tid;
-                const int nn = item2 % N, t = item2 / N;
-                const int c8 = t % (D / 8), mod = t / (D / 8);
-                float out[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) out[e] = (comb[(tid * PARTS + 0) * 8 + e] + comb[(tid * PARTS + 1) * 8 + e]) + comb[(tid * PARTS + 2) * 8 + e];
-                st_v8(p.d_inst + ((size_t)(mod * p.NS + nn) * D + c8 * 8), out);
-            }
-            __syncthreads();
+        for (int i = 0; i < 5; ++i) {
+            S += (lane + 32 * i < tiles) ? ex2(l[i] - M) : 0.f;
+            sx += z[i].x; sy += z[i].y;
+        }
+        S = warp_sum(S); sx = warp_sum(sx); sy = warp_sum(sy);
+        if (lane == 0) {
+            const int64_t lab = p.labels[n];
+            const bool bad_label = lab < 0 || lab >= (int64_t)p.C;       // the reference raises; here the row's loss becomes NaN
+            const float l2 = M + log2f(S);
+            p.rows_inst[mod * p.NS + n] = bad_label ? CUDART_NAN_F : l2 * F_LN2 - (1.0f - p.eps) * sy - (p.eps / (float)p.C) * sx;
         }
     }
+}
+
+// after the second grid barrier: every CTA takes an equal share of the fixed-order partial reductions
+// `fi` of `G` finishing CTAs
+__device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm, int fi, int G) {
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int N = p.N, D = p.D, Dp = p.KC * 64;
+    // the last CTA only forms the loss scalars; the partial reductions are shared by the others
+    const int GW = p.reduce_losses && G > 1 ? G - 1 : G;
+    const bool worker = fi < GW;
+    // d_inst[row, 8 columns] = sum over the instance tiles of their partial tiles.  One tile's partial is M = 2 * (Dp/8) * 128
+    // 16-byte slots in memory order [row block][8-column chunk][row]; a finishing CTA owns one contiguous slot range, so its
+    // share of EVERY tile is one contiguous piece; asynchronous copies land all of them in shared memory at
+    // once (one L2 round trip instead of one per register batch), issued before and completed under the InfoNCE rows below.
+    const bool inst_work = p.want_grad && p.n_inst && worker;
+    const int M = 2 * (Dp / 8) * 128;
+    const int per_cta = (M + GW - 1) / GW;
+    const int lo = fi * per_cta, hi = min(M, lo + per_cta);
+    const int chunk = max(1, min(per_cta, (int)(F_OFF_MISC / (16 * p.T_inst + 32 * FIN_PARTS))));     // slots per pass: data + combine scratch
+    uint8_t* buf = sm.E;                                     // E | DZ | WB are contiguous and dead by now
+    // 16-byte asynchronous copies (LDGSTS): no registers are held per load, so the whole share is in flight at once; warp w
+    // takes the tiles w, w + 8, ... (one contiguous piece each, consecutive lanes -> consecutive 16 bytes)
+    auto issue = [&](int base) {
+        const int cnt = min(chunk, hi - base);
+        __syncthreads();                                     // the previous pass (or phase) is done with the region
+#pragma unroll 1
+        for (int t = w; t < p.T_inst; t += F_THREADS / 32) {
+            const uint4* src = p.part_inst + (size_t)t * M + base;
+            const uint32_t dst = smem_u32(buf) + (uint32_t)(t * cnt) * 16u;
+#pragma unroll 1
+            for (int i = lane; i < cnt; i += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(src + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (inst_work && lo < hi) issue(lo);
+    F_STAMP(12);
     if (p.want_grad && p.n_nce) {      // (no block-level synchronisation below: idle CTAs / warps simply fall through)
         // d_nce[row] = normalise-backward( sum_tiles dq_part + dpos * key )   one warp per row, rows dealt round-robin to CTAs;
         // lane = 8-column chunk
-        for (int row = blockIdx.x + GW * (7 - w); worker && row < 2 * N; row += GW * 8) {
+        for (int row = fi + GW * (7 - w); worker && row < 2 * N; row += GW * 8) {
             const int mod = row / N, nn = row % N;
             const int grow = mod * p.NS + nn;                     // position in the full-batch arrays
-            const float dp = __ldcg(p.dpos + grow);
             const float* key = p.key_n[mod] + (int64_t)nn * D;
             const float* qr = p.qn + (int64_t)grow * D;
             const bool on = lane * 8 < D;
+            // every load of the row is issued before the first use: one L2 round trip, not four dependent ones
+            const float dp = __ldcg(p.dpos + grow);
+            const float inv = __ldcg(p.inv_q + grow);
+            float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, q0 = k0, q1 = k0;
+            if (on) {
+                k0 = __ldcg(reinterpret_cast<const float4*>(key + lane * 8)); k1 = __ldcg(reinterpret_cast<const float4*>(key + lane * 8 + 4));
+                q0 = __ldcg(reinterpret_cast<const float4*>(qr + lane * 8)); q1 = __ldcg(reinterpret_cast<const float4*>(qr + lane * 8 + 4));
+            }
             float g[8], qv[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) g[e] = qv[e] = 0.f;
@@ -1074,8 +1064,6 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
                         }
                     }
                 }
-                const float4 k0 = *reinterpret_cast<const float4*>(key + lane * 8), k1 = *reinterpret_cast<const float4*>(key + lane * 8 + 4);
-                const float4 q0 = *reinterpret_cast<const float4*>(qr + lane * 8), q1 = *reinterpret_cast<const float4*>(qr + lane * 8 + 4);
                 const float kk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
                 const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
@@ -1086,7 +1074,6 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
                 }
             }
             dot = warp_sum(dot);
-            const float inv = p.inv_q[grow];
             if (on) {
                 float o[8];
 #pragma unroll
@@ -1095,7 +1082,68 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
             }
         }
     }
-    if (p.reduce_losses && blockIdx.x == G - 1) {
+    F_STAMP(13);
+    if (inst_work) {
+        for (int base = lo; base < hi; base += chunk) {
+            const int cnt = min(chunk, hi - base);
+            if (base > lo) issue(base);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            F_STAMP(14);
+            // FIN_PARTS work units per slot (a quarter of the tiles each, fixed order), combined through shared memory
+            // (slot-minor layout: consecutive threads touch consecutive 16-byte words -- no bank conflicts)
+            float4* comb = reinterpret_cast<float4*>(buf + (size_t)p.T_inst * cnt * 16);    // [FIN_PARTS][2][cnt] x 16 bytes
+            const int th = (p.T_inst + FIN_PARTS - 1) / FIN_PARTS;
+#ifdef FIN_WARPSTAMPS
+            if (p.dbg != nullptr && lane == 0) p.dbg[blockIdx.x * 16 + 8 + w] = globaltimer_ns();
+#endif
+            for (int u = tid; u < FIN_PARTS * cnt; u += F_THREADS) {
+                const int i = u % cnt, part = u / cnt;
+                const int tlo = part * th, thi = min(p.T_inst, tlo + th);
+                const uint4* src = reinterpret_cast<const uint4*>(buf) + i;
+                float acc[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll FIN_UNROLL_C
+                for (int t = tlo; t < thi; ++t) {
+                    const uint4 x = src[(size_t)t * cnt];
+                    const uint32_t r[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#ifdef FIN_NOALU
+                        acc[2 * k] = __uint_as_float(__float_as_uint(acc[2 * k]) ^ r[k]);
+#else
+                        acc[2 * k] += __uint_as_float(r[k] << 16);
+                        acc[2 * k + 1] += __uint_as_float(r[k] & 0xffff0000u);
+#endif
+                    }
+                }
+                comb[(part * 2 + 0) * cnt + i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                comb[(part * 2 + 1) * cnt + i] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+#ifdef FIN_WARPSTAMPS
+            if (p.dbg != nullptr && lane == 0) p.dbg[blockIdx.x * 16 + w] = globaltimer_ns();
+#endif
+            __syncthreads();
+            F_STAMP(15);
+            for (int i = tid; i < cnt; i += F_THREADS) {
+                const int m = base + i, g = m >> 7, row = m & 127;
+                const int mt = g / (Dp / 8), c8 = g % (Dp / 8);
+                if (row < N && c8 * 8 < D) {
+                    float4 a = comb[i], c = comb[cnt + i];
+#pragma unroll
+                    for (int q = 1; q < FIN_PARTS; ++q) {
+                        const float4 x = comb[(q * 2) * cnt + i], y = comb[(q * 2 + 1) * cnt + i];
+                        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+                        c.x += y.x; c.y += y.y; c.z += y.z; c.w += y.w;
+                    }
+                    const float out[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+                    st_v8(p.d_inst + ((size_t)(mt * p.NS + row) * D + c8 * 8), out);
+                }
+            }
+        }
+    }
+    if (p.reduce_losses && fi == G - 1) {
         float a = 0.f, b = 0.f, c = 0.f;
         for (int i = tid; i < 2 * N; i += F_THREADS) { a += __ldcg(p.rows_inst + i); b += __ldcg(p.rows_nce + i); }
         for (int i = tid; i < N; i += F_THREADS) c += __ldcg(p.rows_ga + i);
@@ -1114,30 +1162,34 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm) {
 // of writing past the row / the allocation.
 __device__ __forceinline__ void enqueue_slice(const FP& p, int part, int parts) {
     const int N = p.N, D = p.D, K = p.K;
-    const int64_t ptr = *p.enq_ptr;
-    const int total = 2 * D * N;
-    const int per = (total + parts - 1) / parts;
-    const int lo = part * per, hi = min(total, lo + per);
-    for (int e0 = lo + (int)threadIdx.x; e0 < hi; e0 += 8 * F_THREADS) {
-        float x[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = (int)(((*p.enq_ptr % K) + K) % K);        // one 64-bit division per thread; 32-bit arithmetic below
+    // one warp per queue row (modality, d): lanes sweep the N batch columns, four loads in flight per lane
+#pragma unroll 1
+    for (int r = part * 8 + w; r < 2 * D; r += parts * 8) {
+        const int mod = r >= D, d = r - mod * D;
+        const float* src = (mod ? p.key_n[0] : p.key_n[1]) + d;                     // key_n[0] = t_key_n, key_n[1] = v_key_n
+        float* dst = p.enq_queue[mod] + (int64_t)d * K;
+#pragma unroll 1
+        for (int n0 = lane; n0 < N; n0 += 128) {
+            float x[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int e = min(e0 + i * F_THREADS, hi - 1);
-            const int mod = e / (D * N), r = e % (D * N), d = r / N, n = r % N;
-            x[i] = __ldcg((mod ? p.key_n[0] : p.key_n[1]) + (int64_t)n * D + d);     // key_n[0] = t_key_n, key_n[1] = v_key_n
-        }
+            for (int i = 0; i < 4; ++i) x[i] = __ldcg(src + (int64_t)min(n0 + 32 * i, N - 1) * D);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int e = e0 + i * F_THREADS;
-            if (e < hi) {
-                const int mod = e / (D * N), r = e % (D * N), d = r / N, n = r % N;
-                const int64_t col = (((ptr + n) % K) + K) % K;
-                p.enq_queue[mod][(int64_t)d * K + col] = x[i];
+            for (int i = 0; i < 4; ++i) {
+                const int n = n0 + 32 * i;
+                int col = p0 + n;
+                col -= col >= K ? K : 0;
+                if (n < N) dst[col] = x[i];
             }
         }
     }
     if (part == parts - 1)
-        for (int n = threadIdx.x; n < N; n += F_THREADS) p.enq_ids[(((ptr + n) % K) + K) % K] = p.labels[n];
+        for (int n = threadIdx.x; n < N; n += F_THREADS) {
+            int col = p0 + n;
+            col -= col >= K ? K : 0;
+            p.enq_ids[col] = p.labels[n];
+        }
 }
 
 __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
@@ -1161,45 +1213,61 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
         mbar_init(sm.bar_dw, 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(sm.tmem_slot, 512);
+    // CTA roles by block index: instance tiles, InfoNCE tiles, the align CTA, then SPARE CTAs (the rest of the SMs) that own no
+    // tile and only take part in the reductions at the end
+    const int b = blockIdx.x, G = (int)gridDim.x;
+    const int n_tiles = p.n_inst + p.n_nce + p.n_ga;
+    const bool has_tile = b < n_tiles;
+    if (warp == 0 && has_tile) tmem_alloc(sm.tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *sm.tmem_slot;
+    const uint32_t tmem = has_tile ? *sm.tmem_slot : 0u;
     F_STAMP(0);
 
-    const int b = blockIdx.x;
     if (b < p.n_inst) tile_program<true>(p, sm, tmem, 0, b);
     else if (b < p.n_inst + p.n_nce) tile_program<false>(p, sm, tmem, (b - p.n_inst) / p.T_k, (b - p.n_inst) % p.T_k);
-    else align_program(p, sm, tmem);
+    else if (has_tile) align_program(p, sm, tmem);
+    else griddep_wait();                 // spare CTAs: the counters they poll are cleared by the prologue launch
 
-    if (p.enq_ptr != nullptr && b >= p.n_inst) enqueue_slice(p, b - p.n_inst, p.n_nce + p.n_ga);
-    grid_barrier(p.bar + 1, gridDim.x);
-    F_STAMP(8);
-    // every enqueue slice has read the old pointer before the barrier: head.py:108-109
-    if (p.enq_ptr != nullptr && b == (int)gridDim.x - 1 && threadIdx.x == 0) *p.enq_ptr = (*p.enq_ptr + p.N) % p.K;
-    finish_phase(p, sm);
-    F_STAMP(9);
+    // Second counter: every tile CTA arrives once its partial dE tiles (and enqueue slice) are written.  With `fin_early` the
+    // instance tiles -- the longest chain of the kernel -- arrived before their dW epilogue (tile_program), the align CTA after
+    // its row losses (align_program), and both are done here: the fixed-order reductions of the partial tiles belong to the
+    // InfoNCE CTAs (which finish early) and the spare CTAs, so they run UNDER the dW writes instead of after them.
+    // Otherwise every CTA reduces a share.
+    const bool is_nce = b >= p.n_inst && b < p.n_inst + p.n_nce;
+    if (p.enq_ptr != nullptr && (is_nce || (has_tile && b >= p.n_inst && !p.fin_early)))
+        enqueue_slice(p, b - p.n_inst, p.n_nce + (p.fin_early ? 0 : p.n_ga));
+    const bool finisher = !p.fin_early || is_nce || !has_tile;
+    if (!has_tile && b - n_tiles < p.row_helpers) {          // spare CTAs: instance row losses once every tile's statistics are out
+        grid_wait(p.bar, (unsigned)p.n_inst);
+        spare_rows_program(p, b - n_tiles, p.row_helpers);
+        grid_arrive(p.bar + 1);
+    }
+    if (has_tile && (!p.fin_early || is_nce)) grid_arrive(p.bar + 1);
+    if (finisher) {
+        const int fi = !p.fin_early ? b : (is_nce ? b - p.n_inst : b - p.n_inst - p.n_ga);
+        const int nf = !p.fin_early ? G : G - p.n_inst - p.n_ga;
+        grid_wait(p.bar + 1, (unsigned)(n_tiles + p.row_helpers));
+        F_STAMP(8);
+        // every enqueue slice has read the old pointer before it arrived: head.py:108-109
+        if (p.enq_ptr != nullptr && fi == nf - 1 && threadIdx.x == 0) *p.enq_ptr = (*p.enq_ptr + p.N) % p.K;
+        finish_phase(p, sm, fi, nf);
+        F_STAMP(9);
+    }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0 && has_tile) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
-    }
-    // no prologue launch clears the barrier words in merged mode: the last CTA to leave puts them back to zero
-    if (p.merged && threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(p.bar + 4, 1u) == gridDim.x - 1) {
-            p.bar[0] = 0u; p.bar[1] = 0u; p.bar[2] = 0u; p.bar[3] = 0u; p.bar[4] = 0u;
-            __threadfence();
-        }
     }
 }
 
 struct Scratch {
     uint8_t *Ep, *ENp, *QNp, *QUp;
-    float2 *ms_inst, *zz_inst, *ms_nce;
+    float *ls_inst, *ls_nce;
+    float2* zz_inst;
     uint4 *part_inst, *part_nce;
     unsigned* bar;
     unsigned long long* dbg;       // [160][16] phase timestamps (TRB_FUSED_DEBUG)
@@ -1217,9 +1285,9 @@ Scratch carve_scratch(uint8_t* base, int N, int D, int K, int C) {
     const int64_t img = (int64_t)2 * KC * BLOCK_BYTES;
     s.Ep = take(img); s.ENp = take(img); s.QNp = take(img);
     s.QUp = take((int64_t)2 * T_k * F_WB_BYTES);
-    s.ms_inst = reinterpret_cast<float2*>(take((int64_t)256 * T_inst * 8));
+    s.ls_inst = reinterpret_cast<float*>(take((int64_t)256 * T_inst * 4));
     s.zz_inst = reinterpret_cast<float2*>(take((int64_t)256 * T_inst * 8));
-    s.ms_nce = reinterpret_cast<float2*>(take((int64_t)256 * T_k * 8));
+    s.ls_nce = reinterpret_cast<float*>(take((int64_t)256 * T_k * 4));
     s.part_inst = reinterpret_cast<uint4*>(take((int64_t)T_inst * 256 * Dp * 2));
     s.part_nce = reinterpret_cast<uint4*>(take((int64_t)2 * T_k * 128 * Dp * 2));
     s.bar = reinterpret_cast<unsigned*>(take(256));
@@ -1272,14 +1340,7 @@ static ProArgs make_pro_args(const FusedLossArgs& a, const Scratch& s) {
     return q;
 }
 
-// Measured on B200 (profiles/r01_loss_fused.md): running the prologue tasks inside the cooperative kernel costs more on its
-// critical path (row tasks + flag wait + operand copy through registers, 52 us) than the separate small launch whose outputs
-// arrive by bulk copy under the W stream (48 us), so the two-launch form is the default; TRB_FUSED_MERGED=1 selects the
-// one-launch form.
-static bool merged_prologue(const FusedLossArgs& a) { return a.roles == 7 && getenv("TRB_FUSED_MERGED") != nullptr; }
-
 int fused_loss_prologue(const FusedLossArgs& a, cudaStream_t st) {
-    if (merged_prologue(a)) return 0;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a.scratch) + 1023) & ~uintptr_t(1023));
     const Scratch s = carve_scratch(base, a.N, a.D, a.K, a.C);
     static TrbDeviceOnce attr;
@@ -1318,7 +1379,7 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     p.labels = a.labels; p.id_queue = a.id_queue;
     p.Ep = s.Ep; p.ENp = s.ENp; p.QNp = s.QNp; p.QUp = s.QUp;
     p.en = a.en; p.qn = a.qn; p.inv_e = a.inv_e; p.inv_q = a.inv_q; p.pos = a.pos;
-    p.ms_inst = s.ms_inst; p.zz_inst = s.zz_inst; p.ms_nce = s.ms_nce;
+    p.ls_inst = s.ls_inst; p.zz_inst = s.zz_inst; p.ls_nce = s.ls_nce;
     // debug only (both live in the caller's workspace): phase timestamps of every CTA / the logits of one instance tile
     p.dbg = getenv("TRB_FUSED_DEBUG") ? s.dbg : nullptr;
     p.dbg_logits = nullptr;
@@ -1328,10 +1389,15 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     p.dpos = a.dpos; p.rows_inst = a.rows_inst; p.rows_nce = a.rows_nce; p.rows_ga = a.rows_ga;
     p.losses = a.losses; p.d_inst = a.d_inst; p.d_nce = a.d_nce; p.d_ga = a.d_ga; p.d_proj = a.d_proj;
     p.bar = s.bar;
-    p.pro = make_pro_args(a, s);
-    p.merged = merged_prologue(a) ? 1 : 0;
-    const int grid = p.n_inst + p.n_nce + p.n_ga;
-    if (grid == 0) return 0;
+    const int n_tiles = p.n_inst + p.n_nce + p.n_ga;
+    if (n_tiles == 0) return 0;
+    // one CTA per SM: the SMs without a tile get a spare CTA that only reduces partial tiles at the end
+    int dev = 0, sms = 0;
+    TRB_CUDA_OK(cudaGetDevice(&dev));
+    TRB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = n_tiles > sms ? n_tiles : sms;
+    p.fin_early = (p.n_inst > 0 && p.want_grad && grid - p.n_inst - p.n_ga >= 24) ? 1 : 0;
+    p.row_helpers = p.n_inst > 0 ? (grid - n_tiles < 16 ? grid - n_tiles : 16) : 0;
 
     static TrbDeviceOnce attr;
     if (trb_first_on_device(attr))
@@ -1343,11 +1409,15 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     cfg.blockDim = dim3(F_THREADS);
     cfg.dynamicSmemBytes = F_SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
+    // programmatic dependent launch behind the prologue kernel (TRB_FUSED_PDL=0 turns it off)
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = getenv("TRB_FUSED_NO_COOP") ? 0 : 1;
+    const char* pdl = getenv("TRB_FUSED_PDL");
+    cfg.numAttrs = (a.after_prologue && !(pdl && atoi(pdl) == 0)) ? 2 : 1;
     TRB_CUDA_OK(cudaLaunchKernelEx(&cfg, fused_loss_kernel, p));
     return 0;
 }

@@ -28,6 +28,7 @@ struct FusedLossArgs {
     const int64_t* mask_labels;
     int roles;          // bit 0 instance, bit 1 InfoNCE, bit 2 global-align: which branches the fused kernel runs
     int reduce_losses;  // the fused kernel also forms the three loss scalars (all roles fused)
+    int after_prologue; // this launch directly follows fused_loss_prologue on the stream (programmatic dependent launch allowed)
 };
 
 // shape gate: D a multiple of 64 up to 256, N <= 128, and one CTA per 128-class / 128-slot tile must fit the device

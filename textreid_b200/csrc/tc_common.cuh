@@ -60,15 +60,17 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
         : "memory");
     return ok != 0;
 }
-// Bounded waits: a protocol bug must surface as a trap (-> launch failure), never as a hung GPU.
+// Bounded waits: a protocol bug must surface as a trap (-> launch failure), never as a hung GPU.  The report is out of line
+// so that a wait costs a handful of instructions at its call site (the fused loss kernel is instruction-fetch sensitive).
+static __device__ __noinline__ void wait_timed_out(int what) {
+    printf("trb: %s wait timed out (block %d thread %d)\n", what == 0 ? "mbarrier" : "grid barrier", blockIdx.x, threadIdx.x);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {      // latency-critical single threads
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
-            printf("trb: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
+        if (clock64() - t0 > 4000000000LL) wait_timed_out(0);   // ~2 s at 2 GHz
     }
 }
 __device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {   // whole warps
@@ -76,10 +78,7 @@ __device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity,
     if (hint_ns == 0) { mbar_wait(bar, parity); return; }
     const long long t0 = clock64();
     while (!mbar_try_wait_hint(bar, parity, hint_ns)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("trb: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
+        if (clock64() - t0 > 4000000000LL) wait_timed_out(0);
     }
 }
 

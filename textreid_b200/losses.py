@@ -35,10 +35,8 @@ _workspaces: Dict[Tuple, torch.Tensor] = {}
 
 
 def _alloc_workspace(nbytes: int, device) -> torch.Tensor:
-    """The one-launch form of the fused kernel (TRB_FUSED_MERGED=1) needs its grid-barrier words zero at the first call; the
-    default two-launch form clears them itself, so no fill kernel is spent (or captured into a caller's CUDA graph)."""
-    if os.environ.get("TRB_FUSED_MERGED"):
-        return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    """Uninitialised: the prologue launch clears the grid-barrier words itself, so no fill kernel is spent (or captured into a
+    caller's CUDA graph)."""
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 

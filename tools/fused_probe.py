@@ -47,8 +47,9 @@ def print_stamps(lib, roles, K, Cn, tag, ws=None, sh=None):
     T_inst, T_k = (Cn + 127) // 128, (K + 127) // 128
     n_inst = T_inst if roles & 1 else 0
     n_nce = 2 * T_k if roles & 2 else 0
-    groups = [("inst", 0, n_inst), ("nce", n_inst, n_inst + n_nce), ("align", n_inst + n_nce, n_inst + n_nce + (1 if roles & 4 else 0))]
-    t0 = st[:n_inst + n_nce + 1, 0]
+    n_tiles = n_inst + n_nce + (1 if roles & 4 else 0)
+    groups = [("inst", 0, n_inst), ("nce", n_inst, n_inst + n_nce), ("align", n_inst + n_nce, n_tiles), ("spare", n_tiles, 148)]
+    t0 = st[:n_tiles, 0]
     t0 = int(t0[t0 > 0].min())
     for name, lo, hi in groups:
         if hi <= lo:
