@@ -24,14 +24,7 @@ namespace {
 using namespace tc;
 
 constexpr int F_THREADS = 256;
-#ifndef FIN_PARTS_N
-#define FIN_PARTS_N 4
-#endif
-#ifndef FIN_UNROLL
-#define FIN_UNROLL 4
-#endif
-constexpr int FIN_UNROLL_C = FIN_UNROLL;
-constexpr int FIN_PARTS = FIN_PARTS_N;              // final reduction: work units per 16-byte slot
+constexpr int FIN_PARTS = 4;                        // final reduction: threads per 16-byte slot
 constexpr int F_TILE = 128;                         // classes / queue slots per CTA
 constexpr int F_E_BYTES = 8 * BLOCK_BYTES;          // 128 KiB  embedding rows: [2 row-blocks][<=4 k-chunks][16 KiB]
 constexpr int F_DZ_BYTES = 2 * BLOCK_BYTES;         // 32 KiB   logit gradient of one 128-row block: [2 column chunks][16 KiB]
@@ -59,6 +52,7 @@ struct FP {
     const int64_t* mask_labels;     // ids of the WHOLE batch (queue mask, head.py:148-157), n_mask of them
     int n_mask;
     int accum_dw;                   // the projection gradient of this window is added to what the previous windows left
+    int fin_U;                      // 16-byte slots per work unit of the partial-tile reduction (layout of part_inst)
     int row_helpers;                // this many spare CTAs form the instance row losses (0: tile 0 does)
     int fin_early;                  // the partial reductions belong to the CTAs behind the instance tiles (see fused_loss_kernel)
     float T, eps, alpha, beta, sp, sn;
@@ -72,9 +66,11 @@ struct FP {
     float *ls_inst, *ls_nce;                // per-tile softmax statistics [tile][256 rows]: log2 sum_c 2^(z2_c) over the tile's columns
     float2* zz_inst;                        // ... and (sum z, z_y) of the instance tiles (label smoothing / target logit)
     unsigned long long* dbg;                // optional phase timestamps [cta][16] (TRB_FUSED_DEBUG)
-    uint4 *part_inst, *part_nce;            // partial dE tiles, bf16: [tile][row block][8-column chunk][128 rows] x 16 bytes
+    uint4 *part_inst, *part_nce;            // partial dE tiles, bf16 x 8 per 16 bytes: InfoNCE [tile][8-column chunk][128 rows],
+                                            // instance [unit][tile][U slots] (see PartialReducer)
     float *dpos, *rows_inst, *rows_nce, *rows_ga, *losses, *d_inst, *d_nce, *d_ga, *d_proj;
-    unsigned* bar;                  // [0] instance statistics, [1] partial tiles written, [2], [3] InfoNCE statistics per modality;
+    unsigned* bar;                  // [0] instance statistics, [1] partial tiles written, [2], [3] InfoNCE statistics per modality,
+                                    // [4] next work unit of the partial-tile reduction;
                                     // zeroed by the prologue launch
     // _dequeue_and_enqueue (head.py:96-109) folded into the kernel: the InfoNCE / align CTAs, which reach the second grid barrier
     // long before the instance tiles, write the normalised keys and ids into the queues; the pointer moves after the barrier
@@ -199,7 +195,7 @@ __device__ __forceinline__ void load_tile_bf16(const float* __restrict__ src, in
 struct Smem {
     uint8_t *E, *DZ, *WB;
     float2* col;           // [128] per column: (scale * log2(e), 0 or F_NEG); scale = 1/||w_c|| (instance) or 1/T (InfoNCE), 0 if excluded
-    uint64_t *bar_load, *bar_mma, *bar_dw;
+    uint64_t *bar_load, *bar_mma, *bar_dw, *bar_fin;     // bar_fin[2]: the two buffers of the final reduction
     uint32_t* tmem_slot;
     float* red32;          // [32]  block_sum scratch
 };
@@ -400,7 +396,7 @@ __device__ __forceinline__ void pro_task(const ProArgs& a, int t, int lane) {
 // stand-alone prologue (some branches unfused): one warp per task, also clears the grid-barrier words
 __global__ void __launch_bounds__(256) fused_prologue_kernel(const ProArgs a, unsigned* __restrict__ bar, int ntasks) {
     griddep_launch_dependents();         // the cooperative kernel may start streaming W now; it waits for this grid before it reads
-    if (blockIdx.x == 0 && threadIdx.x < 4) bar[threadIdx.x] = 0u;
+    if (blockIdx.x == 0 && threadIdx.x < 8) bar[threadIdx.x] = 0u;
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (t < ntasks) pro_task(a, t, threadIdx.x & 31);
 }
@@ -668,7 +664,11 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             // partials are rounded to bf16 (their own error from the bf16 operands is 2^-8; they are summed in fp32) and laid out
             // [tile][row block][8-column chunk][128 rows] x 16 bytes: the 32 rows of a warp write 512 contiguous bytes
             if (INST) {
-                uint4* dst = p.part_inst + (size_t)(tile * 2 + mt) * (Dp / 8) * 128 + n;
+                // slot m = (row block * Dp/8 + 8-column chunk) * 128 + row; layout [unit = m / U][tile][m % U] (U divides 128): the
+                // share of all tiles in one work unit of the final reduction is ONE contiguous piece (see PartialReducer)
+                const int U = p.fin_U, upr = 128 / U;                    // units per 128-row group
+                uint4* dst = p.part_inst + ((size_t)(n / U) * p.T_inst + tile) * U + (n % U);
+                const size_t gstride = (size_t)upr * p.T_inst * U;       // one (row block, chunk) group further
 #pragma unroll 1
                 for (int rj = 0; rj < (two ? 4 : 2); ++rj) {
                     const int r = rj >> 1, jj = rj & 1;
@@ -677,7 +677,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                     if (n < N) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            __stcg(dst + (size_t)(r * 16 + h * 8 + jj * 4 + k) * 128,
+                            __stcg(dst + (size_t)(mt * (Dp / 8) + r * 16 + h * 8 + jj * 4 + k) * gstride,
                                    make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
                                               pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
                     }
@@ -954,6 +954,99 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
     }
 }
 
+// d_inst[row, 8 columns] = sum over the instance tiles of their partial dE tiles, in a fixed order.  One tile's partial is
+// M = 2 * (Dp/8) * 128 16-byte slots m = (row block * Dp/8 + 8-column chunk) * 128 + row.  Work unit = U consecutive slots; the
+// tiles store their partials as [unit][tile][U slots], so a unit's share of EVERY tile is one contiguous piece of T * U * 16
+// bytes that a single bulk copy (TMA engine) lands in shared memory; FIN_PARTS threads per slot then add their tiles and the
+// partial sums are combined through shared memory.  Units are handed out by a grid-wide counter (bar[4]) and double buffered:
+// the phase is bound by the bytes an SM can pull from L2 (~40 GB/s each), so every CTA that gets here -- early or late -- keeps
+// taking units until none is left, and the copy of the next unit runs under the additions of the current one.  Which CTA
+// reduces a unit does not change the order of any sum: results are bit-identical from call to call.
+struct PartialReducer {
+    const FP& p;
+    const Smem& sm;
+    int tid, Dp, M, U, n_units, cur, nxt, k;
+    uint32_t ph0, ph1;              // mbarrier phases of the two buffers (scalars: no dynamically indexed local array)
+    int* s_next;
+    __device__ __forceinline__ PartialReducer(const FP& p_, const Smem& sm_) : p(p_), sm(sm_) {
+        tid = threadIdx.x;
+        Dp = p.KC * 64;
+        M = 2 * (Dp / 8) * 128;
+        U = p.fin_U;
+        n_units = M / U;
+        s_next = reinterpret_cast<int*>(sm.red32 + 32);
+        cur = nxt = n_units; k = 0;
+        ph0 = ph1 = 0;
+    }
+    __device__ __forceinline__ uint8_t* buffer(int which) const { return sm.E + (size_t)which * (F_OFF_MISC / 2); }
+    // all threads: take the next unit (thread 0 asks the counter, the answer goes round through shared memory) and start its
+    // copy into buffer `which`; the barriers also order every earlier generic access of that buffer before the async-proxy writes
+    __device__ __forceinline__ int grab_and_copy(int which) {
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const int unit = (int)atomicAdd(p.bar + 4, 1u);
+            *s_next = unit;
+            if (unit < n_units) {
+                const uint32_t bytes = (uint32_t)(p.T_inst * U * 16);
+                mbar_expect_tx(sm.bar_fin + which, bytes);
+                bulk_g2s(buffer(which), p.part_inst + (size_t)unit * p.T_inst * U, bytes, sm.bar_fin + which);
+            }
+        }
+        __syncthreads();
+        return *s_next;
+    }
+    __device__ __forceinline__ void start() { cur = grab_and_copy(0); }
+    __device__ __forceinline__ void run() {
+        const int N = p.N, D = p.D;
+        const int th = (p.T_inst + FIN_PARTS - 1) / FIN_PARTS;
+        while (cur < n_units) {
+            nxt = grab_and_copy(k ^ 1);
+            mbar_wait_sleepy(sm.bar_fin + k, k ? ph1 : ph0, 32);
+            if (k) ph1 ^= 1; else ph0 ^= 1;
+            const uint4* data = reinterpret_cast<const uint4*>(buffer(k));
+            float4* comb = reinterpret_cast<float4*>(buffer(k) + (size_t)p.T_inst * U * 16);     // [FIN_PARTS][2][U] x 16 bytes
+            for (int u = tid; u < FIN_PARTS * U; u += F_THREADS) {
+                const int i = u % U, part = u / U;
+                const int tlo = part * th, thi = min(p.T_inst, tlo + th);
+                float acc[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+                for (int t = tlo; t < thi; ++t) {
+                    const uint4 x = data[(size_t)t * U + i];
+                    const uint32_t r[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        acc[2 * q] += __uint_as_float(r[q] << 16);
+                        acc[2 * q + 1] += __uint_as_float(r[q] & 0xffff0000u);
+                    }
+                }
+                comb[(part * 2 + 0) * U + i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                comb[(part * 2 + 1) * U + i] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+            __syncthreads();
+            for (int i = tid; i < U; i += F_THREADS) {
+                const int m = cur * U + i, g = m >> 7, row = m & 127;
+                const int mt = g / (Dp / 8), c8 = g % (Dp / 8);
+                if (row < N && c8 * 8 < D) {
+                    float4 a = comb[i], c = comb[U + i];
+#pragma unroll
+                    for (int q = 1; q < FIN_PARTS; ++q) {
+                        const float4 x = comb[(q * 2) * U + i], y = comb[(q * 2 + 1) * U + i];
+                        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+                        c.x += y.x; c.y += y.y; c.z += y.z; c.w += y.w;
+                    }
+                    const float out[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+                    st_v8(p.d_inst + ((size_t)(mt * p.NS + row) * D + c8 * 8), out);
+                }
+            }
+            cur = nxt;
+            k ^= 1;
+        }
+    }
+};
+
 // Instance row losses (losses.py:26-39 with label smoothing) on spare CTA `hs` of `H`: the sums of z and z_y over all tiles are
 // 176 KB that only the loss value needs -- on tile 0 they made that CTA the straggler of the whole grid.  One warp per row,
 // lanes over the tiles (at most 160), fixed shuffle order.
@@ -997,32 +1090,8 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm, int fi
     // the last CTA only forms the loss scalars; the partial reductions are shared by the others
     const int GW = p.reduce_losses && G > 1 ? G - 1 : G;
     const bool worker = fi < GW;
-    // d_inst[row, 8 columns] = sum over the instance tiles of their partial tiles.  One tile's partial is M = 2 * (Dp/8) * 128
-    // 16-byte slots in memory order [row block][8-column chunk][row]; a finishing CTA owns one contiguous slot range, so its
-    // share of EVERY tile is one contiguous piece; asynchronous copies land all of them in shared memory at
-    // once (one L2 round trip instead of one per register batch), issued before and completed under the InfoNCE rows below.
-    const bool inst_work = p.want_grad && p.n_inst && worker;
-    const int M = 2 * (Dp / 8) * 128;
-    const int per_cta = (M + GW - 1) / GW;
-    const int lo = fi * per_cta, hi = min(M, lo + per_cta);
-    const int chunk = max(1, min(per_cta, (int)(F_OFF_MISC / (16 * p.T_inst + 32 * FIN_PARTS))));     // slots per pass: data + combine scratch
-    uint8_t* buf = sm.E;                                     // E | DZ | WB are contiguous and dead by now
-    // 16-byte asynchronous copies (LDGSTS): no registers are held per load, so the whole share is in flight at once; warp w
-    // takes the tiles w, w + 8, ... (one contiguous piece each, consecutive lanes -> consecutive 16 bytes)
-    auto issue = [&](int base) {
-        const int cnt = min(chunk, hi - base);
-        __syncthreads();                                     // the previous pass (or phase) is done with the region
-#pragma unroll 1
-        for (int t = w; t < p.T_inst; t += F_THREADS / 32) {
-            const uint4* src = p.part_inst + (size_t)t * M + base;
-            const uint32_t dst = smem_u32(buf) + (uint32_t)(t * cnt) * 16u;
-#pragma unroll 1
-            for (int i = lane; i < cnt; i += 32)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(src + i) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (inst_work && lo < hi) issue(lo);
+    PartialReducer red(p, sm);
+    if (p.want_grad && p.n_inst) red.start();             // first unit in flight under the InfoNCE rows below
     F_STAMP(12);
     if (p.want_grad && p.n_nce) {      // (no block-level synchronisation below: idle CTAs / warps simply fall through)
         // d_nce[row] = normalise-backward( sum_tiles dq_part + dpos * key )   one warp per row, rows dealt round-robin to CTAs;
@@ -1083,66 +1152,7 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm, int fi
         }
     }
     F_STAMP(13);
-    if (inst_work) {
-        for (int base = lo; base < hi; base += chunk) {
-            const int cnt = min(chunk, hi - base);
-            if (base > lo) issue(base);
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncthreads();
-            F_STAMP(14);
-            // FIN_PARTS work units per slot (a quarter of the tiles each, fixed order), combined through shared memory
-            // (slot-minor layout: consecutive threads touch consecutive 16-byte words -- no bank conflicts)
-            float4* comb = reinterpret_cast<float4*>(buf + (size_t)p.T_inst * cnt * 16);    // [FIN_PARTS][2][cnt] x 16 bytes
-            const int th = (p.T_inst + FIN_PARTS - 1) / FIN_PARTS;
-#ifdef FIN_WARPSTAMPS
-            if (p.dbg != nullptr && lane == 0) p.dbg[blockIdx.x * 16 + 8 + w] = globaltimer_ns();
-#endif
-            for (int u = tid; u < FIN_PARTS * cnt; u += F_THREADS) {
-                const int i = u % cnt, part = u / cnt;
-                const int tlo = part * th, thi = min(p.T_inst, tlo + th);
-                const uint4* src = reinterpret_cast<const uint4*>(buf) + i;
-                float acc[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll FIN_UNROLL_C
-                for (int t = tlo; t < thi; ++t) {
-                    const uint4 x = src[(size_t)t * cnt];
-                    const uint32_t r[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-#ifdef FIN_NOALU
-                        acc[2 * k] = __uint_as_float(__float_as_uint(acc[2 * k]) ^ r[k]);
-#else
-                        acc[2 * k] += __uint_as_float(r[k] << 16);
-                        acc[2 * k + 1] += __uint_as_float(r[k] & 0xffff0000u);
-#endif
-                    }
-                }
-                comb[(part * 2 + 0) * cnt + i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                comb[(part * 2 + 1) * cnt + i] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            }
-#ifdef FIN_WARPSTAMPS
-            if (p.dbg != nullptr && lane == 0) p.dbg[blockIdx.x * 16 + w] = globaltimer_ns();
-#endif
-            __syncthreads();
-            F_STAMP(15);
-            for (int i = tid; i < cnt; i += F_THREADS) {
-                const int m = base + i, g = m >> 7, row = m & 127;
-                const int mt = g / (Dp / 8), c8 = g % (Dp / 8);
-                if (row < N && c8 * 8 < D) {
-                    float4 a = comb[i], c = comb[cnt + i];
-#pragma unroll
-                    for (int q = 1; q < FIN_PARTS; ++q) {
-                        const float4 x = comb[(q * 2) * cnt + i], y = comb[(q * 2 + 1) * cnt + i];
-                        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-                        c.x += y.x; c.y += y.y; c.z += y.z; c.w += y.w;
-                    }
-                    const float out[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-                    st_v8(p.d_inst + ((size_t)(mt * p.NS + row) * D + c8 * 8), out);
-                }
-            }
-        }
-    }
+    if (p.want_grad && p.n_inst) red.run();
     if (p.reduce_losses && fi == G - 1) {
         float a = 0.f, b = 0.f, c = 0.f;
         for (int i = tid; i < 2 * N; i += F_THREADS) { a += __ldcg(p.rows_inst + i); b += __ldcg(p.rows_nce + i); }
@@ -1204,6 +1214,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
     sm.bar_mma = reinterpret_cast<uint64_t*>(misc + 1032);
     sm.bar_dw = reinterpret_cast<uint64_t*>(misc + 1040);
     sm.tmem_slot = reinterpret_cast<uint32_t*>(misc + 1048);
+    sm.bar_fin = reinterpret_cast<uint64_t*>(misc + 1056);
     sm.red32 = reinterpret_cast<float*>(misc + 1088);
     const int warp = threadIdx.x >> 5;
 
@@ -1211,6 +1222,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
         mbar_init(sm.bar_load, 1);
         mbar_init(sm.bar_mma, 1);
         mbar_init(sm.bar_dw, 1);
+        mbar_init(sm.bar_fin, 1);
+        mbar_init(sm.bar_fin + 1, 1);
         mbar_fence_init();
     }
     // CTA roles by block index: instance tiles, InfoNCE tiles, the align CTA, then SPARE CTAs (the rest of the SMs) that own no
@@ -1253,6 +1266,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
         // every enqueue slice has read the old pointer before it arrived: head.py:108-109
         if (p.enq_ptr != nullptr && fi == nf - 1 && threadIdx.x == 0) *p.enq_ptr = (*p.enq_ptr + p.N) % p.K;
         finish_phase(p, sm, fi, nf);
+        F_STAMP(9);
+    } else if (p.want_grad) {
+        // an instance tile that is done with its dW epilogue: take whatever units of the partial-tile reduction are left
+        grid_wait(p.bar + 1, (unsigned)(n_tiles + p.row_helpers));
+        PartialReducer red(p, sm);
+        red.start();
+        red.run();
         F_STAMP(9);
     }
 
@@ -1397,6 +1417,10 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     TRB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = n_tiles > sms ? n_tiles : sms;
     p.fin_early = (p.n_inst > 0 && p.want_grad && grid - p.n_inst - p.n_ga >= 24) ? 1 : 0;
+    {
+        const int cap = (F_OFF_MISC / 2) / (16 * p.T_inst + 32 * FIN_PARTS);     // per buffer: data + combine scratch
+        p.fin_U = cap >= 64 ? 64 : (cap >= 32 ? 32 : (cap >= 16 ? 16 : 8));
+    }
     p.row_helpers = p.n_inst > 0 ? (grid - n_tiles < 16 ? grid - n_tiles : 16) : 0;
 
     static TrbDeviceOnce attr;
