@@ -415,6 +415,24 @@ def test_sharded_tie_heavy_exact_fixture(precision):
     check_against_matrix(res, sim, tpid, ipid, ap_rtol=2e-6)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_sharded_nccl_fixture_on_one_device(world, precision):
+    """The fixture of tests/test_sharded.py::test_sharded_nccl (tie-heavy +-1/8 rows, D = 64, uneven shards that are not
+    multiples of the 256-row gallery tile) through the single-process driver: same per-shard kernels, no NCCL.  Regression for a
+    double count: a relevant item of a HIGHER shard whose global index falls into this shard's zero-padded last tile was taken
+    for an item of the chunk by the tie correction (hit ranks off by the number of ties before it; 3 and 4 shards only)."""
+    from tests.sharded_worker import make_case as nccl_case, shard_slices
+    from textreid_b200.sharded import retrieve_sharded_local
+    Q, G, D = 151, 700, 64
+    text, image, tpid, ipid = nccl_case(Q, G, D, G // 5, seed=5, exact=True)
+    sl = shard_slices(G, world)
+    res = retrieve_sharded_local(T(text), [T(image[a:b]) for a, b in sl], T(tpid), [T(ipid[a:b]) for a, b in sl], (1, 5, 10), True,
+                                 precision)
+    sim = O.similarity_matrix(text, image)                  # exact arithmetic: identical in fp32 and from bf16 operands
+    check_against_matrix(res, sim, tpid, ipid, ap_rtol=2e-6)
+
+
 # ----------------------------------------------------------------------------------------------
 # round 2: parity AT the sizes the numbers are quoted on -- BASELINE configs[0] in full, configs[3] on a query sample
 # ----------------------------------------------------------------------------------------------

@@ -1415,7 +1415,13 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     int dev = 0, sms = 0;
     TRB_CUDA_OK(cudaGetDevice(&dev));
     TRB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = n_tiles > sms ? n_tiles : sms;
+    // spare CTAs: all remaining SMs when the whole step is this one launch; a launch that shares the device with the unfused
+    // branches on the helper streams (row windows, partial roles) keeps 30 SMs free for them -- a cooperative grid that covers
+    // every SM would have to wait until those kernels have drained; without instance tiles spare CTAs have nothing to do
+    int spare = sms - n_tiles;
+    if (spare < 0 || p.n_inst == 0) spare = 0;
+    if (a.roles != 7 && spare > 32) spare = 32;
+    const int grid = n_tiles + spare;
     p.fin_early = (p.n_inst > 0 && p.want_grad && grid - p.n_inst - p.n_ga >= 24) ? 1 : 0;
     {
         const int cap = (F_OFF_MISC / 2) / (16 * p.T_inst + 32 * FIN_PARTS);     // per buffer: data + combine scratch

@@ -378,7 +378,11 @@ __device__ __forceinline__ void pad_list(const Params& p, int64_t q, int64_t nli
 __device__ __noinline__ void fix_own_chunk(const Params& p, const float* lv, int g0, int64_t s_lo, int64_t s_end, uint32_t slow) {
     for (int64_t slot = s_lo; slot < s_end; ++slot) {
         if ((slow >> (int)(slot - s_lo)) & 1u) continue;           // counted exactly by count_exact
-        const int64_t l = p.thr_gidx[slot] - p.g_base - g0;        // position of the item inside this chunk
+        const int64_t lg = p.thr_gidx[slot] - p.g_base;            // local row of the item
+        // an item of a HIGHER shard whose index falls into this shard's zero-padded tail is not in this chunk: its slot
+        // never switched to the strict compare, so the ties before it are already counted
+        if (lg >= p.G) continue;
+        const int64_t l = lg - g0;                                 // position of the item inside this chunk
         if (l < 0 || l >= CH) continue;
         const float th = p.thr[slot];
         int c = 0;
