@@ -209,7 +209,11 @@ int64_t trb_moco_loss_workspace_bytes(const trb_moco_shape* shape, int precision
 
 /* Kernel launches one trb_moco_loss call issues for this shape on the current device: 2 when precision = 1 takes the fused
  * path (a small prologue + ONE cooperative tcgen05 kernel for the three losses and all gradients; needs N <= 128, D a multiple
- * of 64 up to 256 and ceil(C/128) + 2*ceil(K/128) + 1 <= #SMs), otherwise the length of the unfused launch sequence. */
+ * of 64 up to 256 and ceil(C/128) + 2*ceil(K/128) + 1 <= #SMs), otherwise the length of the unfused launch sequence.
+ * The cooperative kernel occupies every SM of the device (one CTA per class / queue tile, spare CTAs on the rest that share the
+ * final reductions) and is launched as a programmatic dependent launch behind the prologue (it starts while the prologue still
+ * runs and waits for it on the device); both survive CUDA-graph capture.  Batches of 129..1024 rows run the same kernel once per
+ * 128-row window and branch. */
 int trb_moco_loss_launches(const trb_moco_shape* shape, int precision);
 
 /* Loss dict and its gradients in one stream-ordered call (fwd and bwd fused: the softmax
@@ -249,7 +253,7 @@ int trb_moco_loss(const float* v_embed, const float* t_embed, const float* v_qra
  * train branch does after the encoders.  Same arguments as trb_moco_loss; the queues, id_queue and queue_ptr [1] (int64, read
  * and advanced on the device: no int(queue_ptr) sync) are written after the last read of the old queue contents.  Requires
  * K % N == 0 like the reference's assert (head.py:101).  On the fused bf16 path the enqueue rides inside the cooperative
- * kernel (the InfoNCE CTAs, idle at that point, write the key columns; the pointer moves after the last grid barrier), so the
+ * kernel (the InfoNCE CTAs, idle at that point, write the key columns; the pointer moves after every tile has arrived at the kernel's last grid-wide counter), so the
  * whole step stays at trb_moco_loss_launches() launches; otherwise two small launches follow the loss sequence.
  * A queue_ptr outside [0, K-N] (a checkpoint written with another batch size) wraps modulo K instead of writing out of bounds. */
 int trb_moco_step(const float* v_embed, const float* t_embed, const float* v_qraw, const float* t_qraw,
