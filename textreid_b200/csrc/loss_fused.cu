@@ -41,6 +41,8 @@ struct ProArgs {
     int normalize_keys, N, D, KC, K, T_k;
     int NS;            // stride between the two modalities in the row-indexed fp32 arrays (= the FULL batch size; see FP::NS)
     int skip_pack;     // the queue images of this step are already in QUp (a later row window of the same step)
+    const float* W;    // projection [D, C] for the L2 prefetch (NULL: none)
+    int64_t W_bytes;
 };
 
 struct FP {
@@ -396,6 +398,20 @@ __device__ __forceinline__ void pro_task(const ProArgs& a, int t, int lane) {
 // stand-alone prologue (some branches unfused): one warp per task, also clears the grid-barrier words
 __global__ void __launch_bounds__(256) fused_prologue_kernel(const ProArgs a, unsigned* __restrict__ bar, int ntasks) {
     griddep_launch_dependents();         // the cooperative kernel may start streaming W now; it waits for this grid before it reads
+    // W towards L2 as ONE sequential sweep (bulk prefetch, a slice per CTA): the instance tiles read it as 256 row segments of
+    // 512 bytes each, a pattern that pulls from cold DRAM at a quarter of the rate of a contiguous stream
+    if (a.W != nullptr && threadIdx.x == 0) {
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(a.W) + 15) & ~uintptr_t(15);
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(a.W) + (uintptr_t)a.W_bytes) & ~uintptr_t(15);
+        if (hi > lo) {
+            const uintptr_t per = (((hi - lo) / gridDim.x) + 16) & ~uintptr_t(15);
+            const uintptr_t b0 = lo + per * blockIdx.x;
+            if (b0 < hi) {
+                const uint32_t n = (uint32_t)((hi - b0 < per) ? hi - b0 : per);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0), "r"(n) : "memory");
+            }
+        }
+    }
     if (blockIdx.x == 0 && threadIdx.x < 8) bar[threadIdx.x] = 0u;
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (t < ntasks) pro_task(a, t, threadIdx.x & 31);
@@ -1357,6 +1373,9 @@ static ProArgs make_pro_args(const FusedLossArgs& a, const Scratch& s) {
     q.T_k = (a.K + F_TILE - 1) / F_TILE;
     q.NS = a.NS > 0 ? a.NS : a.N;
     q.skip_pack = a.skip_pack;
+    // (later row windows find W in L2 from the first one)
+    q.W = ((a.roles & 1) && !a.skip_pack && !getenv("TRB_FUSED_NO_PREFETCH")) ? a.projection : nullptr;
+    q.W_bytes = (int64_t)a.D * a.C * 4;
     return q;
 }
 
