@@ -384,10 +384,9 @@ int trb_moco_loss_launches_impl(const trb_moco_shape* s, int precision) {
     if (use_tc && fused_windows_supported(s->N, s->D, s->K, s->C, sm_count())) {
         const char* e = getenv("TRB_FUSED_ROLES");
         if (e == nullptr || (atoi(e) & 3) == 3) {
-            // shared prologue + the unfused global-align branch (3 contractions, pair losses, normalise backward) + per 128-row
-            // window a fused prologue and one cooperative launch per role + loss reduce
-            const int windows = (s->N + 127) / 128;
-            return 1 + (3 * per_gemm + 2) + 3 * windows + 1;
+            // shared prologue + the unfused global-align branch (3 contractions, pair losses, normalise backward) + the fused
+            // prologue and one cooperative launch per role (the row windows are walked inside the kernel) + loss reduce
+            return 1 + (3 * per_gemm + 2) + 3 + 1;
         }
     }
     // prologue, mask, column norms, 3 row kernels, 2 normalise-backward, projection backward, loss reduce, 3 partial reductions
@@ -472,30 +471,20 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     TRB_CUDA_OK(cudaStreamWaitEvent(s_ga, fk->fork, 0));
     if (roles && !windows && (rc = fused_loss_launch(fa, st))) return rc;
     if (roles && windows) {
-        // ---- row windows on the caller's stream: per window a prologue (operand images of the window; the queue images only once)
-        //      and one cooperative launch per role -- 86 instance + 2 x 32 InfoNCE tiles do not fit the SMs together at K = 4096
-        for (int r0 = 0; r0 < N; r0 += 128) {
-            FusedLossArgs fw = fa;
-            const int64_t o = (int64_t)r0 * D;
-            fw.N = N - r0 < 128 ? N - r0 : 128;
-            fw.NS = N; fw.mask_labels = labels; fw.n_mask = N; fw.accum_dw = r0 > 0; fw.skip_pack = r0 > 0;
-            fw.v_embed = v_embed + o; fw.t_embed = t_embed + o; fw.v_qraw = v_qraw + o; fw.t_qraw = t_qraw + o;
-            fw.v_key = v_key + o; fw.t_key = t_key + o; fw.v_key_n = v_key_n + o; fw.t_key_n = t_key_n + o;
-            fw.labels = labels + r0;
-            fw.E2 = w.E2 + o; fw.en = w.en + o; fw.qn = w.qn + o; fw.inv_e = w.inv_e + r0; fw.inv_q = w.inv_q + r0;
-            fw.pos = w.pos + r0; fw.dpos = w.dpos + r0; fw.rows_inst = w.rows_inst + r0; fw.rows_nce = w.rows_nce + r0;
-            fw.d_inst = d_inst ? d_inst + o : nullptr; fw.d_nce = d_nce ? d_nce + o : nullptr;
-            fw.reduce_losses = 0;
-            fw.roles = 3;
-            if ((rc = fused_loss_prologue(fw, st))) return rc;
-            fw.roles = 1;
-            fw.after_prologue = 1;
-            if ((rc = fused_loss_launch(fw, st))) return rc;
-            fw.after_prologue = 0;
-            if ((rc = fused_loss_reset_barriers(fw, st))) return rc;
-            fw.roles = 2;
-            if ((rc = fused_loss_launch(fw, st))) return rc;
-        }
+        // ---- batches above 128 rows on the caller's stream: ONE prologue (operand images of every 128-row window, queue images)
+        //      and one cooperative launch per role -- 86 instance + 2 x 32 InfoNCE tiles do not fit the SMs together at
+        //      K = 4096; each launch walks the windows inside the kernel with its W / queue tile resident
+        fa.reduce_losses = 0;
+        fa.roles = 3;
+        if ((rc = fused_loss_prologue(fa, st))) return rc;
+        fa.roles = 1;
+        fa.after_prologue = 1;
+        if ((rc = fused_loss_launch(fa, st))) return rc;
+        fa.after_prologue = 0;
+        if ((rc = fused_loss_reset_barriers(fa, st))) return rc;
+        fa.roles = 2;
+        if ((rc = fused_loss_launch(fa, st))) return rc;
+        fa.roles = roles;
     }
 
     // ---- InfoNCE branch (helper stream 1): mask, logits of v queries x text queue and t queries x image queue

@@ -38,22 +38,17 @@ struct ProArgs {
     const float *v_embed, *t_embed, *v_qraw, *t_qraw, *v_key, *t_key, *v_queue, *t_queue;
     float *v_key_n, *t_key_n, *E2, *en, *inv_e, *qn, *inv_q, *pos;
     uint8_t *Ep, *ENp, *QNp, *QUp;
-    int normalize_keys, N, D, KC, K, T_k;
-    int NS;            // stride between the two modalities in the row-indexed fp32 arrays (= the FULL batch size; see FP::NS)
-    int skip_pack;     // the queue images of this step are already in QUp (a later row window of the same step)
+    int normalize_keys, N, D, KC, K, T_k;      // N = the whole batch: ceil(N / 128) windows of 2 x 128 padded rows
     const float* W;    // projection [D, C] for the L2 prefetch (NULL: none)
     int64_t W_bytes;
 };
 
 struct FP {
     int N, D, K, C, KC, T_inst, T_k, n_inst, n_nce, n_ga, want_grad, reduce_losses, roles;
-    // Row windows: a batch of more than 128 rows runs as several launches of <= 128 rows each (N = rows of this window).  The
-    // row-indexed arrays keep their full-batch layout [modality][Nn rows]: every pointer below is pre-offset to the window's
-    // first row by the host, `NS` (= Nn) is the stride between the modalities, and every mean is taken over the full batch Nn.
+    // Row windows: a batch of more than 128 rows is processed in ceil(N / 128) windows of <= 128 rows per modality INSIDE the
+    // kernel (tile_program); row-indexed arrays are [modality][N rows], NS (= N) the stride between the modalities, Nn (= N) the
+    // batch size every mean is taken over.  The queue mask (head.py:148-157) always uses the ids of the whole batch.
     int NS, Nn;
-    const int64_t* mask_labels;     // ids of the WHOLE batch (queue mask, head.py:148-157), n_mask of them
-    int n_mask;
-    int accum_dw;                   // the projection gradient of this window is added to what the previous windows left
     int fin_U;                      // 16-byte slots per work unit of the partial-tile reduction (layout of part_inst)
     int row_helpers;                // this many spare CTAs form the instance row losses (0: tile 0 does)
     int fin_early;                  // the partial reductions belong to the CTAs behind the instance tiles (see fused_loss_kernel)
@@ -329,16 +324,17 @@ __device__ __forceinline__ void pro_pack_task(const ProArgs& a, int mod, int d, 
     }
 }
 
-__device__ __forceinline__ void pro_row_task(const ProArgs& p, int prow, int lane) {
+__device__ __forceinline__ void pro_row_task(const ProArgs& p, int task, int lane) {
     const int N = p.N, D = p.D, KC = p.KC;
-    const int mod = prow >> 7, n = prow & 127;                     // padded row: modality * 128 + n
+    const int win = task >> 8, prow = task & 255;                  // window, padded row inside it: modality * 128 + local row
+    const int mod = prow >> 7, n = (win << 7) + (prow & 127);      // n = row of the batch
     const int k0 = lane * 8;
     const bool in_pad = k0 < KC * 64;
     float a[8], b[8], c[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = b[i] = c[i] = 0.f;
     const bool live = n < N && k0 < D;
-    const int row = mod * p.NS + n;
+    const int row = mod * N + n;
     if (live) {                                                              // 16-byte aligned rows (checked by the caller)
         const float4* e = reinterpret_cast<const float4*>((mod ? p.t_embed : p.v_embed) + (int64_t)n * D + k0);
         const float4* r = reinterpret_cast<const float4*>((mod ? p.t_qraw : p.v_qraw) + (int64_t)n * D + k0);
@@ -378,7 +374,7 @@ __device__ __forceinline__ void pro_row_task(const ProArgs& p, int prow, int lan
     }
     if (n < N && lane == 0) { p.inv_e[row] = __fdiv_rn(1.0f, ne); p.inv_q[row] = __fdiv_rn(1.0f, nr); p.pos[row] = dot; }
     if (in_pad) {
-        const int64_t off = packed_offset_bytes(prow, lane, KC);
+        const int64_t off = (int64_t)win * 2 * KC * BLOCK_BYTES + packed_offset_bytes(prow, lane, KC);
         uint4 o;
         o.x = pack2(a[0], a[1]); o.y = pack2(a[2], a[3]); o.z = pack2(a[4], a[5]); o.w = pack2(a[6], a[7]);
         *reinterpret_cast<uint4*>(p.Ep + off) = o;
@@ -389,10 +385,11 @@ __device__ __forceinline__ void pro_row_task(const ProArgs& p, int prow, int lan
     }
 }
 
-// task t of the prologue: [0, 256) embedding rows, then the queue rows (2 * Dp) when `pack`
+// task t of the prologue: 256 padded embedding rows per window, then the queue rows (2 * Dp) when `pack`
 __device__ __forceinline__ void pro_task(const ProArgs& a, int t, int lane) {
-    if (t < 256) pro_row_task(a, t, lane);
-    else { const int q = t - 256, Dp = a.KC * 64; pro_pack_task(a, q / Dp, q % Dp, lane); }
+    const int nrow = 256 * ((a.N + 127) / 128);
+    if (t < nrow) pro_row_task(a, t, lane);
+    else { const int q = t - nrow, Dp = a.KC * 64; pro_pack_task(a, q / Dp, q % Dp, lane); }
 }
 
 // stand-alone prologue (some branches unfused): one warp per task, also clears the grid-barrier words
@@ -424,30 +421,32 @@ template <bool INST>
 __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32_t tmem, int mod, int tile) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, q = w & 3, h = w >> 2;
     const int n = q * 32 + lane;                       // row inside a 128-row block = TMEM lane
-    const int N = p.N, Dp = p.KC * 64;
+    const int Dp = p.KC * 64;
     const int c0 = tile * F_TILE;
     constexpr int MT = INST ? 2 : 1;
+    const int NW = (p.N + 127) / 128;                  // 128-row windows of the batch, processed one after the other
+    const size_t img_bytes = (size_t)2 * p.KC * BLOCK_BYTES;            // packed operand image of one window
     const int ncols = INST ? p.C : p.K;
     const int tiles = INST ? p.T_inst : p.T_k;
     const uint32_t lanes = (uint32_t)(q * 32) << 16;
     uint32_t mma_phase = 0;
     // scratch inside the logit-gradient region while no gradient is staged there
     float* red = reinterpret_cast<float*>(sm.DZ);                        // [8][128] column partials
-    int64_t* s_lab = reinterpret_cast<int64_t*>(sm.DZ + 8192);           // [128] batch ids (InfoNCE mask)
+    int64_t* s_lab = reinterpret_cast<int64_t*>(sm.DZ + 8192);           // [<= 1024] ids of the whole batch (InfoNCE mask)
     float* s_lse2 = reinterpret_cast<float*>(sm.DZ + 16384);             // [256] base-2 row log-sum-exp
 
     // operand rows (and, InfoNCE, the queue tile image) are written by the prologue launch, which may still be running
     // (programmatic dependent launch): wait for it, then thread 0 starts the bulk copies (TMA engine).  The instance tiles
     // do this with their whole W tile already in flight.
-    auto after_prologue = [&]() {
-        griddep_wait();
+    // operand rows of window `win` -> shared memory (thread 0; the first window also brings the InfoNCE queue tile)
+    auto load_rows = [&](int win) {
         if (tid == 0) {
-            const uint8_t* src = INST ? p.Ep : p.QNp + (size_t)mod * p.KC * BLOCK_BYTES;
+            const uint8_t* src = (INST ? p.Ep : p.QNp + (size_t)mod * p.KC * BLOCK_BYTES) + (size_t)win * img_bytes;
             const int blocks = MT * p.KC;
-            mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES + (INST ? 0u : (uint32_t)F_WB_BYTES));
+            mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES + ((INST || win > 0) ? 0u : (uint32_t)F_WB_BYTES));
 #pragma unroll 1
             for (int b = 0; b < blocks; ++b) bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, src + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
-            if (!INST) {
+            if (!INST && win == 0) {
                 const uint8_t* qsrc = p.QUp + ((size_t)mod * p.T_k + tile) * F_WB_BYTES;
 #pragma unroll 1
                 for (int b = 0; b < F_WB_BYTES / BLOCK_BYTES; ++b)
@@ -455,9 +454,14 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             }
         }
     };
+    auto after_prologue = [&]() {
+        griddep_wait();
+        load_rows(0);
+    };
     int64_t slot_id = -1;
     if (!INST) {
-        s_lab[tid] = tid < p.n_mask ? p.mask_labels[tid] : INT64_MIN;       // 256 threads: up to 256 batch ids
+        for (int i = tid; i < ((p.N + 7) & ~7); i += F_THREADS)               // up to 1024 batch ids (8 KB of the region)
+            s_lab[i] = i < p.N ? p.labels[i] : INT64_MIN;
         if (tid < 128 && c0 + tid < ncols) slot_id = p.id_queue[c0 + tid];
         after_prologue();
     }
@@ -476,7 +480,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
         } else {
             if (ok) {                                                           // head.py:148-157: drop slots holding a batch id
                 bool hit = false;
-                const int nm = (p.n_mask + 7) & ~7;
+                const int nm = (p.N + 7) & ~7;
 #pragma unroll 8
                 for (int i = 0; i < nm; ++i) hit |= (s_lab[i] == slot_id);
                 ok = !hit;
@@ -489,9 +493,21 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     __syncthreads();
     F_STAMP(1);
 
+    const bool do_dw = INST && p.want_grad && p.d_proj != nullptr;
+    const int NH = Dp / 128;
+    float csum0 = 0.f, csum1 = 0.f;                    // <dz', z2>_rows of this thread's two 32-column chunks (column = lane)
+    // ---- the batch in windows of 128 rows per modality: the W / queue tile, its column scales and the dWs accumulator (TMEM)
+    //      stay resident, only the operand rows change.  One window for the BASELINE batch of 128.
+#pragma unroll 1
+  for (int win = 0; win < NW; ++win) {
+    const int r0 = win * 128;
+    const int N = min(128, p.N - r0);                  // rows of this window
+    const size_t stat_off = (size_t)win * tiles * 256;
+    if (win > 0) load_rows(win);                       // every MMA that read the previous rows has completed (waited below)
+
     // ---- forward logits: z[mt] = E[mt] . Wb   (M = 128 rows, N = 128 columns, K = Dp)
     if (tid == 0) {
-        mbar_wait(sm.bar_load, 0);
+        mbar_wait(sm.bar_load, (uint32_t)(win & 1));
         tc_fence_after();
         const uint32_t id_f = idesc(128, 128, 0, 1);
         const uint32_t e0 = smem_u32(sm.E), wb0 = smem_u32(sm.WB);
@@ -508,7 +524,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     F_STAMP(2);
 
     // ---- debug: the logits of one instance tile leave the SM (never on the product path: dbg_logits is NULL)
-    if (INST && p.dbg_logits != nullptr && tile == p.dbg_tile && h < MT) {
+    if (INST && p.dbg_logits != nullptr && tile == p.dbg_tile && h < MT && win == 0) {
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             float v[32];
@@ -519,7 +535,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     }
     // ---- per-row partial softmax statistics of this tile, base 2 (thread = row n of block h): z2 = acc * scale * log2(e)
     // a label outside [0, C) makes the reference raise (scatter_ / CrossEntropyLoss); here the row's loss becomes NaN
-    const int64_t lab_n = INST ? p.labels[n < N ? n : 0] : 0;
+    const int64_t lab_n = INST ? p.labels[r0 + (n < N ? n : 0)] : 0;
     const bool bad_label = INST && (lab_n < 0 || lab_n >= (int64_t)p.C);
     const int y = INST ? (bad_label ? -(1 << 30) : (int)lab_n - c0) : -1;
     if (h < MT) {
@@ -549,7 +565,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
             m = nm;
         }
         if (n < N) {
-            const size_t at = (size_t)tile * 256 + (INST ? h : mod) * 128 + n;
+            const size_t at = stat_off + (size_t)tile * 256 + (INST ? h : mod) * 128 + n;
             (INST ? p.ls_inst : p.ls_nce)[at] = m + log2f(s);      // s >= 1 (the maximum contributes 2^0)
             if (INST) p.zz_inst[at] = make_float2(sz2 * F_LN2, zy2 * F_LN2);
         }
@@ -561,7 +577,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     {
         unsigned* ctr = INST ? p.bar : p.bar + 2 + mod;
         grid_arrive(ctr);
-        grid_wait(ctr, (unsigned)tiles);
+        grid_wait(ctr, (unsigned)(tiles * (win + 1)));      // one arrival per tile and window
     }
     F_STAMP(4);
 
@@ -569,19 +585,19 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     if (h < MT && n < N) {
         if (INST) {
             const int row = h * 128 + n;
-            const float l2 = lse2_of_row(p.ls_inst, row, tiles, F_NEG);
+            const float l2 = lse2_of_row(p.ls_inst + stat_off, row, tiles, F_NEG);
             s_lse2[row] = l2;
             if (tile == 0 && p.row_helpers == 0) {                              // losses.py:26-39 with label smoothing (else: spare CTAs)
-                const float2 zz = sum_of_row(p.zz_inst, row, tiles);
-                p.rows_inst[h * p.NS + n] = bad_label ? CUDART_NAN_F : l2 * F_LN2 - (1.0f - p.eps) * zz.y - (p.eps / (float)p.C) * zz.x;
+                const float2 zz = sum_of_row(p.zz_inst + stat_off, row, tiles);
+                p.rows_inst[h * p.NS + r0 + n] = bad_label ? CUDART_NAN_F : l2 * F_LN2 - (1.0f - p.eps) * zz.y - (p.eps / (float)p.C) * zz.x;
             }
         } else {
-            const float z02 = __fdiv_rn(p.pos[mod * p.NS + n], p.T) * F_LOG2E;     // column 0 of the reference's logits (base 2)
-            const float l2 = lse2_of_row(p.ls_nce, mod * 128 + n, tiles, z02);
+            const float z02 = __fdiv_rn(p.pos[mod * p.NS + r0 + n], p.T) * F_LOG2E;     // column 0 of the reference's logits (base 2)
+            const float l2 = lse2_of_row(p.ls_nce + stat_off, mod * 128 + n, tiles, z02);
             s_lse2[n] = l2;
             if (tile == 0) {                                                    // losses.py:206-217, target 0
-                p.rows_nce[mod * p.NS + n] = (l2 - z02) * F_LN2;                // exactly 0 when only the positive is left
-                p.dpos[mod * p.NS + n] = (exp2f(z02 - l2) - 1.0f) / ((float)p.Nn * p.T);
+                p.rows_nce[mod * p.NS + r0 + n] = (l2 - z02) * F_LN2;                // exactly 0 when only the positive is left
+                p.dpos[mod * p.NS + r0 + n] = (exp2f(z02 - l2) - 1.0f) / ((float)p.Nn * p.T);
             }
         }
     }
@@ -596,9 +612,6 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
         const float rs = n < N ? F_LN2 / (float)p.Nn : 0.f;          // dz' = (softmax - target) / N * scale, scale = col.x * ln 2
         const float uni = INST ? p.eps / (float)p.C : 0.f;
         const float uni_hot = uni + (INST ? 1.0f - p.eps : 0.f);
-        const bool do_dw = INST && p.d_proj != nullptr;
-        const int NH = Dp / 128;
-        float csum0 = 0.f, csum1 = 0.f;                // <dz', z2>_rows of this thread's two 32-column chunks (column = lane)
         // TMEM columns: Z0 = [0,128) and Z1 = [128,256) hold the logits of row blocks 0 / 1, W0|W1 = [256,512) the dWs accumulator.
         // Row block 0: dE halves go to Z0 (its logits are consumed) and W0 (dWs has not started); once they are drained, dWs(0)
         // is issued and runs under the gradient math of row block 1.  Row block 1: dE halves go to Z1 and Z0, dWs(1)
@@ -636,7 +649,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                     if (jj) csum1 += t; else csum0 += t;
                 }
                 if (mt == 1 && jj == 0 && do_dw) {     // dWs(0) still reads the previous image
-                    mbar_wait_sleepy(sm.bar_dw, 0, 32);
+                    mbar_wait_sleepy(sm.bar_dw, (uint32_t)(win & 1), 32);
                     tc_fence_after();
                 }
 #pragma unroll
@@ -649,69 +662,83 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
 
             const bool two = INST && NH == 2;          // dE has two 128-column halves
             const uint32_t colA = INST ? (uint32_t)(mt * 128) : 256u;            // half a (InfoNCE: all Dp columns)
-            const uint32_t colB = mt == 0 ? 256u : 0u;                           // half b
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t e0 = smem_u32(sm.E), wb0 = smem_u32(sm.WB), dz0 = smem_u32(sm.DZ);
-                // dE[row, d] = sum_c dz'[row, c] * Wb[d, c]           (M = 128 rows, N = d, K = 128 columns)
-                const uint32_t id_e = idesc(128, INST ? 128 : Dp, 0, 0);
-                for (int r = 0; r < (two ? 2 : 1); ++r)
+            // half b: row block 0 borrows W0 while dWs has not started -- from the second window on W0 holds the accumulated
+            // dWs, and the two halves of row block 0 go through Z0 one after the other
+            const bool serial = two && mt == 0 && win > 0;
+            const uint32_t colB = serial ? colA : (mt == 0 ? 256u : 0u);
+            const int halves = two ? 2 : 1;
 #pragma unroll 1
-                    for (int ks = 0; ks < 8; ++ks)
-                        umma_bf16(tmem + (r ? colB : colA), umma_desc_sw128(dz0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
-                                  umma_desc_sw128(wb0 + (ks >> 2) * F_WB_CHUNK + r * (128 * 128) + (ks & 3) * 32), id_e,
-                                  (uint32_t)(ks > 0));
-                if (do_dw && mt == 1) {
-                    // dWs[d, c] += sum_rows E[row, d] * dz'[row, c]   (M = 128 d per half, N = 128 columns, K = 128 rows)
-                    const uint32_t id_w = idesc(128, 128, 1, 1);
-                    for (int hh = 0; hh < NH; ++hh)
+            for (int pass = 0; pass < (serial ? 2 : 1); ++pass) {
+                const int r_lo = serial ? pass : 0, r_hi = serial ? pass + 1 : halves;
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t e0 = smem_u32(sm.E), wb0 = smem_u32(sm.WB), dz0 = smem_u32(sm.DZ);
+                    // dE[row, d] = sum_c dz'[row, c] * Wb[d, c]           (M = 128 rows, N = d, K = 128 columns)
+                    const uint32_t id_e = idesc(128, INST ? 128 : Dp, 0, 0);
+#pragma unroll 1
+                    for (int r = r_lo; r < r_hi; ++r)
 #pragma unroll 1
                         for (int ks = 0; ks < 8; ++ks)
-                            umma_bf16(tmem + 256 + hh * 128,
-                                      desc_mn(e0 + (p.KC + 2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES),
-                                      desc_mn(dz0 + ks * 2048, BLOCK_BYTES), id_w, 1u);
-                }
-                umma_commit(sm.bar_mma);
-            }
-            mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
-            mma_phase ^= 1;
-            tc_fence_after();
-            // -- drain the partial dE of this tile to global (reduced over tiles after the second grid barrier)
-            // partials are rounded to bf16 (their own error from the bf16 operands is 2^-8; they are summed in fp32) and laid out
-            // [tile][row block][8-column chunk][128 rows] x 16 bytes: the 32 rows of a warp write 512 contiguous bytes
-            if (INST) {
-                // slot m = (row block * Dp/8 + 8-column chunk) * 128 + row; layout [unit = m / U][tile][m % U] (U divides 128): the
-                // share of all tiles in one work unit of the final reduction is ONE contiguous piece (see PartialReducer)
-                const int U = p.fin_U, upr = 128 / U;                    // units per 128-row group
-                uint4* dst = p.part_inst + ((size_t)(n / U) * p.T_inst + tile) * U + (n % U);
-                const size_t gstride = (size_t)upr * p.T_inst * U;       // one (row block, chunk) group further
+                            umma_bf16(tmem + (r ? colB : colA), umma_desc_sw128(dz0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
+                                      umma_desc_sw128(wb0 + (ks >> 2) * F_WB_CHUNK + r * (128 * 128) + (ks & 3) * 32), id_e,
+                                      (uint32_t)(ks > 0));
+                    if (do_dw && mt == 1) {
+                        // dWs[d, c] += sum_rows E[row, d] * dz'[row, c]   (M = 128 d per half, N = 128 columns, K = 128 rows)
+                        const uint32_t id_w = idesc(128, 128, 1, 1);
+                        for (int hh = 0; hh < NH; ++hh)
 #pragma unroll 1
-                for (int rj = 0; rj < (two ? 4 : 2); ++rj) {
-                    const int r = rj >> 1, jj = rj & 1;
-                    float v[32];
-                    tmem_ld32(tmem + lanes + (r ? colB : colA) + (uint32_t)(h * 64 + jj * 32), v);
-                    if (n < N) {
+                            for (int ks = 0; ks < 8; ++ks)
+                                umma_bf16(tmem + 256 + hh * 128,
+                                          desc_mn(e0 + (p.KC + 2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES),
+                                          desc_mn(dz0 + ks * 2048, BLOCK_BYTES), id_w, 1u);
+                    }
+                    umma_commit(sm.bar_mma);
+                }
+                mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
+                mma_phase ^= 1;
+                tc_fence_after();
+                // -- drain the partial dE of this tile to global (reduced over the tiles at the end of the kernel); partials are
+                // rounded to bf16 (their own error from the bf16 operands is 2^-8; they are summed in fp32)
+                if (INST) {
+                    // slot m = (row block * Dp/8 + 8-column chunk) * 128 + row; layout [window][unit = m / U][tile][m % U] (U
+                    // divides 128): the share of all tiles in one work unit of the final reduction is ONE contiguous piece (see
+                    // PartialReducer); the 32 rows of a warp write 512 contiguous bytes
+                    const int U = p.fin_U, upr = 128 / U;                    // units per 128-row group
+                    const size_t win_off = (size_t)win * p.T_inst * (2 * (Dp / 8) * 128);
+                    uint4* dst = p.part_inst + win_off + ((size_t)(n / U) * p.T_inst + tile) * U + (n % U);
+                    const size_t gstride = (size_t)upr * p.T_inst * U;       // one (row block, chunk) group further
+#pragma unroll 1
+                    for (int rj = 2 * r_lo; rj < 2 * r_hi; ++rj) {
+                        const int r = rj >> 1, jj = rj & 1;
+                        float v[32];
+                        tmem_ld32(tmem + lanes + (r ? colB : colA) + (uint32_t)(h * 64 + jj * 32), v);
+                        if (n < N) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            __stcg(dst + (size_t)(mt * (Dp / 8) + r * 16 + h * 8 + jj * 4 + k) * gstride,
-                                   make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
-                                              pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
+                            for (int k = 0; k < 4; ++k)
+                                __stcg(dst + (size_t)(mt * (Dp / 8) + r * 16 + h * 8 + jj * 4 + k) * gstride,
+                                       make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
+                                                  pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
+                        }
+                    }
+                } else {
+                    const int half = Dp / 2;
+                    uint4* dst = p.part_nce + ((size_t)win * 2 * p.T_k + (size_t)(mod * p.T_k + tile)) * (Dp / 8) * 128 + n;
+#pragma unroll 1
+                    for (int jj = 0; jj < half / 32; ++jj) {
+                        float v[32];
+                        tmem_ld32(tmem + lanes + (uint32_t)(256 + h * half + jj * 32), v);
+                        if (n < N) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                __stcg(dst + (size_t)((h * half + jj * 32) / 8 + k) * 128,
+                                       make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
+                                                  pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
+                        }
                     }
                 }
-            } else {
-                const int half = Dp / 2;
-                uint4* dst = p.part_nce + (size_t)(mod * p.T_k + tile) * (Dp / 8) * 128 + n;
-#pragma unroll 1
-                for (int jj = 0; jj < half / 32; ++jj) {
-                    float v[32];
-                    tmem_ld32(tmem + lanes + (uint32_t)(256 + h * half + jj * 32), v);
-                    if (n < N) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            __stcg(dst + (size_t)((h * half + jj * 32) / 8 + k) * 128,
-                                   make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
-                                              pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
-                    }
+                if (serial && pass == 0) {             // Z0 is re-used by the second half
+                    tc_fence_before();
+                    __syncthreads();
                 }
             }
             tc_fence_before();
@@ -725,10 +752,13 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
 #pragma unroll 1
                     for (int ks = 0; ks < 8; ++ks)
                         umma_bf16(tmem + 256 + hh * 128, desc_mn(e0 + (2 * hh) * BLOCK_BYTES + ks * 2048, BLOCK_BYTES),
-                                  desc_mn(dz0 + ks * 2048, BLOCK_BYTES), id_w, (uint32_t)(ks > 0));
+                                  desc_mn(dz0 + ks * 2048, BLOCK_BYTES), id_w, (uint32_t)(win > 0 || ks > 0));
                 umma_commit(sm.bar_dw);
             }
         }
+    }      // want_grad
+  }        // windows
+    if (p.want_grad) {
         F_STAMP(6);
         // the partial dE tiles are out: the CTAs that reduce them (InfoNCE / align / spare CTAs, see fused_loss_kernel) can start
         // while this CTA still writes its dW tile
@@ -784,20 +814,6 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                         const float wv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(wsrc[j] + i * 1024));
                         o[u][j] = fmaf(-wv, sc[j], tile1[d * 128 + ((((c >> 2) ^ w)) << 2) + (c & 3)]);
                     }
-                }
-                if (p.accum_dw) {                      // a later row window: add to the gradient the earlier windows wrote
-                    float old[8][4];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int d = w + 8 * (i0 + u);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) old[u][j] = __ldcg(p.d_proj + (int64_t)d * p.C + min(c0 + cc[j], p.C - 1));
-                    }
-                    asm volatile("" ::: "memory");
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) o[u][j] += old[u][j];
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -981,7 +997,7 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
 struct PartialReducer {
     const FP& p;
     const Smem& sm;
-    int tid, Dp, M, U, n_units, cur, nxt, k;
+    int tid, Dp, M, U, upw, n_units, cur, nxt, k;
     uint32_t ph0, ph1;              // mbarrier phases of the two buffers (scalars: no dynamically indexed local array)
     int* s_next;
     __device__ __forceinline__ PartialReducer(const FP& p_, const Smem& sm_) : p(p_), sm(sm_) {
@@ -989,7 +1005,8 @@ struct PartialReducer {
         Dp = p.KC * 64;
         M = 2 * (Dp / 8) * 128;
         U = p.fin_U;
-        n_units = M / U;
+        upw = M / U;                                  // units per 128-row window
+        n_units = upw * ((p.N + 127) / 128);
         s_next = reinterpret_cast<int*>(sm.red32 + 32);
         cur = nxt = n_units; k = 0;
         ph0 = ph1 = 0;
@@ -1043,7 +1060,8 @@ struct PartialReducer {
             }
             __syncthreads();
             for (int i = tid; i < U; i += F_THREADS) {
-                const int m = cur * U + i, g = m >> 7, row = m & 127;
+                const int win = cur / upw;
+                const int m = (cur - win * upw) * U + i, g = m >> 7, row = win * 128 + (m & 127);
                 const int mt = g / (Dp / 8), c8 = g % (Dp / 8);
                 if (row < N && c8 * 8 < D) {
                     float4 a = comb[i], c = comb[U + i];
@@ -1066,19 +1084,22 @@ struct PartialReducer {
 // Instance row losses (losses.py:26-39 with label smoothing) on spare CTA `hs` of `H`: the sums of z and z_y over all tiles are
 // 176 KB that only the loss value needs -- on tile 0 they made that CTA the straggler of the whole grid.  One warp per row,
 // lanes over the tiles (at most 160), fixed shuffle order.
-__device__ __forceinline__ void spare_rows_program(const FP& p, int hs, int H) {
+__device__ __forceinline__ void spare_rows_program(const FP& p, int hs, int H, int win) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.T_inst;
+    const int r0 = win * 128, Nw = min(128, p.N - r0);
+    const float* ls = p.ls_inst + (size_t)win * tiles * 256;
+    const float2* zz = p.zz_inst + (size_t)win * tiles * 256;
 #pragma unroll 1
-    for (int r = hs * 8 + w; r < 2 * p.N; r += H * 8) {
-        const int mod = r / p.N, n = r - mod * p.N, srow = mod * 128 + n;
+    for (int r = hs * 8 + w; r < 2 * Nw; r += H * 8) {
+        const int mod = r / Nw, n = r - mod * Nw, srow = mod * 128 + n;
         float l[5];
         float2 z[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const int t = lane + 32 * i;
-            l[i] = t < tiles ? fmaxf(__ldcg(p.ls_inst + (size_t)t * 256 + srow), F_NEG) : F_NEG;
-            z[i] = t < tiles ? __ldcg(p.zz_inst + (size_t)t * 256 + srow) : make_float2(0.f, 0.f);
+            l[i] = t < tiles ? fmaxf(__ldcg(ls + (size_t)t * 256 + srow), F_NEG) : F_NEG;
+            z[i] = t < tiles ? __ldcg(zz + (size_t)t * 256 + srow) : make_float2(0.f, 0.f);
         }
         float M = fmaxf(fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3])), l[4]);
         M = warp_max(M);
@@ -1090,10 +1111,10 @@ __device__ __forceinline__ void spare_rows_program(const FP& p, int hs, int H) {
         }
         S = warp_sum(S); sx = warp_sum(sx); sy = warp_sum(sy);
         if (lane == 0) {
-            const int64_t lab = p.labels[n];
+            const int64_t lab = p.labels[r0 + n];
             const bool bad_label = lab < 0 || lab >= (int64_t)p.C;       // the reference raises; here the row's loss becomes NaN
             const float l2 = M + log2f(S);
-            p.rows_inst[mod * p.NS + n] = bad_label ? CUDART_NAN_F : l2 * F_LN2 - (1.0f - p.eps) * sy - (p.eps / (float)p.C) * sx;
+            p.rows_inst[mod * p.NS + r0 + n] = bad_label ? CUDART_NAN_F : l2 * F_LN2 - (1.0f - p.eps) * sy - (p.eps / (float)p.C) * sx;
         }
     }
 }
@@ -1131,7 +1152,8 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm, int fi
             for (int e = 0; e < 8; ++e) g[e] = qv[e] = 0.f;
             float dot = 0.f;
             if (on) {
-                const uint4* src = p.part_nce + (size_t)(mod * p.T_k) * (Dp / 8) * 128 + (size_t)lane * 128 + nn;
+                const uint4* src = p.part_nce + ((size_t)(nn >> 7) * 2 * p.T_k + (size_t)(mod * p.T_k)) * (Dp / 8) * 128 +
+                                   (size_t)lane * 128 + (nn & 127);                     // [window][modality][tile][chunk][row]
                 for (int t0 = 0; t0 < p.T_k; t0 += 16) {
                     uint4 x[16];
 #pragma unroll
@@ -1269,8 +1291,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
         enqueue_slice(p, b - p.n_inst, p.n_nce + (p.fin_early ? 0 : p.n_ga));
     const bool finisher = !p.fin_early || is_nce || !has_tile;
     if (!has_tile && b - n_tiles < p.row_helpers) {          // spare CTAs: instance row losses once every tile's statistics are out
-        grid_wait(p.bar, (unsigned)p.n_inst);
-        spare_rows_program(p, b - n_tiles, p.row_helpers);
+        for (int win = 0; win < (p.N + 127) / 128; ++win) {
+            grid_wait(p.bar, (unsigned)(p.n_inst * (win + 1)));
+            spare_rows_program(p, b - n_tiles, p.row_helpers, win);
+        }
         grid_arrive(p.bar + 1);
     }
     if (has_tile && (!p.fin_early || is_nce)) grid_arrive(p.bar + 1);
@@ -1312,20 +1336,20 @@ struct Scratch {
 };
 
 Scratch carve_scratch(uint8_t* base, int N, int D, int K, int C) {
-    (void)N;
+    const int64_t NW = (N + 127) / 128;               // per-window buffers: operand images, statistics, partial tiles
     const int KC = (D + 127) / 128 * 2, Dp = KC * 64;
     const int T_inst = (C + F_TILE - 1) / F_TILE, T_k = (K + F_TILE - 1) / F_TILE;
     Scratch s;
     uint8_t* p = base;
     auto take = [&](int64_t bytes) { uint8_t* r = p; p += (bytes + 1023) / 1024 * 1024; return r; };
-    const int64_t img = (int64_t)2 * KC * BLOCK_BYTES;
+    const int64_t img = NW * 2 * KC * BLOCK_BYTES;
     s.Ep = take(img); s.ENp = take(img); s.QNp = take(img);
     s.QUp = take((int64_t)2 * T_k * F_WB_BYTES);
-    s.ls_inst = reinterpret_cast<float*>(take((int64_t)256 * T_inst * 4));
-    s.zz_inst = reinterpret_cast<float2*>(take((int64_t)256 * T_inst * 8));
-    s.ls_nce = reinterpret_cast<float*>(take((int64_t)256 * T_k * 4));
-    s.part_inst = reinterpret_cast<uint4*>(take((int64_t)T_inst * 256 * Dp * 2));
-    s.part_nce = reinterpret_cast<uint4*>(take((int64_t)2 * T_k * 128 * Dp * 2));
+    s.ls_inst = reinterpret_cast<float*>(take(NW * 256 * T_inst * 4));
+    s.zz_inst = reinterpret_cast<float2*>(take(NW * 256 * T_inst * 8));
+    s.ls_nce = reinterpret_cast<float*>(take(NW * 256 * T_k * 4));
+    s.part_inst = reinterpret_cast<uint4*>(take(NW * T_inst * 256 * Dp * 2));
+    s.part_nce = reinterpret_cast<uint4*>(take(NW * 2 * T_k * 128 * Dp * 2));
     s.bar = reinterpret_cast<unsigned*>(take(256));
     s.dbg = reinterpret_cast<unsigned long long*>(take(160 * 16 * 8));
     s.dbg_logits = reinterpret_cast<float*>(take(256 * 128 * 4));
@@ -1350,7 +1374,7 @@ bool fused_loss_supported(int N, int D, int K, int C, int sm_count) {
 }
 
 bool fused_windows_supported(int N, int D, int K, int C, int sm_count) {
-    if (N <= 128 || N > 1024 || D < 64 || D > 256 || (D % 64) != 0) return false;
+    if (N <= 128 || N > 1024 || D < 64 || D > 256 || (D % 64) != 0 || (D % 8) != 0) return false;
     return (C + F_TILE - 1) / F_TILE <= sm_count && 2 * ((K + F_TILE - 1) / F_TILE) <= sm_count;
 }
 
@@ -1371,10 +1395,7 @@ static ProArgs make_pro_args(const FusedLossArgs& a, const Scratch& s) {
     q.Ep = s.Ep; q.ENp = s.ENp; q.QNp = s.QNp; q.QUp = s.QUp;
     q.normalize_keys = a.normalize_keys; q.N = a.N; q.D = a.D; q.KC = (a.D + 127) / 128 * 2; q.K = a.K;
     q.T_k = (a.K + F_TILE - 1) / F_TILE;
-    q.NS = a.NS > 0 ? a.NS : a.N;
-    q.skip_pack = a.skip_pack;
-    // (later row windows find W in L2 from the first one)
-    q.W = ((a.roles & 1) && !a.skip_pack && !getenv("TRB_FUSED_NO_PREFETCH")) ? a.projection : nullptr;
+    q.W = ((a.roles & 1) && !getenv("TRB_FUSED_NO_PREFETCH")) ? a.projection : nullptr;
     q.W_bytes = (int64_t)a.D * a.C * 4;
     return q;
 }
@@ -1386,7 +1407,7 @@ int fused_loss_prologue(const FusedLossArgs& a, cudaStream_t st) {
     if (trb_first_on_device(attr))   // same shared-memory carve-out as the cooperative kernel that follows: no SM reconfiguration between the two
         TRB_CUDA_OK(cudaFuncSetAttribute(fused_prologue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     const ProArgs q = make_pro_args(a, s);
-    const int ntasks = 256 + (((a.roles & 2) && !q.skip_pack) ? 2 * q.KC * 64 : 0);     // queue re-pack only for fused InfoNCE tiles
+    const int ntasks = 256 * ((a.N + 127) / 128) + ((a.roles & 2) ? 2 * q.KC * 64 : 0);   // queue re-pack only for fused InfoNCE tiles
     fused_prologue_kernel<<<(ntasks + 7) / 8, 256, 0, st>>>(q, s.bar, ntasks);
     TRB_LAUNCH_OK();
     return 0;
@@ -1399,11 +1420,8 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     memset(&p, 0, sizeof(p));
     p.N = a.N; p.D = a.D; p.K = a.K; p.C = a.C;
     p.KC = (a.D + 127) / 128 * 2;
-    p.NS = a.NS > 0 ? a.NS : a.N;
-    p.Nn = a.NS > 0 ? a.NS : a.N;
-    p.mask_labels = a.mask_labels ? a.mask_labels : a.labels;
-    p.n_mask = a.mask_labels ? a.n_mask : a.N;
-    p.accum_dw = a.accum_dw;
+    p.NS = a.N;
+    p.Nn = a.N;
     p.T_inst = (a.C + F_TILE - 1) / F_TILE; p.T_k = (a.K + F_TILE - 1) / F_TILE;
     p.roles = a.roles;
     p.n_inst = (a.roles & 1) ? p.T_inst : 0;

@@ -20,12 +20,6 @@ struct FusedLossArgs {
     // _dequeue_and_enqueue folded into the cooperative kernel (all roles fused only); NULL enq_ptr = no enqueue
     float *enq_v_queue, *enq_t_queue;
     int64_t *enq_ids, *enq_ptr;
-    // row windows (batches of more than 128 rows): N = rows of this window, every row-indexed pointer above pre-offset to the
-    // window's first row, NS = full batch size (stride between the modalities; 0 = N), mask_labels / n_mask = ids of the whole
-    // batch (NULL = labels / N), accum_dw = add the projection gradient to the earlier windows', skip_pack = queue images
-    // already packed by an earlier window of this step
-    int NS, n_mask, accum_dw, skip_pack;
-    const int64_t* mask_labels;
     int roles;          // bit 0 instance, bit 1 InfoNCE, bit 2 global-align: which branches the fused kernel runs
     int reduce_losses;  // the fused kernel also forms the three loss scalars (all roles fused)
     int after_prologue; // this launch directly follows fused_loss_prologue on the stream (programmatic dependent launch allowed)
@@ -33,7 +27,8 @@ struct FusedLossArgs {
 
 // shape gate: D a multiple of 64 up to 256, N <= 128, and one CTA per 128-class / 128-slot tile must fit the device
 bool fused_loss_supported(int N, int D, int K, int C, int sm_count);
-// 128 < N <= 1024 in row windows of 128: one cooperative launch per window and role; each role's tiles must fit the device
+// 128 < N <= 1024: the kernel walks the batch in row windows of 128 (W / queue tiles resident); instance and InfoNCE tiles run
+// as two cooperative launches (together they may exceed the SMs, e.g. 86 + 64 at C = 11003, K = 4096); each must fit the device
 bool fused_windows_supported(int N, int D, int K, int C, int sm_count);
 // zero the grid-barrier words between two cooperative launches that share one prologue
 int fused_loss_reset_barriers(const FusedLossArgs& a, cudaStream_t st);
