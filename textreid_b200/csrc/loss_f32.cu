@@ -385,8 +385,8 @@ int trb_moco_loss_launches_impl(const trb_moco_shape* s, int precision) {
         const char* e = getenv("TRB_FUSED_ROLES");
         if (e == nullptr || (atoi(e) & 3) == 3) {
             // shared prologue + the unfused global-align branch (3 contractions, pair losses, normalise backward) + the fused
-            // prologue and one cooperative launch per role (the row windows are walked inside the kernel) + loss reduce
-            return 1 + (3 * per_gemm + 2) + 3 + 1;
+            // prologue and one cooperative launch (the row windows are walked inside the kernel) + loss reduce
+            return 1 + (3 * per_gemm + 2) + 2 + 1;
         }
     }
     // prologue, mask, column norms, 3 row kernels, 2 normalise-backward, projection backward, loss reduce, 3 partial reductions
@@ -472,18 +472,14 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     if (roles && !windows && (rc = fused_loss_launch(fa, st))) return rc;
     if (roles && windows) {
         // ---- batches above 128 rows on the caller's stream: ONE prologue (operand images of every 128-row window, queue images)
-        //      and one cooperative launch per role -- 86 instance + 2 x 32 InfoNCE tiles do not fit the SMs together at
-        //      K = 4096; each launch walks the windows inside the kernel with its W / queue tile resident
+        //      and ONE cooperative launch that walks the windows inside the kernel with its W / queue tiles resident; an InfoNCE
+        //      CTA takes its tile of both modalities in turn (86 instance + 2 x 32 InfoNCE tiles would not fit 148 SMs)
         fa.reduce_losses = 0;
         fa.roles = 3;
         if ((rc = fused_loss_prologue(fa, st))) return rc;
-        fa.roles = 1;
         fa.after_prologue = 1;
         if ((rc = fused_loss_launch(fa, st))) return rc;
         fa.after_prologue = 0;
-        if ((rc = fused_loss_reset_barriers(fa, st))) return rc;
-        fa.roles = 2;
-        if ((rc = fused_loss_launch(fa, st))) return rc;
         fa.roles = roles;
     }
 
@@ -597,7 +593,7 @@ int trb_moco_step_extra_launches_impl(const trb_moco_shape* s, int precision) {
 
 // debug read-back from the caller's workspace (fused bf16 path only)
 int trb_moco_loss_debug_impl(const void* workspace, const trb_moco_shape* s, int what, void* host_out) {
-    if (!fused_loss_supported(s->N, s->D, s->K, s->C, sm_count())) {
+    if (!fused_loss_supported(s->N, s->D, s->K, s->C, sm_count()) && !fused_windows_supported(s->N, s->D, s->K, s->C, sm_count())) {
         trb_set_error("moco_loss debug: the shape does not take the fused path");
         return TRB_ERR_UNSUPPORTED;
     }

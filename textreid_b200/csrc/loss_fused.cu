@@ -49,6 +49,8 @@ struct FP {
     // kernel (tile_program); row-indexed arrays are [modality][N rows], NS (= N) the stride between the modalities, Nn (= N) the
     // batch size every mean is taken over.  The queue mask (head.py:148-157) always uses the ids of the whole batch.
     int NS, Nn;
+    int nce_dual;                   // an InfoNCE CTA takes tile t of BOTH modalities, one after the other (n_nce = T_k CTAs): the
+                                    // instance tiles run more than twice as long, and 86 + 2 x 32 tiles would not fit 148 SMs
     int fin_U;                      // 16-byte slots per work unit of the partial-tile reduction (layout of part_inst)
     int row_helpers;                // this many spare CTAs form the instance row losses (0: tile 0 does)
     int fin_early;                  // the partial reductions belong to the CTAs behind the instance tiles (see fused_loss_kernel)
@@ -417,8 +419,11 @@ __global__ void __launch_bounds__(256) fused_prologue_kernel(const ProArgs a, un
 // ------------------------------------------------------------------------------------------------------------------------
 // instance (INST) / InfoNCE tile
 // ------------------------------------------------------------------------------------------------------------------------
+// `mma_phase` / `load_phase`: parities of the CTA's MMA and operand-load mbarriers, carried across calls (an InfoNCE CTA in dual
+// mode runs the program twice, once per modality)
 template <bool INST>
-__device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32_t tmem, int mod, int tile) {
+__device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32_t tmem, int mod, int tile, uint32_t& mma_phase,
+                                             uint32_t& load_phase) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, q = w & 3, h = w >> 2;
     const int n = q * 32 + lane;                       // row inside a 128-row block = TMEM lane
     const int Dp = p.KC * 64;
@@ -429,7 +434,6 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     const int ncols = INST ? p.C : p.K;
     const int tiles = INST ? p.T_inst : p.T_k;
     const uint32_t lanes = (uint32_t)(q * 32) << 16;
-    uint32_t mma_phase = 0;
     // scratch inside the logit-gradient region while no gradient is staged there
     float* red = reinterpret_cast<float*>(sm.DZ);                        // [8][128] column partials
     int64_t* s_lab = reinterpret_cast<int64_t*>(sm.DZ + 8192);           // [<= 1024] ids of the whole batch (InfoNCE mask)
@@ -507,7 +511,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
 
     // ---- forward logits: z[mt] = E[mt] . Wb   (M = 128 rows, N = 128 columns, K = Dp)
     if (tid == 0) {
-        mbar_wait(sm.bar_load, (uint32_t)(win & 1));
+        mbar_wait(sm.bar_load, load_phase);
         tc_fence_after();
         const uint32_t id_f = idesc(128, 128, 0, 1);
         const uint32_t e0 = smem_u32(sm.E), wb0 = smem_u32(sm.WB);
@@ -520,6 +524,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
     }
     mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
     mma_phase ^= 1;
+    load_phase ^= 1;                                   // one operand load per window
     tc_fence_after();
     F_STAMP(2);
 
@@ -1276,9 +1281,19 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
     const uint32_t tmem = has_tile ? *sm.tmem_slot : 0u;
     F_STAMP(0);
 
-    if (b < p.n_inst) tile_program<true>(p, sm, tmem, 0, b);
-    else if (b < p.n_inst + p.n_nce) tile_program<false>(p, sm, tmem, (b - p.n_inst) / p.T_k, (b - p.n_inst) % p.T_k);
-    else if (has_tile) align_program(p, sm, tmem);
+    uint32_t mma_phase = 0, load_phase = 0;
+    if (b < p.n_inst) tile_program<true>(p, sm, tmem, 0, b, mma_phase, load_phase);
+    else if (b < p.n_inst + p.n_nce) {
+        if (p.nce_dual) {                // one CTA per queue tile index: the image queries' tile, then the text queries' tile
+#pragma unroll 1
+            for (int mod = 0; mod < 2; ++mod) {
+                tile_program<false>(p, sm, tmem, mod, b - p.n_inst, mma_phase, load_phase);
+                __syncthreads();         // the shared scratch of the first pass is re-used by the second
+            }
+        } else {
+            tile_program<false>(p, sm, tmem, (b - p.n_inst) / p.T_k, (b - p.n_inst) % p.T_k, mma_phase, load_phase);
+        }
+    } else if (has_tile) align_program(p, sm, tmem);
     else griddep_wait();                 // spare CTAs: the counters they poll are cleared by the prologue launch
 
     // Second counter: every tile CTA arrives once its partial dE tiles (and enqueue slice) are written.  With `fin_early` the
@@ -1375,7 +1390,7 @@ bool fused_loss_supported(int N, int D, int K, int C, int sm_count) {
 
 bool fused_windows_supported(int N, int D, int K, int C, int sm_count) {
     if (N <= 128 || N > 1024 || D < 64 || D > 256 || (D % 64) != 0 || (D % 8) != 0) return false;
-    return (C + F_TILE - 1) / F_TILE <= sm_count && 2 * ((K + F_TILE - 1) / F_TILE) <= sm_count;
+    return (C + F_TILE - 1) / F_TILE + (K + F_TILE - 1) / F_TILE <= sm_count;
 }
 
 int fused_loss_reset_barriers(const FusedLossArgs& a, cudaStream_t st) {
@@ -1425,7 +1440,8 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     p.T_inst = (a.C + F_TILE - 1) / F_TILE; p.T_k = (a.K + F_TILE - 1) / F_TILE;
     p.roles = a.roles;
     p.n_inst = (a.roles & 1) ? p.T_inst : 0;
-    p.n_nce = (a.roles & 2) ? 2 * p.T_k : 0;
+    p.nce_dual = (a.roles & 2) && a.N > 128 ? 1 : 0;
+    p.n_nce = (a.roles & 2) ? (p.nce_dual ? p.T_k : 2 * p.T_k) : 0;
     p.n_ga = (a.roles & 4) ? 1 : 0;
     p.want_grad = a.d_inst != nullptr;
     p.reduce_losses = a.reduce_losses;
@@ -1453,11 +1469,11 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     TRB_CUDA_OK(cudaGetDevice(&dev));
     TRB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // spare CTAs: all remaining SMs when the whole step is this one launch; a launch that shares the device with the unfused
-    // branches on the helper streams (row windows, partial roles) keeps 30 SMs free for them -- a cooperative grid that covers
+    // branches on the helper streams (batches above 128 rows, partial roles) keeps 16+ SMs free for them -- a cooperative grid that covers
     // every SM would have to wait until those kernels have drained; without instance tiles spare CTAs have nothing to do
     int spare = sms - n_tiles;
     if (spare < 0 || p.n_inst == 0) spare = 0;
-    if (a.roles != 7 && spare > 32) spare = 32;
+    if (a.roles != 7) spare = spare - 16 > 32 ? 32 : (spare > 16 ? spare - 16 : 0);
     const int grid = n_tiles + spare;
     p.fin_early = (p.n_inst > 0 && p.want_grad && grid - p.n_inst - p.n_ga >= 24) ? 1 : 0;
     {

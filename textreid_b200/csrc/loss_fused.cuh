@@ -27,8 +27,8 @@ struct FusedLossArgs {
 
 // shape gate: D a multiple of 64 up to 256, N <= 128, and one CTA per 128-class / 128-slot tile must fit the device
 bool fused_loss_supported(int N, int D, int K, int C, int sm_count);
-// 128 < N <= 1024: the kernel walks the batch in row windows of 128 (W / queue tiles resident); instance and InfoNCE tiles run
-// as two cooperative launches (together they may exceed the SMs, e.g. 86 + 64 at C = 11003, K = 4096); each must fit the device
+// 128 < N <= 1024: the kernel walks the batch in row windows of 128 (W / queue tiles resident); an InfoNCE CTA takes its tile
+// index for both modalities in turn, so ceil(C/128) + ceil(K/128) CTAs must fit the device (86 + 32 at C = 11003, K = 4096)
 bool fused_windows_supported(int N, int D, int K, int C, int sm_count);
 // zero the grid-barrier words between two cooperative launches that share one prologue
 int fused_loss_reset_barriers(const FusedLossArgs& a, cudaStream_t st);

@@ -49,6 +49,9 @@ def print_stamps(lib, roles, K, Cn, tag, ws=None, sh=None):
     n_nce = 2 * T_k if roles & 2 else 0
     n_tiles = n_inst + n_nce + (1 if roles & 4 else 0)
     groups = [("inst", 0, n_inst), ("nce", n_inst, n_inst + n_nce), ("align", n_inst + n_nce, n_tiles), ("spare", n_tiles, 148)]
+    if sh.N > 128:      # two launches (instance tiles, then InfoNCE tiles from block 0): the second overwrote the first's low blocks
+        groups = [("nce launch, all blocks", 0, 2 * T_k), ("inst launch, blocks >= %d (tiles then spare)" % (2 * T_k), 2 * T_k, T_inst + 32)]
+        n_tiles = 2 * T_k
     t0 = st[:n_tiles, 0]
     t0 = int(t0[t0 > 0].min())
     for name, lo, hi in groups:
@@ -97,8 +100,10 @@ def child(roles, variant):
                         float((g[..., 128:] - r[..., 128:]).abs().max() / r.abs().max()) if D > 128 else 0.0))
         print(("PASS " if ok else "FAIL ") + " ".join(line), flush=True)
         ok_all &= ok
-    # timing at the headline shape: eager library call and CUDA-graph replay of it
+    # timing at the headline shape (or TRB_PROBE_TIMED="N,D,K,C"): eager library call and CUDA-graph replay of it
     N, D, K, Cn, masked = SHAPES[0]
+    if os.environ.get("TRB_PROBE_TIMED"):
+        N, D, K, Cn = (int(x) for x in os.environ["TRB_PROBE_TIMED"].split(","))
     inp = {k: v.cuda().contiguous() for k, v in loss_inputs(N, D, K, Cn, seed=1, masked=masked).items()}
     inp["id_queue"] = inp["id_queue"].reshape(-1).contiguous()
     sh = _lib.MocoShape(N, D, K, Cn)
