@@ -272,10 +272,12 @@ def test_fused_shape_gate():
     assert _launches(128, 256, 2048, 11003, 1) == 2          # BASELINE configs[1]
     assert _launches(32, 64, 128, 257, 1) == 2               # D padded to 128
     assert _launches(100, 192, 200, 257, 1) == 2             # ragged K and C tiles
-    # N > 128 (BASELINE configs[2]): row windows of 128 walked inside the kernel -- shared prologue + unfused global-align branch
-    # (11 launches on the tensor-core sequence) + fused prologue and ONE cooperative launch + loss reduce
-    assert _launches(256, 256, 4096, 11003, 1) == 1 + 11 + 2 + 1
-    assert _launches(200, 128, 512, 700, 1) == 1 + 11 + 2 + 1          # ragged second window
+    # 128 < N <= 256 (BASELINE configs[2]): the 128-row windows are walked inside the same kernel -- still two launches
+    assert _launches(256, 256, 4096, 11003, 1) == 2
+    assert _launches(200, 128, 512, 700, 1) == 2                       # ragged second window
+    # N > 256: instance + InfoNCE fused (one launch), the global-align branch unfused: shared prologue + 11 launches on the
+    # tensor-core sequence + fused prologue and ONE cooperative launch + loss reduce
+    assert _launches(384, 64, 768, 300, 1) == 1 + 11 + 2 + 1
     assert _launches(20, 48, 60, 77, 1) > 2                  # D not a multiple of 64
     assert _launches(128, 256, 2048, 40000, 1) > 2           # more tiles than SMs
     assert _launches(128, 256, 2048, 11003, 0) > 2           # fp32 path is never fused
@@ -289,7 +291,7 @@ def test_fused_matches_unfused_bf16(monkeypatch, N, D, K, Cn, masked):
     gradients far inside the bf16 budget.  Both are checked against the fp64 oracle.  N > 128 runs the fused kernel in 128-row
     windows (instance and InfoNCE tiles; projection gradient accumulated over the windows; queue mask from the whole batch --
     the (384, .., "some") case has batch ids beyond the first 256 rows that must mask their queue slots too)."""
-    assert _launches(N, D, K, Cn, 1) == (2 if N <= 128 else 15)
+    assert _launches(N, D, K, Cn, 1) == (2 if N <= 256 else 15)
     inp = synth_loss_inputs(N, D, K, Cn, seed=N + K, masked=masked)
     fused = run_fused(inp, 0.1, precision="bf16")
     monkeypatch.setenv("TRB_FUSED_ROLES", "0")

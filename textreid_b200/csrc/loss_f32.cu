@@ -422,9 +422,9 @@ static int moco_loss_impl(const float* v_embed, const float* t_embed, const floa
     int roles = 0;
     FusedLossArgs fa;
     memset(&fa, 0, sizeof(fa));
-    // batches of more than 128 rows run the fused kernel once per 128-row window and role (instance tiles, InfoNCE tiles); the
-    // global-align branch, whose N x N similarity couples the windows, stays on the unfused tensor-core sequence (helper stream)
-    const bool windows = w.fused != nullptr && N > 128;
+    // up to 256 rows everything is one cooperative launch; above that (up to 1024) the instance and InfoNCE branches are, and
+    // the global-align branch, whose N x N similarity couples all 128-row windows, stays on the unfused tensor-core sequence
+    const bool windows = w.fused != nullptr && !fused_loss_supported(N, D, K, C, sm_count());
     if (w.fused != nullptr) {
         roles = windows ? 3 : 7;
         if (const char* e = getenv("TRB_FUSED_ROLES")) roles = windows ? (((atoi(e) & 3) == 3) ? 3 : 0) : (atoi(e) & 7);

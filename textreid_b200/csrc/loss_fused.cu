@@ -65,6 +65,7 @@ struct FP {
     float *ls_inst, *ls_nce;                // per-tile softmax statistics [tile][256 rows]: log2 sum_c 2^(z2_c) over the tile's columns
     float2* zz_inst;                        // ... and (sum z, z_y) of the instance tiles (label smoothing / target logit)
     unsigned long long* dbg;                // optional phase timestamps [cta][16] (TRB_FUSED_DEBUG)
+    float* ga_part;                         // align, batches above 128 rows: dq_t contribution of block (iw, jw), fp32 [128][Dp]
     uint4 *part_inst, *part_nce;            // partial dE tiles, bf16 x 8 per 16 bytes: InfoNCE [tile][8-column chunk][128 rows],
                                             // instance [unit][tile][U slots] (see PartialReducer)
     float *dpos, *rows_inst, *rows_nce, *rows_ga, *losses, *d_inst, *d_nce, *d_ga, *d_proj;
@@ -851,91 +852,102 @@ __device__ __forceinline__ void smem_row_chunk(const uint8_t* blk0, int row, int
 // global align (losses.py:102-128): S = en_v en_t^T, pair losses, dS, dq_v = dS en_t, dq_t = dS^T en_v, normalise backward.
 // One CTA; the bf16-rounded normalised embeddings in shared memory are used consistently (MMA operands and projection).
 // ------------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint32_t tmem) {
+// Batches above 128 rows: one align CTA per 128-row window `iw` of the IMAGE rows; it walks the 128-row windows `jw` of the text
+// rows (block S[iw, jw] at a time), accumulates dq_v[iw] in TMEM over them and hands the dq_t contribution of every block to
+// global memory; after a counter among the align CTAs, CTA `iw` reduces and finishes the text rows of window iw.
+__device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint32_t tmem, int iw) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, q = w & 3, h = w >> 2;
     const int n = q * 32 + lane;
-    const int N = p.N, D = p.D, Dp = p.KC * 64;
+    const int Nall = p.N, D = p.D, Dp = p.KC * 64;
+    const int NW = (Nall + 127) / 128;
+    const int ri = iw * 128, Ni = min(128, Nall - ri);                  // image rows of this CTA
     const uint32_t lanes = (uint32_t)(q * 32) << 16;
-    uint32_t mma_phase = 0;
-    int64_t* s_lab = reinterpret_cast<int64_t*>(sm.WB);                 // [128]
-    float* s_part = reinterpret_cast<float*>(sm.WB + 2048);             // [2][128]
+    const size_t img_bytes = (size_t)2 * p.KC * BLOCK_BYTES;           // packed image of one window: [v rows][t rows]
+    uint32_t mma_phase = 0, load_phase = 0;
+    int64_t* s_labi = reinterpret_cast<int64_t*>(sm.WB);               // [128] ids of the image rows
+    int64_t* s_labj = reinterpret_cast<int64_t*>(sm.WB + 1024);        // [128] ids of the text rows of the current block
+    float* s_part = reinterpret_cast<float*>(sm.WB + 2048);            // [2][128]
+    const uint32_t e0 = smem_u32(sm.E), dz0 = smem_u32(sm.DZ);
+    const uint32_t et0 = e0 + p.KC * BLOCK_BYTES;                      // text rows
+    const int half = Dp / 2;
 
     griddep_wait();
-    if (tid == 0) {
-        const int blocks = 2 * p.KC;
-        mbar_expect_tx(sm.bar_load, (uint32_t)blocks * BLOCK_BYTES);
+    if (tid < 128) s_labi[tid] = tid < Ni ? p.labels[ri + tid] : INT64_MIN;
+    float acc = 0.f;                                                   // pair losses of (row n, column half h) over all blocks
 #pragma unroll 1
-        for (int b = 0; b < blocks; ++b) bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, p.ENp + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
-    }
-    if (tid < 128) s_lab[tid] = tid < N ? p.labels[tid] : INT64_MIN;
-    fence_async_smem();
-    __syncthreads();
-    const uint32_t e0 = smem_u32(sm.E), dz0 = smem_u32(sm.DZ);
-    const uint32_t et0 = e0 + p.KC * BLOCK_BYTES;                       // text rows
-    if (tid == 0) {
-        mbar_wait(sm.bar_load, 0);
-        tc_fence_after();
-        const uint32_t id_s = idesc(128, 128, 0, 0);
+    for (int jw = 0; jw < NW; ++jw) {
+        const int rj = jw * 128, Nj = min(128, Nall - rj);
+        if (tid == 0) {                                                // (every MMA that read the previous text rows has completed)
+            const int first = jw == 0 ? 0 : p.KC;                      // the image rows arrive once
+            mbar_expect_tx(sm.bar_load, (uint32_t)(2 * p.KC - first) * BLOCK_BYTES);
 #pragma unroll 1
-        for (int ks = 0; ks < Dp / 16; ++ks)
-            umma_bf16(tmem, umma_desc_sw128(e0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
-                      umma_desc_sw128(et0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32), id_s, (uint32_t)(ks > 0));
-        umma_commit(sm.bar_mma);
-    }
-    mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
-    mma_phase ^= 1;
-    tc_fence_after();
-    F_STAMP(2);
-
-    {
-        const int64_t yi = s_lab[n];
-        const float two_over_n = 2.0f / (float)N;
-        const float c_same = -p.sp * two_over_n, c_diff = p.sn * two_over_n;
-        float acc = 0.f;
-#pragma unroll 1
-        for (int jj = 0; jj < 2; ++jj) {
-            const int j = h * 2 + jj;
-            float v[32];
-            tmem_ld32(tmem + lanes + (uint32_t)(j * 32), v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int col = j * 32 + i;
-                const bool ok = n < N && col < N;
-                const bool same = s_lab[col] == yi;
-                const float x = same ? -p.sp * (v[i] - p.alpha) : p.sn * (v[i] - p.beta);
-                const float e = __expf(x);
-                const float ope = 1.0f + e;
-                acc += ok ? __logf(ope) : 0.f;                           // the reference's literal log(1+exp(x)), losses.py:123-124
-                v[i] = ok ? (same ? c_same : c_diff) * __fdividef(e, ope) : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint4 o;
-                o.x = pack2(v[8 * k + 0], v[8 * k + 1]); o.y = pack2(v[8 * k + 2], v[8 * k + 3]);
-                o.z = pack2(v[8 * k + 4], v[8 * k + 5]); o.w = pack2(v[8 * k + 6], v[8 * k + 7]);
-                *reinterpret_cast<uint4*>(sm.DZ + dz_offset(h, n, jj * 4 + k)) = o;
+            for (int b = first; b < 2 * p.KC; ++b) {
+                const int win = b < p.KC ? iw : jw;
+                bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, p.ENp + (size_t)win * img_bytes + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
             }
         }
-        s_part[h * 128 + n] = acc;
-    }
-    tc_fence_before();
-    fence_async_smem();
-    __syncthreads();
-    if (h == 0 && n < N) p.rows_ga[n] = s_part[n] + s_part[128 + n];
-    F_STAMP(3);
-    // nothing the reducing CTAs need comes after the row losses: arrive now, the gradient below runs beside the reductions
-    if (p.fin_early) grid_arrive(p.bar + 1);
+        if (tid < 128) s_labj[tid] = tid < Nj ? p.labels[rj + tid] : INT64_MIN;
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(sm.bar_load, load_phase);
+            tc_fence_after();
+            const uint32_t id_s = idesc(128, 128, 0, 0);
+#pragma unroll 1
+            for (int ks = 0; ks < Dp / 16; ++ks)
+                umma_bf16(tmem, umma_desc_sw128(e0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
+                          umma_desc_sw128(et0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32), id_s, (uint32_t)(ks > 0));
+            umma_commit(sm.bar_mma);
+        }
+        mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
+        mma_phase ^= 1;
+        load_phase ^= 1;
+        tc_fence_after();
+        F_STAMP(2);
 
-    if (p.want_grad) {
+        {
+            const int64_t yi = s_labi[n];
+            const float two_over_n = 2.0f / (float)Nall;
+            const float c_same = -p.sp * two_over_n, c_diff = p.sn * two_over_n;
+#pragma unroll 1
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = h * 2 + jj;
+                float v[32];
+                tmem_ld32(tmem + lanes + (uint32_t)(j * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int col = j * 32 + i;
+                    const bool ok = n < Ni && col < Nj;
+                    const bool same = s_labj[col] == yi;
+                    const float x = same ? -p.sp * (v[i] - p.alpha) : p.sn * (v[i] - p.beta);
+                    const float e = __expf(x);
+                    const float ope = 1.0f + e;
+                    acc += ok ? __logf(ope) : 0.f;                       // the reference's literal log(1+exp(x)), losses.py:123-124
+                    v[i] = ok ? (same ? c_same : c_diff) * __fdividef(e, ope) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint4 o;
+                    o.x = pack2(v[8 * k + 0], v[8 * k + 1]); o.y = pack2(v[8 * k + 2], v[8 * k + 3]);
+                    o.z = pack2(v[8 * k + 4], v[8 * k + 5]); o.w = pack2(v[8 * k + 6], v[8 * k + 7]);
+                    *reinterpret_cast<uint4*>(sm.DZ + dz_offset(h, n, jj * 4 + k)) = o;
+                }
+            }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncthreads();
+        if (!p.want_grad) continue;
+
         if (tid == 0) {
             tc_fence_after();
-            // dq_v[i, d] = sum_j dS[i, j] en_t[j, d]   -> columns [256, 256 + Dp)
+            // dq_v[i, d] += sum_j dS[i, j] en_t[j, d]   -> columns [256, 256 + Dp), accumulated over the text windows
             const uint32_t id_v = idesc(128, Dp, 0, 1);
 #pragma unroll 1
             for (int ks = 0; ks < 8; ++ks)
                 umma_bf16(tmem + 256, umma_desc_sw128(dz0 + (ks >> 2) * BLOCK_BYTES + (ks & 3) * 32),
-                          desc_mn(et0 + ks * 2048, BLOCK_BYTES), id_v, (uint32_t)(ks > 0));
-            // dq_t[j, d] = sum_i dS[i, j] en_v[i, d]   -> columns [0, Dp)
+                          desc_mn(et0 + ks * 2048, BLOCK_BYTES), id_v, (uint32_t)(jw > 0 || ks > 0));
+            // dq_t[j, d] = sum_i dS[i, j] en_v[i, d]   -> columns [0, Dp): this block's contribution
             const uint32_t id_t = idesc(128, Dp, 1, 1);
 #pragma unroll 1
             for (int ks = 0; ks < 8; ++ks)
@@ -946,17 +958,74 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
         mbar_wait_sleepy(sm.bar_mma, mma_phase, 32);
         mma_phase ^= 1;
         tc_fence_after();
+        if (NW > 1) {
+            // several image windows contribute to these text rows: fp32 block [128 rows][Dp] to global, summed after the counter
+            float* part = p.ga_part + ((size_t)(iw * NW + jw) * 128 + n) * Dp + h * half;
+#pragma unroll 1
+            for (int jj = 0; jj < half / 32; ++jj) {
+                float v[32];
+                tmem_ld32(tmem + lanes + (uint32_t)(h * half + jj * 32), v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st_v8(part + jj * 32 + 8 * k, &v[8 * k]);
+            }
+            tc_fence_before();
+            __syncthreads();                                             // S of the next block overwrites these columns
+        }
+    }
+    s_part[h * 128 + n] = acc;
+    __syncthreads();
+    if (h == 0 && n < Ni) p.rows_ga[ri + n] = s_part[n] + s_part[128 + n];
+    __syncthreads();
+    F_STAMP(3);
+    // nothing the reducing CTAs need comes after the row losses: arrive now, the rest runs beside the reductions
+    if (p.fin_early) grid_arrive(p.bar + 1);
+
+    if (p.want_grad) {
         F_STAMP(5);
         // normalise backward: d_ga[row] = (g - <g, en> en) / ||e||, thread = (row n, column half h)
-        const int half = Dp / 2;
+        // image rows of window iw: g = dq_v in TMEM; text rows: one window -> dq_t in TMEM, else the summed block contributions
         for (int mod = 0; mod < 2; ++mod) {
+            const bool from_tmem = mod == 0 || NW == 1;
             const uint32_t col0 = (mod == 0 ? 256u : 0u) + (uint32_t)(h * half);
             const uint8_t* blk0 = sm.E + (size_t)mod * p.KC * BLOCK_BYTES;
+            if (!from_tmem) {
+                // every align CTA has written its blocks; the text rows of window iw (packed rows back into shared memory)
+                grid_arrive(p.bar + 5);
+                grid_wait(p.bar + 5, (unsigned)NW);
+                if (iw != NW - 1) {                                      // (the last block left window NW-1's text rows there)
+                    if (tid == 0) {
+                        mbar_expect_tx(sm.bar_load, (uint32_t)p.KC * BLOCK_BYTES);
+#pragma unroll 1
+                        for (int b = p.KC; b < 2 * p.KC; ++b)
+                            bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, p.ENp + (size_t)iw * img_bytes + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
+                    }
+                    mbar_wait_sleepy(sm.bar_load, load_phase, 32);
+                    load_phase ^= 1;
+                }
+            }
+            auto load_g = [&](int jj, float (&v)[32]) {
+                if (from_tmem) {
+                    tmem_ld32(tmem + lanes + col0 + (uint32_t)(jj * 32), v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll 1
+                    for (int i2 = 0; i2 < NW; ++i2) {                    // fixed order over the image windows
+                        const float4* src = reinterpret_cast<const float4*>(p.ga_part + ((size_t)(i2 * NW + iw) * 128 + n) * Dp + h * half + jj * 32);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 x = __ldcg(src + k);
+                            v[4 * k] += x.x; v[4 * k + 1] += x.y; v[4 * k + 2] += x.z; v[4 * k + 3] += x.w;
+                        }
+                    }
+                }
+            };
+            const int Nm = Ni;                                           // rows of window iw in either modality
             float dot = 0.f;
 #pragma unroll 1
             for (int jj = 0; jj < half / 32; ++jj) {
                 float v[32];
-                tmem_ld32(tmem + lanes + col0 + (uint32_t)(jj * 32), v);
+                load_g(jj, v);
                 const int d0 = h * half + jj * 32;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -970,12 +1039,12 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
             s_part[h * 128 + n] = dot;
             __syncthreads();
             dot = s_part[n] + s_part[128 + n];
-            const float inv = n < N ? p.inv_e[mod * N + n] : 0.f;
-            float* out = p.d_ga + ((int64_t)mod * N + (n < N ? n : 0)) * D;
+            const float inv = n < Nm ? p.inv_e[mod * Nall + ri + n] : 0.f;
+            float* out = p.d_ga + ((int64_t)mod * Nall + ri + (n < Nm ? n : 0)) * D;
 #pragma unroll 1
             for (int jj = 0; jj < half / 32; ++jj) {
                 float v[32];
-                tmem_ld32(tmem + lanes + col0 + (uint32_t)(jj * 32), v);
+                load_g(jj, v);
                 const int d0 = h * half + jj * 32;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -983,7 +1052,7 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
                     smem_row_chunk(blk0, n, d0 + 8 * k, e8);
 #pragma unroll
                     for (int t = 0; t < 8; ++t) o[t] = (v[8 * k + t] - dot * e8[t]) * inv;
-                    if (n < N && d0 + 8 * k < D) st_v8(out + d0 + 8 * k, o);
+                    if (n < Nm && d0 + 8 * k < D) st_v8(out + d0 + 8 * k, o);
                 }
             }
         }
@@ -1293,7 +1362,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
         } else {
             tile_program<false>(p, sm, tmem, (b - p.n_inst) / p.T_k, (b - p.n_inst) % p.T_k, mma_phase, load_phase);
         }
-    } else if (has_tile) align_program(p, sm, tmem);
+    } else if (has_tile) align_program(p, sm, tmem, b - p.n_inst - p.n_nce);
     else griddep_wait();                 // spare CTAs: the counters they poll are cleared by the prologue launch
 
     // Second counter: every tile CTA arrives once its partial dE tiles (and enqueue slice) are written.  With `fin_early` the
@@ -1344,6 +1413,7 @@ struct Scratch {
     float *ls_inst, *ls_nce;
     float2* zz_inst;
     uint4 *part_inst, *part_nce;
+    float* ga_part;
     unsigned* bar;
     unsigned long long* dbg;       // [160][16] phase timestamps (TRB_FUSED_DEBUG)
     float* dbg_logits;             // [256][128] logits of one instance tile (TRB_FUSED_DEBUG_LOGITS)
@@ -1365,6 +1435,7 @@ Scratch carve_scratch(uint8_t* base, int N, int D, int K, int C) {
     s.ls_nce = reinterpret_cast<float*>(take(NW * 256 * T_k * 4));
     s.part_inst = reinterpret_cast<uint4*>(take(NW * T_inst * 256 * Dp * 2));
     s.part_nce = reinterpret_cast<uint4*>(take(NW * 2 * T_k * 128 * Dp * 2));
+    s.ga_part = reinterpret_cast<float*>(take(NW > 1 ? NW * NW * 128 * Dp * 4 : 0));
     s.bar = reinterpret_cast<unsigned*>(take(256));
     s.dbg = reinterpret_cast<unsigned long long*>(take(160 * 16 * 8));
     s.dbg_logits = reinterpret_cast<float*>(take(256 * 128 * 4));
@@ -1382,12 +1453,17 @@ int fused_loss_debug_copy(const uint8_t* scratch, int N, int D, int K, int C, in
     return (int)cudaMemcpy(host_out, s.dbg_logits, 256 * 128 * 4, cudaMemcpyDeviceToHost);
 }
 
+// everything in one cooperative launch (2 launches per step with the prologue)
 bool fused_loss_supported(int N, int D, int K, int C, int sm_count) {
-    if (N < 1 || N > 128 || D < 64 || D > 256 || (D % 64) != 0) return false;
-    const int ctas = (C + F_TILE - 1) / F_TILE + 2 * ((K + F_TILE - 1) / F_TILE) + 1;
+    if (N < 1 || N > 256 || D < 64 || D > 256 || (D % 64) != 0) return false;
+    const int T_inst = (C + F_TILE - 1) / F_TILE, T_k = (K + F_TILE - 1) / F_TILE;
+    // up to 128 rows: one CTA per InfoNCE tile and modality, one align CTA; up to 256 rows: an InfoNCE CTA takes both modalities
+    // of its tile in turn, one align CTA per 128-row window
+    const int ctas = N <= 128 ? T_inst + 2 * T_k + 1 : T_inst + T_k + 2;
     return ctas <= sm_count;
 }
 
+// instance + InfoNCE branches in one cooperative launch, global-align on the unfused sequence: batches of up to 1024 rows
 bool fused_windows_supported(int N, int D, int K, int C, int sm_count) {
     if (N <= 128 || N > 1024 || D < 64 || D > 256 || (D % 64) != 0 || (D % 8) != 0) return false;
     return (C + F_TILE - 1) / F_TILE + (K + F_TILE - 1) / F_TILE <= sm_count;
@@ -1442,7 +1518,7 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     p.n_inst = (a.roles & 1) ? p.T_inst : 0;
     p.nce_dual = (a.roles & 2) && a.N > 128 ? 1 : 0;
     p.n_nce = (a.roles & 2) ? (p.nce_dual ? p.T_k : 2 * p.T_k) : 0;
-    p.n_ga = (a.roles & 4) ? 1 : 0;
+    p.n_ga = (a.roles & 4) ? (a.N + 127) / 128 : 0;      // one align CTA per 128-row window of the image rows
     p.want_grad = a.d_inst != nullptr;
     p.reduce_losses = a.reduce_losses;
     p.T = a.T; p.eps = a.eps; p.alpha = a.alpha; p.beta = a.beta; p.sp = a.sp; p.sn = a.sn;
@@ -1458,7 +1534,7 @@ int fused_loss_launch(const FusedLossArgs& a, cudaStream_t st) {
     p.dbg_logits = nullptr;
     if (const char* e = getenv("TRB_FUSED_DEBUG_LOGITS")) { p.dbg_logits = s.dbg_logits; p.dbg_tile = atoi(e); }
     p.enq_queue[0] = a.enq_v_queue; p.enq_queue[1] = a.enq_t_queue; p.enq_ids = a.enq_ids; p.enq_ptr = a.enq_ptr;
-    p.part_inst = s.part_inst; p.part_nce = s.part_nce;
+    p.part_inst = s.part_inst; p.part_nce = s.part_nce; p.ga_part = s.ga_part;
     p.dpos = a.dpos; p.rows_inst = a.rows_inst; p.rows_nce = a.rows_nce; p.rows_ga = a.rows_ga;
     p.losses = a.losses; p.d_inst = a.d_inst; p.d_nce = a.d_nce; p.d_ga = a.d_ga; p.d_proj = a.d_proj;
     p.bar = s.bar;
