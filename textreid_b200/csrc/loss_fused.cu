@@ -66,7 +66,7 @@ struct FP {
     float2* zz_inst;                        // ... and (sum z, z_y) of the instance tiles (label smoothing / target logit)
     unsigned long long* dbg;                // optional phase timestamps [cta][16] (TRB_FUSED_DEBUG)
     float* ga_part;                         // align, batches above 128 rows: dq_t contribution of block (iw, jw), fp32 [128][Dp]
-    uint4 *part_inst, *part_nce;            // partial dE tiles, bf16 x 8 per 16 bytes: InfoNCE [tile][8-column chunk][128 rows],
+    uint4 *part_inst, *part_nce;            // partial dE tiles, bf16 x 8 per 16 bytes: InfoNCE [tile][128 rows][8-column chunk],
                                             // instance [unit][tile][U slots] (see PartialReducer)
     float *dpos, *rows_inst, *rows_nce, *rows_ga, *losses, *d_inst, *d_nce, *d_ga, *d_proj;
     unsigned* bar;                  // [0] instance statistics, [1] partial tiles written, [2], [3] InfoNCE statistics per modality,
@@ -728,7 +728,9 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                     }
                 } else {
                     const int half = Dp / 2;
-                    uint4* dst = p.part_nce + ((size_t)win * 2 * p.T_k + (size_t)(mod * p.T_k + tile)) * (Dp / 8) * 128 + n;
+                    // [window][modality][tile][row][8-column chunk]: the reader (one warp per row, lane = chunk) pulls 512
+                    // contiguous bytes per tile; a thread writes 64 contiguous bytes per TMEM chunk
+                    uint4* dst = p.part_nce + ((size_t)win * 2 * p.T_k + (size_t)(mod * p.T_k + tile)) * (Dp / 8) * 128 + (size_t)n * (Dp / 8);
 #pragma unroll 1
                     for (int jj = 0; jj < half / 32; ++jj) {
                         float v[32];
@@ -736,7 +738,7 @@ __device__ __forceinline__ void tile_program(const FP& p, const Smem& sm, uint32
                         if (n < N) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                __stcg(dst + (size_t)((h * half + jj * 32) / 8 + k) * 128,
+                                __stcg(dst + ((h * half + jj * 32) / 8 + k),
                                        make_uint4(pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
                                                   pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])));
                         }
@@ -854,7 +856,7 @@ __device__ __forceinline__ void smem_row_chunk(const uint8_t* blk0, int row, int
 // ------------------------------------------------------------------------------------------------------------------------
 // Batches above 128 rows: one align CTA per 128-row window `iw` of the IMAGE rows; it walks the 128-row windows `jw` of the text
 // rows (block S[iw, jw] at a time), accumulates dq_v[iw] in TMEM over them and hands the dq_t contribution of every block to
-// global memory; after a counter among the align CTAs, CTA `iw` reduces and finishes the text rows of window iw.
+// global memory; the reducing CTAs sum them and finish the text rows (finish_phase, one warp per row).
 __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint32_t tmem, int iw) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, q = w & 3, h = w >> 2;
     const int n = q * 32 + lane;
@@ -983,43 +985,12 @@ __device__ __forceinline__ void align_program(const FP& p, const Smem& sm, uint3
     if (p.want_grad) {
         F_STAMP(5);
         // normalise backward: d_ga[row] = (g - <g, en> en) / ||e||, thread = (row n, column half h)
-        // image rows of window iw: g = dq_v in TMEM; text rows: one window -> dq_t in TMEM, else the summed block contributions
-        for (int mod = 0; mod < 2; ++mod) {
-            const bool from_tmem = mod == 0 || NW == 1;
+        // image rows of window iw: g = dq_v in TMEM; text rows of a single-window batch: dq_t in TMEM
+        // (with several windows the text rows are finished by the reducing CTAs, one warp per row: finish_phase)
+        for (int mod = 0; mod < (NW == 1 ? 2 : 1); ++mod) {
             const uint32_t col0 = (mod == 0 ? 256u : 0u) + (uint32_t)(h * half);
             const uint8_t* blk0 = sm.E + (size_t)mod * p.KC * BLOCK_BYTES;
-            if (!from_tmem) {
-                // every align CTA has written its blocks; the text rows of window iw (packed rows back into shared memory)
-                grid_arrive(p.bar + 5);
-                grid_wait(p.bar + 5, (unsigned)NW);
-                if (iw != NW - 1) {                                      // (the last block left window NW-1's text rows there)
-                    if (tid == 0) {
-                        mbar_expect_tx(sm.bar_load, (uint32_t)p.KC * BLOCK_BYTES);
-#pragma unroll 1
-                        for (int b = p.KC; b < 2 * p.KC; ++b)
-                            bulk_g2s(sm.E + (size_t)b * BLOCK_BYTES, p.ENp + (size_t)iw * img_bytes + (size_t)b * BLOCK_BYTES, BLOCK_BYTES, sm.bar_load);
-                    }
-                    mbar_wait_sleepy(sm.bar_load, load_phase, 32);
-                    load_phase ^= 1;
-                }
-            }
-            auto load_g = [&](int jj, float (&v)[32]) {
-                if (from_tmem) {
-                    tmem_ld32(tmem + lanes + col0 + (uint32_t)(jj * 32), v);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-#pragma unroll 1
-                    for (int i2 = 0; i2 < NW; ++i2) {                    // fixed order over the image windows
-                        const float4* src = reinterpret_cast<const float4*>(p.ga_part + ((size_t)(i2 * NW + iw) * 128 + n) * Dp + h * half + jj * 32);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const float4 x = __ldcg(src + k);
-                            v[4 * k] += x.x; v[4 * k + 1] += x.y; v[4 * k + 2] += x.z; v[4 * k + 3] += x.w;
-                        }
-                    }
-                }
-            };
+            auto load_g = [&](int jj, float (&v)[32]) { tmem_ld32(tmem + lanes + col0 + (uint32_t)(jj * 32), v); };
             const int Nm = Ni;                                           // rows of window iw in either modality
             float dot = 0.f;
 #pragma unroll 1
@@ -1227,7 +1198,7 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm, int fi
             float dot = 0.f;
             if (on) {
                 const uint4* src = p.part_nce + ((size_t)(nn >> 7) * 2 * p.T_k + (size_t)(mod * p.T_k)) * (Dp / 8) * 128 +
-                                   (size_t)lane * 128 + (nn & 127);                     // [window][modality][tile][chunk][row]
+                                   (size_t)(nn & 127) * (Dp / 8) + lane;                // [window][modality][tile][row][chunk]
                 for (int t0 = 0; t0 < p.T_k; t0 += 16) {
                     uint4 x[16];
 #pragma unroll
@@ -1260,6 +1231,50 @@ __device__ __forceinline__ void finish_phase(const FP& p, const Smem& sm, int fi
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = (g[e] - dot * qv[e]) * inv;
                 st_v8(p.d_nce + (int64_t)grow * D + lane * 8, o);
+            }
+        }
+    }
+    if (p.want_grad && p.n_ga > 1) {
+        // global-align gradient of the TEXT rows for batches above 128 rows: dq_t[row] = sum over the image windows of the block
+        // contributions the align CTAs left (fixed order), then normalise backward against the bf16-rounded normalised row (the
+        // value the MMAs saw).  One warp per row, taken from the low warp numbers (the InfoNCE rows above start at warp 7).
+        const int NW = p.n_ga;
+        for (int row = fi + GW * w; worker && row < N; row += GW * 8) {
+            const int jw = row >> 7, nl = row & 127;
+            const bool on = lane * 8 < D;
+            float g[8], en[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = en[e] = 0.f;
+            const float inv = __ldcg(p.inv_e + N + row);
+            if (on) {
+                const float4* er = reinterpret_cast<const float4*>(p.en + (size_t)(N + row) * D + lane * 8);
+                const float4 e0 = __ldcg(er), e1 = __ldcg(er + 1);
+                float4 x[8][2];
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    const float4* src = reinterpret_cast<const float4*>(p.ga_part + ((size_t)(min(i2, NW - 1) * NW + jw) * 128 + nl) * Dp + lane * 8);
+                    x[i2][0] = __ldcg(src); x[i2][1] = __ldcg(src + 1);
+                }
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    if (i2 < NW) {
+                        g[0] += x[i2][0].x; g[1] += x[i2][0].y; g[2] += x[i2][0].z; g[3] += x[i2][0].w;
+                        g[4] += x[i2][1].x; g[5] += x[i2][1].y; g[6] += x[i2][1].z; g[7] += x[i2][1].w;
+                    }
+                }
+                const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) en[e] = __bfloat162float(__float2bfloat16_rn(ee[e]));
+            }
+            float dot = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dot = fmaf(g[e], en[e], dot);
+            dot = warp_sum(dot);
+            if (on) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = (g[e] - dot * en[e]) * inv;
+                st_v8(p.d_ga + (size_t)(N + row) * D + lane * 8, o);
             }
         }
     }
@@ -1371,21 +1386,28 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
     // InfoNCE CTAs (which finish early) and the spare CTAs, so they run UNDER the dW writes instead of after them.
     // Otherwise every CTA reduces a share.
     const bool is_nce = b >= p.n_inst && b < p.n_inst + p.n_nce;
-    if (p.enq_ptr != nullptr && (is_nce || (has_tile && b >= p.n_inst && !p.fin_early)))
-        enqueue_slice(p, b - p.n_inst, p.n_nce + (p.fin_early ? 0 : p.n_ga));
+    // _dequeue_and_enqueue: the queues were last read by the prologue's re-pack, so the CTAs with time to spare write the key
+    // columns -- the spare CTAs (idle until the reductions) when there are any, else the InfoNCE / align CTAs after their tiles
+    const int n_spare = G - n_tiles;
+    if (p.enq_ptr != nullptr) {
+        if (n_spare > 0) { if (!has_tile) enqueue_slice(p, b - n_tiles, n_spare); }
+        else if (is_nce || (has_tile && b >= p.n_inst && !p.fin_early)) enqueue_slice(p, b - p.n_inst, p.n_nce + (p.fin_early ? 0 : p.n_ga));
+    }
     const bool finisher = !p.fin_early || is_nce || !has_tile;
-    if (!has_tile && b - n_tiles < p.row_helpers) {          // spare CTAs: instance row losses once every tile's statistics are out
-        for (int win = 0; win < (p.N + 127) / 128; ++win) {
-            grid_wait(p.bar, (unsigned)(p.n_inst * (win + 1)));
-            spare_rows_program(p, b - n_tiles, p.row_helpers, win);
+    if (!has_tile) {                                         // spare CTAs: instance row losses once every tile's statistics are out
+        if (b - n_tiles < p.row_helpers) {
+            for (int win = 0; win < (p.N + 127) / 128; ++win) {
+                grid_wait(p.bar, (unsigned)(p.n_inst * (win + 1)));
+                spare_rows_program(p, b - n_tiles, p.row_helpers, win);
+            }
         }
-        grid_arrive(p.bar + 1);
+        grid_arrive(p.bar + 1);                              // (their enqueue slices and row losses are out)
     }
     if (has_tile && (!p.fin_early || is_nce)) grid_arrive(p.bar + 1);
     if (finisher) {
         const int fi = !p.fin_early ? b : (is_nce ? b - p.n_inst : b - p.n_inst - p.n_ga);
         const int nf = !p.fin_early ? G : G - p.n_inst - p.n_ga;
-        grid_wait(p.bar + 1, (unsigned)(n_tiles + p.row_helpers));
+        grid_wait(p.bar + 1, (unsigned)G);                   // every tile CTA and every spare CTA arrives once
         F_STAMP(8);
         // every enqueue slice has read the old pointer before it arrived: head.py:108-109
         if (p.enq_ptr != nullptr && fi == nf - 1 && threadIdx.x == 0) *p.enq_ptr = (*p.enq_ptr + p.N) % p.K;
@@ -1393,7 +1415,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_loss_kernel(const FP p) {
         F_STAMP(9);
     } else if (p.want_grad) {
         // an instance tile that is done with its dW epilogue: take whatever units of the partial-tile reduction are left
-        grid_wait(p.bar + 1, (unsigned)(n_tiles + p.row_helpers));
+        grid_wait(p.bar + 1, (unsigned)G);
         PartialReducer red(p, sm);
         red.start();
         red.run();

@@ -49,9 +49,11 @@ def print_stamps(lib, roles, K, Cn, tag, ws=None, sh=None):
     n_nce = 2 * T_k if roles & 2 else 0
     n_tiles = n_inst + n_nce + (1 if roles & 4 else 0)
     groups = [("inst", 0, n_inst), ("nce", n_inst, n_inst + n_nce), ("align", n_inst + n_nce, n_tiles), ("spare", n_tiles, 148)]
-    if sh.N > 128:      # two launches (instance tiles, then InfoNCE tiles from block 0): the second overwrote the first's low blocks
-        groups = [("nce launch, all blocks", 0, 2 * T_k), ("inst launch, blocks >= %d (tiles then spare)" % (2 * T_k), 2 * T_k, T_inst + 32)]
-        n_tiles = 2 * T_k
+    if sh.N > 128:      # an InfoNCE CTA per tile index (both modalities in turn), one align CTA per 128-row window; the per-window
+        n_nce = T_k if roles & 2 else 0      # stamps show the LAST window
+        n_ga = (sh.N + 127) // 128 if roles & 4 else 0
+        n_tiles = n_inst + n_nce + n_ga
+        groups = [("inst", 0, n_inst), ("nce", n_inst, n_inst + n_nce), ("align", n_inst + n_nce, n_tiles), ("spare", n_tiles, 148)]
     t0 = st[:n_tiles, 0]
     t0 = int(t0[t0 > 0].min())
     for name, lo, hi in groups:
