@@ -208,12 +208,13 @@ typedef struct trb_moco_hparams {
 int64_t trb_moco_loss_workspace_bytes(const trb_moco_shape* shape, int precision);
 
 /* Kernel launches one trb_moco_loss call issues for this shape on the current device: 2 when precision = 1 takes the fused
- * path (a small prologue + ONE cooperative tcgen05 kernel for the three losses and all gradients; needs N <= 128, D a multiple
- * of 64 up to 256 and ceil(C/128) + 2*ceil(K/128) + 1 <= #SMs), otherwise the length of the unfused launch sequence.
+ * path (a small prologue + ONE cooperative tcgen05 kernel for the three losses and all gradients; needs D a multiple of 64 up
+ * to 256 and, for N <= 128, ceil(C/128) + 2*ceil(K/128) + 1 <= #SMs or, for 128 < N <= 256, ceil(C/128) + ceil(K/128) + 2 <=
+ * #SMs), otherwise the length of the launch sequence (N up to 1024: instance and InfoNCE branches still one cooperative launch).
  * The cooperative kernel occupies every SM of the device (one CTA per class / queue tile, spare CTAs on the rest that share the
  * final reductions) and is launched as a programmatic dependent launch behind the prologue (it starts while the prologue still
- * runs and waits for it on the device); both survive CUDA-graph capture.  Batches of 129..1024 rows run the same kernel once per
- * 128-row window and branch. */
+ * runs and waits for it on the device); both survive CUDA-graph capture.  Batches above 128 rows are walked in 128-row windows
+ * inside the kernel. */
 int trb_moco_loss_launches(const trb_moco_shape* shape, int precision);
 
 /* Loss dict and its gradients in one stream-ordered call (fwd and bwd fused: the softmax
