@@ -135,7 +135,8 @@ def test_fused_loss_gate_and_argument_validation_without_gpu(lib):
 
     assert launches(128, 256, 2048, 11003, 1) == 2         # prologue + one cooperative kernel
     assert launches(128, 256, 2048, 11003, 0) > 2          # fp32 parity path: launch sequence
-    assert launches(256, 256, 4096, 11003, 1) > 2          # N > 128
+    assert launches(256, 256, 4096, 11003, 1) == 2         # BASELINE configs[2]: 128-row windows walked inside the same kernel
+    assert launches(384, 256, 4096, 11003, 1) == 15        # N > 256: the global-align branch stays on the unfused sequence
     assert launches(128, 320, 2048, 11003, 1) > 2          # D > 256
     assert launches(128, 256, 2048, 20000, 1) > 2          # 157 + 32 + 1 tiles > 148 SMs
     assert launches(0, 256, 2048, 11003, 1) == -1          # rejected shape
