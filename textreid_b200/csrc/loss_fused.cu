@@ -1491,13 +1491,6 @@ bool fused_windows_supported(int N, int D, int K, int C, int sm_count) {
     return (C + F_TILE - 1) / F_TILE + (K + F_TILE - 1) / F_TILE <= sm_count;
 }
 
-int fused_loss_reset_barriers(const FusedLossArgs& a, cudaStream_t st) {
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a.scratch) + 1023) & ~uintptr_t(1023));
-    const Scratch s = carve_scratch(base, a.N, a.D, a.K, a.C);
-    TRB_CUDA_OK(cudaMemsetAsync(s.bar, 0, 32, st));
-    return 0;
-}
-
 int64_t fused_loss_scratch_bytes(int N, int D, int K, int C) { return carve_scratch(nullptr, N, D, K, C).bytes + 1024; }
 
 static ProArgs make_pro_args(const FusedLossArgs& a, const Scratch& s) {

@@ -30,8 +30,6 @@ bool fused_loss_supported(int N, int D, int K, int C, int sm_count);
 // 128 < N <= 1024: the kernel walks the batch in row windows of 128 (W / queue tiles resident); an InfoNCE CTA takes its tile
 // index for both modalities in turn, so ceil(C/128) + ceil(K/128) CTAs must fit the device (86 + 32 at C = 11003, K = 4096)
 bool fused_windows_supported(int N, int D, int K, int C, int sm_count);
-// zero the grid-barrier words between two cooperative launches that share one prologue
-int fused_loss_reset_barriers(const FusedLossArgs& a, cudaStream_t st);
 int64_t fused_loss_scratch_bytes(int N, int D, int K, int C);
 // prologue (row norms, positive logits, packed bf16 operand images, barrier reset) on `st`
 int fused_loss_prologue(const FusedLossArgs& a, cudaStream_t st);
