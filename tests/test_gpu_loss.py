@@ -285,12 +285,15 @@ def test_fused_shape_gate():
 
 @pytest.mark.parametrize("N,D,K,Cn,masked", [(128, 256, 2048, 11003, "some"), (100, 192, 200, 257, "some"), (32, 64, 128, 1000, "empty"),
                                               (8, 128, 384, 130, "some"), (256, 256, 4096, 11003, "some"), (200, 128, 512, 700, "some"),
-                                              (384, 64, 256, 300, "empty"), (384, 64, 768, 300, "some")])
+                                              (384, 64, 256, 300, "empty"), (384, 64, 768, 300, "some"),
+                                              (32, 64, 1024, 16640, "some"), (32, 64, 1024, 16768, "some")])
 def test_fused_matches_unfused_bf16(monkeypatch, N, D, K, Cn, masked):
     """The fused kernel and the generic bf16 launch sequence round the same operands to bf16: losses agree to fp32 level,
     gradients far inside the bf16 budget.  Both are checked against the fp64 oracle.  N > 128 runs the fused kernel in 128-row
     windows (instance and InfoNCE tiles; projection gradient accumulated over the windows; queue mask from the whole batch --
-    the (384, .., "some") case has batch ids beyond the first 256 rows that must mask their queue slots too)."""
+    the (384, .., "some") case has batch ids beyond the first 256 rows that must mask their queue slots too).  The two shapes with
+    130 / 131 class tiles leave one / no SM without a tile on a 148-SM device: every CTA then takes a share of the final
+    reductions (no early arrival of the instance tiles), and without a spare CTA tile 0 forms the row losses."""
     assert _launches(N, D, K, Cn, 1) == (2 if N <= 256 else 15)
     inp = synth_loss_inputs(N, D, K, Cn, seed=N + K, masked=masked)
     fused = run_fused(inp, 0.1, precision="bf16")
@@ -353,10 +356,12 @@ def test_fused_separate_queries_and_key_normalisation():
         assert float(err) < 2e-2, float(err)
 
 
-def test_fused_forward_only_and_repeatability():
+@pytest.mark.parametrize("shape", [(128, 256, 2048, 11003), (256, 256, 4096, 11003), (200, 128, 512, 700)])
+def test_fused_forward_only_and_repeatability(shape):
     """No tensor requires grad -> the library skips the backward half; repeated calls are bit-identical (fixed-order reductions,
-    no atomics)."""
-    inp = {k: v.to(DEV) for k, v in synth_loss_inputs(128, 256, 2048, 11003, seed=9).items()}
+    no floating-point atomics; the work-stealing reduction of the partial tiles hands units to whichever CTA is free, which must
+    not change any sum).  Also at the windowed shapes (two 128-row windows inside the kernel, ragged second window)."""
+    inp = {k: v.to(DEV) for k, v in synth_loss_inputs(*shape, seed=9).items()}
     ptr = torch.zeros(1, dtype=torch.int64, device=DEV)
 
     def call(grad):
