@@ -33,18 +33,33 @@ constexpr int STAGE_BYTES = 2 * BLOCK_BYTES;   // 256 gallery rows x 64 k  = 32 
 constexpr int EPI_WARP0 = 2;
 constexpr int NUM_THREADS = 32 * EPI_WARP0 + 32 * TRB_EPI_WARPS;
 constexpr int NUM_EPI_WARPS = TRB_EPI_WARPS;
-constexpr int COLS_PER_WARP = TILE_N / (NUM_EPI_WARPS / 4);   // 64 accumulator columns per epilogue warp
+constexpr int NUM_COLGRP = NUM_EPI_WARPS / 4;                 // epilogue warps per TMEM lane quarter (= per SM sub-partition)
 #ifndef TRB_TC_CHUNK
 #define TRB_TC_CHUNK 32
 #endif
 constexpr int CH = TRB_TC_CHUNK;                               // accumulator columns a thread holds in registers at a time (16 | 32)
-constexpr int CHUNKS_PER_WARP = COLS_PER_WARP / CH;
-constexpr int LISTS_PER_SPLIT = NUM_EPI_WARPS / 4;            // candidate lists a query gets per gallery split
+constexpr int TILE_CHUNKS = TILE_N / CH;
+constexpr bool COLGRP_CONTIGUOUS = TILE_CHUNKS % NUM_COLGRP == 0;
+// column group cg takes a contiguous run of chunks when the groups divide the tile evenly, otherwise chunks cg, cg + groups, ...
+// (3 groups over 8 chunks: 3 + 3 + 2; TRB_EPI_WARPS=12 measured 55.8 vs 56.0 ms: the epilogue is throughput bound, not latency
+// bound); either way a warp walks its chunks in ascending gallery order
+__host__ __device__ constexpr int chunks_of(int cg) {
+    return COLGRP_CONTIGUOUS ? TILE_CHUNKS / NUM_COLGRP : (TILE_CHUNKS - cg + NUM_COLGRP - 1) / NUM_COLGRP;
+}
+__host__ __device__ constexpr int chunk_col(int cg, int i) {
+    return (COLGRP_CONTIGUOUS ? cg * (TILE_CHUNKS / NUM_COLGRP) + i : i * NUM_COLGRP + cg) * CH;
+}
+constexpr int LISTS_PER_SPLIT = NUM_COLGRP;                   // candidate lists a query gets per gallery split
 constexpr int MAX_STAGES = 8;
 // Build-time tuning knobs (A/B builds through textreid_b200.build.build_variant):
 //   TRB_TC_SKIP_R   : thresholds per row (sorted descending) that get a warp-uniform "no value of this chunk reaches it" test
 //   TRB_TC_HOT_SPIN : 1 = the producer / MMA threads poll their mbarriers in a hot loop (round-1 behaviour)
-//   TRB_TC_COUNT_FMA: 1 = rank counting on the FMA pipe (FFMA.SAT indicator + FADD), 0 = FADD + LEA.HI (FMA + ALU pipe)
+//   TRB_TC_COUNT_FMA: 1 = FFMA.SAT indicator + packed fp32 add (FADD2), all on the FMA pipe (shipped);
+//                     2 = FFMA.SAT indicator + INTEGER sums of the 1.0f bit patterns on the ALU pipe: three indicators per IADD3,
+//                         one shifted accumulate (LEA.HI, >> 23 = 127 per hit) per group -- 5 instructions per 3 (value, threshold)
+//                         pairs on two pipes; measured 59.6 vs 57.5 ms (the micro-benchmark puts every formulation at 2.2 - 2.4
+//                         SM cycles per pair: profiles/r02_stream_experiments.md);
+//                     0 = FADD + LEA.HI (FMA + ALU pipe)
 #ifndef TRB_TC_SKIP_R
 #define TRB_TC_SKIP_R 0
 #endif
@@ -59,6 +74,10 @@ constexpr int MAX_STAGES = 8;
 
 #ifndef TRB_TC_HOT_SPIN
 #define TRB_TC_HOT_SPIN 0
+#endif
+//   TRB_TC_FAST_CHUNK: 1 = one warp-uniform test per chunk ("nothing rare in any lane") in front of the per-condition branches
+#ifndef TRB_TC_FAST_CHUNK
+#define TRB_TC_FAST_CHUNK 1
 #endif
 constexpr int SMEM_MAX = 232448;      // 227 KiB opt-in limit per CTA on sm_100
 
@@ -233,7 +252,9 @@ struct RowState {
     // scales to >= 1); thresholds closer to zero than that take the exact slow path (`slow`, CSR positions).
     float te[RTN];
     int sw[RTN];             // first chunk start g0 at which te switches to thr (= local row of the item - (CH - 1)); INT32_MAX = done
-#if TRB_TC_COUNT_FMA
+#if TRB_TC_COUNT_FMA == 2
+    uint32_t ci[RTN];             // 127 x hits: (k x 0x3F800000) >> 23 = 127 k for the k <= 3 indicators of a group
+#elif TRB_TC_COUNT_FMA
     unsigned long long cf[RTN];   // two fp32 counters per slot (even / odd values of a chunk), bumped by one FADD2 per value pair
 #else
     int cnt[RTN];
@@ -245,20 +266,25 @@ struct RowState {
 
     __device__ __forceinline__ int slot_of(int r) const { return (int)((perm >> (4 * r)) & 15u); }
     __device__ __forceinline__ void clear(int r) {
-#if TRB_TC_COUNT_FMA
+#if TRB_TC_COUNT_FMA == 2
+        ci[r] = 0u;
+#elif TRB_TC_COUNT_FMA
         cf[r] = 0ull;
 #else
         cnt[r] = 0;
 #endif
     }
     __device__ __forceinline__ int count_of(int r) const {
-#if TRB_TC_COUNT_FMA
+#if TRB_TC_COUNT_FMA == 2
+        return (int)(ci[r] / 127u);
+#elif TRB_TC_COUNT_FMA
         return __float2int_rn(__uint_as_float((uint32_t)cf[r]) + __uint_as_float((uint32_t)(cf[r] >> 32)));
 #else
         return cnt[r];
 #endif
     }
-    // fp32 counters are exact up to 2^24: the epilogue drains them into the global counters every 256 tiles (<= 8192 per lane)
+    // fp32 counters are exact up to 2^24, the scaled integer counters up to 2^32 / 127: the epilogue drains them into the
+    // global counters every 256 tiles (<= 16384 hits per lane)
     __device__ __forceinline__ void drain(const Params& p) {
 #pragma unroll
         for (int r = 0; r < RTN; ++r) {
@@ -404,9 +430,55 @@ __device__ __noinline__ void count_exact(const Params& p, const float* lv, int g
     }
 }
 
+// the register-resident rank counts of one chunk: every value against every threshold slot of the row
+template <int RTN>
+__device__ __forceinline__ void count_chunk(RowState<RTN>& st, const float (&v)[CH], float cmax) {
+#pragma unroll
+    for (int r = 0; r < RTN; ++r) {
+        // no value of the chunk, in any row of the warp, reaches the r-th best threshold: nothing to count (thresholds of
+        // relevant items sit in the upper tail of the similarity distribution, so the first slots skip most chunks)
+#if TRB_TC_COUNT_FMA
+        const float c = st.te[r];                  // = -te * 2^100
+        if (r < TRB_TC_SKIP_R && !__any_sync(0xffffffffu, fmaf(cmax, COUNT_SCALE, c) > 0.f)) continue;
+#if TRB_TC_COUNT_FMA == 2
+        uint32_t acc = st.ci[r];
+#pragma unroll
+        for (int j = 0; j < CH; j += 3) {
+            uint32_t a = __float_as_uint(__saturatef(fmaf(v[j], COUNT_SCALE, c)));
+            if (j + 1 < CH) a += __float_as_uint(__saturatef(fmaf(v[j + 1], COUNT_SCALE, c)));
+            if (j + 2 < CH) a += __float_as_uint(__saturatef(fmaf(v[j + 2], COUNT_SCALE, c)));
+            acc += a >> 23;
+        }
+        st.ci[r] = acc;
+#else
+        unsigned long long acc = st.cf[r];
+#pragma unroll
+        for (int j = 0; j < CH; j += 2)            // 2 x FFMA.SAT (immediate form) + 1 x FADD2: 1.5 instructions per value, FMA pipe
+            add2(acc, __saturatef(fmaf(v[j], COUNT_SCALE, c)), __saturatef(fmaf(v[j + 1], COUNT_SCALE, c)));
+        st.cf[r] = acc;
+#endif
+#else
+        if (r < TRB_TC_SKIP_R && !__any_sync(0xffffffffu, cmax > st.te[r])) continue;
+        const float te = st.te[r];
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+            c0 += __float_as_uint(te - v[j]) >> 31;           // te - v < 0  <=>  v > te   (x - x = +0, never -0)
+            c1 += __float_as_uint(te - v[j + 1]) >> 31;
+            c2 += __float_as_uint(te - v[j + 2]) >> 31;
+            c3 += __float_as_uint(te - v[j + 3]) >> 31;
+        }
+        st.cnt[r] += (int)((c0 + c1) + (c2 + c3));
+#endif
+    }
+}
+
+// `fast_ok`: the tile holds no zero-padded tail rows.  The common chunk -- no top-10 candidate, no threshold switching to its
+// strict compare, no row that needs the exact slow path, in ANY lane of the warp -- takes one warp-uniform branch and runs the
+// counting loop; everything else falls through to the general path, which re-tests each condition per lane.
 template <int RTN>
 __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st, const float (&v)[CH], int g0, bool row_valid,
-                                             bool warp_has_thr) {
+                                             bool warp_has_thr, bool fast_ok, bool row_slow) {
     // chunk maximum for the top-10 filter; ptxas folds this into 3-input FMNMX3
     constexpr int NG = CH / 4;
     float m8[NG];
@@ -414,6 +486,15 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
     for (int i = 0; i < NG; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
     float cmax = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
     if (NG == 8) cmax = fmaxf(cmax, fmaxf(fmaxf(m8[NG - 4], m8[NG - 3]), fmaxf(m8[NG - 2], m8[NG - 1])));
+#if TRB_TC_FAST_CHUNK
+    if (fast_ok) {
+        const bool rare = (row_valid && cmax > st.ts[TRB_TOPK - 1]) || g0 >= st.next_sw || row_slow;
+        if (!__any_sync(0xffffffffu, rare)) {
+            if (warp_has_thr) count_chunk<RTN>(st, v, cmax);
+            return;
+        }
+    }
+#endif
 
     // ---- top-10: candidates are rare after the first tiles; only 4-value groups whose maximum beats the current
     //      10th best are scanned, and the hits go through a bit mask + select tree (keeps the hot loop compact) ----
@@ -441,33 +522,8 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
     if (!warp_has_thr) return;
     bool own = false;
     if (g0 >= st.next_sw) own = st.pass_items(p, g0);      // rare: 1 + (relevant items of the row) times per stream
-#pragma unroll
-    for (int r = 0; r < RTN; ++r) {
-        // no value of the chunk, in any row of the warp, reaches the r-th best threshold: nothing to count (thresholds of
-        // relevant items sit in the upper tail of the similarity distribution, so the first slots skip most chunks)
-#if TRB_TC_COUNT_FMA
-        const float c = st.te[r];                  // = -te * 2^100
-        if (r < TRB_TC_SKIP_R && !__any_sync(0xffffffffu, fmaf(cmax, COUNT_SCALE, c) > 0.f)) continue;
-        unsigned long long acc = st.cf[r];
-#pragma unroll
-        for (int j = 0; j < CH; j += 2)            // 2 x FFMA.SAT (immediate form) + 1 x FADD2: 1.5 instructions per value, FMA pipe
-            add2(acc, __saturatef(fmaf(v[j], COUNT_SCALE, c)), __saturatef(fmaf(v[j + 1], COUNT_SCALE, c)));
-        st.cf[r] = acc;
-#else
-        if (r < TRB_TC_SKIP_R && !__any_sync(0xffffffffu, cmax > st.te[r])) continue;
-        const float te = st.te[r];
-        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-#pragma unroll
-        for (int j = 0; j < CH; j += 4) {
-            c0 += __float_as_uint(te - v[j]) >> 31;           // te - v < 0  <=>  v > te   (x - x = +0, never -0)
-            c1 += __float_as_uint(te - v[j + 1]) >> 31;
-            c2 += __float_as_uint(te - v[j + 2]) >> 31;
-            c3 += __float_as_uint(te - v[j + 3]) >> 31;
-        }
-        st.cnt[r] += (int)((c0 + c1) + (c2 + c3));
-#endif
-    }
-    const bool overflow = row_valid && ((st.s_hi - st.s_lo > RTN) || st.slow != 0u);
+    count_chunk<RTN>(st, v, cmax);
+    const bool overflow = row_slow;
     own = own && row_valid;
     if (own || overflow) {
         float lv[CH];
@@ -581,9 +637,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
     } else if (warp >= EPI_WARP0) {
         // ------------------------------- epilogue -------------------------------------------
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
-        const int colgrp = (warp - EPI_WARP0) >> 2;      // which COLS_PER_WARP slice of the 256 accumulator columns
+        const int colgrp = (warp - EPI_WARP0) >> 2;      // which share of the 256 accumulator columns (chunks_of / chunk_col)
         const int row = quarter * 32 + lane;
-        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colgrp * COLS_PER_WARP);
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int my_chunks = chunks_of(colgrp);
         int tbuf = 0;
         uint32_t tphase = 0;
         for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
@@ -602,6 +659,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 slot_base = p.rel_ptr[q] + p.rel_off[prow];
             }
             const bool warp_has_thr = MODE == 0 && __any_sync(0xffffffffu, st.s_hi > st.s_lo);
+            // rows with more relevant items than register slots, or with a threshold too close to zero for the scaled compare
+            const bool row_slow = MODE == 0 && q >= 0 && ((st.s_hi - st.s_lo > RTN) || st.slow != 0u);
 
             for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
                 mbar_wait_sleepy(t_full + tbuf, tphase, p.wait_hint_ns);
@@ -609,7 +668,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 const bool tail_tile = (t + 1) * TILE_N > p.G;         // only the last tile holds zero padding rows
                 const uint32_t taddr0 = lane_taddr + (uint32_t)(tbuf * TILE_N);
                 auto consume = [&](float (&v)[CH], int chunk) {
-                    const int g0 = (int)(t * TILE_N) + colgrp * COLS_PER_WARP + chunk * CH;   // packed gallery row of v[0]
+                    const int g0 = (int)(t * TILE_N) + chunk_col(colgrp, chunk);   // packed gallery row of v[0]
 #ifdef TRB_TC_PROBE
                     if (p.debug & 3) { if (v[5] == 12345.678f) p.cand_sim[0] = v[7]; return; }
 #endif
@@ -632,7 +691,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                         for (int j = 0; j < CH; ++j)
                             if (g0 + j >= gvalid) v[j] = -CUDART_INF_F;
                     }
-                    stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr);
+                    stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr, !tail_tile, row_slow);
                 };
                 auto release = [&]() {                     // accumulator fully read by this warp: hand it back
                     tc_fence_before();
@@ -640,32 +699,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 };
 #if TRB_TC_PREFETCH
                 // two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is consumed
-                static_assert(CHUNKS_PER_WARP % 2 == 0, "the prefetching epilogue consumes chunks in pairs");
+                static_assert(COLGRP_CONTIGUOUS && (TILE_CHUNKS / NUM_COLGRP) % 2 == 0, "the prefetching epilogue consumes chunks in pairs");
+                constexpr int CHUNKS_PER_WARP = TILE_CHUNKS / NUM_COLGRP;
                 float va[CH], vb[CH];
                 __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
-                tmem_ld_issue(taddr0, va);
+                tmem_ld_issue(taddr0 + (uint32_t)chunk_col(colgrp, 0), va);
                 tmem_ld_wait(va);
 #pragma unroll 1
                 for (int chunk = 0; chunk < CHUNKS_PER_WARP; chunk += 2) {
                     __syncwarp();
-                    tmem_ld_issue(taddr0 + (uint32_t)((chunk + 1) * CH), vb);
+                    tmem_ld_issue(taddr0 + (uint32_t)chunk_col(colgrp, chunk + 1), vb);
                     consume(va, chunk);
                     tmem_ld_wait(vb);
                     const bool more = chunk + 2 < CHUNKS_PER_WARP;
                     __syncwarp();
-                    if (more) tmem_ld_issue(taddr0 + (uint32_t)((chunk + 2) * CH), va);
+                    if (more) tmem_ld_issue(taddr0 + (uint32_t)chunk_col(colgrp, chunk + 2), va);
                     else release();
                     consume(vb, chunk + 1);
                     if (more) tmem_ld_wait(va);
                 }
 #else
 #pragma unroll 1
-                for (int chunk = 0; chunk < CHUNKS_PER_WARP; ++chunk) {
+                for (int chunk = 0; chunk < my_chunks; ++chunk) {
                     float v[CH];
                     __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
-                    tmem_ld_issue(taddr0 + (uint32_t)(chunk * CH), v);
+                    tmem_ld_issue(taddr0 + (uint32_t)chunk_col(colgrp, chunk), v);
                     tmem_ld_wait(v);
-                    if (chunk == CHUNKS_PER_WARP - 1) release();
+                    if (chunk == my_chunks - 1) release();
                     consume(v, chunk);
                 }
 #endif

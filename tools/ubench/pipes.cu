@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, float*
                 f2 = __saturatef(fmaf(v[j + 2], H, f2)); f3 = __saturatef(fmaf(v[j + 3], H, f3));
             } else if (MODE == 7) { // FADD2 only
                 add2(a0, v[j], v[j + 1]); add2(a1, v[j + 2], v[j + 3]);
+            } else if (MODE == 9) { // FFMA.SAT x4 + integer adds of the 1.0f bit patterns: 3 per IADD3, one shifted accumulate (>> 23 = 127 per hit) per group
+                const unsigned i0 = __float_as_uint(__saturatef(fmaf(v[j], H, cc))), i1 = __float_as_uint(__saturatef(fmaf(v[j + 1], H, cc)));
+                const unsigned i2 = __float_as_uint(__saturatef(fmaf(v[j + 2], H, cc))), i3 = __float_as_uint(__saturatef(fmaf(v[j + 3], H, cc)));
+                c0 += (i0 + i1 + i2 + i3) >> 23;          // 4 x 0x3F800000 = 0xFE000000 still fits
             } else if (MODE == 8) { // FFMA.SAT + IADD-style accumulate of the indicator bits (ALU)  (acc += bits >> 29)
                 c0 += __float_as_uint(__saturatef(fmaf(v[j], H, cc))) >> 29; c1 += __float_as_uint(__saturatef(fmaf(v[j + 1], H, cc))) >> 29;
                 c2 += __float_as_uint(__saturatef(fmaf(v[j + 2], H, cc))) >> 29; c3 += __float_as_uint(__saturatef(fmaf(v[j + 3], H, cc))) >> 29;
@@ -56,6 +60,43 @@ __global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, float*
     long long t1 = clock64();
     out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(c0 + c1 + c2 + c3) + f0 + f1 + f2 + f3 + __uint_as_float((unsigned)a0) + __uint_as_float((unsigned)(a0 >> 32)) + __uint_as_float((unsigned)a1) + __uint_as_float((unsigned)(a1 >> 32));
     if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+// Groups of G indicators summed as integers (IADD3 takes three), then ONE shifted accumulate per group.
+template <int G>
+__global__ void __launch_bounds__(512, 1) kg(const float* __restrict__ in, float* out, float c, long long* cycles) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = in[(threadIdx.x * 32 + i) & 1023];
+    unsigned c0 = 0, c1 = 0;
+    const float H = 1.2676506002282294e30f;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it) {
+        const float te = c + (float)it;
+        const float cc = -te * H;
+        unsigned ind[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ind[j] = __float_as_uint(__saturatef(fmaf(v[j], H, cc)));
+        int g = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += G) {
+            unsigned a = 0;
+#pragma unroll
+            for (int i = 0; i < G; ++i) if (j + i < 32) a += ind[j + i];
+            if (g & 1) c1 += a >> 23; else c0 += a >> 23;
+            ++g;
+        }
+    }
+    long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(c0 + c1);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+template <int G> void rung(const float* in, float* out, long long* cyc, int threads) {
+    for (int rep = 0; rep < 2; ++rep) { kg<G><<<148, threads>>>(in, out, 0.5f, cyc); cudaDeviceSynchronize(); }
+    long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    const double warps_per_smsp = threads / 32.0 / 4.0;
+    printf("FFMA.SAT + integer group sums of %d + one shifted accumulate, %2.0f warps per SMSP: %8lld cycles  %.3f SMSP-cycles per (value,threshold) warp-op\n",
+           G, warps_per_smsp, h, (double)h / (ITER * 32.0 * warps_per_smsp));
 }
 // Four thresholds per value like the stream epilogue: NF of them counted on the FMA pipe (2 x FFMA.SAT + FADD2 per value pair),
 // the rest with a packed difference (FADD2 te2 - v2) and two LEA.HI sign-bit accumulates on the ALU pipe.
@@ -102,6 +143,84 @@ __global__ void __launch_bounds__(512, 1) k4(const float* __restrict__ in, float
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
+// Four thresholds, the shipped formulation: FFMA.SAT indicators, integer sums of three (IADD3), one shifted accumulate (LEA.HI)
+template <int G>
+__global__ void __launch_bounds__(512, 1) k4i(const float* __restrict__ in, float* out, float c, long long* cycles) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = in[(threadIdx.x * 32 + i) & 1023];
+    unsigned cnt[4] = {0, 0, 0, 0};
+    const float H = 1.2676506002282294e30f;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float cc = -(c + (float)(it + r)) * H;
+            unsigned acc = cnt[r];
+#pragma unroll
+            for (int j = 0; j < 32; j += G) {
+                unsigned a = 0;
+#pragma unroll
+                for (int i = 0; i < G; ++i) if (j + i < 32) a += __float_as_uint(__saturatef(fmaf(v[j + i], H, cc)));
+                acc += a >> 23;
+            }
+            cnt[r] = acc;
+        }
+    }
+    long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(cnt[0] + cnt[1] + cnt[2] + cnt[3]);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+// the same with the indicators as volatile asm: ptxas keeps them in source order (threshold-major), so every FFMA.SAT of a
+// threshold finds its compare value in the operand reuse cache
+__device__ __forceinline__ unsigned ind_v(float v, float cc) {
+    float r;
+    asm volatile("fma.rn.sat.f32 %0, %1, 0f71800000, %2;" : "=f"(r) : "f"(v), "f"(cc));
+    return __float_as_uint(r);
+}
+template <int G>
+__global__ void __launch_bounds__(512, 1) k4v(const float* __restrict__ in, float* out, float c, long long* cycles) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = in[(threadIdx.x * 32 + i) & 1023];
+    unsigned cnt[4] = {0, 0, 0, 0};
+    const float H = 1.2676506002282294e30f;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float cc = -(c + (float)(it + r)) * H;
+            unsigned acc = cnt[r];
+#pragma unroll
+            for (int j = 0; j < 32; j += G) {
+                unsigned a = 0;
+#pragma unroll
+                for (int i = 0; i < G; ++i) if (j + i < 32) a += ind_v(v[j + i], cc);
+                acc += a >> 23;
+            }
+            cnt[r] = acc;
+        }
+    }
+    long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(cnt[0] + cnt[1] + cnt[2] + cnt[3]);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+template <int G> void run4v(const float* in, float* out, long long* cyc, int threads) {
+    for (int rep = 0; rep < 2; ++rep) { k4v<G><<<148, threads>>>(in, out, 0.5f, cyc); cudaDeviceSynchronize(); }
+    long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    const double warps_per_smsp = threads / 32.0 / 4.0;
+    printf("4 thresholds, volatile FFMA.SAT + IADD3 sums of %d + LEA.HI, %2.0f warps per SMSP: %8lld cycles  %.3f SMSP-cycles per (value,threshold) warp-op\n",
+           G, warps_per_smsp, h, (double)h / (ITER * 32.0 * 4.0 * warps_per_smsp));
+}
+template <int G> void run4i(const float* in, float* out, long long* cyc, int threads) {
+    for (int rep = 0; rep < 2; ++rep) { k4i<G><<<148, threads>>>(in, out, 0.5f, cyc); cudaDeviceSynchronize(); }
+    long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    const double warps_per_smsp = threads / 32.0 / 4.0;
+    printf("4 thresholds, FFMA.SAT + IADD3 sums of %d + LEA.HI, %2.0f warps per SMSP: %8lld cycles  %.3f SMSP-cycles per (value,threshold) warp-op\n",
+           G, warps_per_smsp, h, (double)h / (ITER * 32.0 * 4.0 * warps_per_smsp));
+}
 template <int NF> void run4(const float* in, float* out, long long* cyc, int threads) {
     for (int rep = 0; rep < 2; ++rep) { k4<NF><<<148, threads>>>(in, out, 0.5f, cyc); cudaDeviceSynchronize(); }
     long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
@@ -133,7 +252,11 @@ int main() {
     run<6>("FFMA.SAT only", in, out, cyc);
     run<7>("FADD2 only (1 per 2 values)", in, out, cyc);
     run<8>("FFMA.SAT + LEA.HI(bits>>29)", in, out, cyc);
-    for (int threads : {256, 512}) {
+    run<9>("4 FFMA.SAT + 2 IADD3 + LEA.HI(>>23)", in, out, cyc);
+    for (int threads : {256, 512}) { rung<2>(in, out, cyc, threads); rung<3>(in, out, cyc, threads); rung<4>(in, out, cyc, threads); }
+    for (int threads : {128, 256, 512}) { run4v<3>(in, out, cyc, threads); run4v<4>(in, out, cyc, threads); }
+    for (int threads : {128, 256, 512}) { run4i<3>(in, out, cyc, threads); run4i<4>(in, out, cyc, threads); }
+    for (int threads : {128, 256, 512}) {
         run4<4>(in, out, cyc, threads); run4<3>(in, out, cyc, threads); run4<2>(in, out, cyc, threads);
         run4<1>(in, out, cyc, threads); run4<0>(in, out, cyc, threads);
     }
