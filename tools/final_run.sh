@@ -24,7 +24,8 @@ for k, v in d["secondary"].items():
               v.get("roofline", {}).get("frac") if isinstance(v.get("roofline"), dict) else None)
 PY
 if [ "${1:-}" != "noncu" ]; then
-  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 80 --csv --log-file gpurun_out/r02_launches_retrieval_1m_step.csv \
+  TRB_BENCH_CUDA_PROFILER=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+      --log-file gpurun_out/r02_launches_retrieval_1m_step.csv \
       python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
   echo "retrieval launch list exit $?"
   TRB_LOSS_PRECISION=bf16 TRB_LOSS_GRAPH=0 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 40 --csv \

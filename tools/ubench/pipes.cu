@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdint.h>
+#include <cuda_fp16.h>
 #define ITER 2000
 __device__ __forceinline__ void add2(unsigned long long& acc, float a, float b) {
     unsigned long long t;
@@ -221,6 +222,67 @@ template <int G> void run4i(const float* in, float* out, long long* cyc, int thr
     printf("4 thresholds, FFMA.SAT + IADD3 sums of %d + LEA.HI, %2.0f warps per SMSP: %8lld cycles  %.3f SMSP-cycles per (value,threshold) warp-op\n",
            G, warps_per_smsp, h, (double)h / (ITER * 32.0 * 4.0 * warps_per_smsp));
 }
+// Four thresholds counted in packed half precision: the 32 values are rounded toward zero to 16 half2 pairs once (F2FP), then per
+// threshold one HFMA2.SAT (indicator: 0 below, 0.5 equal, 1 above) and one HADD2 per PAIR of values.  FLUSH = also fold the four
+// half2 sums into integer counters and test them for a fractional part once per 32 values, like the epilogue would.
+template <int FLUSH>
+__global__ void __launch_bounds__(512, 1) k4h(const float* __restrict__ in, float* out, float c, long long* cycles) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = in[(threadIdx.x * 32 + i) & 1023];
+    unsigned cnt[4] = {0, 0, 0, 0};
+    unsigned amb = 0;
+    __half2 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = __float2half2_rn(0.f);
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it) {
+        __half2 hv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            unsigned u;
+            asm("cvt.rz.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(v[2 * j + 1] + (float)it), "f"(v[2 * j]));
+            hv[j] = *reinterpret_cast<__half2*>(&u);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const __half2 sc = __float2half2_rn(512.f + (float)r);
+            const __half2 cc = __float2half2_rn(0.5f - (c + (float)(it + r)) * 512.f);
+            __half2 a = FLUSH ? __float2half2_rn(0.f) : acc[r];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a = __hadd2(a, __hfma2_sat(hv[j], sc, cc));
+            if (FLUSH) {
+                const float t = __low2float(a) + __high2float(a);
+                const int ti = (int)t;
+                amb |= (t != (float)ti);
+                cnt[r] += ti;
+            } else acc[r] = a;
+        }
+    }
+    long long t1 = clock64();
+    float sres = (float)(cnt[0] + cnt[1] + cnt[2] + cnt[3] + amb);
+    for (int r = 0; r < 4; ++r) sres += __low2float(acc[r]) + __high2float(acc[r]);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sres;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+template <int FLUSH> void run4h(const float* in, float* out, long long* cyc, int threads) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k4h<FLUSH><<<148, threads>>>(in, out, 0.5f, cyc); cudaDeviceSynchronize();
+    cudaEventRecord(e0); k4h<FLUSH><<<148, threads>>>(in, out, 0.5f, cyc); cudaEventRecord(e1); cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    const double warps_per_smsp = threads / 32.0 / 4.0;
+    printf("4 thresholds in half2 (F2FP once, HFMA2.SAT + HADD2 per pair)%s, %2.0f warps per SMSP: %8lld cycles  %.3f SMSP-cycles per (value,threshold) warp-op  [%.3f ms whole kernel]\n",
+           FLUSH ? " + per-chunk flush" : "", warps_per_smsp, h, (double)h / (ITER * 32.0 * 4.0 * warps_per_smsp), ms);
+}
+template <int G> void run4e(const float* in, float* out, long long* cyc, int threads) {   // event-timed reference: the IADD3 formulation
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k4i<G><<<148, threads>>>(in, out, 0.5f, cyc); cudaDeviceSynchronize();
+    cudaEventRecord(e0); k4i<G><<<148, threads>>>(in, out, 0.5f, cyc); cudaEventRecord(e1); cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("   (reference, event-timed: FFMA.SAT + IADD3 sums of %d, %d threads: %.3f ms whole kernel)\n", G, threads, ms);
+}
 template <int NF> void run4(const float* in, float* out, long long* cyc, int threads) {
     for (int rep = 0; rep < 2; ++rep) { k4<NF><<<148, threads>>>(in, out, 0.5f, cyc); cudaDeviceSynchronize(); }
     long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
@@ -254,6 +316,7 @@ int main() {
     run<8>("FFMA.SAT + LEA.HI(bits>>29)", in, out, cyc);
     run<9>("4 FFMA.SAT + 2 IADD3 + LEA.HI(>>23)", in, out, cyc);
     for (int threads : {256, 512}) { rung<2>(in, out, cyc, threads); rung<3>(in, out, cyc, threads); rung<4>(in, out, cyc, threads); }
+    for (int threads : {256, 512}) { run4h<0>(in, out, cyc, threads); run4h<1>(in, out, cyc, threads); run4e<3>(in, out, cyc, threads); }
     for (int threads : {128, 256, 512}) { run4v<3>(in, out, cyc, threads); run4v<4>(in, out, cyc, threads); }
     for (int threads : {128, 256, 512}) { run4i<3>(in, out, cyc, threads); run4i<4>(in, out, cyc, threads); }
     for (int threads : {128, 256, 512}) {
