@@ -21,9 +21,19 @@ namespace {
 using namespace tc;
 
 constexpr int TILE_M = 128;          // queries per CTA tile (TMEM lanes)
-constexpr int TILE_N = 256;          // gallery rows per MMA tile (TMEM columns per buffer)
+// Gallery rows per MMA tile = TMEM columns per accumulator buffer.  The 512 TMEM columns hold 512 / TILE_N accumulators: a ring of
+// FOUR 128-column tiles instead of two 256-column ones lets the MMAs run up to three tiles ahead of the slowest epilogue warp (with
+// two buffers the MMAs of tile t + 2 wait for the last warp's release of tile t: per-tile time stamps, profiles/r02_stream_timeline.md)
+#ifndef TRB_TC_TILE_N
+#define TRB_TC_TILE_N 256
+#endif
+constexpr int TILE_N = TRB_TC_TILE_N;
+static_assert(TILE_N == 128 || TILE_N == 256, "TILE_N: one or two 128-row gallery blocks");
+constexpr int NTB = 512 / TILE_N;    // accumulator buffers in TMEM
+constexpr int PACK_ROWS = 256;       // row padding of the packed operands (independent of the tile width)
 constexpr int UMMA_K = 16;
-constexpr int STAGE_BYTES = 2 * BLOCK_BYTES;   // 256 gallery rows x 64 k  = 32 KiB
+constexpr int TILE_BLOCKS = TILE_N / 128;
+constexpr int STAGE_BYTES = TILE_BLOCKS * BLOCK_BYTES;   // TILE_N gallery rows x 64 k  = 16 / 32 KiB
 #ifndef TRB_EPI_WARPS
 #define TRB_EPI_WARPS 8
 #endif
@@ -50,7 +60,7 @@ __host__ __device__ constexpr int chunk_col(int cg, int i) {
     return (COLGRP_CONTIGUOUS ? cg * (TILE_CHUNKS / NUM_COLGRP) + i : i * NUM_COLGRP + cg) * CH;
 }
 constexpr int LISTS_PER_SPLIT = NUM_COLGRP;                   // candidate lists a query gets per gallery split
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 16;
 // Build-time tuning knobs (A/B builds through textreid_b200.build.build_variant):
 //   TRB_TC_SKIP_R   : thresholds per row (sorted descending) that get a warp-uniform "no value of this chunk reaches it" test
 //   TRB_TC_HOT_SPIN : 1 = the producer / MMA threads poll their mbarriers in a hot loop (round-1 behaviour)
@@ -74,6 +84,10 @@ constexpr int MAX_STAGES = 8;
 
 #ifndef TRB_TC_HOT_SPIN
 #define TRB_TC_HOT_SPIN 0
+#endif
+//   TRB_TC_UNROLL_CHUNKS: 1 = the chunk loop of a tile is fully unrolled (static chunk index: no release test, no loop branch)
+#ifndef TRB_TC_UNROLL_CHUNKS
+#define TRB_TC_UNROLL_CHUNKS 0
 #endif
 //   TRB_TC_FAST_CHUNK: 1 = one warp-uniform test per chunk ("nothing rare in any lane") in front of the per-condition branches
 #ifndef TRB_TC_FAST_CHUNK
@@ -104,7 +118,8 @@ struct Params {
     int64_t full_qtiles;     // mode 0: query tiles [0, full_qtiles) stream the whole gallery in one unit (whole waves of the
                              // persistent grid); the remaining tiles are cut into nsplit gallery pieces to balance the last wave
     uint32_t wait_hint_ns;   // suspend-time hint of the epilogue warps' accumulator waits
-    int debug;               // builds with -DTRB_TC_PROBE only (TRB_TC_DEBUG env): 1 = epilogue skips the arithmetic, 2 = and the TMEM read
+    int debug;               // builds with -DTRB_TC_PROBE only (TRB_TC_DEBUG env): 1 = epilogue skips the arithmetic, 2 = and the TMEM read,
+                             // 4 = the producer stops loading gallery tiles once the ring is full, 8 = no top-10 maintenance
 };
 
 // Waits of the two single-thread roles.  Polling costs issue slots on the scheduler that also runs a quarter of the epilogue
@@ -129,6 +144,26 @@ __device__ __forceinline__ void role_wait(uint64_t* bar, uint32_t parity, uint32
     }
 #endif
 }
+
+#ifdef TRB_TC_PROBE
+// probe: per-tile time stamps of CTA 0 (TRB_TC_DEBUG & 16): [0] MMA issuer got the accumulator back (t_empty), [1] MMA issuer
+// committed the tile, [2] epilogue warp 2 saw the tile complete (t_full), [3] epilogue warp 2 released it,
+// [4] epilogue warp 6 saw it, [5] epilogue warp 6 released it
+constexpr int STAMP_TILES = 48, STAMP_FIRST = 1000;
+__device__ unsigned long long g_stamps[16][STAMP_TILES];   // [6 + w]: epilogue warp 2 + w released the tile (w < 8); [14] MMA issuer starts to wait for the accumulator
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRB_STAMP(row, t)                                                                                              \
+    do {                                                                                                               \
+        if ((p.debug & 16) && blockIdx.x == 0 && (t) >= STAMP_FIRST && (t) < STAMP_FIRST + STAMP_TILES)                 \
+            g_stamps[row][(t) - STAMP_FIRST] = gtime();                                                                \
+    } while (0)
+#else
+#define TRB_STAMP(row, t) do { } while (0)
+#endif
 
 struct UnitInfo {
     int64_t qt, split, t_lo, t_hi;
@@ -451,11 +486,22 @@ __device__ __forceinline__ void count_chunk(RowState<RTN>& st, const float (&v)[
         }
         st.ci[r] = acc;
 #else
+#if TRB_TC_COUNT_FMA == 3
+        // the same two fp32 counters, bumped by two scalar FADDs instead of one packed FADD2
+        float a0 = __uint_as_float((uint32_t)st.cf[r]), a1 = __uint_as_float((uint32_t)(st.cf[r] >> 32));
+#pragma unroll
+        for (int j = 0; j < CH; j += 2) {
+            a0 += __saturatef(fmaf(v[j], COUNT_SCALE, c));
+            a1 += __saturatef(fmaf(v[j + 1], COUNT_SCALE, c));
+        }
+        st.cf[r] = (unsigned long long)__float_as_uint(a0) | ((unsigned long long)__float_as_uint(a1) << 32);
+#else
         unsigned long long acc = st.cf[r];
 #pragma unroll
         for (int j = 0; j < CH; j += 2)            // 2 x FFMA.SAT (immediate form) + 1 x FADD2: 1.5 instructions per value, FMA pipe
             add2(acc, __saturatef(fmaf(v[j], COUNT_SCALE, c)), __saturatef(fmaf(v[j + 1], COUNT_SCALE, c)));
         st.cf[r] = acc;
+#endif
 #endif
 #else
         if (r < TRB_TC_SKIP_R && !__any_sync(0xffffffffu, cmax > st.te[r])) continue;
@@ -488,6 +534,9 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
     if (NG == 8) cmax = fmaxf(cmax, fmaxf(fmaxf(m8[NG - 4], m8[NG - 3]), fmaxf(m8[NG - 2], m8[NG - 1])));
 #if TRB_TC_FAST_CHUNK
     if (fast_ok) {
+#ifdef TRB_TC_PROBE
+        if (p.debug & 8) row_valid = false;
+#endif
         const bool rare = (row_valid && cmax > st.ts[TRB_TOPK - 1]) || g0 >= st.next_sw || row_slow;
         if (!__any_sync(0xffffffffu, rare)) {
             if (warp_has_thr) count_chunk<RTN>(st, v, cmax);
@@ -498,6 +547,9 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
 
     // ---- top-10: candidates are rare after the first tiles; only 4-value groups whose maximum beats the current
     //      10th best are scanned, and the hits go through a bit mask + select tree (keeps the hot loop compact) ----
+#ifdef TRB_TC_PROBE
+    if (p.debug & 8) row_valid = false;        // probe: rank counts only, no top-10 maintenance
+#endif
     if (row_valid && cmax > st.ts[TRB_TOPK - 1]) {
         const float kth = st.ts[TRB_TOPK - 1];
         uint32_t cand = 0;
@@ -544,18 +596,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)NS * STAGE_BYTES);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
-    uint64_t* t_full = bars + 2;      // [2]
-    uint64_t* t_empty = bars + 4;     // [2]
-    uint64_t* b_full = bars + 6;      // [NS]
-    uint64_t* b_empty = bars + 6 + MAX_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * MAX_STAGES);
+    uint64_t* t_full = bars + 2;            // [NTB]
+    uint64_t* t_empty = bars + 2 + NTB;     // [NTB]
+    uint64_t* b_full = bars + 2 + 2 * NTB;  // [NS]
+    uint64_t* b_empty = bars + 2 + 2 * NTB + MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * NTB + 2 * MAX_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, NUM_EPI_WARPS); }
+        for (int i = 0; i < NTB; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, NUM_EPI_WARPS); }
         for (int i = 0; i < NS; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         mbar_fence_init();
     }
@@ -591,8 +643,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
 #endif
                         mbar_expect_tx(b_full + stage, STAGE_BYTES);
                         uint8_t* dst = sB + (size_t)stage * STAGE_BYTES;
-                        bulk_g2s(dst, p.g_packed + ((size_t)(2 * t) * KC + kc) * BLOCK_BYTES, BLOCK_BYTES, b_full + stage);
-                        bulk_g2s(dst + BLOCK_BYTES, p.g_packed + ((size_t)(2 * t + 1) * KC + kc) * BLOCK_BYTES, BLOCK_BYTES, b_full + stage);
+#pragma unroll
+                        for (int b = 0; b < TILE_BLOCKS; ++b)
+                            bulk_g2s(dst + b * BLOCK_BYTES, p.g_packed + ((size_t)(TILE_BLOCKS * t + b) * KC + kc) * BLOCK_BYTES, BLOCK_BYTES,
+                                     b_full + stage);
                         if (++stage == NS) { stage = 0; bphase ^= 1; }
                     }
                 }
@@ -612,8 +666,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 aphase ^= 1;
                 tc_fence_after();
                 for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
+                    TRB_STAMP(14, t);
                     role_wait(t_empty + tbuf, tphase ^ 1, 256);     // epilogue has drained this accumulator
                     tc_fence_after();
+                    TRB_STAMP(0, t);
                     const uint32_t d_tmem = tmem_base + (uint32_t)tbuf * TILE_N;
                     for (int kc = 0; kc < KC; ++kc) {
                         role_wait(b_full + stage, bphase, 64);
@@ -628,8 +684,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                         if (++stage == NS) { stage = 0; bphase ^= 1; }
                     }
                     umma_commit(t_full + tbuf);                // accumulator complete -> epilogue
-                    tbuf ^= 1;
-                    if (tbuf == 0) tphase ^= 1;
+                    TRB_STAMP(1, t);
+                    if (++tbuf == NTB) { tbuf = 0; tphase ^= 1; }
                 }
                 umma_commit(a_empty);                          // query tile may be overwritten
             }
@@ -665,6 +721,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
             for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
                 mbar_wait_sleepy(t_full + tbuf, tphase, p.wait_hint_ns);
                 tc_fence_after();
+                if (lane == 0 && (warp == 2 || warp == 6)) TRB_STAMP(warp == 2 ? 2 : 4, t);
                 const bool tail_tile = (t + 1) * TILE_N > p.G;         // only the last tile holds zero padding rows
                 const uint32_t taddr0 = lane_taddr + (uint32_t)(tbuf * TILE_N);
                 auto consume = [&](float (&v)[CH], int chunk) {
@@ -695,6 +752,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 };
                 auto release = [&]() {                     // accumulator fully read by this warp: hand it back
                     tc_fence_before();
+                    if (lane == 0) TRB_STAMP(6 + warp - EPI_WARP0, t);
                     if (lane == 0) mbar_arrive(t_empty + tbuf);
                 };
 #if TRB_TC_PREFETCH
@@ -719,8 +777,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                     if (more) tmem_ld_wait(va);
                 }
 #else
+#if TRB_TC_UNROLL_CHUNKS
+                static_assert(COLGRP_CONTIGUOUS, "the unrolled chunk loop needs evenly divided column groups");
+#pragma unroll
+                for (int chunk = 0; chunk < TILE_CHUNKS / NUM_COLGRP; ++chunk) {
+#else
 #pragma unroll 1
                 for (int chunk = 0; chunk < my_chunks; ++chunk) {
+#endif
                     float v[CH];
                     __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
                     tmem_ld_issue(taddr0 + (uint32_t)chunk_col(colgrp, chunk), v);
@@ -729,8 +793,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                     consume(v, chunk);
                 }
 #endif
-                tbuf ^= 1;
-                if (tbuf == 0) tphase ^= 1;
+                if (lane == 0 && (warp == 2 || warp == 6)) TRB_STAMP(warp == 2 ? 3 : 5, t);
+
+                if (++tbuf == NTB) { tbuf = 0; tphase ^= 1; }
                 if (MODE == 0 && TRB_TC_COUNT_FMA && ((t - ui.t_lo) & 255) == 255 && warp_has_thr) st.drain(p);
             }
 
@@ -815,7 +880,7 @@ pack_rows_kernel(const void* __restrict__ src, const int64_t* __restrict__ perm,
 
 extern "C" int trb_retrieval_tc_lists_per_split(void) { return LISTS_PER_SPLIT; }
 
-extern "C" int64_t trb_packed_rows(int64_t rows) { return rows <= 0 ? 0 : ((rows + TILE_N - 1) / TILE_N) * TILE_N; }
+extern "C" int64_t trb_packed_rows(int64_t rows) { return rows <= 0 ? 0 : ((rows + PACK_ROWS - 1) / PACK_ROWS) * PACK_ROWS; }
 
 extern "C" int64_t trb_packed_bytes(int64_t rows, int64_t dim) {
     if (dim <= 0 || dim % 64 != 0) return 0;
@@ -872,7 +937,7 @@ extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packe
     p.Q = Q; p.G = G;
     p.kchunks = (int)(D / 64);
     const int a_bytes = p.kchunks * BLOCK_BYTES;
-    const int fixed_bytes = (6 + 2 * MAX_STAGES) * 8 + 16 + 1024;   // barriers + TMEM slot + alignment slack
+    const int fixed_bytes = (2 + 2 * NTB + 2 * MAX_STAGES) * 8 + 16 + 1024;   // barriers + TMEM slot + alignment slack
     int ns = (SMEM_MAX - fixed_bytes - a_bytes) / STAGE_BYTES;
     p.nstages = ns > MAX_STAGES ? MAX_STAGES : ns;
     TRB_REQUIRE(p.nstages >= 2, "stream_tc: not enough shared memory for a 2-stage ring at D=%lld", (long long)D);
@@ -905,6 +970,24 @@ extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packe
     else if (max_rel <= 4) TRB_LAUNCH_TC(0, 4);
     else TRB_LAUNCH_TC(0, 8);
 #undef TRB_LAUNCH_TC
+#ifdef TRB_TC_PROBE
+    if ((p.debug & 16) && mode == 0) {
+        unsigned long long h[16][STAMP_TILES];
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpyFromSymbol(h, g_stamps, sizeof(h));
+        fprintf(stderr, "STAMPS tile: mma_start mma_commit | epi2_ready epi2_done | epi6_ready epi6_done   (ns after the first stamp)\n");
+        for (int i = 0; i < STAMP_TILES; ++i)
+        {
+            unsigned long long rmax = 0;
+            for (int w = 0; w < 8; ++w) rmax = h[6 + w][i] > rmax ? h[6 + w][i] : rmax;
+            fprintf(stderr, "STAMPS %4d: wait %7lld start %7lld commit %7lld | epi2 %7lld..%7lld epi6 %7lld..%7lld | released by all at %7lld; w2..w9:", STAMP_FIRST + i,
+                    (long long)(h[14][i] - h[0][0]), (long long)(h[0][i] - h[0][0]), (long long)(h[1][i] - h[0][0]), (long long)(h[2][i] - h[0][0]),
+                    (long long)(h[3][i] - h[0][0]), (long long)(h[4][i] - h[0][0]), (long long)(h[5][i] - h[0][0]), (long long)(rmax - h[0][0]));
+            for (int w = 0; w < 8; ++w) fprintf(stderr, " %lld", (long long)(h[6 + w][i] - h[0][0]));
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     TRB_LAUNCH_OK();
     return 0;
 }

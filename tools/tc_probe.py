@@ -27,6 +27,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         run(Q, G, 256, True, 250000, iters=1)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "r4":
+        run(Q, G, 256, True, 250000, iters=3)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "quick":
         run(Q, G, 256, True, 250000, iters=5)
         run(Q, G, 256, False, 250000)
