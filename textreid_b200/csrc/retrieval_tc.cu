@@ -15,6 +15,7 @@
 //                   128-column slice (w-2)/4 of the 256-column accumulator, 32 columns at a time
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -88,6 +89,18 @@ constexpr int MAX_STAGES = 16;
 //   TRB_TC_UNROLL_CHUNKS: 1 = the chunk loop of a tile is fully unrolled (static chunk index: no release test, no loop branch)
 #ifndef TRB_TC_UNROLL_CHUNKS
 #define TRB_TC_UNROLL_CHUNKS 0
+#endif
+//   TRB_TC_COUNT_FIRST: 1 = the register counts of a chunk are taken BEFORE the rare-case vote is consumed (its four dependent
+//                       instructions overlap the arithmetic); the rare path then corrects instead of preparing: a threshold that
+//                       switches to its strict compare in this chunk takes back the ties at / after its item, the padded tile
+//                       takes back its zero rows
+#ifndef TRB_TC_COUNT_FIRST
+#define TRB_TC_COUNT_FIRST 1
+#endif
+//   TRB_TC_SYNC_RARE: 1 = the warp re-converges explicitly (__syncwarp) at the END OF THE RARE PATH -- the only place where the lanes
+//                     of an epilogue warp diverge -- and once per tile, instead of in front of every tcgen05.ld
+#ifndef TRB_TC_SYNC_RARE
+#define TRB_TC_SYNC_RARE 0
 #endif
 //   TRB_TC_FAST_CHUNK: 1 = one warp-uniform test per chunk ("nothing rare in any lane") in front of the per-condition branches
 #ifndef TRB_TC_FAST_CHUNK
@@ -164,6 +177,13 @@ __device__ __forceinline__ unsigned long long gtime() {
 #else
 #define TRB_STAMP(row, t) do { } while (0)
 #endif
+
+// tail flag of a tile: a compile-time constant (std::true_type / std::false_type) or a run-time value
+template <class T>
+__device__ __forceinline__ constexpr uint32_t tail_value(T v) {
+    if constexpr (std::is_same<T, uint32_t>::value) return v;
+    else return T::value ? 1u : 0u;
+}
 
 struct UnitInfo {
     int64_t qt, split, t_lo, t_hi;
@@ -318,6 +338,16 @@ struct RowState {
         return cnt[r];
 #endif
     }
+    // take n hits back from register slot r (correction paths of TRB_TC_COUNT_FIRST)
+    __device__ __forceinline__ void sub(int r, int n) {
+#if TRB_TC_COUNT_FMA == 2
+        ci[r] -= 127u * (uint32_t)n;
+#elif TRB_TC_COUNT_FMA
+        cf[r] = (cf[r] & 0xffffffff00000000ull) | (unsigned long long)__float_as_uint(__uint_as_float((uint32_t)cf[r]) - (float)n);
+#else
+        cnt[r] -= n;
+#endif
+    }
     // fp32 counters are exact up to 2^24, the scaled integer counters up to 2^32 / 127: the epilogue drains them into the
     // global counters every 256 tiles (<= 16384 hits per lane)
     __device__ __forceinline__ void drain(const Params& p) {
@@ -451,6 +481,15 @@ __device__ __noinline__ void fix_own_chunk(const Params& p, const float* lv, int
         if (c) atomicAdd(p.cnt + slot, c);
     }
 }
+// TRB_TC_COUNT_FIRST: the chunk was counted against nextbelow(thr) (">=" semantics) although the slot switches to the strict
+// compare here: values equal to thr AT or AFTER the item (position l in the chunk; l < 0: the item precedes the chunk) go back.
+__device__ __noinline__ void unfix_switched_slot(const Params& p, const float* lv, int g0, int64_t slot) {
+    const int64_t l = p.thr_gidx[slot] - p.g_base - g0;
+    const float th = p.thr[slot];
+    int c = 0;
+    for (int j = l > 0 ? (int)l : 0; j < CH; ++j) c += (lv[j] == th) ? 1 : 0;
+    if (c) atomicAdd(p.cnt + slot, -c);
+}
 // exact count of this chunk for the CSR positions >= rtn (rows with more relevant items than register slots) and the
 // positions flagged in `slow`
 __device__ __noinline__ void count_exact(const Params& p, const float* lv, int g0, int64_t s_lo, int64_t s_hi, int rtn, uint32_t slow) {
@@ -522,29 +561,71 @@ __device__ __forceinline__ void count_chunk(RowState<RTN>& st, const float (&v)[
 // `fast_ok`: the tile holds no zero-padded tail rows.  The common chunk -- no top-10 candidate, no threshold switching to its
 // strict compare, no row that needs the exact slow path, in ANY lane of the warp -- takes one warp-uniform branch and runs the
 // counting loop; everything else falls through to the general path, which re-tests each condition per lane.
-template <int RTN>
-__device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st, const float (&v)[CH], int g0, bool row_valid,
-                                             bool warp_has_thr, bool fast_ok, bool row_slow) {
-    // chunk maximum for the top-10 filter; ptxas folds this into 3-input FMNMX3
+// chunk maximum (and the maxima of its 4-value groups) for the top-10 filter; ptxas folds this into 3-input FMNMX3
+__device__ __forceinline__ float chunk_max(const float (&v)[CH], float (&m8)[CH / 4]) {
     constexpr int NG = CH / 4;
-    float m8[NG];
 #pragma unroll
     for (int i = 0; i < NG; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
     float cmax = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
     if (NG == 8) cmax = fmaxf(cmax, fmaxf(fmaxf(m8[NG - 4], m8[NG - 3]), fmaxf(m8[NG - 2], m8[NG - 1])));
-#if TRB_TC_FAST_CHUNK
-    if (fast_ok) {
+    return cmax;
+}
+
+// `tail` (a register flag, the same for every chunk of a tile): the tile holds zero-padded gallery rows, which must not rank.
+// Returns (warp-uniformly) whether the rare path ran, i.e. whether the lanes may have diverged.
+template <int RTN>
+__device__ __forceinline__ bool stream_chunk(const Params& p, RowState<RTN>& st, float (&v)[CH], int g0, bool row_valid,
+                                             bool warp_has_thr, uint32_t tail, bool row_slow) {
+    constexpr int NG = CH / 4;
+    float m8[NG];
+    float cmax = chunk_max(v, m8);
+#if TRB_TC_COUNT_FIRST
+    static_assert(TRB_TC_COUNT_FMA != 0, "count-first needs the scaled compare values");
+    {
 #ifdef TRB_TC_PROBE
         if (p.debug & 8) row_valid = false;
 #endif
-        const bool rare = (row_valid && cmax > st.ts[TRB_TOPK - 1]) || g0 >= st.next_sw || row_slow;
+        const bool rare = (row_valid && cmax > st.ts[TRB_TOPK - 1]) || g0 >= st.next_sw || row_slow || tail != 0u;
+        const bool any_rare = __any_sync(0xffffffffu, rare);
+        if (warp_has_thr) count_chunk<RTN>(st, v, cmax);       // unconditional: the vote resolves under these instructions
+        if (!any_rare) return false;
+    }
+    if (tail != 0u) {                          // padded gallery rows (zero vectors, similarity exactly 0) never rank
+        const int gvalid = (int)p.G;
+        const int npad = min(max(g0 + CH - gvalid, 0), CH);
+        if (warp_has_thr && npad > 0) {
+#pragma unroll
+            for (int r = 0; r < RTN; ++r)
+                if (st.te[r] > 0.f) st.sub(r, npad);           // te holds -t * 2^100: the zeros were counted iff t < 0
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+            if (g0 + j >= gvalid) v[j] = -CUDART_INF_F;
+        cmax = chunk_max(v, m8);
+    }
+#else
+#if TRB_TC_FAST_CHUNK
+    {
+#ifdef TRB_TC_PROBE
+        if (p.debug & 8) row_valid = false;
+#endif
+        // the tail flag rides in the same test: no separate per-chunk branch for the one padded tile of a gallery
+        const bool rare = (row_valid && cmax > st.ts[TRB_TOPK - 1]) || g0 >= st.next_sw || row_slow || tail != 0u;
         if (!__any_sync(0xffffffffu, rare)) {
             if (warp_has_thr) count_chunk<RTN>(st, v, cmax);
-            return;
+            return false;
         }
     }
 #endif
+    if (tail != 0u) {                          // padded gallery rows (zero vectors) never rank
+        const int gvalid = (int)p.G;
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+            if (g0 + j >= gvalid) v[j] = -CUDART_INF_F;
+        cmax = chunk_max(v, m8);
+    }
 
+#endif
     // ---- top-10: candidates are rare after the first tiles; only 4-value groups whose maximum beats the current
     //      10th best are scanned, and the hits go through a bit mask + select tree (keeps the hot loop compact) ----
 #ifdef TRB_TC_PROBE
@@ -571,7 +652,22 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
     }
 
     // ---- exact rank counts ----
-    if (!warp_has_thr) return;
+    if (!warp_has_thr) return true;
+#if TRB_TC_COUNT_FIRST
+    const bool switching = row_valid && g0 >= st.next_sw;
+    if (switching || row_slow) {
+        float lv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) lv[j] = v[j];
+        if (switching) {
+#pragma unroll
+            for (int r = 0; r < RTN; ++r)
+                if (g0 >= st.sw[r]) unfix_switched_slot(p, lv, g0, st.s_lo + st.slot_of(r));
+        }
+        if (row_slow) count_exact(p, lv, g0, st.s_lo, st.s_hi, RTN, st.slow);
+    }
+    if (g0 >= st.next_sw) st.pass_items(p, g0);            // the following chunks compare strictly
+#else
     bool own = false;
     if (g0 >= st.next_sw) own = st.pass_items(p, g0);      // rare: 1 + (relevant items of the row) times per stream
     count_chunk<RTN>(st, v, cmax);
@@ -584,6 +680,8 @@ __device__ __forceinline__ void stream_chunk(const Params& p, RowState<RTN>& st,
         if (own) fix_own_chunk(p, lv, g0, st.s_lo, min(st.s_lo + RTN, st.s_hi), st.slow);
         if (overflow) count_exact(p, lv, g0, st.s_lo, st.s_hi, RTN, st.slow);
     }
+#endif
+    return true;
 }
 
 template <int MODE, int RTN>
@@ -718,11 +816,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
             // rows with more relevant items than register slots, or with a threshold too close to zero for the scaled compare
             const bool row_slow = MODE == 0 && q >= 0 && ((st.s_hi - st.s_lo > RTN) || st.slow != 0u);
 
-            for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) {
+            // Only the last tile of the gallery holds zero padding rows.  The tile body exists twice, with the tail handling as a
+            // compile-time constant: the hot copy carries no per-chunk test against p.G (the compiler re-derived a run-time flag
+            // inside every chunk: a constant-bank load and a 64-bit compare, 5 % of the chunk loop), the cold copy runs once per unit.
+            // (RTN = 8: one copy with a run-time flag -- two copies of its 6 KB chunk loop cost more in instruction fetch, 81 vs 72 ms.)
+            auto tile_body = [&](const int64_t t, auto tail_c) {
+                const uint32_t tail_flag = tail_value(tail_c);
                 mbar_wait_sleepy(t_full + tbuf, tphase, p.wait_hint_ns);
                 tc_fence_after();
                 if (lane == 0 && (warp == 2 || warp == 6)) TRB_STAMP(warp == 2 ? 2 : 4, t);
-                const bool tail_tile = (t + 1) * TILE_N > p.G;         // only the last tile holds zero padding rows
                 const uint32_t taddr0 = lane_taddr + (uint32_t)(tbuf * TILE_N);
                 auto consume = [&](float (&v)[CH], int chunk) {
                     const int g0 = (int)(t * TILE_N) + chunk_col(colgrp, chunk);   // packed gallery row of v[0]
@@ -742,13 +844,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                         }
                         return;
                     }
-                    if (tail_tile) {                       // padded gallery rows (zero vectors) never rank
-                        const int gvalid = (int)p.G;
-#pragma unroll
-                        for (int j = 0; j < CH; ++j)
-                            if (g0 + j >= gvalid) v[j] = -CUDART_INF_F;
-                    }
-                    stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr, !tail_tile, row_slow);
+                    const bool diverged = stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr, tail_flag, row_slow);
+#if TRB_TC_SYNC_RARE
+                    if (diverged) __syncwarp();            // tcgen05.ld is warp-collective (.sync.aligned)
+#else
+                    (void)diverged;
+#endif
                 };
                 auto release = [&]() {                     // accumulator fully read by this warp: hand it back
                     tc_fence_before();
@@ -777,6 +878,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                     if (more) tmem_ld_wait(va);
                 }
 #else
+#if TRB_TC_SYNC_RARE
+                __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
+#endif
 #if TRB_TC_UNROLL_CHUNKS
                 static_assert(COLGRP_CONTIGUOUS, "the unrolled chunk loop needs evenly divided column groups");
 #pragma unroll
@@ -786,7 +890,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 for (int chunk = 0; chunk < my_chunks; ++chunk) {
 #endif
                     float v[CH];
+#if !TRB_TC_SYNC_RARE
                     __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
+#endif
                     tmem_ld_issue(taddr0 + (uint32_t)chunk_col(colgrp, chunk), v);
                     tmem_ld_wait(v);
                     if (chunk == my_chunks - 1) release();
@@ -797,6 +903,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
 
                 if (++tbuf == NTB) { tbuf = 0; tphase ^= 1; }
                 if (MODE == 0 && TRB_TC_COUNT_FMA && ((t - ui.t_lo) & 255) == 255 && warp_has_thr) st.drain(p);
+            };
+            if (RTN <= 4) {
+                const bool has_tail = MODE == 0 && ui.t_hi * TILE_N > p.G;      // then it is tile t_hi - 1
+                const int64_t t_fast_end = has_tail ? ui.t_hi - 1 : ui.t_hi;
+                for (int64_t t = ui.t_lo; t < t_fast_end; ++t) tile_body(t, std::false_type{});
+                if (has_tail) tile_body(ui.t_hi - 1, std::true_type{});
+            } else {
+                for (int64_t t = ui.t_lo; t < ui.t_hi; ++t) tile_body(t, (uint32_t)((t + 1) * TILE_N > p.G ? 1u : 0u));
             }
 
             if (MODE == 0 && q >= 0) {
