@@ -140,7 +140,11 @@ struct Params {
 // suspend hint compiles to TRYWAIT + NANOSLEEP.SYNCS, which wakes on every mbarrier event of the CTA, i.e. every ~16 ns here).
 // A plain nanosleep really parks the thread; the double-buffered accumulator and the multi-stage ring give both roles a full
 // tile / several stages of slack, so a wake-up granularity of `ns` costs nothing.
+#ifndef TRB_TC_ROLE_NS_SCALE
+#define TRB_TC_ROLE_NS_SCALE 1
+#endif
 __device__ __forceinline__ void role_wait(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    ns *= TRB_TC_ROLE_NS_SCALE;
 #if TRB_TC_HOT_SPIN
     mbar_wait(bar, parity);
 #else
@@ -715,7 +719,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+#ifndef TRB_TC_SWAP_ROLES
+#define TRB_TC_SWAP_ROLES 0
+#endif
+    constexpr int PRODUCER_WARP = TRB_TC_SWAP_ROLES ? 1 : 0, MMA_WARP = TRB_TC_SWAP_ROLES ? 0 : 1;
+    if (warp == PRODUCER_WARP) {
         // ------------------------------- producer -------------------------------------------
         if (lane == 0) {
             int stage = 0;
@@ -750,7 +758,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         // ------------------------------- MMA issuer -----------------------------------------
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
