@@ -1,8 +1,10 @@
 // bf16 tensor-core retrieval stream for sm_100a: tcgen05.mma (M=128, N=256, K=16, fp32 accumulate in
 // TMEM), operands staged into shared memory by cp.async.bulk (TMA engine) from the packed
-// pre-swizzled HBM layout of tc_common.cuh, a 4-stage mbarrier ring, double-buffered TMEM
+// pre-swizzled HBM layout of tc_common.cuh, a 5-stage mbarrier ring (D = 256), double-buffered TMEM
 // accumulators, and an epilogue that consumes the similarity tile straight out of TMEM:
 // per-query top-10 and exact rank counts.  The [Q,G] similarity matrix never exists in HBM.
+// What bounds it and every build-time knob below (TRB_TC_*): profiles/r02_stream_timeline.md,
+// profiles/r02_stream_experiments.md.
 //
 // Replaces (with evaluation.py:117-120 fused in by trb_pack_rows_bf16) the reference's
 //   similarity = text @ image.T ; argsort ; matches ; cumsum        lib/data/metrics/evaluation.py:11-37,120
@@ -482,6 +484,7 @@ __device__ __forceinline__ void pad_list(const Params& p, int64_t q, int64_t nli
 //  fix_own_chunk : the chunk contains relevant items of this row; the fast path compared it against thr itself (">"),
 //                  values equal to thr that precede the item must be added.
 //  count_overflow: rows with more than RTN relevant items -- exact count of the extra slots for this chunk.
+#if !TRB_TC_COUNT_FIRST
 __device__ __noinline__ void fix_own_chunk(const Params& p, const float* lv, int g0, int64_t s_lo, int64_t s_end, uint32_t slow) {
     for (int64_t slot = s_lo; slot < s_end; ++slot) {
         if ((slow >> (int)(slot - s_lo)) & 1u) continue;           // counted exactly by count_exact
@@ -497,6 +500,7 @@ __device__ __noinline__ void fix_own_chunk(const Params& p, const float* lv, int
         if (c) atomicAdd(p.cnt + slot, c);
     }
 }
+#endif
 // TRB_TC_COUNT_FIRST: the chunk was counted against nextbelow(thr) (">=" semantics) although the slot switches to the strict
 // compare here: values equal to thr AT or AFTER the item (position l in the chunk; l < 0: the item precedes the chunk) go back.
 __device__ __noinline__ void unfix_switched_slot(const Params& p, const float* lv, int g0, int64_t slot) {
@@ -574,9 +578,11 @@ __device__ __forceinline__ void count_chunk(RowState<RTN>& st, const float (&v)[
     }
 }
 
-// `fast_ok`: the tile holds no zero-padded tail rows.  The common chunk -- no top-10 candidate, no threshold switching to its
-// strict compare, no row that needs the exact slow path, in ANY lane of the warp -- takes one warp-uniform branch and runs the
-// counting loop; everything else falls through to the general path, which re-tests each condition per lane.
+// One chunk (CH accumulator columns of a row, in registers) through the epilogue.  The common chunk -- no top-10 candidate, no
+// threshold switching to its strict compare, no row that needs the exact slow path, no padded tail tile, in ANY lane of the warp --
+// costs the chunk maximum, one warp-uniform vote and the counting loop.  With TRB_TC_COUNT_FIRST (shipped) the counting loop runs
+// BEFORE the vote is consumed, so that the vote's dependent instructions resolve under the arithmetic, and the rare path corrects
+// the counts afterwards; otherwise the rare path prepares (switches thresholds, masks the tail) and counts itself.
 // chunk maximum (and the maxima of its 4-value groups) for the top-10 filter; ptxas folds this into 3-input FMNMX3
 __device__ __forceinline__ float chunk_max(const float (&v)[CH], float (&m8)[CH / 4]) {
     constexpr int NG = CH / 4;
