@@ -706,7 +706,9 @@ __device__ __forceinline__ bool stream_chunk(const Params& p, RowState<RTN>& st,
     return true;
 }
 
-template <int MODE, int RTN>
+// COUNTS: the launch carries thresholds (rank counts wanted).  A compile-time constant so that the chunk loop has no "does this warp
+// have thresholds" branch; a warp whose 32 rows happen to have none counts against -inf (nothing), which is rare and harmless.
+template <int MODE, int RTN, bool COUNTS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -906,7 +908,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 bhi = p.band_hi[prow];
                 slot_base = p.rel_ptr[q] + p.rel_off[prow];
             }
-            const bool warp_has_thr = MODE == 0 && __any_sync(0xffffffffu, st.s_hi > st.s_lo);
+            constexpr bool warp_has_thr = MODE == 0 && COUNTS;
             // rows with more relevant items than register slots, or with a threshold too close to zero for the scaled compare
             const bool row_slow = MODE == 0 && q >= 0 && ((st.s_hi - st.s_lo > RTN) || st.slow != 0u);
 
@@ -1179,15 +1181,16 @@ extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packe
 
     const int smem_bytes = a_bytes + p.nstages * STAGE_BYTES + fixed_bytes;
     const unsigned grid = (unsigned)(p.num_units < sms ? p.num_units : sms);
-#define TRB_LAUNCH_TC(MODE_, RTN_)                                                                                     \
-    do {                                                                                                               \
-        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<MODE_, RTN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         smem_bytes));                                                                 \
-        retrieval_tc_kernel<MODE_, RTN_><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                   \
+#define TRB_LAUNCH_TC(MODE_, RTN_, COUNTS_)                                                                                      \
+    do {                                                                                                                         \
+        TRB_CUDA_OK(cudaFuncSetAttribute(retrieval_tc_kernel<MODE_, RTN_, COUNTS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         smem_bytes));                                                                           \
+        retrieval_tc_kernel<MODE_, RTN_, COUNTS_><<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                    \
     } while (0)
-    if (mode == 1) TRB_LAUNCH_TC(1, 4);
-    else if (max_rel <= 4) TRB_LAUNCH_TC(0, 4);
-    else TRB_LAUNCH_TC(0, 8);
+    if (mode == 1) TRB_LAUNCH_TC(1, 4, false);
+    else if (rel_ptr == nullptr) TRB_LAUNCH_TC(0, 4, false);      // top-k only
+    else if (max_rel <= 4) TRB_LAUNCH_TC(0, 4, true);
+    else TRB_LAUNCH_TC(0, 8, true);
 #undef TRB_LAUNCH_TC
 #ifdef TRB_TC_PROBE
     if ((p.debug & 16) && mode == 0) {
