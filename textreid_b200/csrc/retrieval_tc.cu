@@ -88,21 +88,12 @@ constexpr int MAX_STAGES = 16;
 #ifndef TRB_TC_HOT_SPIN
 #define TRB_TC_HOT_SPIN 0
 #endif
-//   TRB_TC_UNROLL_CHUNKS: 1 = the chunk loop of a tile is fully unrolled (static chunk index: no release test, no loop branch)
-#ifndef TRB_TC_UNROLL_CHUNKS
-#define TRB_TC_UNROLL_CHUNKS 0
-#endif
 //   TRB_TC_COUNT_FIRST: 1 = the register counts of a chunk are taken BEFORE the rare-case vote is consumed (its four dependent
 //                       instructions overlap the arithmetic); the rare path then corrects instead of preparing: a threshold that
 //                       switches to its strict compare in this chunk takes back the ties at / after its item, the padded tile
 //                       takes back its zero rows
 #ifndef TRB_TC_COUNT_FIRST
 #define TRB_TC_COUNT_FIRST 1
-#endif
-//   TRB_TC_SYNC_RARE: 1 = the warp re-converges explicitly (__syncwarp) at the END OF THE RARE PATH -- the only place where the lanes
-//                     of an epilogue warp diverge -- and once per tile, instead of in front of every tcgen05.ld
-#ifndef TRB_TC_SYNC_RARE
-#define TRB_TC_SYNC_RARE 0
 #endif
 //   TRB_TC_FAST_CHUNK: 1 = one warp-uniform test per chunk ("nothing rare in any lane") in front of the per-condition branches
 #ifndef TRB_TC_FAST_CHUNK
@@ -142,11 +133,7 @@ struct Params {
 // suspend hint compiles to TRYWAIT + NANOSLEEP.SYNCS, which wakes on every mbarrier event of the CTA, i.e. every ~16 ns here).
 // A plain nanosleep really parks the thread; the double-buffered accumulator and the multi-stage ring give both roles a full
 // tile / several stages of slack, so a wake-up granularity of `ns` costs nothing.
-#ifndef TRB_TC_ROLE_NS_SCALE
-#define TRB_TC_ROLE_NS_SCALE 1
-#endif
 __device__ __forceinline__ void role_wait(uint64_t* bar, uint32_t parity, uint32_t ns) {
-    ns *= TRB_TC_ROLE_NS_SCALE;
 #if TRB_TC_HOT_SPIN
     mbar_wait(bar, parity);
 #else
@@ -183,18 +170,6 @@ __device__ __forceinline__ unsigned long long gtime() {
 #else
 #define TRB_STAMP(row, t) do { } while (0)
 #endif
-
-//   TRB_TC_EPI_ISSUE: 1 = no polling MMA thread: the epilogue warp that is the LAST to hand an accumulator back issues the MMAs of the
-//                     tile that re-uses it (tile n + NTB) itself, from a cursor in shared memory; warp 1 only primes the first NTB tiles
-#ifndef TRB_TC_EPI_ISSUE
-#define TRB_TC_EPI_ISSUE 0
-#endif
-struct IssueCursor {
-    long long u, t, t_hi;     // unit, next tile of the unit, end of the unit
-    int stage, tb;            // gallery ring stage and accumulator buffer of the next tile
-    uint32_t bphase, aphase;
-    int new_unit, done;
-};
 
 // tail flag of a tile: a compile-time constant (std::true_type / std::false_type) or a run-time value
 template <class T>
@@ -545,22 +520,11 @@ __device__ __forceinline__ void count_chunk(RowState<RTN>& st, const float (&v)[
         }
         st.ci[r] = acc;
 #else
-#if TRB_TC_COUNT_FMA == 3
-        // the same two fp32 counters, bumped by two scalar FADDs instead of one packed FADD2
-        float a0 = __uint_as_float((uint32_t)st.cf[r]), a1 = __uint_as_float((uint32_t)(st.cf[r] >> 32));
-#pragma unroll
-        for (int j = 0; j < CH; j += 2) {
-            a0 += __saturatef(fmaf(v[j], COUNT_SCALE, c));
-            a1 += __saturatef(fmaf(v[j + 1], COUNT_SCALE, c));
-        }
-        st.cf[r] = (unsigned long long)__float_as_uint(a0) | ((unsigned long long)__float_as_uint(a1) << 32);
-#else
         unsigned long long acc = st.cf[r];
 #pragma unroll
         for (int j = 0; j < CH; j += 2)            // 2 x FFMA.SAT (immediate form) + 1 x FADD2: 1.5 instructions per value, FMA pipe
             add2(acc, __saturatef(fmaf(v[j], COUNT_SCALE, c)), __saturatef(fmaf(v[j + 1], COUNT_SCALE, c)));
         st.cf[r] = acc;
-#endif
 #endif
 #else
         if (r < TRB_TC_SKIP_R && !__any_sync(0xffffffffu, cmax > st.te[r])) continue;
@@ -723,11 +687,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
     uint64_t* b_full = bars + 2 + 2 * NTB;  // [NS]
     uint64_t* b_empty = bars + 2 + 2 * NTB + MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * NTB + 2 * MAX_STAGES);
-#if TRB_TC_EPI_ISSUE
-    uint32_t* rel_cnt = tmem_slot + 4;                                   // [NTB] epilogue warps that released the buffer
-    uint32_t* issue_lock = tmem_slot + 4 + NTB;
-    IssueCursor* cur = reinterpret_cast<IssueCursor*>(tmem_slot + 16);   // 64 bytes after the slot, 8-byte aligned
-#endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -737,17 +696,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
         for (int i = 0; i < NTB; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, NUM_EPI_WARPS); }
         for (int i = 0; i < NS; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         mbar_fence_init();
-#if TRB_TC_EPI_ISSUE
-        for (int i = 0; i < NTB; ++i) rel_cnt[i] = 0;
-        *issue_lock = 0;
-        IssueCursor c{};
-        c.done = 1;
-        for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-            const UnitInfo ui = unit_info<MODE>(p, u);
-            if (ui.t_lo < ui.t_hi) { c.u = u; c.t = ui.t_lo; c.t_hi = ui.t_hi; c.new_unit = 1; c.done = 0; break; }
-        }
-        *cur = c;
-#endif
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -755,59 +703,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-#if TRB_TC_EPI_ISSUE
-    // issue the MMAs of the next tile of this CTA (one thread at a time: `issue_lock`)
-    auto issue_next = [&]() {
-        IssueCursor c = *cur;
-        if (c.done) return;
-        constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
-        const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-        if (c.new_unit) {
-            role_wait(a_full, c.aphase, 128);
-            c.aphase ^= 1;
-            c.new_unit = 0;
-        }
-        tc_fence_after();
-        TRB_STAMP(0, c.t);
-        const uint32_t d_tmem = tmem_base + (uint32_t)c.tb * TILE_N;
-        for (int kc = 0; kc < KC; ++kc) {
-            role_wait(b_full + c.stage, c.bphase, 64);
-            tc_fence_after();
-            const uint32_t a0 = a_addr + (uint32_t)kc * BLOCK_BYTES;
-            const uint32_t b0 = b_addr + (uint32_t)c.stage * STAGE_BYTES;
-#pragma unroll
-            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-                umma_bf16(d_tmem, umma_desc_sw128(a0 + kk * UMMA_K * 2), umma_desc_sw128(b0 + kk * UMMA_K * 2), idesc,
-                          (uint32_t)((kc | kk) != 0));
-            umma_commit(b_empty + c.stage);
-            if (++c.stage == NS) { c.stage = 0; c.bphase ^= 1; }
-        }
-        umma_commit(t_full + c.tb);
-        TRB_STAMP(1, c.t);
-        if (++c.tb == NTB) c.tb = 0;
-        if (++c.t == c.t_hi) {
-            umma_commit(a_empty);              // the tensor pipe retires the MMAs of a CTA in issue order: all of the unit are done
-            c.done = 1;
-            for (int64_t u = c.u + gridDim.x; u < p.num_units; u += gridDim.x) {
-                const UnitInfo ui = unit_info<MODE>(p, u);
-                if (ui.t_lo < ui.t_hi) { c.u = u; c.t = ui.t_lo; c.t_hi = ui.t_hi; c.new_unit = 1; c.done = 0; break; }
-            }
-        }
-        *cur = c;
-    };
-    auto issue_locked = [&](int count) {
-        while (atomicCAS(issue_lock, 0u, 1u) != 0u) __nanosleep(32);
-        __threadfence_block();
-        for (int i = 0; i < count; ++i) issue_next();
-        __threadfence_block();
-        atomicExch(issue_lock, 0u);
-    };
-#endif
-#ifndef TRB_TC_SWAP_ROLES
-#define TRB_TC_SWAP_ROLES 0
-#endif
-    constexpr int PRODUCER_WARP = TRB_TC_SWAP_ROLES ? 1 : 0, MMA_WARP = TRB_TC_SWAP_ROLES ? 0 : 1;
-    if (warp == PRODUCER_WARP) {
+    if (warp == 0) {
         // ------------------------------- producer -------------------------------------------
         if (lane == 0) {
             int stage = 0;
@@ -842,11 +738,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 }
             }
         }
-    } else if (warp == MMA_WARP) {
+    } else if (warp == 1) {
         // ------------------------------- MMA issuer -----------------------------------------
-#if TRB_TC_EPI_ISSUE
-        if (lane == 0) issue_locked(NTB);      // prime the accumulator ring; the epilogue warps issue everything after that
-#else
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
             int stage = 0, tbuf = 0;
@@ -883,7 +776,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                 umma_commit(a_empty);                          // query tile may be overwritten
             }
         }
-#endif
     } else if (warp >= EPI_WARP0) {
         // ------------------------------- epilogue -------------------------------------------
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
@@ -940,28 +832,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                         }
                         return;
                     }
-                    const bool diverged = stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr, tail_flag, row_slow);
-#if TRB_TC_SYNC_RARE
-                    if (diverged) __syncwarp();            // tcgen05.ld is warp-collective (.sync.aligned)
-#else
-                    (void)diverged;
-#endif
+                    stream_chunk<RTN>(p, st, v, g0, q >= 0, warp_has_thr, tail_flag, row_slow);
                 };
                 auto release = [&]() {                     // accumulator fully read by this warp: hand it back
                     tc_fence_before();
                     if (lane == 0) TRB_STAMP(6 + warp - EPI_WARP0, t);
-#if TRB_TC_EPI_ISSUE
-                    if (lane == 0) {
-                        __threadfence_block();
-                        if (atomicAdd(rel_cnt + tbuf, 1u) == NUM_EPI_WARPS - 1) {      // last one out: the buffer is free
-                            rel_cnt[tbuf] = 0;
-                            __threadfence_block();
-                            issue_locked(1);
-                        }
-                    }
-#else
                     if (lane == 0) mbar_arrive(t_empty + tbuf);
-#endif
                 };
 #if TRB_TC_PREFETCH
                 // two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is consumed
@@ -985,21 +861,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) retrieval_tc_kernel(const Para
                     if (more) tmem_ld_wait(va);
                 }
 #else
-#if TRB_TC_SYNC_RARE
-                __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
-#endif
-#if TRB_TC_UNROLL_CHUNKS
-                static_assert(COLGRP_CONTIGUOUS, "the unrolled chunk loop needs evenly divided column groups");
-#pragma unroll
-                for (int chunk = 0; chunk < TILE_CHUNKS / NUM_COLGRP; ++chunk) {
-#else
-#pragma unroll 1
+#pragma unroll 1                           // a fully unrolled loop (17 KB) falls out of the instruction cache: 85 vs 57 ms
                 for (int chunk = 0; chunk < my_chunks; ++chunk) {
-#endif
                     float v[CH];
-#if !TRB_TC_SYNC_RARE
                     __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
-#endif
                     tmem_ld_issue(taddr0 + (uint32_t)chunk_col(colgrp, chunk), v);
                     tmem_ld_wait(v);
                     if (chunk == my_chunks - 1) release();
@@ -1158,7 +1023,7 @@ extern "C" int trb_retrieval_stream_tc(const void* q_packed, const void* g_packe
     p.Q = Q; p.G = G;
     p.kchunks = (int)(D / 64);
     const int a_bytes = p.kchunks * BLOCK_BYTES;
-    const int fixed_bytes = (2 + 2 * NTB + 2 * MAX_STAGES) * 8 + 16 + 128 + 1024;   // barriers + TMEM slot + issue cursor + alignment slack
+    const int fixed_bytes = (2 + 2 * NTB + 2 * MAX_STAGES) * 8 + 16 + 1024;   // barriers + TMEM slot + alignment slack
     int ns = (SMEM_MAX - fixed_bytes - a_bytes) / STAGE_BYTES;
     p.nstages = ns > MAX_STAGES ? MAX_STAGES : ns;
     TRB_REQUIRE(p.nstages >= 2, "stream_tc: not enough shared memory for a 2-stage ring at D=%lld", (long long)D);
